@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+metric : CG iterations / second (Jacobi-PCG, Eigen ordering) with the SpMV kernel's achieved HBM
+         bandwidth against the measured roofline (MEASURED_PEAKS.json).
+config : configs[1] of BASELINE.json -- 10M-DoF (216^3) 3-D Poisson 7-point, Jacobi-PCG, tol 1e-8.
+step   : one complete solve(b, x) from x0 = 0 to the relative residual 1e-8.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n GRID]
+
+`value` : device-resident (b, x in HBM), CUDA events on the solver's stream, max over ranks.
+`e2e`   : the same metric through the public C-ABI call path with HOST buffers: every step does
+          factorize_csc(host values) + solve(host b, host x), so the H2D of the matrix values and
+          of b/x and the D2H of x are inside the timed region.
+`--impl reference`: the reference's CPU path (Eigen::ConjugateGradient restatement from oracle/,
+          see DESIGN.md: Eigen/AMGCL are not installable offline) on the box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "cg_iters_per_sec"
+UNIT = "iter/s"
+TOL = 1e-8
+MAX_ITER = 10000
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi during the timed region (B200_PROFILING.md 'clocks line')."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, val in zip(names, r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_problem(n):
+    from polysolve_b200 import problems as P
+    N = n ** 3
+    outer, inner, vals = P.poisson3d(n)
+    xstar = P.splitmix64(42, N)
+    b = P.spmv_csr(outer, inner, vals, xstar)
+    return N, outer, inner, vals, b, xstar
+
+
+def pinned_copy(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    n = args.n
+    N, outer, inner, vals, b, _ = build_problem(n)
+    threads = O.lib().orc_num_threads()
+    sample_iters = args.ref_iters
+    # warm-up + timed steps; one step = `sample_iters` loop trips of the CG on the full-size system
+    # (a bounded sample: the complete solve needs ~650 trips, i.e. minutes on a CPU)
+    mode = 1  # all host cores: row-parallel OpenMP CSR SpMV/dots (symmetric matrix: CSC arrays == CSR)
+    for _ in range(max(1, min(args.warmup, 1))):
+        O.eigen_cg(outer, inner, vals, b, tol=TOL, max_iters=MAX_ITER, mode=mode, stop_after=2)
+    t0 = time.perf_counter()
+    its = 0
+    for _ in range(args.steps):
+        _, it, _, _ = O.eigen_cg(outer, inner, vals, b, tol=TOL, max_iters=MAX_ITER, mode=mode, stop_after=sample_iters)
+        its += it
+    dt = time.perf_counter() - t0
+    value = its / dt
+    # disclosure: the literally faithful path (CSC column scatter, 1 thread = what
+    # Solver::create("Eigen::ConjugateGradient") executes for a column-major matrix)
+    t1 = time.perf_counter()
+    _, it1, _, _ = O.eigen_cg(outer, inner, vals, b, tol=TOL, max_iters=MAX_ITER, mode=0, stop_after=max(4, sample_iters // 4))
+    faithful = it1 / (time.perf_counter() - t1)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"poisson3d_{n}^3 ({N} DoF, 7-pt), Jacobi-PCG tol {TOL}", "n": N, "nnz": int(outer[-1]),
+                   "note": "reference deps Eigen 5.0.1 / AMGCL 1.4.3 not installable offline; CPU numbers are from an "
+                           "in-repo restatement (oracle/) following SURVEY Appendix A"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} x {sample_iters} CG iterations on the full {N}-DoF system, OpenMP row-parallel CSR",
+                         "eigen_faithful_1thread": faithful},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import polysolve_b200 as psb
+    from polysolve_b200 import problems as P
+
+    rank, world, local = dist_env()
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1 (one process per GPU)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n = args.n
+    # weak scaling: every rank owns a full C2-sized system (replicas until the row-partitioned path lands)
+    N, outer, inner, vals, b, xstar = build_problem(n)
+    nnz = int(outer[-1])
+    hbm_peak, peak_src = peaks()
+
+    s = psb.Solver.create("CUDA", "")
+    s.set_parameters({"CUDA": {"krylov": "cg", "precond": "jacobi", "tolerance": TOL, "max_iter": MAX_ITER,
+                               "check_every": args.check_every, "device": local}})
+    t0 = time.perf_counter()
+    s.analyze_pattern_raw(N, outer, inner, N)
+    t_analyze = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    s.factorize_raw(N, outer, inner, vals)
+    t_factorize = time.perf_counter() - t0
+
+    stream = torch.cuda.ExternalStream(s.stream())
+    db = torch.from_numpy(b).cuda()
+    dx = torch.zeros(N, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        with torch.cuda.stream(stream):
+            dx.zero_()
+        s.solve_device(db.data_ptr(), dx.data_ptr(), N)
+        return s.get_info()["solver_iter"]
+
+    # ---- device-resident timed region
+    for _ in range(args.warmup):
+        device_step()
+    launches0 = s.get_info()["gpu_launches"]
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    iters = 0
+    for _ in range(args.steps):
+        iters += device_step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = s.get_info()["gpu_launches"] - launches0
+    info = s.get_info()
+    x = dx.cpu().numpy()
+    rel_res = float(np.linalg.norm(P.spmv_csr(outer, inner, vals, x) - b) / np.linalg.norm(b))
+
+    # ---- e2e: host buffers through the C ABI (factorize values + solve), pinned host memory
+    hv, hb = pinned_copy(vals), pinned_copy(b)
+    hx = pinned_copy(np.zeros(N))
+    for _ in range(min(args.warmup, 2)):
+        hx.zero_()
+        s.factorize_raw(N, outer, inner, hv.numpy())
+        s.solve(hb.numpy(), hx.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    e2e_iters = 0
+    for _ in range(args.steps):
+        hx.zero_()
+        s.factorize_raw(N, outer, inner, hv.numpy())
+        s.solve(hb.numpy(), hx.numpy())
+        e2e_iters += s.get_info()["solver_iter"]
+    barrier()
+    e2e_dt = time.perf_counter() - t0
+
+    # ---- max over ranks / whole-job aggregate
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms, e2e_dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_dt = float(t[0]), float(t[1])
+        c = torch.tensor([iters, e2e_iters, launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        iters, e2e_iters, launches = int(c[0]), int(c[1]), int(c[2])
+
+    if rank != 0:
+        return
+    value = iters / (ms * 1e-3)
+    e2e_value = e2e_iters / e2e_dt
+
+    # ---- roofline of the dominant kernel (fused SpMV + p.Ap), measured live: one extra solve with CUDA
+    #      events around every launch on the solver's stream (graphs off), after the timed region.
+    s.set_parameters({"CUDA": {"profile": True}})
+    device_step()
+    prof = s.get_info().get("profile", {})
+    s.set_parameters({"CUDA": {"profile": False}})
+    total_prof_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    k = prof.get("spmv_dot", {"ms": 0.0, "launches": 1})
+    spmv_ms = k["ms"] / max(1, k["launches"])
+    b_spmv = P.spmv_bytes(N, nnz)
+    achieved = b_spmv / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else 0.0
+    plain_ms = s.bench_spmv(reps=50)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("spmv_dot_dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    iter_bytes = P.pcg_iter_bytes(N, nnz)
+    ms_per_iter = ms / max(1, iters) * world
+
+    # ---- CPU baseline on a bounded sample (rank 0, N == 1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        from oracle import oracle as O
+        threads = O.lib().orc_num_threads()
+        O.eigen_cg(outer, inner, vals, b, tol=TOL, max_iters=MAX_ITER, mode=1, stop_after=2)
+        t0 = time.perf_counter()
+        _, itc, _, _ = O.eigen_cg(outer, inner, vals, b, tol=TOL, max_iters=MAX_ITER, mode=1, stop_after=args.ref_iters)
+        cpu_val = itc / (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        _, it1, _, _ = O.eigen_cg(outer, inner, vals, b, tol=TOL, max_iters=MAX_ITER, mode=0, stop_after=max(4, args.ref_iters // 4))
+        faithful = it1 / (time.perf_counter() - t0)
+        cpu = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{args.ref_iters} CG iterations on the full {N}-DoF system, OpenMP row-parallel CSR (oracle/)",
+               "eigen_faithful_1thread": faithful}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"poisson3d_{n}^3 ({N} DoF, 7-pt), Jacobi-PCG tol {TOL}", "n": N, "nnz": nnz,
+                   "per_gpu": "one full system per GPU (replicas)" if world > 1 else "single system",
+                   "l2_policy": "inputs_exceed_l2 (0.88 GB matrix + 0.4 GB vectors per iteration vs 126 MB L2)",
+                   "iters_per_solve": iters / args.steps / world, "rel_residual": rel_res,
+                   "spmv_kernel": info["spmv_kernel"], "check_every": args.check_every,
+                   "analyze_s": t_analyze, "factorize_s": t_factorize},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * nnz + 16 * N, "d2h_bytes_per_step": 8 * N,
+                "what": "factorize_csc(host values) + solve(host b, x) per step, pinned host buffers"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "spmv_stream_kernel<EpiDot> (fused SpMV + p.Ap)", "achieved": achieved,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": b_spmv, "avg_launch_ms": spmv_ms,
+                     "kernel_share_of_step": k["ms"] / total_prof_ms,
+                     "plain_spmv_gbs": b_spmv / (plain_ms * 1e-3) / 1e9,
+                     "pcg_iter_gbs": iter_bytes / (ms_per_iter * 1e-3) / 1e9, "pcg_iter_frac": iter_bytes / (ms_per_iter * 1e-3) / 1e9 / hbm_peak,
+                     "profile_ms": {kk: vv["ms"] for kk, vv in prof.items()}},
+    }
+    if cpu:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=216, help="grid points per side (216 -> 10,077,696 DoF)")
+    ap.add_argument("--check-every", type=int, default=16)
+    ap.add_argument("--ref-iters", type=int, default=40, help="CG iterations per CPU sample step")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

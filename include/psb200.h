@@ -1,0 +1,104 @@
+/* psb200 -- C ABI of the B200-native linear-solver backend for polysolve.
+ *
+ * This is the drop-in boundary: every entry point below is what a
+ * polysolve::linear::Solver subclass ("CUDA", see adapter/CUDASolver.hpp) binds, one call per
+ * virtual of the reference interface (reference src/polysolve/linear/Solver.hpp:90-131).
+ * Plain pointers and sizes only; no C++/torch types. All functions return 0 on success and a
+ * non-zero status otherwise; psb200_last_error() then holds the message. The C++ adapter turns a
+ * non-zero status into std::runtime_error, the reference's error convention
+ * (src/polysolve/Utils.cpp:65-69), so Newton's factorize fallback keeps working
+ * (src/polysolve/nonlinear/descent_strategies/Newton.cpp:191-202).
+ *
+ * Matrices cross the boundary exactly as polysolve holds them: Eigen compressed-column
+ * (StiffnessMatrix = Eigen::SparseMatrix<double, ColMajor, int>, src/polysolve/Types.hpp:11-15):
+ * outer = outerIndexPtr() int32[n+1], inner = innerIndexPtr() int32[nnz], vals = valuePtr() f64[nnz].
+ */
+#ifndef PSB200_H
+#define PSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct psb200_solver *psb200_handle;
+
+#define PSB200_OK 0
+#define PSB200_ERR_INVALID 1   /* bad argument / protocol violation */
+#define PSB200_ERR_CUDA 2      /* CUDA runtime / kernel failure, out of memory */
+#define PSB200_ERR_NUMERIC 3   /* zero / non-finite diagonal, breakdown detected in setup */
+#define PSB200_ERR_COMM 4      /* NCCL / peer-memory failure */
+
+/* Solver::create("CUDA", precond)  -- reference Solver.cpp:307-496 (MAS branch :402-404 is the template).
+ * json_params may be NULL; otherwise the same document set_parameters() takes. */
+int psb200_create(psb200_handle *out, const char *json_params);
+int psb200_destroy(psb200_handle h);
+
+/* Solver::set_parameters(const json&) -- Solver.hpp:93. Reads the "CUDA" object of the document:
+ *   krylov: "cg"|"bicgstab"; precond: "jacobi"|"amg"|"none"; tolerance; max_iter; check_every;
+ *   use_graph; spmv_kernel; device; amg: {max_levels, coarse_enough, ncycle, npre, npost, degree,
+ *   power_iters, higher, lower, relax, eps_strong, ...} mirroring AMGCL.cpp:32-65.               */
+int psb200_set_parameters(psb200_handle h, const char *json);
+/* Solver::set_tolerance(double) -- Solver.hpp:116-117 (relative to ||b||, as Eigen/AMGCL). */
+int psb200_set_tolerance(psb200_handle h, double tol);
+/* Solver::set_block_size(int) -- Solver.hpp:110. */
+int psb200_set_block_size(psb200_handle h, int block_size);
+
+/* Solver::analyze_pattern(const StiffnessMatrix&, int precond_num) -- Solver.hpp:99.
+ * Index work only: CSC -> CSR transpose map, SpMV tiling, (multi-GPU) row partition + halo lists.
+ * Idempotent: an unchanged pattern (hash) is detected and skipped, because Newton calls this every
+ * iteration (Newton.cpp:189). */
+int psb200_analyze_pattern_csc(psb200_handle h, int64_t n, int64_t nnz, const int32_t *outer,
+                               const int32_t *inner, int precond_num);
+/* Solver::factorize(const StiffnessMatrix&) -- Solver.hpp:102. Values only when the pattern is
+ * known (test "pre_factor", tests/test_linear_solver.cpp:241-307); builds the preconditioner
+ * (Jacobi inverse diagonal / SA-AMG hierarchy). The matrix is borrowed only for this call. */
+int psb200_factorize_csc(psb200_handle h, int64_t n, int64_t nnz, const int32_t *outer,
+                         const int32_t *inner, const double *vals);
+/* Solver::solve(b, x) -- Solver.hpp:119-128. x is in/out: its content is the initial guess
+ * (tests/test_linear_solver.cpp:400-455 pin "converged guess => 0 iterations"). Host pointers. */
+int psb200_solve(psb200_handle h, const double *b, double *x_inout, int64_t n);
+/* Same, with b and x resident in device memory of the solver's GPU. */
+int psb200_solve_device(psb200_handle h, const double *d_b, double *d_x_inout, int64_t n);
+
+/* Solver::get_info(json&) -- Solver.hpp:96. Writes a JSON object with both key conventions:
+ * "solver_iter","solver_error" (EigenSolver.tpp:88-89) and "num_iterations","final_res_norm"
+ * (AMGCL.cpp:142-143), plus "solver_status" (MASSolver.cu:214-219) and timing/hierarchy details.
+ * Returns PSB200_ERR_INVALID if cap is too small (required size in *needed when non-NULL). */
+int psb200_get_info(psb200_handle h, char *json_out, size_t cap, size_t *needed);
+/* Solver::name() -- Solver.hpp:131. Returns "CUDA". */
+const char *psb200_name(psb200_handle h);
+const char *psb200_last_error(psb200_handle h);
+
+/* ---- multi-GPU (one process per GPU). The unique id (128 bytes) is produced on rank 0
+ * and distributed by the host application (torch.distributed / MPI); after psb200_dist_init the
+ * handle owns rows [offsets[rank], offsets[rank+1]) of every system it is given: analyze/factorize
+ * still receive the full CSC matrix on every rank, solve receives full-length b/x on every rank. */
+int psb200_dist_unique_id(char id128[128]);
+int psb200_dist_init(psb200_handle h, int rank, int world, const char id128[128]);
+
+/* ---- test / bench hooks (not part of the polysolve interface) */
+/* CSR produced by analyze_pattern: row_ptr int32[n+1], col_idx int32[nnz], perm int32[nnz] with
+ * vals_csr[k] = vals_csc[perm[k]]. Compared bit-exactly against the oracle's stable transpose. */
+int psb200_debug_get_csr(psb200_handle h, int32_t *row_ptr, int32_t *col_idx, int32_t *perm);
+/* y = A x through the product SpMV kernel (host buffers, full length). */
+int psb200_spmv(psb200_handle h, const double *x, double *y, int64_t n);
+/* reps launches of the product SpMV kernel on resident device vectors, timed with CUDA events on
+ * the solver's stream; *ms_avg = average per launch. kernel: NULL/"" = the configured one. */
+int psb200_bench_spmv(psb200_handle h, const char *kernel, int reps, double *ms_avg);
+/* cudaStream_t the solver launches on (so callers can bracket it with their own events). */
+void *psb200_get_stream(psb200_handle h);
+/* AMG hooks: impose aggregates for level `level` before factorize (parity vs the oracle's greedy
+ * aggregation); read back hierarchy matrices. which: 0=A 1=P 2=R. */
+int psb200_debug_set_aggregates(psb200_handle h, int level, const int32_t *agg, int64_t n);
+int psb200_debug_get_level(psb200_handle h, int level, int which, int64_t *rows, int64_t *cols,
+                           int64_t *nnz, int32_t *row_ptr, int32_t *col_idx, double *vals);
+/* z = M^-1 r : one application of the configured preconditioner (host buffers). */
+int psb200_precond_apply(psb200_handle h, const double *r, double *z, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSB200_H */

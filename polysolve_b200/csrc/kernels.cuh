@@ -1,0 +1,908 @@
+// Device kernels of the Krylov hot path: CSR SpMV (three schedules) with fused epilogues, fused
+// vector updates with deterministic reductions, and the device-resident solver state.
+// Everything is fp64 values + int32 indices (reference Types.hpp:11-15).
+#pragma once
+#include "common.cuh"
+
+#include <cfloat>
+
+namespace psb {
+
+// ---------------------------------------------------------------------------------- solver state
+// Lives in device memory; the host reads a copy when it polls. Scalars never round-trip through the
+// host inside the iteration (policy precedent: reference MASSolver.cu:46-56 keeps alpha/beta on device).
+struct KState
+{
+    double rz, rz_new, pAp, rn2, bn2, thr, tol;
+    double rho, rho_old, alpha, omega, r0v, tt, ts, r0n2;
+    int iter, done, status, max_iter, restart, restarts, pad0, pad1;
+};
+enum : int
+{
+    ST_RUNNING = 0,
+    ST_CONVERGED = 1,
+    ST_MAXITER = 2,
+    ST_BREAKDOWN = 3,
+    ST_ZERO_RHS = 4
+};
+
+struct CsrView
+{
+    const int *rp;
+    const int *ci;
+    const double *va;
+    int n;
+};
+
+// ---------------------------------------------------------------------------------- SpMV epilogues
+// Called once per row by the lane that holds the row sum. NV = number of fused reduction values.
+struct EpiStore
+{
+    static constexpr int NV = 0;
+    double *y;
+    __device__ __forceinline__ void operator()(int row, double s, double (&)[1]) const { y[row] = s; }
+};
+// y = A x and u.y  (PCG: p.Ap; BiCGSTAB: r0.v)
+struct EpiDot
+{
+    static constexpr int NV = 1;
+    double *y;
+    const double *u;
+    __device__ __forceinline__ void operator()(int row, double s, double (&acc)[1]) const
+    {
+        y[row] = s;
+        acc[0] += u[row] * s;
+    }
+};
+// t = A z, t.t and t.s (BiCGSTAB omega)
+struct EpiDot2
+{
+    static constexpr int NV = 2;
+    double *y;
+    const double *u;
+    __device__ __forceinline__ void operator()(int row, double s, double (&acc)[2]) const
+    {
+        y[row] = s;
+        acc[0] += s * s;
+        acc[1] += s * u[row];
+    }
+};
+// r = b - A x with ||r||^2, ||b||^2 and r.(dinv r)
+struct EpiResidualNorms
+{
+    static constexpr int NV = 3;
+    double *r;
+    const double *b;
+    const double *dinv;
+    __device__ __forceinline__ void operator()(int row, double s, double (&acc)[3]) const
+    {
+        const double bi = b[row];
+        const double ri = bi - s;
+        r[row] = ri;
+        acc[0] += ri * ri;
+        acc[1] += bi * bi;
+        acc[2] += ri * ri * dinv[row];
+    }
+};
+// BiCGSTAB restart: r = b - A x, r0 = r, ||r||^2
+struct EpiResidualRestart
+{
+    static constexpr int NV = 1;
+    double *r, *r0;
+    const double *b;
+    __device__ __forceinline__ void operator()(int row, double s, double (&acc)[1]) const
+    {
+        const double ri = b[row] - s;
+        r[row] = ri;
+        r0[row] = ri;
+        acc[0] += ri * ri;
+    }
+};
+// r = b - A x (AMG residual before restriction)
+struct EpiResidual
+{
+    static constexpr int NV = 0;
+    double *r;
+    const double *b;
+    __device__ __forceinline__ void operator()(int row, double s, double (&)[1]) const { r[row] = b[row] - s; }
+};
+// One Chebyshev step fused into the SpMV (amgcl relaxation/chebyshev.hpp solve()):
+//   res = M (b - A x_in);  p = alpha res + beta p;  x_out = x_in + p.     x_in != x_out (ping-pong).
+struct EpiCheb
+{
+    static constexpr int NV = 0;
+    const double *b, *dinv, *xin;
+    double *p, *xout;
+    double alpha, beta;
+    __device__ __forceinline__ void operator()(int row, double s, double (&)[1]) const
+    {
+        const double res = dinv[row] * (b[row] - s);
+        double pn = alpha * res;
+        if (beta != 0.0)
+            pn += beta * p[row];
+        p[row] = pn;
+        xout[row] = xin[row] + pn;
+    }
+};
+// Damped Jacobi / generic diagonal relaxation: x_out = x_in + w[row] (b - A x_in)
+struct EpiRelaxDiag
+{
+    static constexpr int NV = 0;
+    const double *b, *w, *xin;
+    double *xout;
+    __device__ __forceinline__ void operator()(int row, double s, double (&)[1]) const
+    {
+        xout[row] = xin[row] + w[row] * (b[row] - s);
+    }
+};
+// x += P u  (prolongation-and-correct)
+struct EpiAddTo
+{
+    static constexpr int NV = 0;
+    double *x;
+    __device__ __forceinline__ void operator()(int row, double s, double (&)[1]) const { x[row] += s; }
+};
+// power iteration on D^-1 A : b1 = dinv (A b0); ||b1||^2 and |b1.b0|-sum (amgcl spectral_radius)
+struct EpiPower
+{
+    static constexpr int NV = 2;
+    double *b1;
+    const double *b0, *dinv;
+    __device__ __forceinline__ void operator()(int row, double s, double (&acc)[2]) const
+    {
+        const double v = s * dinv[row];
+        b1[row] = v;
+        acc[0] += v * v;
+        acc[1] += fabs(v * b0[row]);
+    }
+};
+
+// ---------------------------------------------------------------------------------- finalizers
+// Run by thread 0 of the last CTA with the grid totals.
+struct FinNone
+{
+    __device__ __forceinline__ void operator()(const double *) const {}
+};
+struct FinStore
+{
+    double *out;
+    int nv;
+    __device__ __forceinline__ void operator()(const double *t) const
+    {
+        for (int i = 0; i < nv; ++i)
+            out[i] = t[i];
+    }
+};
+struct FinPAp
+{
+    KState *st;
+    __device__ __forceinline__ void operator()(const double *t) const { st->pAp = t[0]; }
+};
+// Eigen conjugate_gradient() prologue: thresholds and the two early exits.
+struct FinInitEigen
+{
+    KState *st;
+    __device__ __forceinline__ void operator()(const double *t) const
+    {
+        st->rn2 = t[0];
+        st->bn2 = t[1];
+        st->rz = t[2];
+        st->thr = fmax(st->tol * st->tol * t[1], DBL_MIN);
+        if (t[1] == 0.0)
+        {
+            st->done = 1;
+            st->status = ST_ZERO_RHS;
+        }
+        else if (t[0] < st->thr)
+        {
+            st->done = 1;
+            st->status = ST_CONVERGED;
+        }
+        else if (!(t[0] == t[0]) || isinf(t[0]))
+        {
+            st->done = 1;
+            st->status = ST_BREAKDOWN;
+        }
+    }
+};
+// amgcl::solver::cg prologue (SURVEY A.3 "CG"): eps = max(tol ||b||, min), loop condition ||r|| > eps.
+struct FinInitAmgcl
+{
+    KState *st;
+    __device__ __forceinline__ void operator()(const double *t) const
+    {
+        st->rn2 = t[0];
+        st->bn2 = t[1];
+        const double nb = sqrt(t[1]);
+        st->thr = fmax(st->tol * nb, DBL_MIN);
+        if (nb < DBL_EPSILON)
+        {
+            st->done = 1;
+            st->status = ST_ZERO_RHS;
+        }
+        else if (!(sqrt(t[0]) > st->thr))
+        {
+            st->done = 1;
+            st->status = (t[0] == t[0]) ? ST_CONVERGED : ST_BREAKDOWN;
+        }
+    }
+};
+struct FinCgUpdateEigen
+{
+    KState *st;
+    __device__ __forceinline__ void operator()(const double *t) const
+    {
+        st->rn2 = t[0];
+        st->rz_new = t[1];
+        if (t[0] < st->thr) // Eigen breaks before i++
+        {
+            st->done = 1;
+            st->status = ST_CONVERGED;
+        }
+        else if (!(t[0] == t[0]) || isinf(t[0]))
+        {
+            st->done = 1;
+            st->status = ST_BREAKDOWN;
+        }
+    }
+};
+struct FinCgDirEigen
+{
+    KState *st;
+    __device__ __forceinline__ void operator()(const double *) const
+    {
+        st->rz = st->rz_new;
+        st->iter += 1;
+        if (st->iter >= st->max_iter)
+        {
+            st->done = 1;
+            st->status = ST_MAXITER;
+        }
+    }
+};
+struct FinRhoAmgcl
+{
+    KState *st;
+    __device__ __forceinline__ void operator()(const double *t) const
+    {
+        st->rho_old = st->rho;
+        st->rho = t[0];
+    }
+};
+struct FinCgUpdateAmgcl
+{
+    KState *st;
+    __device__ __forceinline__ void operator()(const double *t) const
+    {
+        st->rn2 = t[0];
+        st->iter += 1;
+        if (!(sqrt(t[0]) > st->thr))
+        {
+            st->done = 1;
+            st->status = (t[0] == t[0]) ? ST_CONVERGED : ST_BREAKDOWN;
+        }
+        else if (st->iter >= st->max_iter)
+        {
+            st->done = 1;
+            st->status = ST_MAXITER;
+        }
+    }
+};
+// Eigen bicgstab()
+struct FinInitBicg
+{
+    KState *st;
+    __device__ __forceinline__ void operator()(const double *t) const
+    {
+        st->rn2 = t[0];
+        st->bn2 = t[1];
+        st->r0n2 = t[0];
+        st->thr = st->tol * st->tol * t[1];
+        st->rho = 1;
+        st->alpha = 1;
+        st->omega = 1;
+        if (t[1] == 0.0)
+        {
+            st->done = 1;
+            st->status = ST_ZERO_RHS;
+        }
+        else if (!(t[0] > st->thr))
+        {
+            st->done = 1;
+            st->status = (t[0] == t[0]) ? ST_CONVERGED : ST_BREAKDOWN;
+        }
+        else
+        {
+            // first loop trip: rho = r0.r = ||r0||^2
+            st->rho_old = 1;
+            st->rho = t[0];
+            st->restart = (fabs(t[0]) < DBL_EPSILON * DBL_EPSILON * t[0]) ? 1 : 0;
+        }
+    }
+};
+struct FinBicgAlpha
+{
+    KState *st;
+    __device__ __forceinline__ void operator()(const double *t) const
+    {
+        st->r0v = t[0];
+        st->alpha = st->rho / t[0];
+    }
+};
+struct FinBicgOmega
+{
+    KState *st;
+    __device__ __forceinline__ void operator()(const double *t) const
+    {
+        st->tt = t[0];
+        st->ts = t[1];
+        st->omega = t[0] > 0.0 ? t[1] / t[0] : 0.0;
+    }
+};
+// end of a BiCGSTAB trip: t[0] = ||r||^2, t[1] = r0.r for the next trip
+struct FinBicgEnd
+{
+    KState *st;
+    __device__ __forceinline__ void operator()(const double *t) const
+    {
+        st->rn2 = t[0];
+        st->iter += 1;
+        if (!(t[0] > st->thr))
+        {
+            st->done = 1;
+            st->status = (t[0] == t[0]) ? ST_CONVERGED : ST_BREAKDOWN;
+        }
+        else if (st->iter >= st->max_iter)
+        {
+            st->done = 1;
+            st->status = ST_MAXITER;
+        }
+        else
+        {
+            st->rho_old = st->rho;
+            st->rho = t[1];
+            st->restart = (fabs(t[1]) < DBL_EPSILON * DBL_EPSILON * st->r0n2) ? 1 : 0;
+        }
+    }
+};
+// restart: r = b - A x recomputed, r0 = r; t[0] = ||r||^2
+struct FinBicgRestart
+{
+    KState *st;
+    __device__ __forceinline__ void operator()(const double *t) const
+    {
+        st->rho = t[0];
+        st->r0n2 = t[0];
+        st->rn2 = t[0];
+        if (st->restarts++ == 0)
+            st->iter = 0;
+        st->restart = 0;
+    }
+};
+
+// ---------------------------------------------------------------------------------- SpMV: vector schedule
+// LPR lanes cooperate on one row (LPR = 1 is the scalar thread-per-row schedule). Grid-stride over rows.
+template <class Epi, class Fin, int LPR, int THREADS>
+__global__ void __launch_bounds__(THREADS) spmv_vector_kernel(CsrView A, const double *__restrict__ x, Epi epi, RedCtx rc,
+                                                              Fin fin, const int *done, const int *only_if)
+{
+    if (done && *done)
+        return;
+    if (only_if && !*only_if)
+        return;
+    constexpr int NVA = Epi::NV > 0 ? Epi::NV : 1;
+    double acc[NVA];
+#pragma unroll
+    for (int i = 0; i < NVA; ++i)
+        acc[i] = 0;
+    const int lane = threadIdx.x % LPR;
+    const int rows_per_cta = THREADS / LPR;
+    for (long long base = (long long)blockIdx.x * rows_per_cta; base < A.n; base += (long long)gridDim.x * rows_per_cta)
+    {
+        const int row = (int)base + threadIdx.x / LPR;
+        double s = 0;
+        if (row < A.n)
+        {
+            const int kb = __ldg(A.rp + row), ke = __ldg(A.rp + row + 1);
+            for (int k = kb + lane; k < ke; k += LPR)
+                s += __ldg(A.va + k) * __ldg(x + __ldg(A.ci + k));
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1)
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (row < A.n && lane == 0)
+            epi(row, s, acc);
+    }
+    double tot[NVA];
+    if (grid_reduce<Epi::NV, THREADS>(acc, rc, tot) && threadIdx.x == 0)
+        fin(tot);
+}
+
+// ---------------------------------------------------------------------------------- SpMV: TMA-staged stream schedule
+// For short rows (stencils): a CTA walks tiles of THREADS consecutive rows. The tile's contiguous
+// val/col ranges are pulled into shared memory by 1-D TMA bulk copies (cp.async.bulk, completion on
+// an mbarrier) STAGES tiles ahead, so HBM streams the matrix at full line efficiency regardless of
+// row length; each thread then reduces its own row from shared memory, which makes the x gathers of
+// a warp hit consecutive addresses for banded matrices. Tiles whose nnz exceed CAP fall back to
+// direct global loads (correct for any matrix).
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar, unsigned long long policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+
+template <int CAP, int STAGES>
+struct StreamSmem
+{
+    static constexpr size_t val_bytes = (size_t)STAGES * CAP * sizeof(double);
+    static constexpr size_t col_bytes = (size_t)STAGES * CAP * sizeof(int);
+    static constexpr size_t bytes = val_bytes + col_bytes + 128;
+};
+
+template <class Epi, class Fin, int THREADS, int CAP, int STAGES>
+__global__ void __launch_bounds__(THREADS) spmv_stream_kernel(CsrView A, const double *__restrict__ x, Epi epi, RedCtx rc,
+                                                              Fin fin, const int *done, const int *only_if)
+{
+    if (done && *done)
+        return;
+    if (only_if && !*only_if)
+        return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sval = reinterpret_cast<double *>(smem_raw);
+    int *scol = reinterpret_cast<int *>(smem_raw + StreamSmem<CAP, STAGES>::val_bytes);
+    __shared__ __align__(8) unsigned long long bar[STAGES];
+
+    constexpr int NVA = Epi::NV > 0 ? Epi::NV : 1;
+    double acc[NVA];
+#pragma unroll
+    for (int i = 0; i < NVA; ++i)
+        acc[i] = 0;
+
+    const int ntiles = (A.n + THREADS - 1) / THREADS;
+    unsigned long long policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+            mbar_init(&bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto issue = [&](int tile, int s) {
+        const int r0 = tile * THREADS;
+        const int r1 = min(A.n, r0 + THREADS);
+        const int k0 = __ldg(A.rp + r0), k1 = __ldg(A.rp + r1);
+        const int ka = k0 & ~3;
+        const int cnt4 = (k1 - ka + 3) & ~3;
+        if (cnt4 > 0 && cnt4 <= CAP)
+        {
+            mbar_expect_tx(&bar[s], (unsigned)cnt4 * 12u);
+            tma_bulk_g2s(sval + (size_t)s * CAP, A.va + ka, (unsigned)cnt4 * 8u, &bar[s], policy);
+            tma_bulk_g2s(scol + (size_t)s * CAP, A.ci + ka, (unsigned)cnt4 * 4u, &bar[s], policy);
+        }
+        else
+            mbar_arrive(&bar[s]);
+    };
+
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+        {
+            const int tile = blockIdx.x + s * gridDim.x;
+            if (tile < ntiles)
+                issue(tile, s);
+        }
+    }
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it)
+    {
+        const int s = it % STAGES;
+        const unsigned parity = (it / STAGES) & 1;
+        const int r0 = tile * THREADS;
+        const int row = r0 + threadIdx.x;
+        int kb = 0, ke = 0;
+        if (row < A.n)
+        {
+            kb = __ldg(A.rp + row);
+            ke = __ldg(A.rp + row + 1);
+        }
+        const int k0 = __ldg(A.rp + r0);
+        const int k1 = __ldg(A.rp + min(A.n, r0 + THREADS));
+        const int ka = k0 & ~3;
+        const bool staged = ((k1 - ka + 3) & ~3) <= CAP;
+        mbar_wait(&bar[s], parity);
+        double sum = 0;
+        if (staged)
+        {
+            const double *sv = sval + (size_t)s * CAP - ka;
+            const int *sc = scol + (size_t)s * CAP - ka;
+            // 4 gathers in flight per trip; products are still added in k order
+            for (int k = kb; k < ke; k += 4)
+            {
+                double v[4], xx[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                {
+                    const bool ok = k + u < ke;
+                    const int c = ok ? sc[k + u] : 0;
+                    v[u] = ok ? sv[k + u] : 0.0;
+                    xx[u] = ok ? __ldg(x + c) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (k + u < ke)
+                        sum += v[u] * xx[u];
+            }
+        }
+        else
+        {
+            for (int k = kb; k < ke; ++k)
+                sum += __ldg(A.va + k) * __ldg(x + __ldg(A.ci + k));
+        }
+        if (row < A.n)
+            epi(row, sum, acc);
+        __syncthreads(); // every thread is done reading stage s
+        if (threadIdx.x == 0)
+        {
+            const int next = tile + STAGES * gridDim.x;
+            if (next < ntiles)
+                issue(next, s);
+        }
+    }
+    double tot[NVA];
+    if (grid_reduce<Epi::NV, THREADS>(acc, rc, tot) && threadIdx.x == 0)
+        fin(tot);
+}
+
+// ---------------------------------------------------------------------------------- fused vector kernels
+// Element-wise ops over double2 (128-bit) lanes with up to kMaxRed fused reductions. Vectors are
+// padded with zeros to an even length, so no tail handling is needed. n2 = padded_length / 2.
+template <class Op, class Fin, int THREADS>
+__global__ void __launch_bounds__(THREADS) vec_kernel(long long n2, Op op, RedCtx rc, Fin fin, const int *done, const int *only_if)
+{
+    if (done && *done)
+        return;
+    if (only_if && !*only_if)
+        return;
+    constexpr int NVA = Op::NV > 0 ? Op::NV : 1;
+    double acc[NVA];
+#pragma unroll
+    for (int i = 0; i < NVA; ++i)
+        acc[i] = 0;
+    op.prologue();
+    const long long stride = (long long)gridDim.x * THREADS;
+    long long j = (long long)blockIdx.x * THREADS + threadIdx.x;
+    // two independent 128-bit lanes per trip for memory-level parallelism
+    for (; j + stride < n2; j += 2 * stride)
+    {
+        op.template apply<2>(j, stride, acc);
+    }
+    if (j < n2)
+        op.template apply<1>(j, stride, acc);
+    double tot[NVA];
+    if (grid_reduce<Op::NV, THREADS>(acc, rc, tot) && threadIdx.x == 0)
+        fin(tot);
+}
+
+__device__ __forceinline__ double2 ld2(const double *p, long long j) { return reinterpret_cast<const double2 *>(p)[j]; }
+__device__ __forceinline__ void st2(double *p, long long j, double2 v) { reinterpret_cast<double2 *>(p)[j] = v; }
+
+// Eigen CG: x += alpha p; r -= alpha q; ||r||^2; r.(dinv r)   (SURVEY A.1 loop body, first half)
+struct OpCgUpdateEigen
+{
+    static constexpr int NV = 2;
+    double *x, *r;
+    const double *p, *q, *dinv;
+    const KState *st;
+    double alpha;
+    __device__ __forceinline__ void prologue() { alpha = st->rz / st->pAp; }
+    template <int U>
+    __device__ __forceinline__ void apply(long long j, long long stride, double (&acc)[2])
+    {
+        double2 xv[U], rv[U], pv[U], qv[U], dv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            xv[u] = ld2(x, j + u * stride);
+            rv[u] = ld2(r, j + u * stride);
+            pv[u] = ld2(p, j + u * stride);
+            qv[u] = ld2(q, j + u * stride);
+            dv[u] = ld2(dinv, j + u * stride);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            xv[u].x += alpha * pv[u].x;
+            xv[u].y += alpha * pv[u].y;
+            rv[u].x -= alpha * qv[u].x;
+            rv[u].y -= alpha * qv[u].y;
+            st2(x, j + u * stride, xv[u]);
+            st2(r, j + u * stride, rv[u]);
+            acc[0] += rv[u].x * rv[u].x + rv[u].y * rv[u].y;
+            acc[1] += rv[u].x * rv[u].x * dv[u].x + rv[u].y * rv[u].y * dv[u].y;
+        }
+    }
+};
+// Eigen CG: p = dinv r + beta p   (FIRST: p = dinv r)
+template <bool FIRST>
+struct OpCgDirEigen
+{
+    static constexpr int NV = 0;
+    double *p;
+    const double *r, *dinv;
+    const KState *st;
+    double beta;
+    __device__ __forceinline__ void prologue() { beta = FIRST ? 0.0 : st->rz_new / st->rz; }
+    template <int U>
+    __device__ __forceinline__ void apply(long long j, long long stride, double (&)[1])
+    {
+        double2 rv[U], pv[U], dv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            rv[u] = ld2(r, j + u * stride);
+            dv[u] = ld2(dinv, j + u * stride);
+            if (!FIRST)
+                pv[u] = ld2(p, j + u * stride);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            double2 o;
+            o.x = dv[u].x * rv[u].x;
+            o.y = dv[u].y * rv[u].y;
+            if (!FIRST)
+            {
+                o.x += beta * pv[u].x;
+                o.y += beta * pv[u].y;
+            }
+            st2(p, j + u * stride, o);
+        }
+    }
+};
+// generic dot a.b
+struct OpDot
+{
+    static constexpr int NV = 1;
+    const double *a, *b;
+    __device__ __forceinline__ void prologue() {}
+    template <int U>
+    __device__ __forceinline__ void apply(long long j, long long stride, double (&acc)[1])
+    {
+        double2 av[U], bv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            av[u] = ld2(a, j + u * stride);
+            bv[u] = ld2(b, j + u * stride);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            acc[0] += av[u].x * bv[u].x + av[u].y * bv[u].y;
+    }
+};
+// amgcl cg: p = s + (rho/rho_old) p, or p = s on the first trip
+struct OpCgDirAmgcl
+{
+    static constexpr int NV = 0;
+    double *p;
+    const double *s;
+    const KState *st;
+    double beta;
+    __device__ __forceinline__ void prologue() { beta = st->iter ? st->rho / st->rho_old : 0.0; }
+    template <int U>
+    __device__ __forceinline__ void apply(long long j, long long stride, double (&)[1])
+    {
+        double2 sv[U], pv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            sv[u] = ld2(s, j + u * stride);
+            pv[u] = ld2(p, j + u * stride);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            double2 o;
+            o.x = sv[u].x + (beta != 0.0 ? beta * pv[u].x : 0.0);
+            o.y = sv[u].y + (beta != 0.0 ? beta * pv[u].y : 0.0);
+            st2(p, j + u * stride, o);
+        }
+    }
+};
+// amgcl cg: x += alpha p; r -= alpha q; ||r||^2   with alpha = rho / p.q
+struct OpCgUpdateAmgcl
+{
+    static constexpr int NV = 1;
+    double *x, *r;
+    const double *p, *q;
+    const KState *st;
+    double alpha;
+    __device__ __forceinline__ void prologue() { alpha = st->rho / st->pAp; }
+    template <int U>
+    __device__ __forceinline__ void apply(long long j, long long stride, double (&acc)[1])
+    {
+        double2 xv[U], rv[U], pv[U], qv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            xv[u] = ld2(x, j + u * stride);
+            rv[u] = ld2(r, j + u * stride);
+            pv[u] = ld2(p, j + u * stride);
+            qv[u] = ld2(q, j + u * stride);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            xv[u].x += alpha * pv[u].x;
+            xv[u].y += alpha * pv[u].y;
+            rv[u].x -= alpha * qv[u].x;
+            rv[u].y -= alpha * qv[u].y;
+            st2(x, j + u * stride, xv[u]);
+            st2(r, j + u * stride, rv[u]);
+            acc[0] += rv[u].x * rv[u].x + rv[u].y * rv[u].y;
+        }
+    }
+};
+// BiCGSTAB: p = r + beta (p - omega v);  y = dinv p      beta = (rho/rho_old)(alpha/omega)
+struct OpBicgP
+{
+    static constexpr int NV = 0;
+    double *p, *y;
+    const double *r, *v, *dinv;
+    const KState *st;
+    double beta, omega;
+    __device__ __forceinline__ void prologue()
+    {
+        beta = (st->rho / st->rho_old) * (st->alpha / st->omega);
+        omega = st->omega;
+    }
+    template <int U>
+    __device__ __forceinline__ void apply(long long j, long long stride, double (&)[1])
+    {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            const long long i = j + u * stride;
+            const double2 rv = ld2(r, i), pv = ld2(p, i), vv = ld2(v, i), dv = ld2(dinv, i);
+            double2 o, yo;
+            o.x = rv.x + beta * (pv.x - omega * vv.x);
+            o.y = rv.y + beta * (pv.y - omega * vv.y);
+            yo.x = dv.x * o.x;
+            yo.y = dv.y * o.y;
+            st2(p, i, o);
+            st2(y, i, yo);
+        }
+    }
+};
+// BiCGSTAB: s = r - alpha v (in place in r);  z = dinv s
+struct OpBicgS
+{
+    static constexpr int NV = 0;
+    double *r, *z;
+    const double *v, *dinv;
+    const KState *st;
+    double alpha;
+    __device__ __forceinline__ void prologue() { alpha = st->alpha; }
+    template <int U>
+    __device__ __forceinline__ void apply(long long j, long long stride, double (&)[1])
+    {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            const long long i = j + u * stride;
+            const double2 rv = ld2(r, i), vv = ld2(v, i), dv = ld2(dinv, i);
+            double2 s, zo;
+            s.x = rv.x - alpha * vv.x;
+            s.y = rv.y - alpha * vv.y;
+            zo.x = dv.x * s.x;
+            zo.y = dv.y * s.y;
+            st2(r, i, s);
+            st2(z, i, zo);
+        }
+    }
+};
+// BiCGSTAB: x += alpha y + omega z;  r = s - omega t;  ||r||^2;  r0.r
+struct OpBicgEnd
+{
+    static constexpr int NV = 2;
+    double *x, *r;
+    const double *y, *z, *t, *r0;
+    const KState *st;
+    double alpha, omega;
+    __device__ __forceinline__ void prologue()
+    {
+        alpha = st->alpha;
+        omega = st->omega;
+    }
+    template <int U>
+    __device__ __forceinline__ void apply(long long j, long long stride, double (&acc)[2])
+    {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            const long long i = j + u * stride;
+            double2 xv = ld2(x, i), rv = ld2(r, i);
+            const double2 yv = ld2(y, i), zv = ld2(z, i), tv = ld2(t, i), r0v = ld2(r0, i);
+            xv.x += alpha * yv.x + omega * zv.x;
+            xv.y += alpha * yv.y + omega * zv.y;
+            rv.x -= omega * tv.x;
+            rv.y -= omega * tv.y;
+            st2(x, i, xv);
+            st2(r, i, rv);
+            acc[0] += rv.x * rv.x + rv.y * rv.y;
+            acc[1] += r0v.x * rv.x + r0v.y * rv.y;
+        }
+    }
+};
+// y = a (copy), used for r0 = r
+struct OpCopy
+{
+    static constexpr int NV = 0;
+    double *y;
+    const double *a;
+    __device__ __forceinline__ void prologue() {}
+    template <int U>
+    __device__ __forceinline__ void apply(long long j, long long stride, double (&)[1])
+    {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            st2(y, j + u * stride, ld2(a, j + u * stride));
+    }
+};
+// y = s * a
+struct OpScale
+{
+    static constexpr int NV = 0;
+    double *y;
+    const double *a;
+    const double *scal; // device scalar: y = a / sqrt(*scal)
+    double f;
+    __device__ __forceinline__ void prologue() { f = rsqrt(*scal); }
+    template <int U>
+    __device__ __forceinline__ void apply(long long j, long long stride, double (&)[1])
+    {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            double2 v = ld2(a, j + u * stride);
+            v.x *= f;
+            v.y *= f;
+            st2(y, j + u * stride, v);
+        }
+    }
+};
+
+} // namespace psb

@@ -1,0 +1,228 @@
+// Host-side launch layer: device CSR container, per-solver execution context (stream, reduction
+// scratch, profiling) and the SpMV / vector-kernel dispatchers.
+#pragma once
+#include "kernels.cuh"
+
+#include <map>
+#include <string>
+#include <vector>
+
+namespace psb {
+
+constexpr int kMaxBlocks = 4096;
+constexpr int kVecThreads = 256;
+constexpr int kSpmvThreads = 256;
+constexpr int kStreamCap = 2560; // nnz per 256-row tile staged in shared memory (<= 10 nnz/row on average)
+constexpr int kStreamStages = 3;
+
+enum SpmvKind : int
+{
+    SPMV_VECTOR = 0,
+    SPMV_STREAM = 1
+};
+
+struct CsrDev
+{
+    int n = 0, ncols = 0;
+    long long nnz = 0;
+    DevBuf<int> rp, ci;
+    DevBuf<double> va;
+    int kind = SPMV_VECTOR;
+    int lpr = 1; // lanes per row for the vector schedule
+    CsrView view() const { return CsrView{rp.p, ci.p, va.p, n}; }
+    // choose the schedule from the average row length
+    void plan(const std::string &forced = "auto")
+    {
+        const double avg = n > 0 ? (double)nnz / n : 0;
+        if (forced == "stream" || (forced == "auto" && avg <= 9.5 && n >= 4 * kSpmvThreads))
+        {
+            kind = SPMV_STREAM;
+            return;
+        }
+        kind = SPMV_VECTOR;
+        if (forced == "scalar")
+            lpr = 1;
+        else if (avg <= 3)
+            lpr = 1;
+        else if (avg <= 6)
+            lpr = 2;
+        else if (avg <= 12)
+            lpr = 4;
+        else if (avg <= 24)
+            lpr = 8;
+        else if (avg <= 48)
+            lpr = 16;
+        else
+            lpr = 32;
+        if (forced.rfind("vector", 0) == 0 && forced.size() > 6)
+            lpr = std::stoi(forced.substr(6));
+    }
+};
+
+struct ProfEntry
+{
+    double ms = 0;
+    long long launches = 0;
+};
+
+// Execution context shared by every kernel a solver launches: one stream, one reduction scratch
+// (reference precedent: one stream + one pool per solver, MASSolver.cu:154-156,193-195).
+struct Ctx
+{
+    cudaStream_t stream = nullptr;
+    DevBuf<double> partials;
+    DevBuf<unsigned int> counter;
+    long long launches = 0;
+    // profiling (events around every launch; only when enabled, never inside graph capture)
+    bool profile = false;
+    bool capturing = false;
+    std::map<std::string, ProfEntry> prof;
+    struct Pending
+    {
+        std::string name;
+        cudaEvent_t a, b;
+    };
+    std::vector<Pending> pending;
+    std::vector<cudaEvent_t> ev_pool;
+
+    void init()
+    {
+        PSB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        partials.alloc((size_t)kMaxRed * kMaxBlocks, true);
+        counter.alloc(4, true);
+    }
+    void destroy()
+    {
+        for (auto &p : pending)
+        {
+            cudaEventDestroy(p.a);
+            cudaEventDestroy(p.b);
+        }
+        pending.clear();
+        for (auto e : ev_pool)
+            cudaEventDestroy(e);
+        ev_pool.clear();
+        if (stream)
+            cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
+    RedCtx red() const { return RedCtx{partials.p, counter.p, kMaxBlocks}; }
+    cudaEvent_t get_event()
+    {
+        if (!ev_pool.empty())
+        {
+            cudaEvent_t e = ev_pool.back();
+            ev_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        PSB_CUDA(cudaEventCreate(&e));
+        return e;
+    }
+    void prof_begin(const char *name)
+    {
+        ++launches;
+        if (!profile || capturing)
+            return;
+        Pending p{name, get_event(), get_event()};
+        PSB_CUDA(cudaEventRecord(p.a, stream));
+        pending.push_back(p);
+    }
+    void prof_end()
+    {
+        if (!profile || capturing)
+            return;
+        PSB_CUDA(cudaEventRecord(pending.back().b, stream));
+    }
+    // call after a stream synchronize
+    void prof_collect()
+    {
+        for (auto &p : pending)
+        {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess)
+            {
+                prof[p.name].ms += ms;
+                prof[p.name].launches += 1;
+            }
+            ev_pool.push_back(p.a);
+            ev_pool.push_back(p.b);
+        }
+        pending.clear();
+    }
+};
+
+inline void check_launch()
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        throw CudaError(std::string("kernel launch failed: ") + cudaGetErrorString(e));
+}
+
+inline int vec_grid(long long n2)
+{
+    long long need = (n2 + kVecThreads - 1) / kVecThreads;
+    need = (need + 1) / 2; // two lanes per thread per trip
+    const long long cap = (long long)kSMs * 8;
+    return (int)std::max<long long>(1, std::min(need, cap));
+}
+
+template <class Op, class Fin>
+void launch_vec(Ctx &c, const char *name, long long n_pad, Op op, Fin fin, const int *done = nullptr, const int *only_if = nullptr)
+{
+    const long long n2 = n_pad / 2;
+    if (n2 == 0)
+        return;
+    c.prof_begin(name);
+    vec_kernel<Op, Fin, kVecThreads><<<vec_grid(n2), kVecThreads, 0, c.stream>>>(n2, op, c.red(), fin, done, only_if);
+    check_launch();
+    c.prof_end();
+}
+
+template <class Epi, class Fin, int LPR>
+void launch_spmv_vector(Ctx &c, const CsrDev &A, const double *x, Epi epi, Fin fin, const int *done, const int *only_if)
+{
+    const int rows_per_cta = kSpmvThreads / LPR;
+    long long need = ((long long)A.n + rows_per_cta - 1) / rows_per_cta;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(need, (long long)kSMs * 16));
+    spmv_vector_kernel<Epi, Fin, LPR, kSpmvThreads><<<grid, kSpmvThreads, 0, c.stream>>>(A.view(), x, epi, c.red(), fin, done, only_if);
+}
+
+template <class Epi, class Fin>
+void launch_spmv(Ctx &c, const char *name, const CsrDev &A, const double *x, Epi epi, Fin fin, const int *done = nullptr,
+                 const int *only_if = nullptr)
+{
+    if (A.n == 0)
+        return;
+    c.prof_begin(name);
+    if (A.kind == SPMV_STREAM)
+    {
+        using SM = StreamSmem<kStreamCap, kStreamStages>;
+        auto kern = spmv_stream_kernel<Epi, Fin, kSpmvThreads, kStreamCap, kStreamStages>;
+        static bool attr_set = false;
+        if (!attr_set)
+        {
+            PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes));
+            attr_set = true;
+        }
+        const int ntiles = (A.n + kSpmvThreads - 1) / kSpmvThreads;
+        const int grid = std::min(ntiles, kSMs * 2);
+        kern<<<grid, kSpmvThreads, SM::bytes, c.stream>>>(A.view(), x, epi, c.red(), fin, done, only_if);
+    }
+    else
+    {
+        switch (A.lpr)
+        {
+        case 1: launch_spmv_vector<Epi, Fin, 1>(c, A, x, epi, fin, done, only_if); break;
+        case 2: launch_spmv_vector<Epi, Fin, 2>(c, A, x, epi, fin, done, only_if); break;
+        case 4: launch_spmv_vector<Epi, Fin, 4>(c, A, x, epi, fin, done, only_if); break;
+        case 8: launch_spmv_vector<Epi, Fin, 8>(c, A, x, epi, fin, done, only_if); break;
+        case 16: launch_spmv_vector<Epi, Fin, 16>(c, A, x, epi, fin, done, only_if); break;
+        default: launch_spmv_vector<Epi, Fin, 32>(c, A, x, epi, fin, done, only_if); break;
+        }
+    }
+    check_launch();
+    c.prof_end();
+}
+
+} // namespace psb

@@ -1,0 +1,830 @@
+// Host driver of the B200 linear-solver backend: ingest (analyze_pattern / factorize), Jacobi-PCG in
+// Eigen's ordering, BiCGSTAB, AMG-PCG in AMGCL's ordering. Mirrors the call protocol of
+// polysolve::linear::Solver (reference src/polysolve/linear/Solver.hpp:90-131) one method per virtual.
+#include "solver.hpp"
+#include "amg.hpp"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <functional>
+#include <sstream>
+
+namespace psb {
+
+namespace {
+
+double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+// 64-bit hash of the pattern arrays (4 independent lanes so it runs at memory speed on one core).
+unsigned long long hash_words(const void *data, size_t bytes, unsigned long long seed)
+{
+    const unsigned long long *w = (const unsigned long long *)data;
+    const size_t nw = bytes / 8;
+    unsigned long long h[4] = {seed ^ 0x9E3779B97F4A7C15ull, seed ^ 0xBF58476D1CE4E5B9ull, seed ^ 0x94D049BB133111EBull, seed ^ 0xD6E8FEB86659FD93ull};
+    size_t i = 0;
+    for (; i + 4 <= nw; i += 4)
+        for (int l = 0; l < 4; ++l)
+        {
+            unsigned long long v = w[i + l] * 0xFF51AFD7ED558CCDull;
+            v ^= v >> 32;
+            h[l] = (h[l] ^ v) * 0xC4CEB9FE1A85EC53ull;
+            h[l] = (h[l] << 27) | (h[l] >> 37);
+        }
+    unsigned long long r = h[0] ^ (h[1] * 3) ^ (h[2] * 5) ^ (h[3] * 7);
+    const unsigned char *tail = (const unsigned char *)data + i * 8;
+    for (size_t k = i * 8; k < bytes; ++k)
+        r = (r ^ *tail++) * 0x100000001B3ull;
+    r ^= r >> 29;
+    return r * 0xBF58476D1CE4E5B9ull;
+}
+
+// ------------------------------------------------------------------ ingest kernels (analyze_pattern)
+// Symmetric-pattern fast path. If the pattern is symmetric and sorted, CSR(row_ptr, col_idx) ==
+// CSC(outer, inner) as integer arrays and only the value map is needed:
+//   perm[k] (k in row i, col j = inner[k]) = position of row index i inside column j.
+// 8 lanes per row; binary search in column j. Any miss / unsorted column clears *ok.
+__global__ void sym_perm_kernel(int n, const int *__restrict__ outer, const int *__restrict__ inner, int *__restrict__ perm, int *ok)
+{
+    const int lane = threadIdx.x & 7;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    if (row >= n)
+        return;
+    const int kb = outer[row], ke = outer[row + 1];
+    bool good = true;
+    for (int k = kb + lane; k < ke; k += 8)
+    {
+        const int j = inner[k];
+        if (k > kb && inner[k - 1] >= j)
+            good = false; // not strictly ascending
+        if (j < 0 || j >= n)
+        {
+            good = false;
+            continue;
+        }
+        int lo = outer[j], hi = outer[j + 1];
+        while (lo < hi)
+        {
+            const int mid = (lo + hi) >> 1;
+            if (inner[mid] < (int)row)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        if (lo < outer[j + 1] && inner[lo] == (int)row)
+            perm[k] = lo;
+        else
+            good = false;
+    }
+    if (!good)
+        atomicExch(ok, 0);
+}
+
+// General path helpers: column id of every CSC entry, iota, row_ptr from the sorted row keys.
+__global__ void expand_cols_kernel(int ncols, const int *__restrict__ outer, int *__restrict__ col_of)
+{
+    const int lane = threadIdx.x & 7;
+    const long long c = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    if (c >= ncols)
+        return;
+    for (int k = outer[c] + lane; k < outer[c + 1]; k += 8)
+        col_of[k] = (int)c;
+}
+__global__ void iota_kernel(long long n, int *a)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        a[i] = (int)i;
+}
+__global__ void row_ptr_from_sorted_kernel(int nrows, long long nnz, const int *__restrict__ sorted_rows, int *__restrict__ row_ptr)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nrows)
+        return;
+    long long lo = 0, hi = nnz;
+    while (lo < hi)
+    {
+        const long long mid = (lo + hi) >> 1;
+        if (sorted_rows[mid] < (int)i)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    row_ptr[i] = (int)lo;
+}
+__global__ void gather_int_kernel(long long n, const int *__restrict__ src, const int *__restrict__ idx, int *__restrict__ dst)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        dst[i] = src[idx[i]];
+}
+
+// ------------------------------------------------------------------ factorize kernels
+// vals_csr[k] = vals_csc[perm[k]]
+__global__ void gather_vals_kernel(long long n, const double *__restrict__ src, const int *__restrict__ perm, double *__restrict__ dst)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        dst[i] = __ldg(src + __ldg(perm + i));
+}
+// Eigen::DiagonalPreconditioner::factorize: invdiag = (A_ii != 0) ? 1/A_ii : 1. mode 0: ones.
+__global__ void inv_diag_kernel(CsrView A, double *__restrict__ dinv, int mode, int *bad)
+{
+    const int lane = threadIdx.x & 7;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    if (row >= A.n)
+        return;
+    double d = 0;
+    bool found = false;
+    for (int k = A.rp[row] + lane; k < A.rp[row + 1]; k += 8)
+        if (A.ci[k] == (int)row)
+        {
+            d = A.va[k];
+            found = true;
+        }
+    // combine across the 8 lanes
+    for (int o = 4; o > 0; o >>= 1)
+    {
+        const double od = __shfl_xor_sync(0xffffffffu, d, o);
+        const bool of = __shfl_xor_sync(0xffffffffu, (int)found, o);
+        if (of && !found)
+        {
+            d = od;
+            found = true;
+        }
+    }
+    if (lane == 0)
+    {
+        if (!(d == d) || isinf(d))
+            atomicExch(bad, 1);
+        dinv[row] = mode == 0 ? 1.0 : ((found && d != 0.0) ? 1.0 / d : 1.0);
+    }
+}
+
+inline int blocks_for(long long n, int threads) { return (int)std::max<long long>(1, (n + threads - 1) / threads); }
+
+} // namespace
+
+// ==================================================================================== lifecycle
+Solver::Solver() {}
+
+Solver::~Solver()
+{
+    amg.reset();
+    if (graph_exec)
+        cudaGraphExecDestroy(graph_exec);
+    for (auto &e : ev)
+        if (e)
+            cudaEventDestroy(e);
+    if (d_state)
+        cudaFree(d_state);
+    if (h_state)
+        cudaFreeHost(h_state);
+    ctx.destroy();
+}
+
+static void ensure_ctx(Solver &s)
+{
+    if (s.ctx.stream)
+        return;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw CudaError(std::string("psb200: no CUDA device available (") + cudaGetErrorString(e) +
+                        "); the CUDA backend has no CPU fallback");
+    if (s.prm.device >= 0)
+        PSB_CUDA(cudaSetDevice(s.prm.device));
+    PSB_CUDA(cudaGetDevice(&s.device));
+    s.ctx.init();
+    PSB_CUDA(cudaMalloc(&s.d_state, sizeof(KState)));
+    PSB_CUDA(cudaMemset(s.d_state, 0, sizeof(KState)));
+    PSB_CUDA(cudaMallocHost(&s.h_state, 4 * sizeof(KState)));
+    PSB_CUDA(cudaEventCreateWithFlags(&s.ev[0], cudaEventDisableTiming));
+    PSB_CUDA(cudaEventCreateWithFlags(&s.ev[1], cudaEventDisableTiming));
+}
+
+// ==================================================================================== parameters
+static void read_amg(const JValue &j, AmgParams &a)
+{
+    auto num = [&](const JValue &o, const char *k, auto &dst) {
+        if (o.contains(k))
+            dst = (std::remove_reference_t<decltype(dst)>)o.at(k).as_num();
+    };
+    // flat keys
+    num(j, "max_levels", a.max_levels);
+    num(j, "coarse_enough", a.coarse_enough);
+    num(j, "ncycle", a.ncycle);
+    num(j, "npre", a.npre);
+    num(j, "npost", a.npost);
+    num(j, "pre_cycles", a.pre_cycles);
+    if (j.contains("direct_coarse"))
+        a.direct_coarse = j.at("direct_coarse").as_bool();
+    if (j.contains("aggregation"))
+        a.aggregation = j.at("aggregation").as_str();
+    // AMGCL-shaped sub-objects (AMGCL.cpp:32-65): relax{type,degree,power_iters,higher,lower,scale}, coarsening{relax,estimate_spectral_radius,aggr{eps_strong}}
+    if (j.contains("relax") && j.at("relax").is_obj())
+    {
+        const JValue &r = j.at("relax");
+        if (r.contains("type"))
+            a.relax_type = r.at("type").as_str();
+        num(r, "degree", a.degree);
+        num(r, "power_iters", a.power_iters);
+        num(r, "higher", a.higher);
+        num(r, "lower", a.lower);
+        num(r, "damping", a.damping);
+        if (r.contains("scale"))
+            a.scale = r.at("scale").as_bool();
+    }
+    if (j.contains("coarsening") && j.at("coarsening").is_obj())
+    {
+        const JValue &c = j.at("coarsening");
+        num(c, "relax", a.sa_relax);
+        if (c.contains("estimate_spectral_radius"))
+            a.estimate_spectral_radius = c.at("estimate_spectral_radius").as_bool();
+        if (c.contains("aggr") && c.at("aggr").is_obj())
+            num(c.at("aggr"), "eps_strong", a.eps_strong);
+    }
+    if (a.relax_type != "chebyshev" && a.relax_type != "damped_jacobi")
+        throw std::runtime_error("psb200: unsupported amg relax type '" + a.relax_type + "'");
+}
+
+void Solver::set_parameters(const std::string &json)
+{
+    if (json.empty())
+        return;
+    JValue doc = JParser::parse(json);
+    if (!doc.is_obj() || !doc.contains("CUDA"))
+        return; // parameters of other solvers are ignored, like every polysolve backend does
+    const JValue &j = doc.at("CUDA");
+    if (!j.is_obj())
+        throw std::runtime_error("psb200: \"CUDA\" must be an object");
+    Params np = prm; // transactional: a rejected document leaves the solver unchanged
+    if (j.contains("krylov"))
+        np.krylov = j.at("krylov").as_str();
+    if (j.contains("precond"))
+        np.precond = j.at("precond").as_str();
+    if (j.contains("tolerance"))
+        np.tolerance = j.at("tolerance").as_num();
+    if (j.contains("max_iter"))
+        np.max_iter = (int)j.at("max_iter").as_num();
+    if (j.contains("check_every"))
+        np.check_every = std::max(1, (int)j.at("check_every").as_num());
+    if (j.contains("use_graph"))
+        np.use_graph = j.at("use_graph").as_bool();
+    if (j.contains("spmv_kernel"))
+        np.spmv_kernel = j.at("spmv_kernel").as_str();
+    if (j.contains("device"))
+        np.device = (int)j.at("device").as_num();
+    if (j.contains("block_size"))
+        np.block_size = (int)j.at("block_size").as_num();
+    if (j.contains("profile"))
+        np.profile = j.at("profile").as_bool();
+    if (j.contains("verify_pattern"))
+        np.verify_pattern = j.at("verify_pattern").as_bool();
+    if (j.contains("amg") && j.at("amg").is_obj())
+        read_amg(j.at("amg"), np.amg);
+    if (np.krylov != "cg" && np.krylov != "bicgstab")
+        throw std::runtime_error("psb200: unknown krylov '" + np.krylov + "' (cg | bicgstab)");
+    if (np.precond != "jacobi" && np.precond != "amg" && np.precond != "none")
+        throw std::runtime_error("psb200: unknown precond '" + np.precond + "' (jacobi | amg | none)");
+    if (np.krylov == "bicgstab" && np.precond == "amg")
+        throw std::runtime_error("psb200: bicgstab + amg is not available yet");
+    prm = np;
+    // a change of schedule/preconditioner invalidates captured graphs and the factorization
+    if (graph_exec)
+    {
+        cudaGraphExecDestroy(graph_exec);
+        graph_exec = nullptr;
+        graph_key.clear();
+    }
+    if (analyzed)
+        A.plan(prm.spmv_kernel);
+    ctx.profile = prm.profile;
+}
+
+// ==================================================================================== analyze_pattern
+void Solver::analyze_pattern(long long n_, long long nnz_, const int *outer, const int *inner, int precond_num_)
+{
+    if (n_ < 0 || nnz_ < 0 || !outer || (!inner && nnz_ > 0))
+        throw std::invalid_argument("psb200_analyze_pattern_csc: null or negative argument");
+    if (n_ > 0x7fffffffLL - 1024 || nnz_ > 0x7fffffffLL - 1024)
+        throw std::invalid_argument("psb200_analyze_pattern_csc: int32 index range exceeded (reference limit, BSRMatrix.cu:439-442)");
+    if (n_ > 0 && (outer[0] != 0 || outer[n_] != nnz_))
+        throw std::invalid_argument("psb200_analyze_pattern_csc: matrix is not compressed (outer[0] != 0 or outer[n] != nnz); call makeCompressed() first (cf. BSRMatrix.cu:444-452)");
+    ensure_ctx(*this);
+    const double t0 = now_ms();
+    precond_num = precond_num_;
+    unsigned long long h = hash_words(outer, sizeof(int) * (size_t)(n_ + 1), 0x5bd1e995ull + (unsigned long long)n_);
+    h = hash_words(inner, sizeof(int) * (size_t)nnz_, h);
+    if (analyzed && n == n_ && nnz == nnz_ && h == pattern_hash)
+    {
+        analyze_skipped = true; // Newton calls analyze_pattern every iteration with an unchanged pattern (Newton.cpp:189)
+        t_analyze_ms = now_ms() - t0;
+        return;
+    }
+    analyze_skipped = false;
+    analyzed = false;
+    factorized = false;
+    amg.reset();
+    if (graph_exec)
+    {
+        cudaGraphExecDestroy(graph_exec);
+        graph_exec = nullptr;
+        graph_key.clear();
+    }
+    n = n_;
+    nnz = nnz_;
+    pattern_hash = h;
+    n_pad = (n + 3) & ~3ll;
+    cudaStream_t st = ctx.stream;
+
+    csc_outer.alloc(n + 1);
+    csc_inner.alloc(std::max<long long>(nnz, 1));
+    perm.alloc(std::max<long long>(nnz, 1));
+    PSB_CUDA(cudaMemcpyAsync(csc_outer.p, outer, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, st));
+    if (nnz)
+        PSB_CUDA(cudaMemcpyAsync(csc_inner.p, inner, sizeof(int) * nnz, cudaMemcpyHostToDevice, st));
+
+    A.n = (int)n;
+    A.ncols = (int)n;
+    A.nnz = nnz;
+    A.rp.alloc(n + 1);
+    A.ci.alloc(std::max<long long>(nnz, 1), false, 64);
+    A.va.alloc(std::max<long long>(nnz, 1), false, 64);
+
+    // 1) symmetric-pattern fast path
+    int *d_ok = (int *)ctx.counter.p + 2;
+    int one = 1;
+    PSB_CUDA(cudaMemcpyAsync(d_ok, &one, sizeof(int), cudaMemcpyHostToDevice, st));
+    if (n > 0)
+    {
+        sym_perm_kernel<<<blocks_for(n * 8, 256), 256, 0, st>>>((int)n, csc_outer.p, csc_inner.p, perm.p, d_ok);
+        check_launch();
+    }
+    int ok = 0;
+    PSB_CUDA(cudaMemcpyAsync(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PSB_CUDA(cudaStreamSynchronize(st));
+    sym_pattern = ok != 0;
+    if (sym_pattern)
+    {
+        PSB_CUDA(cudaMemcpyAsync(A.rp.p, csc_outer.p, sizeof(int) * (n + 1), cudaMemcpyDeviceToDevice, st));
+        if (nnz)
+            PSB_CUDA(cudaMemcpyAsync(A.ci.p, csc_inner.p, sizeof(int) * nnz, cudaMemcpyDeviceToDevice, st));
+    }
+    else if (nnz > 0)
+    {
+        // 2) general path: stable radix sort of the CSC entries by row index (the reference's own ingest
+        //    sorts with cub too, mas_utils/BSRMatrix.cu:294-309). Stability keeps columns ascending
+        //    inside every row, which is exactly the oracle's counting transpose.
+        for (long long k = 0; k < nnz; ++k)
+            if (inner[k] < 0 || inner[k] >= n)
+                throw std::invalid_argument("psb200_analyze_pattern_csc: inner index out of range");
+        DevBuf<int> iota, sorted_rows, col_of;
+        iota.alloc(nnz);
+        sorted_rows.alloc(nnz);
+        col_of.alloc(nnz);
+        iota_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(nnz, iota.p);
+        expand_cols_kernel<<<blocks_for(n * 8, 256), 256, 0, st>>>((int)n, csc_outer.p, col_of.p);
+        check_launch();
+        int end_bit = 1;
+        while ((1ll << end_bit) < n && end_bit < 31)
+            ++end_bit;
+        size_t tmp_bytes = 0;
+        PSB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, csc_inner.p, sorted_rows.p, iota.p, perm.p, (int)nnz, 0, end_bit, st));
+        DevBuf<unsigned char> tmp;
+        tmp.alloc(tmp_bytes);
+        PSB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_bytes, csc_inner.p, sorted_rows.p, iota.p, perm.p, (int)nnz, 0, end_bit, st));
+        row_ptr_from_sorted_kernel<<<blocks_for(n + 1, 256), 256, 0, st>>>((int)n, nnz, sorted_rows.p, A.rp.p);
+        gather_int_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(nnz, col_of.p, perm.p, A.ci.p);
+        check_launch();
+        PSB_CUDA(cudaStreamSynchronize(st));
+    }
+    else
+    {
+        PSB_CUDA(cudaMemsetAsync(A.rp.p, 0, sizeof(int) * (n + 1), st));
+    }
+    A.plan(prm.spmv_kernel);
+    PSB_CUDA(cudaStreamSynchronize(st));
+    analyzed = true;
+    t_analyze_ms = now_ms() - t0;
+}
+
+// ==================================================================================== factorize
+void Solver::factorize(long long n_, long long nnz_, const int *outer, const int *inner, const double *vals)
+{
+    if (!vals && nnz_ > 0)
+        throw std::invalid_argument("psb200_factorize_csc: null values");
+    ensure_ctx(*this);
+    // factorize() without (or with a stale) analyze_pattern(): analyze now. The Eigen iterative wrappers
+    // accept this order too (EigenSolver.tpp:100-105 only needs the matrix).
+    bool need = !analyzed || n != n_ || nnz != nnz_;
+    if (!need && prm.verify_pattern && outer && inner)
+    {
+        // cheap guard against a silently changed pattern: outer fully, inner strided
+        unsigned long long h = hash_words(outer, sizeof(int) * (size_t)(n_ + 1), 0x5bd1e995ull + (unsigned long long)n_);
+        h = hash_words(inner, sizeof(int) * (size_t)nnz_, h);
+        need = h != pattern_hash;
+    }
+    if (need)
+    {
+        if (!outer || (!inner && nnz_ > 0))
+            throw std::invalid_argument("psb200_factorize_csc: pattern unknown and no index arrays given");
+        analyze_pattern(n_, nnz_, outer, inner, precond_num > 0 ? precond_num : (int)n_);
+    }
+    const double t0 = now_ms();
+    cudaStream_t st = ctx.stream;
+    csc_vals.alloc(std::max<long long>(nnz, 1));
+    if (nnz)
+    {
+        PSB_CUDA(cudaMemcpyAsync(csc_vals.p, vals, sizeof(double) * nnz, cudaMemcpyHostToDevice, st));
+        gather_vals_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(nnz, csc_vals.p, perm.p, A.va.p);
+        check_launch();
+    }
+    dinv.alloc(n_pad, true);
+    int *d_bad = (int *)ctx.counter.p + 3;
+    PSB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    if (n > 0)
+    {
+        inv_diag_kernel<<<blocks_for(n * 8, 256), 256, 0, st>>>(A.view(), dinv.p, prm.precond == "none" ? 0 : 1, d_bad);
+        check_launch();
+    }
+    int bad = 0;
+    PSB_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PSB_CUDA(cudaStreamSynchronize(st));
+    if (bad)
+        throw std::runtime_error("psb200_factorize_csc: non-finite diagonal entry");
+    ensure_vectors();
+    t_setup_precond_ms = 0;
+    if (prm.precond == "amg")
+    {
+        const double t1 = now_ms();
+        amg = std::make_unique<AmgHierarchy>(ctx, prm.amg);
+        amg->setup(A, imposed_aggregates);
+        PSB_CUDA(cudaStreamSynchronize(st));
+        t_setup_precond_ms = now_ms() - t1;
+        if (graph_exec)
+        {
+            cudaGraphExecDestroy(graph_exec);
+            graph_exec = nullptr;
+            graph_key.clear();
+        }
+    }
+    else
+        amg.reset();
+    factorized = true;
+    last_iters = 0;
+    last_error = 0;
+    last_status = 0;
+    t_factorize_ms = now_ms() - t0;
+    build_info();
+}
+
+void Solver::ensure_vectors()
+{
+    const size_t np = (size_t)n_pad;
+    bool realloc = vx.capacity() < np + 16;
+    for (DevBuf<double> *v : {&vb, &vx, &vr, &vp, &vq})
+        v->alloc(np, false);
+    if (prm.krylov == "bicgstab")
+        for (DevBuf<double> *v : {&vz, &vy, &vv, &vt, &vr0})
+            v->alloc(np, false);
+    if (prm.precond == "amg")
+        vz.alloc(np, false);
+    if (realloc && graph_exec)
+    {
+        cudaGraphExecDestroy(graph_exec);
+        graph_exec = nullptr;
+        graph_key.clear();
+    }
+}
+
+// ==================================================================================== solve
+void Solver::solve_host(const double *b, double *x, long long n_)
+{
+    if (!factorized)
+        throw std::runtime_error("psb200_solve: factorize() has not been called");
+    if (n_ != n || !b || !x)
+        throw std::invalid_argument("psb200_solve: size mismatch or null vector");
+    const double t0 = now_ms();
+    cudaStream_t st = ctx.stream;
+    ensure_vectors();
+    if (prm.profile)
+        ctx.prof.clear();
+    PSB_CUDA(cudaMemcpyAsync(vb.p, b, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    PSB_CUDA(cudaMemcpyAsync(vx.p, x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    if (prm.krylov == "bicgstab")
+        run_bicgstab(vb.p);
+    else if (prm.precond == "amg")
+        run_cg_amgcl(vb.p);
+    else
+        run_cg_eigen(vb.p);
+    PSB_CUDA(cudaMemcpyAsync(x, vx.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    PSB_CUDA(cudaStreamSynchronize(st));
+    t_solve_ms = now_ms() - t0;
+    build_info();
+}
+
+void Solver::solve_device(const double *d_b, double *d_x, long long n_)
+{
+    if (!factorized)
+        throw std::runtime_error("psb200_solve_device: factorize() has not been called");
+    if (n_ != n || !d_b || !d_x)
+        throw std::invalid_argument("psb200_solve_device: size mismatch or null vector");
+    const double t0 = now_ms();
+    cudaStream_t st = ctx.stream;
+    ensure_vectors();
+    if (prm.profile)
+        ctx.prof.clear();
+    // x lives in the solver's own buffer so captured graphs keep stable pointers
+    PSB_CUDA(cudaMemcpyAsync(vx.p, d_x, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    if (prm.krylov == "bicgstab")
+        run_bicgstab(d_b);
+    else if (prm.precond == "amg")
+        run_cg_amgcl(d_b);
+    else
+        run_cg_eigen(d_b);
+    PSB_CUDA(cudaMemcpyAsync(d_x, vx.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    PSB_CUDA(cudaStreamSynchronize(st));
+    t_solve_ms = now_ms() - t0;
+    build_info();
+}
+
+// Launches batches of iterations until the device-side `done` flag is seen. Two batches are kept in
+// flight so the GPU never waits for the host; kernels launched after convergence exit immediately
+// (they read st->done first), so x is exactly the iterate at the converged iteration.
+void Solver::drive(const std::function<void()> &enqueue_batch, int batch_iters, const std::string &key)
+{
+    cudaStream_t st = ctx.stream;
+    const bool graph = prm.use_graph && !prm.profile;
+    if (graph && (graph_exec == nullptr || graph_key != key))
+    {
+        if (graph_exec)
+        {
+            cudaGraphExecDestroy(graph_exec);
+            graph_exec = nullptr;
+        }
+        cudaGraph_t g = nullptr;
+        ctx.capturing = true;
+        const long long launches_before = ctx.launches;
+        PSB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+        try
+        {
+            enqueue_batch();
+        }
+        catch (...)
+        {
+            cudaStreamEndCapture(st, &g);
+            if (g)
+                cudaGraphDestroy(g);
+            ctx.capturing = false;
+            throw;
+        }
+        PSB_CUDA(cudaStreamEndCapture(st, &g));
+        ctx.capturing = false;
+        graph_launches_per_batch = ctx.launches - launches_before; // launch accounting for gpu_launches
+        ctx.launches = launches_before;
+        PSB_CUDA(cudaGraphInstantiate(&graph_exec, g, 0));
+        PSB_CUDA(cudaGraphDestroy(g));
+        graph_key = key;
+    }
+    const long long max_batches = (long long)prm.max_iter / std::max(1, batch_iters) + 3;
+    bool finished = false;
+    for (long long k = 0; k < max_batches && !finished; ++k)
+    {
+        if (graph)
+        {
+            PSB_CUDA(cudaGraphLaunch(graph_exec, st));
+            ctx.launches += graph_launches_per_batch;
+        }
+        else
+            enqueue_batch();
+        PSB_CUDA(cudaMemcpyAsync(&h_state[k & 1], d_state, sizeof(KState), cudaMemcpyDeviceToHost, st));
+        PSB_CUDA(cudaEventRecord(ev[k & 1], st));
+        if (k >= 1)
+        {
+            PSB_CUDA(cudaEventSynchronize(ev[(k - 1) & 1]));
+            if (h_state[(k - 1) & 1].done)
+                finished = true;
+        }
+    }
+}
+
+void Solver::finish_solve()
+{
+    cudaStream_t st = ctx.stream;
+    PSB_CUDA(cudaMemcpyAsync(&h_state[2], d_state, sizeof(KState), cudaMemcpyDeviceToHost, st));
+    PSB_CUDA(cudaStreamSynchronize(st));
+    if (prm.profile)
+        ctx.prof_collect();
+    const KState &s = h_state[2];
+    last_iters = s.iter;
+    last_status = s.done ? s.status : ST_MAXITER;
+    if (s.status == ST_ZERO_RHS)
+    {
+        // Eigen / AMGCL: zero right-hand side => x = 0, 0 iterations, error 0
+        PSB_CUDA(cudaMemsetAsync(vx.p, 0, sizeof(double) * n_pad, st));
+        last_error = 0;
+        last_iters = 0;
+        last_status = ST_CONVERGED;
+    }
+    else
+        last_error = s.bn2 > 0 ? std::sqrt(s.rn2 / s.bn2) : 0.0;
+}
+
+static void init_state(Solver &s, double tol, int max_iter)
+{
+    KState &h = s.h_state[3];
+    std::memset(&h, 0, sizeof(KState));
+    h.tol = tol;
+    h.max_iter = max_iter;
+    h.rho = 1;
+    h.rho_old = 1;
+    h.alpha = 1;
+    h.omega = 1;
+    PSB_CUDA(cudaMemcpyAsync(s.d_state, &h, sizeof(KState), cudaMemcpyHostToDevice, s.ctx.stream));
+}
+
+// Jacobi-PCG in Eigen's ordering (reference path EigenSolver.tpp:108-114 -> Eigen
+// conjugate_gradient()). Per iteration: 1 fused SpMV+dot, 1 fused x/r update + ||r||^2 + r.z,
+// 1 direction update = B_spmv + 88 N bytes of compulsory traffic.
+void Solver::run_cg_eigen(const double *d_b)
+{
+    KState *S = d_state;
+    const int *done = &S->done;
+    init_state(*this, prm.tolerance, prm.max_iter);
+    launch_spmv(ctx, "spmv_residual", A, vx.p, EpiResidualNorms{vr.p, d_b, dinv.p}, FinInitEigen{S});
+    launch_vec(ctx, "cg_dir", n_pad, OpCgDirEigen<true>{vp.p, vr.p, dinv.p, S, 0.0}, FinNone{}, done);
+    auto batch = [&]() {
+        for (int i = 0; i < prm.check_every; ++i)
+        {
+            launch_spmv(ctx, "spmv_dot", A, vp.p, EpiDot{vq.p, vp.p}, FinPAp{S}, done);
+            launch_vec(ctx, "cg_update", n_pad, OpCgUpdateEigen{vx.p, vr.p, vp.p, vq.p, dinv.p, S, 0.0}, FinCgUpdateEigen{S}, done);
+            launch_vec(ctx, "cg_dir", n_pad, OpCgDirEigen<false>{vp.p, vr.p, dinv.p, S, 0.0}, FinCgDirEigen{S}, done);
+        }
+    };
+    std::ostringstream key;
+    key << "cg_eigen/" << A.kind << "/" << A.lpr << "/" << n << "/" << (void *)vx.p << "/" << (void *)A.va.p << "/" << prm.check_every;
+    drive(batch, prm.check_every, key.str());
+    finish_solve();
+}
+
+// AMG-PCG in AMGCL's ordering (SURVEY A.3 "CG"; reference path AMGCL.cpp:190-212 -> amgcl::solver::cg).
+void Solver::run_cg_amgcl(const double *d_b)
+{
+    if (!amg)
+        throw std::runtime_error("psb200_solve: AMG hierarchy missing (factorize with precond=amg first)");
+    KState *S = d_state;
+    const int *done = &S->done;
+    init_state(*this, prm.tolerance, prm.max_iter);
+    PSB_CUDA(cudaMemsetAsync(vp.p, 0, sizeof(double) * n_pad, ctx.stream));
+    launch_spmv(ctx, "spmv_residual", A, vx.p, EpiResidualNorms{vr.p, d_b, dinv.p}, FinInitAmgcl{S});
+    auto batch = [&]() {
+        amg->apply(vr.p, vz.p, done);
+        launch_vec(ctx, "dot", n_pad, OpDot{vr.p, vz.p}, FinRhoAmgcl{S}, done);
+        launch_vec(ctx, "cg_dir", n_pad, OpCgDirAmgcl{vp.p, vz.p, S, 0.0}, FinNone{}, done);
+        launch_spmv(ctx, "spmv_dot", A, vp.p, EpiDot{vq.p, vp.p}, FinPAp{S}, done);
+        launch_vec(ctx, "cg_update", n_pad, OpCgUpdateAmgcl{vx.p, vr.p, vp.p, vq.p, S, 0.0}, FinCgUpdateAmgcl{S}, done);
+    };
+    std::ostringstream key;
+    key << "cg_amgcl/" << n << "/" << (void *)vx.p << "/" << (void *)amg.get();
+    drive(batch, 1, key.str());
+    finish_solve();
+}
+
+// Jacobi-BiCGSTAB in Eigen's ordering (reference Solver.cpp:437-439).
+void Solver::run_bicgstab(const double *d_b)
+{
+    KState *S = d_state;
+    const int *done = &S->done;
+    init_state(*this, prm.tolerance, prm.max_iter);
+    cudaStream_t st = ctx.stream;
+    PSB_CUDA(cudaMemsetAsync(vp.p, 0, sizeof(double) * n_pad, st));
+    PSB_CUDA(cudaMemsetAsync(vv.p, 0, sizeof(double) * n_pad, st));
+    launch_spmv(ctx, "spmv_residual", A, vx.p, EpiResidualNorms{vr.p, d_b, dinv.p}, FinInitBicg{S});
+    launch_vec(ctx, "copy", n_pad, OpCopy{vr0.p, vr.p}, FinNone{}, done);
+    auto batch = [&]() {
+        for (int i = 0; i < prm.check_every; ++i)
+        {
+            // restart branch (rare): only runs when the previous trip flagged |rho| < eps^2 ||r0||^2
+            launch_spmv(ctx, "spmv_restart", A, vx.p, EpiResidualRestart{vr.p, vr0.p, d_b}, FinBicgRestart{S}, done, &S->restart);
+            launch_vec(ctx, "bicg_p", n_pad, OpBicgP{vp.p, vy.p, vr.p, vv.p, dinv.p, S, 0.0, 0.0}, FinNone{}, done);
+            launch_spmv(ctx, "spmv_dot", A, vy.p, EpiDot{vv.p, vr0.p}, FinBicgAlpha{S}, done);
+            launch_vec(ctx, "bicg_s", n_pad, OpBicgS{vr.p, vz.p, vv.p, dinv.p, S, 0.0}, FinNone{}, done);
+            launch_spmv(ctx, "spmv_dot2", A, vz.p, EpiDot2{vt.p, vr.p}, FinBicgOmega{S}, done);
+            launch_vec(ctx, "bicg_end", n_pad, OpBicgEnd{vx.p, vr.p, vy.p, vz.p, vt.p, vr0.p, S, 0.0, 0.0}, FinBicgEnd{S}, done);
+        }
+    };
+    std::ostringstream key;
+    key << "bicgstab/" << A.kind << "/" << A.lpr << "/" << n << "/" << (void *)vx.p << "/" << (void *)d_b << "/" << prm.check_every;
+    drive(batch, prm.check_every, key.str());
+    finish_solve();
+}
+
+// ==================================================================================== hooks
+void Solver::spmv_host(const double *x, double *y, long long n_)
+{
+    if (!factorized || n_ != n)
+        throw std::invalid_argument("psb200_spmv: not factorized or size mismatch");
+    ensure_vectors();
+    cudaStream_t st = ctx.stream;
+    PSB_CUDA(cudaMemcpyAsync(vp.p, x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    launch_spmv(ctx, "spmv", A, vp.p, EpiStore{vq.p}, FinNone{});
+    PSB_CUDA(cudaMemcpyAsync(y, vq.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    PSB_CUDA(cudaStreamSynchronize(st));
+}
+
+double Solver::bench_spmv(const std::string &kernel, int reps)
+{
+    if (!factorized)
+        throw std::runtime_error("psb200_bench_spmv: factorize() first");
+    ensure_vectors();
+    cudaStream_t st = ctx.stream;
+    const int kind0 = A.kind, lpr0 = A.lpr;
+    if (!kernel.empty())
+        A.plan(kernel);
+    // a non-trivial resident x
+    launch_vec(ctx, "copy", n_pad, OpCopy{vp.p, dinv.p}, FinNone{});
+    for (int i = 0; i < 3; ++i)
+        launch_spmv(ctx, "spmv", A, vp.p, EpiStore{vq.p}, FinNone{});
+    cudaEvent_t a, b;
+    PSB_CUDA(cudaEventCreate(&a));
+    PSB_CUDA(cudaEventCreate(&b));
+    PSB_CUDA(cudaEventRecord(a, st));
+    for (int i = 0; i < reps; ++i)
+        launch_spmv(ctx, "spmv", A, vp.p, EpiStore{vq.p}, FinNone{});
+    PSB_CUDA(cudaEventRecord(b, st));
+    PSB_CUDA(cudaEventSynchronize(b));
+    float ms = 0;
+    PSB_CUDA(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    A.kind = kind0;
+    A.lpr = lpr0;
+    return (double)ms / std::max(1, reps);
+}
+
+void Solver::precond_apply_host(const double *r, double *z, long long n_)
+{
+    if (!factorized || n_ != n)
+        throw std::invalid_argument("psb200_precond_apply: not factorized or size mismatch");
+    ensure_vectors();
+    cudaStream_t st = ctx.stream;
+    PSB_CUDA(cudaMemcpyAsync(vr.p, r, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    if (amg)
+    {
+        vz.alloc((size_t)n_pad, false);
+        amg->apply(vr.p, vz.p, nullptr);
+        PSB_CUDA(cudaMemcpyAsync(z, vz.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    }
+    else
+    {
+        init_state(*this, 0, 0);
+        launch_vec(ctx, "cg_dir", n_pad, OpCgDirEigen<true>{vp.p, vr.p, dinv.p, d_state, 0.0}, FinNone{});
+        PSB_CUDA(cudaMemcpyAsync(z, vp.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    }
+    PSB_CUDA(cudaStreamSynchronize(st));
+}
+
+void Solver::build_info()
+{
+    static const char *status_str[] = {"Running", "Converged", "Reach max iterations", "Breakdown (non-finite residual)", "Zero right-hand side"};
+    std::ostringstream o;
+    o << "{";
+    // both conventions: Eigen/MAS (EigenSolver.tpp:88-89, MASSolver.cu:214-219) and AMGCL/Hypre (AMGCL.cpp:142-143)
+    o << "\"solver_iter\":" << last_iters << ",\"solver_error\":" << jnum(last_error);
+    o << ",\"num_iterations\":" << last_iters << ",\"final_res_norm\":" << jnum(last_error);
+    o << ",\"solver_status\":" << jstr(status_str[std::min(std::max(last_status, 0), 4)]);
+    o << ",\"krylov\":" << jstr(prm.krylov) << ",\"precond\":" << jstr(prm.precond);
+    o << ",\"n\":" << n << ",\"nnz\":" << nnz;
+    o << ",\"symmetric_pattern\":" << (sym_pattern ? "true" : "false");
+    o << ",\"analyze_skipped\":" << (analyze_skipped ? "true" : "false");
+    o << ",\"spmv_kernel\":" << jstr(A.kind == SPMV_STREAM ? "stream" : ("vector" + std::to_string(A.lpr)));
+    o << ",\"time_analyze_ms\":" << jnum(t_analyze_ms) << ",\"time_factorize_ms\":" << jnum(t_factorize_ms);
+    o << ",\"time_precond_setup_ms\":" << jnum(t_setup_precond_ms) << ",\"time_solve_ms\":" << jnum(t_solve_ms);
+    o << ",\"gpu_launches\":" << ctx.launches;
+    if (amg)
+        o << ",\"amg\":" << amg->info_json();
+    if (!ctx.prof.empty())
+    {
+        o << ",\"profile\":{";
+        bool first = true;
+        for (auto &kv : ctx.prof)
+        {
+            if (!first)
+                o << ",";
+            first = false;
+            o << jstr(kv.first) << ":{\"ms\":" << jnum(kv.second.ms) << ",\"launches\":" << kv.second.launches << "}";
+        }
+        o << "}";
+    }
+    o << "}";
+    info_json = o.str();
+}
+
+} // namespace psb

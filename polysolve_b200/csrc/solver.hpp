@@ -1,0 +1,113 @@
+// Internal solver object behind the C ABI (include/psb200.h).
+#pragma once
+#include "json_mini.hpp"
+#include "launch.cuh"
+
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+namespace psb {
+
+// Mirrors the AMGCL parameter tree polysolve passes (reference AMGCL.cpp:32-65 default_params()).
+struct AmgParams
+{
+    int max_levels = 6;
+    int coarse_enough = 3000;
+    bool direct_coarse = false;
+    int ncycle = 2;
+    int npre = 1, npost = 1, pre_cycles = 1;
+    std::string relax_type = "chebyshev"; // chebyshev | damped_jacobi
+    int degree = 16;
+    int power_iters = 100;
+    double higher = 2.0, lower = 0.008333333333;
+    bool scale = true;
+    double damping = 0.72;
+    double sa_relax = 1.0;
+    bool estimate_spectral_radius = true;
+    double eps_strong = 0.0;
+    std::string aggregation = "mis2"; // mis2 (parallel, deterministic) | imposed via debug hook
+};
+
+struct Params
+{
+    std::string krylov = "cg";      // cg | bicgstab
+    std::string precond = "jacobi"; // jacobi | amg | none
+    double tolerance = 1e-12;       // relative to ||b|| (Eigen / AMGCL semantics); spec default of Eigen iterative solvers
+    int max_iter = 1000;
+    int check_every = 16;
+    bool use_graph = true;
+    std::string spmv_kernel = "auto";
+    int device = -1; // -1: current device
+    int block_size = 1;
+    bool profile = false;
+    bool verify_pattern = true;
+    AmgParams amg;
+};
+
+class AmgHierarchy; // amg.cu
+
+struct DistComm; // dist.cu
+
+struct Solver
+{
+    Params prm;
+    std::string err;
+    std::string info_json = "{}";
+    int device = 0;
+    Ctx ctx;
+
+    // pattern state (analyze_pattern)
+    long long n = 0, nnz = 0;
+    unsigned long long pattern_hash = 0;
+    bool analyzed = false, factorized = false;
+    bool sym_pattern = false;
+    int precond_num = 0;
+    DevBuf<int> csc_outer, csc_inner, perm;
+    DevBuf<double> csc_vals;
+    CsrDev A;
+    DevBuf<double> dinv;
+    long long n_pad = 0;
+
+    // work vectors (padded, zero tails)
+    DevBuf<double> vb, vx, vr, vp, vq, vz, vy, vv, vt, vr0;
+    KState *d_state = nullptr;
+    KState *h_state = nullptr; // pinned, 4 slots
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaGraphExec_t graph_exec = nullptr;
+    std::string graph_key;
+    long long graph_launches_per_batch = 0;
+
+    std::unique_ptr<AmgHierarchy> amg;
+    std::vector<std::vector<int>> imposed_aggregates;
+
+    // last solve
+    long long last_iters = 0;
+    double last_error = 0;
+    int last_status = 0;
+    double t_analyze_ms = 0, t_factorize_ms = 0, t_solve_ms = 0, t_setup_precond_ms = 0;
+    bool analyze_skipped = false;
+
+    Solver();
+    ~Solver();
+    void set_parameters(const std::string &json);
+    void analyze_pattern(long long n, long long nnz, const int *outer, const int *inner, int precond_num);
+    void factorize(long long n, long long nnz, const int *outer, const int *inner, const double *vals);
+    void solve_host(const double *b, double *x, long long n);
+    void solve_device(const double *d_b, double *d_x, long long n);
+    void spmv_host(const double *x, double *y, long long n);
+    double bench_spmv(const std::string &kernel, int reps);
+    void precond_apply_host(const double *r, double *z, long long n);
+    void build_info();
+
+private:
+    void ensure_vectors();
+    void run_cg_eigen(const double *d_b);
+    void run_cg_amgcl(const double *d_b);
+    void run_bicgstab(const double *d_b);
+    void drive(const std::function<void()> &enqueue_batch, int batch_iters, const std::string &key);
+    void finish_solve();
+};
+
+} // namespace psb

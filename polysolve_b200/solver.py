@@ -1,0 +1,184 @@
+"""Host-side mirror of polysolve::linear::Solver for the "CUDA" backend.
+
+Same method names, argument meaning and error behaviour as the reference interface
+(reference src/polysolve/linear/Solver.hpp:31-132); every call forwards to the C ABI
+(include/psb200.h) exactly as adapter/CUDASolver.cpp does on the C++ side. Matrices are
+scipy.sparse CSC (the layout of StiffnessMatrix, reference src/polysolve/Types.hpp:11-15)."""
+import ctypes as C
+import json
+
+import numpy as np
+
+from . import _lib
+
+
+class Solver:
+    """polysolve::linear::Solver, "CUDA" flavour."""
+
+    @staticmethod
+    def available_solvers():
+        # reference Solver.cpp:501-568 (we only provide the new entry)
+        return ["CUDA"]
+
+    @staticmethod
+    def create(solver="CUDA", precond=""):
+        """Solver::create(name, precond) -- reference Solver.cpp:307-496."""
+        if isinstance(solver, dict):
+            params = solver
+            name = params.get("solver", "CUDA")
+            if isinstance(name, (list, tuple)):
+                # priority list (reference Solver.cpp:92-114 select_valid_solver)
+                name = next((s for s in name if s in Solver.available_solvers()), None)
+            if name != "CUDA":
+                raise RuntimeError(f"Unrecognized solver type: {name}")
+            s = Solver()
+            s.set_parameters(params)
+            return s
+        if solver != "CUDA":
+            raise RuntimeError(f"Unrecognized solver type: {solver}")  # Solver.cpp:495
+        s = Solver()
+        if precond:
+            pmap = {"Eigen::DiagonalPreconditioner": "jacobi", "Eigen::IdentityPreconditioner": "none",
+                    "jacobi": "jacobi", "amg": "amg", "none": "none"}
+            if precond not in pmap:
+                raise RuntimeError(f"Unrecognized preconditioner: {precond}")
+            s.set_parameters({"CUDA": {"precond": pmap[precond]}})
+        return s
+
+    def __init__(self):
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        rc = self._L.psb200_create(C.byref(self._h), None)
+        if rc:
+            raise RuntimeError(self._L.psb200_last_error(None).decode())
+        self._keep = None
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.psb200_destroy(h)
+            self._h = None
+
+    def _check(self, rc):
+        if rc:
+            # the reference's error convention: std::runtime_error (Utils.cpp:65-69)
+            raise RuntimeError(self._L.psb200_last_error(self._h).decode())
+
+    # ---- polysolve::linear::Solver virtuals
+    def set_parameters(self, params):
+        self._check(self._L.psb200_set_parameters(self._h, json.dumps(params).encode()))
+
+    def set_tolerance(self, tol):
+        self._check(self._L.psb200_set_tolerance(self._h, float(tol)))
+
+    def set_block_size(self, bs):
+        self._check(self._L.psb200_set_block_size(self._h, int(bs)))
+
+    @staticmethod
+    def _csc(A):
+        import scipy.sparse as sp
+        if not sp.isspmatrix_csc(A):
+            A = sp.csc_matrix(A)
+        outer = np.ascontiguousarray(A.indptr, np.int32)
+        inner = np.ascontiguousarray(A.indices, np.int32)
+        vals = np.ascontiguousarray(A.data, np.float64)
+        return A.shape[0], outer, inner, vals
+
+    def analyze_pattern(self, A, precond_num):
+        n, outer, inner, _ = self._csc(A)
+        self.analyze_pattern_raw(n, outer, inner, precond_num)
+
+    def analyze_pattern_raw(self, n, outer, inner, precond_num):
+        self._check(self._L.psb200_analyze_pattern_csc(self._h, n, int(outer[n]), outer, inner, int(precond_num)))
+
+    def factorize(self, A):
+        n, outer, inner, vals = self._csc(A)
+        self.factorize_raw(n, outer, inner, vals)
+
+    def factorize_raw(self, n, outer, inner, vals):
+        self._check(self._L.psb200_factorize_csc(self._h, n, int(outer[n]), outer, inner, vals))
+
+    def solve(self, b, x):
+        """x is in/out (initial guess), as in the reference (Solver.hpp:119-128)."""
+        b = np.ascontiguousarray(b, np.float64)
+        if not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous):
+            raise TypeError("x must be a contiguous float64 numpy array (it is updated in place)")
+        if b.shape != x.shape:
+            raise RuntimeError("psb200_solve: size mismatch")
+        self._check(self._L.psb200_solve(self._h, b, x, b.shape[0]))
+        return x
+
+    def solve_device(self, b_ptr, x_ptr, n):
+        """b, x resident on the solver's GPU (raw device pointers, e.g. torch.Tensor.data_ptr())."""
+        self._check(self._L.psb200_solve_device(self._h, b_ptr, x_ptr, n))
+
+    def get_info(self):
+        need = C.c_size_t()
+        buf = C.create_string_buffer(1 << 16)
+        rc = self._L.psb200_get_info(self._h, buf, len(buf), C.byref(need))
+        if rc and need.value > len(buf):
+            buf = C.create_string_buffer(need.value)
+            rc = self._L.psb200_get_info(self._h, buf, len(buf), C.byref(need))
+        self._check(rc)
+        return json.loads(buf.value.decode())
+
+    def name(self):
+        return self._L.psb200_name(self._h).decode()
+
+    def is_dense(self):
+        return False
+
+    # ---- multi-GPU
+    @staticmethod
+    def dist_unique_id():
+        buf = C.create_string_buffer(128)
+        rc = _lib.lib().psb200_dist_unique_id(buf)
+        if rc:
+            raise RuntimeError("psb200_dist_unique_id failed")
+        return buf.raw
+
+    def dist_init(self, rank, world, uid):
+        self._check(self._L.psb200_dist_init(self._h, rank, world, uid))
+
+    # ---- test / bench hooks
+    def debug_get_csr(self, n, nnz):
+        rp = np.empty(n + 1, np.int32)
+        ci = np.empty(max(nnz, 1), np.int32)
+        perm = np.empty(max(nnz, 1), np.int32)
+        self._check(self._L.psb200_debug_get_csr(self._h, rp, ci, perm))
+        return rp, ci[:nnz], perm[:nnz]
+
+    def spmv(self, x):
+        x = np.ascontiguousarray(x, np.float64)
+        y = np.empty_like(x)
+        self._check(self._L.psb200_spmv(self._h, x, y, x.shape[0]))
+        return y
+
+    def bench_spmv(self, reps=20, kernel=""):
+        ms = C.c_double()
+        self._check(self._L.psb200_bench_spmv(self._h, kernel.encode(), reps, C.byref(ms)))
+        return ms.value
+
+    def stream(self):
+        return self._L.psb200_get_stream(self._h)
+
+    def debug_set_aggregates(self, level, agg):
+        agg = np.ascontiguousarray(agg, np.int32)
+        self._keep = agg
+        self._check(self._L.psb200_debug_set_aggregates(self._h, level, agg.ctypes.data, agg.shape[0]))
+
+    def debug_get_level(self, level, which):
+        w = {"A": 0, "P": 1, "R": 2}[which]
+        rows, cols, nnz = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self._L.psb200_debug_get_level(self._h, level, w, C.byref(rows), C.byref(cols), C.byref(nnz), None, None, None))
+        rp = np.empty(rows.value + 1, np.int32)
+        ci = np.empty(max(nnz.value, 1), np.int32)
+        va = np.empty(max(nnz.value, 1), np.float64)
+        self._check(self._L.psb200_debug_get_level(self._h, level, w, None, None, None, rp.ctypes.data, ci.ctypes.data, va.ctypes.data))
+        return rows.value, cols.value, rp, ci[:nnz.value], va[:nnz.value]
+
+    def precond_apply(self, r):
+        r = np.ascontiguousarray(r, np.float64)
+        z = np.empty_like(r)
+        self._check(self._L.psb200_precond_apply(self._h, r, z, r.shape[0]))
+        return z

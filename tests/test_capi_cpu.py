@@ -1,0 +1,99 @@
+"""CPU tests of the boundary: the C-ABI library loads and exports every symbol include/psb200.h
+declares, host-side parameter logic works, and -- with no GPU -- compute entry points fail loudly
+instead of falling back to anything."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol(psb):
+    L = psb._lib.lib()
+    header = open(os.path.join(ROOT, "include", "psb200.h")).read()
+    declared = sorted(set(re.findall(r"\b(psb200_[a-z0-9_]+)\s*\(", header)))
+    assert declared, "no declarations parsed"
+    assert sorted(psb._lib.SYMBOLS) == declared
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_product_never_imports_oracle():
+    """The product path must not import, link or execute the oracle (or any CPU fallback)."""
+    pat = re.compile(r"import\s+oracle|from\s+oracle|from\s+\.+oracle|liboracle|orc_[a-z]|oracle\.py|oracle/(?!\))")
+    files = []
+    for d, _, fs in os.walk(os.path.join(ROOT, "polysolve_b200")):
+        files += [os.path.join(d, f) for f in fs if f.endswith((".py", ".cu", ".cuh", ".hpp", ".cpp", ".h", "Makefile"))]
+    files += [os.path.join(ROOT, f) for f in ("adapter/CUDASolver.cpp", "adapter/CUDASolver.hpp", "include/psb200.h")]
+    for p in files:
+        if os.path.exists(p):
+            src = open(p).read().replace("must not depend on oracle/)", "")
+            assert not pat.search(src), p
+
+
+def test_create_name_and_parameters(psb):
+    s = psb.Solver.create("CUDA", "")
+    assert s.name() == "CUDA"
+    assert not s.is_dense()
+    s.set_parameters({"CUDA": {"tolerance": 1e-10, "max_iter": 500, "krylov": "cg", "precond": "jacobi"},
+                      "Eigen::ConjugateGradient": {"tolerance": 1.0}})  # other solvers' keys are ignored
+    s.set_tolerance(1e-9)
+    info = s.get_info()
+    for k in ("solver_iter", "solver_error", "num_iterations", "final_res_norm", "solver_status"):
+        assert k in info
+    with pytest.raises(RuntimeError, match="Unrecognized solver type"):
+        psb.Solver.create("Eigen::SimplicialLDLT", "")
+    with pytest.raises(RuntimeError, match="unknown krylov"):
+        s.set_parameters({"CUDA": {"krylov": "gmres"}})
+    with pytest.raises(RuntimeError, match="unknown precond"):
+        s.set_parameters({"CUDA": {"precond": "ilu"}})
+    with pytest.raises(RuntimeError, match="json parse error"):
+        s._check(s._L.psb200_set_parameters(s._h, b"{not json"))
+
+
+def test_json_factory_priority_list(psb):
+    # reference Solver.cpp:92-114: "solver" may be a priority list
+    s = psb.Solver.create({"solver": ["Hypre", "CUDA", "Eigen::SimplicialLDLT"], "CUDA": {"tolerance": 1e-9}})
+    assert s.name() == "CUDA"
+
+
+def test_protocol_errors(psb):
+    s = psb.Solver.create("CUDA", "")
+    b = np.ones(4)
+    x = np.zeros(4)
+    with pytest.raises(RuntimeError):
+        s.solve(b, x)  # no factorize yet (and, on a CPU box, no device)
+    with pytest.raises(RuntimeError, match="not compressed|null|no CUDA device"):
+        outer = np.array([1, 2, 3, 4, 5], np.int32)
+        inner = np.zeros(4, np.int32)
+        s.analyze_pattern_raw(4, outer, inner, 4)
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
+def test_compute_fails_loudly_without_gpu(psb):
+    s = psb.Solver.create("CUDA", "")
+    o, i, v = psb.problems.poisson2d(4)
+    with pytest.raises(RuntimeError, match="no CUDA device|CUDA error"):
+        s.factorize_raw(16, o, i, v)
+
+
+def test_generators_match_oracle(psb, orc):
+    P = psb.problems
+    for n in (1, 2, 7):
+        for a, b in ((P.poisson2d(n), orc.poisson2d(n)), (P.poisson3d(n), orc.poisson3d(n))):
+            assert all(np.array_equal(u, w) for u, w in zip(a, b))
+    assert np.array_equal(P.splitmix64(42, 257), orc.splitmix64(42, 257))
+    assert P.spmv_bytes(10077696, 70263936) == 1044721156
+    assert P.pcg_iter_bytes(10077696, 70263936) == 1931558404

@@ -1,0 +1,315 @@
+"""GPU parity tests (run with -m gpu on a B200). Every test calls the product through the C ABI
+(polysolve_b200.Solver -> libpsb200.so) and compares with the CPU oracle on the same seeded inputs,
+with the committed golden fixtures, or through size-independent properties at BASELINE sizes.
+
+Bars: bit-exact for the analyze_pattern integer arrays; floating point within the tolerance written
+next to each assertion (the reference's own acceptance is ||Ax-b|| < 1e-8,
+reference tests/test_linear_solver.cpp:160-162)."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def csc(o, i, v):
+    n = len(o) - 1
+    return sp.csc_matrix((v, i, o), shape=(n, n))
+
+
+def make(psb, **kw):
+    s = psb.Solver.create("CUDA", "")
+    if kw:
+        s.set_parameters({"CUDA": kw})
+    return s
+
+
+# ------------------------------------------------------------------ analyze_pattern: bit-exact integers
+@pytest.mark.parametrize("case", ["poisson2d", "poisson3d", "convdiff", "random_unsym", "random_ragged"])
+def test_analyze_pattern_bit_exact(psb, orc, case):
+    rng = np.random.default_rng(3)
+    if case == "poisson2d":
+        o, i, v = orc.poisson2d(32)
+    elif case == "poisson3d":
+        o, i, v = orc.poisson3d(20)
+    elif case == "convdiff":
+        o, i, v = orc.convdiff2d(32, 0.5)
+    else:
+        n = 700
+        A = sp.random(n, n, density=0.01, random_state=rng, format="csc")
+        if case == "random_ragged":
+            # empty rows/columns, one dense row and one dense column
+            A = sp.lil_matrix(A)
+            A[5, :] = 0
+            A[:, 9] = 0
+            A[17, :] = rng.standard_normal(n)
+            A[:, 23] = rng.standard_normal((n, 1))
+            A = sp.csc_matrix(A)
+            A.eliminate_zeros()
+        else:
+            A = sp.csc_matrix(A + sp.eye(n))
+        A.sort_indices()
+        o, i, v = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float64)
+    n = len(o) - 1
+    s = make(psb)
+    s.analyze_pattern_raw(n, o, i, n)
+    rp, ci, perm = s.debug_get_csr(n, int(o[-1]))
+    rp0, ci0, perm0 = orc.csc_to_csr(n, o, i)
+    assert np.array_equal(rp, rp0)
+    assert np.array_equal(ci, ci0)
+    assert np.array_equal(perm, perm0)
+    # and SpMV through the product kernel == oracle SpMV (<= 4 ulp-scaled: different summation order only)
+    s.factorize_raw(n, o, i, v)
+    x = orc.splitmix64(7, n)
+    y = s.spmv(x)
+    y0 = orc.spmv_csc(o, i, v, x)
+    scale = orc.spmv_csc(o, i, np.abs(v), np.abs(x)) + 1e-300
+    assert np.max(np.abs(y - y0) / scale) < 4 * np.finfo(float).eps
+
+
+def test_analyze_pattern_is_idempotent(psb, orc):
+    o, i, v = orc.poisson3d(16)
+    n = 16 ** 3
+    s = make(psb)
+    s.analyze_pattern_raw(n, o, i, n)
+    s.factorize_raw(n, o, i, v)
+    assert not s.get_info()["analyze_skipped"]
+    s.analyze_pattern_raw(n, o, i, n)  # Newton does this every iteration (Newton.cpp:189)
+    assert s.get_info()["analyze_skipped"]
+    o2, i2, _ = orc.poisson3d(15)
+    s.analyze_pattern_raw(15 ** 3, o2, i2, 15 ** 3)
+    assert not s.get_info()["analyze_skipped"]
+
+
+# ------------------------------------------------------------------ SpMV schedules
+@pytest.mark.parametrize("kernel", ["stream", "scalar", "vector4", "vector8", "vector32"])
+def test_spmv_schedules_match_oracle(psb, orc, kernel):
+    o, i, v = orc.poisson3d(40)
+    n = 40 ** 3
+    v = v * (1.0 + 0.1 * orc.splitmix64(11, len(v)))  # non-trivial values
+    s = make(psb, spmv_kernel=kernel)
+    s.factorize_raw(n, o, i, v)
+    assert s.get_info()["spmv_kernel"] == {"scalar": "vector1"}.get(kernel, kernel)
+    x = orc.splitmix64(5, n)
+    y = s.spmv(x)
+    rp, ci, perm = orc.csc_to_csr(n, o, i)
+    y0 = orc.spmv_csr(rp, ci, v[perm], x)
+    scale = orc.spmv_csr(rp, ci, np.abs(v[perm]), np.abs(x))
+    assert np.max(np.abs(y - y0) / scale) < 4 * np.finfo(float).eps
+
+
+def test_spmv_stream_falls_back_on_dense_tiles(psb, orc):
+    """Tiles whose nnz exceed the shared-memory stage take the direct-load path."""
+    rng = np.random.default_rng(5)
+    n = 4096
+    A = sp.random(n, n, density=0.004, random_state=rng, format="lil")
+    A[300:340, :] = rng.standard_normal((40, n))  # 40 dense rows => one tile far above the cap
+    A = sp.csc_matrix(A + sp.eye(n))
+    A.sort_indices()
+    o, i, v = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float64)
+    s = make(psb, spmv_kernel="stream")
+    s.factorize_raw(n, o, i, v)
+    x = orc.splitmix64(9, n)
+    y0 = A @ x
+    np.testing.assert_allclose(s.spmv(x), y0, rtol=1e-12, atol=1e-12)
+
+
+def test_spmv_eigenvector_full_size(psb):
+    """BASELINE size (216^3, 10,077,696 DoF): A v = lambda v for an analytic eigenpair."""
+    P = psb.problems
+    n = 216
+    o, i, v = P.poisson3d(n)
+    k = np.arange(1, n + 1)
+    sx, sy, sz = (np.sin(np.pi * m * k / (n + 1)) for m in (3, 7, 2))
+    vec = np.einsum("i,j,k->kji", sx, sy, sz).ravel()
+    lam = 4 * sum(np.sin(np.pi * m / (2 * (n + 1))) ** 2 for m in (3, 7, 2))
+    s = make(psb)
+    s.factorize_raw(n ** 3, o, i, v)
+    assert s.get_info()["spmv_kernel"] == "stream"
+    y = s.spmv(vec)
+    assert np.max(np.abs(y - lam * vec)) < 1e-13 * 12  # |A|.|v| <= 12
+
+
+# ------------------------------------------------------------------ Jacobi-PCG (Eigen ordering)
+@pytest.mark.parametrize("graph", [True, False])
+def test_c1_known_answer_and_golden(psb, orc, graph):
+    """C1 of BASELINE.json: 32x32 Poisson, tol 1e-10 => 115 iterations, golden x."""
+    g = np.load(os.path.join(GOLD, "c1_poisson2d_32.npz"))
+    o, i, v = psb.problems.poisson2d(32)
+    s = make(psb, tolerance=1e-10, max_iter=1000, use_graph=graph)
+    s.analyze_pattern_raw(1024, o, i, 1024)
+    s.factorize_raw(1024, o, i, v)
+    x = np.zeros(1024)
+    s.solve(g["b"], x)
+    info = s.get_info()
+    assert info["solver_iter"] == int(g["iters"]) == 115
+    assert info["num_iterations"] == 115
+    assert abs(info["solver_error"] - float(g["err"])) < 1e-13
+    assert info["solver_status"] == "Converged"
+    np.testing.assert_allclose(x, g["x"], rtol=0, atol=1e-12)          # oracle (Eigen restatement)
+    np.testing.assert_allclose(x, g["x_direct"], rtol=0, atol=1e-9)    # independent direct solve
+    assert np.linalg.norm(csc(o, i, v) @ x - g["b"]) < 1e-8           # the reference's acceptance bound
+    # warm start: converged x in => 0 iterations, x untouched (test_linear_solver.cpp:432-450)
+    x2 = x.copy()
+    s.solve(g["b"], x2)
+    assert s.get_info()["solver_iter"] == 0
+    assert np.array_equal(x2, x)
+
+
+@pytest.mark.parametrize("n,tol", [(24, 1e-8), (48, 1e-8)])
+def test_pcg_iteration_parity_3d(psb, orc, n, tol):
+    o, i, v = orc.poisson3d(n)
+    N = n ** 3
+    b = orc.spmv_csc(o, i, v, orc.splitmix64(42, N))
+    x0, it0, err0, _ = orc.eigen_cg(o, i, v, b, tol=tol, max_iters=10000)
+    s = make(psb, tolerance=tol, max_iter=10000)
+    s.factorize_raw(N, o, i, v)
+    x = np.zeros(N)
+    s.solve(b, x)
+    info = s.get_info()
+    # same algorithm, different summation order: iteration counts within +-2 %
+    assert abs(info["solver_iter"] - it0) <= max(1, 0.02 * it0)
+    assert info["solver_error"] < tol
+    assert np.linalg.norm(x - x0) / np.linalg.norm(x0) < 10 * tol
+    assert np.linalg.norm(csc(o, i, v) @ x - b) / np.linalg.norm(b) < 2 * tol
+
+
+def test_pcg_identity_precond_and_max_iter(psb, orc):
+    o, i, v = orc.poisson2d(32)
+    b = orc.splitmix64(42, 1024)
+    s = make(psb, tolerance=1e-10, precond="none")
+    s.factorize_raw(1024, o, i, v)
+    x = np.zeros(1024)
+    s.solve(b, x)
+    assert np.linalg.norm(csc(o, i, v) @ x - b) < 1e-8
+    # max_iter cap: Eigen reports iterations() == maxIterations and does not throw
+    s2 = make(psb, tolerance=1e-14, max_iter=10, check_every=4)
+    s2.factorize_raw(1024, o, i, v)
+    x = np.zeros(1024)
+    s2.solve(b, x)
+    info = s2.get_info()
+    assert info["solver_iter"] == 10 and info["solver_status"] == "Reach max iterations"
+    x0, it0, err0, _ = orc.eigen_cg(o, i, v, b, tol=1e-14, max_iters=10)
+    assert it0 == 10
+    np.testing.assert_allclose(x, x0, rtol=0, atol=1e-12)
+    assert abs(info["solver_error"] - err0) < 1e-10
+
+
+def test_zero_rhs_and_tiny_systems(psb, orc):
+    o, i, v = orc.poisson2d(32)
+    s = make(psb, tolerance=1e-10)
+    s.factorize_raw(1024, o, i, v)
+    x = orc.splitmix64(3, 1024)
+    s.solve(np.zeros(1024), x)  # Eigen: ||b|| == 0 => x = 0, 0 iterations
+    assert np.all(x == 0) and s.get_info()["solver_iter"] == 0
+    # 1x1 and 3x3 systems (smaller than any tile / vector width)
+    for n in (1, 2, 3):
+        o, i, v = orc.poisson2d(n)
+        N = n * n
+        s = make(psb, tolerance=1e-12)
+        s.factorize_raw(N, o, i, v)
+        b = orc.splitmix64(1, N)
+        x = np.zeros(N)
+        s.solve(b, x)
+        np.testing.assert_allclose(csc(o, i, v) @ x, b, atol=1e-12)
+
+
+def test_pre_factor_protocol(psb, orc):
+    """reference tests/test_linear_solver.cpp:241-307: analyze once, then 10x factorize(new values on
+    the same pattern) + solve; every solve must reach ||Ax-b|| < 1e-8."""
+    o, i, _ = orc.poisson2d(32)
+    vals = orc.prefactor_values(o, i, rounds=10)
+    s = make(psb, tolerance=1e-10)
+    s.analyze_pattern_raw(1024, o, i, 1024)
+    for r in range(10):
+        b = orc.splitmix64(100 + r, 1024)
+        x = np.zeros(1024)
+        s.factorize_raw(1024, o, i, vals[r])
+        s.solve(b, x)
+        assert np.linalg.norm(csc(o, i, vals[r]) @ x - b) < 1e-8
+        x0, it0, _, _ = orc.eigen_cg(o, i, vals[r], b, tol=1e-10)
+        assert abs(s.get_info()["solver_iter"] - it0) <= 1
+        np.testing.assert_allclose(x, x0, rtol=0, atol=1e-11)
+
+
+def test_solve_device_pointers(psb, orc):
+    import torch
+    o, i, v = orc.poisson3d(24)
+    N = 24 ** 3
+    g = np.load(os.path.join(GOLD, "poisson3d_24.npz"))
+    s = make(psb, tolerance=1e-8, max_iter=10000)
+    s.factorize_raw(N, o, i, v)
+    db = torch.from_numpy(g["b"]).cuda()
+    dx = torch.zeros(N, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    s.solve_device(db.data_ptr(), dx.data_ptr(), N)
+    x = dx.cpu().numpy()
+    assert abs(s.get_info()["solver_iter"] - int(g["iters"])) <= 2
+    assert np.linalg.norm(x - g["xstar"]) / np.linalg.norm(g["xstar"]) < 1e-6
+    assert np.linalg.norm(x - g["x"]) / np.linalg.norm(g["x"]) < 1e-7
+
+
+# ------------------------------------------------------------------ BiCGSTAB (Eigen ordering)
+def test_bicgstab_golden_unsymmetric(psb, orc):
+    g = np.load(os.path.join(GOLD, "convdiff2d_32.npz"))
+    o, i, v = orc.convdiff2d(32, 0.5)
+    s = make(psb, krylov="bicgstab", tolerance=1e-10)
+    s.analyze_pattern_raw(1024, o, i, 1024)
+    assert s.get_info()["symmetric_pattern"]  # pattern symmetric, values not
+    s.factorize_raw(1024, o, i, v)
+    x = np.zeros(1024)
+    s.solve(g["b"], x)
+    info = s.get_info()
+    # BiCGSTAB amplifies rounding differences; same algorithm => iteration count within a few
+    assert abs(info["solver_iter"] - int(g["iters"])) <= 3
+    assert info["solver_error"] < 1e-10
+    np.testing.assert_allclose(x, g["x_direct"], rtol=0, atol=1e-8)
+    assert np.linalg.norm(csc(o, i, v) @ x - g["b"]) < 1e-8
+    x2 = x.copy()
+    s.solve(g["b"], x2)
+    assert s.get_info()["solver_iter"] == 0
+
+
+def test_bicgstab_unsymmetric_pattern(psb, orc):
+    rng = np.random.default_rng(11)
+    n = 600
+    A = sp.random(n, n, density=0.01, random_state=rng, format="csc")
+    A = sp.csc_matrix(A + sp.diags(np.asarray(abs(A).sum(axis=1)).ravel() + 1.0))
+    A.sort_indices()
+    o, i, v = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data.astype(np.float64)
+    b = orc.splitmix64(2, n)
+    s = make(psb, krylov="bicgstab", tolerance=1e-12)
+    s.factorize_raw(n, o, i, v)
+    assert not s.get_info()["symmetric_pattern"]
+    x = np.zeros(n)
+    s.solve(b, x)
+    x0, it0, err0, _ = orc.eigen_bicgstab(o, i, v, b, tol=1e-12)
+    assert abs(s.get_info()["solver_iter"] - it0) <= 2
+    np.testing.assert_allclose(x, x0, rtol=0, atol=1e-10)
+    assert np.linalg.norm(A @ x - b) < 1e-8
+
+
+# ------------------------------------------------------------------ BASELINE-size property test
+def test_pcg_full_size_manufactured_solution(psb):
+    """C2 of BASELINE.json: 216^3 Poisson, b = A x*, Jacobi-PCG to 1e-8. Properties: converges in the
+    ~3n iterations the oracle shows at smaller n, true residual and error are small."""
+    P = psb.problems
+    n = 216
+    N = n ** 3
+    o, i, v = P.poisson3d(n)
+    xstar = P.splitmix64(42, N)
+    b = P.spmv_csr(o, i, v, xstar)
+    s = make(psb, tolerance=1e-8, max_iter=10000)
+    s.analyze_pattern_raw(N, o, i, N)
+    s.factorize_raw(N, o, i, v)
+    x = np.zeros(N)
+    s.solve(b, x)
+    info = s.get_info()
+    assert info["solver_status"] == "Converged"
+    assert 500 <= info["solver_iter"] <= 800
+    r = P.spmv_csr(o, i, v, x) - b
+    assert np.linalg.norm(r) / np.linalg.norm(b) < 2e-8
+    assert np.linalg.norm(x - xstar) / np.linalg.norm(xstar) < 1e-5

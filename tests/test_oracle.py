@@ -1,0 +1,169 @@
+"""CPU tests: the oracle against known answers, analytic eigenpairs, scipy and the committed golden
+fixtures (tests/golden/make_golden.py). The reference holds no golden vectors for this path
+(SURVEY 8c), so these are what pins the restatement."""
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def csc(o, i, v):
+    n = len(o) - 1
+    return sp.csc_matrix((v, i, o), shape=(n, n))
+
+
+def test_splitmix_known_values(orc):
+    b = orc.splitmix64(42, 3)
+    # SURVEY 8d fixes these three values
+    assert b.tolist() == [0.4831297575436466, -0.6801792142461598, -0.4427977394897227]
+
+
+def test_c1_known_answer(orc):
+    """C1 => 115 reported iterations, error() 7.0695e-11, ||Ax-b|| 1.3329e-9."""
+    o, i, v = orc.poisson2d(32)
+    b = orc.splitmix64(42, 1024)
+    x, it, err, spmvs = orc.eigen_cg(o, i, v, b, tol=1e-10, max_iters=1000)
+    assert it == 115 and spmvs == 116
+    assert abs(err - 7.0695e-11) < 1e-14
+    res = np.linalg.norm(csc(o, i, v) @ x - b)
+    assert abs(res - 1.3329e-9) < 1e-12 and res < 1e-8  # reference acceptance: test_linear_solver.cpp:160-162
+    # warm start from the converged x => 0 iterations (property pinned at test_linear_solver.cpp:449)
+    _, it2, _, _ = orc.eigen_cg(o, i, v, b, x0=x, tol=1e-10)
+    assert it2 == 0
+
+
+def test_cg_matches_scipy(orc):
+    o, i, v = orc.poisson2d(32)
+    A = csc(o, i, v)
+    b = orc.splitmix64(42, 1024)
+    x, it, err, _ = orc.eigen_cg(o, i, v, b, tol=1e-10)
+    xs, info = spla.cg(A, b, rtol=1e-10, M=sp.diags(1 / A.diagonal()), maxiter=1000)
+    assert info == 0
+    assert np.abs(xs - x).max() < 1e-12
+
+
+def test_golden_c1(orc):
+    g = np.load(os.path.join(GOLD, "c1_poisson2d_32.npz"))
+    o, i, v = orc.poisson2d(32)
+    x, it, err, _ = orc.eigen_cg(o, i, v, g["b"], tol=1e-10)
+    assert it == int(g["iters"])
+    np.testing.assert_allclose(x, g["x"], rtol=0, atol=1e-13)
+    # and the golden solution really solves the system (independent of the oracle)
+    assert np.linalg.norm(csc(o, i, v) @ g["x"] - g["b"]) < 1e-8
+
+
+def test_golden_bicgstab(orc):
+    g = np.load(os.path.join(GOLD, "convdiff2d_32.npz"))
+    o, i, v = orc.convdiff2d(32, 0.5)
+    x, it, err, _ = orc.eigen_bicgstab(o, i, v, g["b"], tol=1e-10)
+    assert it == int(g["iters"])
+    np.testing.assert_allclose(x, g["x"], rtol=0, atol=1e-12)
+    xs = spla.spsolve(csc(o, i, v).tocsc(), g["b"])
+    assert np.abs(xs - x).max() < 1e-9
+
+
+def test_eigenpairs_poisson3d(orc):
+    """Analytic eigenpairs of the Dirichlet Laplacian: A v = lambda v (SURVEY 8c known-answer (i))."""
+    n = 12
+    o, i, v = orc.poisson3d(n)
+    k = np.arange(1, n + 1)
+    for (a, b_, c) in [(1, 1, 1), (2, 5, 3), (n, n, n)]:
+        s = lambda m: np.sin(np.pi * m * k / (n + 1))
+        vec = np.einsum("i,j,k->kji", s(a), s(b_), s(c)).ravel()  # x fastest
+        lam = 4 * sum(np.sin(np.pi * m / (2 * (n + 1))) ** 2 for m in (a, b_, c))
+        y = orc.spmv_csc(o, i, v, vec)
+        np.testing.assert_allclose(y, lam * vec, atol=1e-12)
+        y2 = orc.spmv_csr(o, i, v, vec)
+        np.testing.assert_allclose(y2, lam * vec, atol=1e-12)
+
+
+def test_transpose_index_oracle(orc):
+    rng = np.random.default_rng(7)
+    A = sp.random(300, 300, density=0.03, random_state=rng, format="csc") + sp.eye(300, format="csc")
+    A = sp.csc_matrix(A)
+    A.sort_indices()
+    o, i, v = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data
+    rp, ci, perm = orc.csc_to_csr(300, o, i)
+    R = A.tocsr()
+    R.sort_indices()
+    assert np.array_equal(rp, R.indptr) and np.array_equal(ci, R.indices)
+    np.testing.assert_array_equal(v[perm], R.data)
+
+
+def test_partition_and_halo_oracle(orc):
+    o, i, v = orc.poisson3d(10)
+    n = 1000
+    off = orc.partition_rows(o, 4)
+    assert off[0] == 0 and off[-1] == n and np.all(np.diff(off) > 0)
+    nnz_share = np.diff(o[off])
+    assert nnz_share.max() - nnz_share.min() <= 2 * 7 * 100  # balanced to within a plane
+    for g in range(4):
+        lc, halo = orc.halo_for_rank(o, i, int(off[g]), int(off[g + 1]))
+        nl = off[g + 1] - off[g]
+        glob = np.where(lc < nl, lc + off[g], 0)
+        glob[lc >= nl] = halo[lc[lc >= nl] - nl]
+        assert np.array_equal(glob, i[o[off[g]]:o[off[g + 1]]])
+        assert np.all(np.diff(halo) > 0)
+
+
+def test_prefactor_values_symmetric_spd(orc):
+    """Value generator of the reference's pattern-reuse test (test_linear_solver.cpp:262-283)."""
+    o, i, _ = orc.poisson2d(8)
+    vals = orc.prefactor_values(o, i, rounds=3)
+    for r in range(3):
+        A = csc(o, i, vals[r])
+        assert abs(A - A.T).max() == 0
+        d = A.diagonal()
+        assert d.min() >= 10 and d.max() <= 500
+        assert np.all(np.linalg.eigvalsh(A.toarray()) > 0)
+    assert not np.array_equal(vals[0], vals[1])
+
+
+def test_amg_known_answer(orc):
+    """32^3 Poisson, polysolve's AMGCL defaults => 32768 -> 4192 -> 117 rows,
+    nnz 223232 / 114356 / 4349, 4 CG iterations to 1e-10 and 3 to 1e-8 (7 / 5 with ncycle 1)."""
+    o, i, v = orc.poisson3d(32)
+    b = orc.spmv_csc(o, i, v, orc.splitmix64(42, 32 ** 3))
+    H = orc.Amg(o, i, v)
+    assert H.num_levels == 3
+    infos = [H.level_info(l) for l in range(3)]
+    assert [q["rows"] for q in infos] == [32768, 4192, 117]
+    assert [q["nnz"] for q in infos] == [223232, 114356, 4349]
+    x, it, rel = H.cg(b, tol=1e-10)
+    assert it == 4 and rel < 1e-10
+    assert np.linalg.norm(csc(o, i, v) @ x - b) / np.linalg.norm(b) < 1e-9
+    _, it8, _ = H.cg(b, tol=1e-8)
+    assert it8 == 3
+    H1 = orc.Amg(o, i, v, ncycle=1)
+    assert H1.cg(b, tol=1e-10)[1] == 7 and H1.cg(b, tol=1e-8)[1] == 5
+    # warm start => 0 iterations (test_linear_solver.cpp:432-450)
+    assert H.cg(b, x0=x, tol=1e-10)[1] == 0
+
+
+def test_amg_galerkin_and_transfer_properties(orc):
+    o, i, v = orc.poisson3d(16)
+    H = orc.Amg(o, i, v, coarse_enough=200)
+    assert H.num_levels >= 2
+    A0 = sp.csr_matrix(H.matrix(0, "A")[::-1][0:1] + H.matrix(0, "A")[1::-1], shape=(4096, 4096)) if False else None
+    pa, ca, va = H.matrix(0, "A")
+    pp, cp, vp = H.matrix(0, "P")
+    pr, cr, vr = H.matrix(0, "R")
+    p1, c1, v1 = H.matrix(1, "A")
+    nc = len(p1) - 1
+    A = sp.csr_matrix((va, ca, pa), shape=(4096, 4096))
+    P = sp.csr_matrix((vp, cp, pp), shape=(4096, nc))
+    R = sp.csr_matrix((vr, cr, pr), shape=(nc, 4096))
+    Ac = sp.csr_matrix((v1, c1, p1), shape=(nc, nc))
+    assert abs(R - P.T).max() == 0
+    assert abs(Ac - R @ A @ P).max() < 1e-12
+    # smoothed-aggregation prolongator preserves constants in the interior: rows of P sum to 1 where
+    # the row of A sums to 0 (P = (I - w D^-1 A) P_tent and P_tent 1 = 1)
+    rows_interior = np.asarray(abs(A @ np.ones(4096)) < 1e-14).ravel()
+    np.testing.assert_allclose(np.asarray(P.sum(axis=1)).ravel()[rows_interior], 1.0, atol=1e-13)
+    agg = H.aggregates(0)
+    assert agg.min() >= 0 and agg.max() == nc - 1 and len(np.unique(agg)) == nc
