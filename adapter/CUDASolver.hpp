@@ -1,0 +1,48 @@
+#pragma once
+// polysolve::linear::CUDASolver -- the "CUDA" entry of Solver::create: a thin PIMPL adapter from
+// polysolve's C++ interface to the C ABI of libpsb200 (include/psb200.h).
+//
+// Drop-in template: reference src/polysolve/linear/MASSolver.hpp:35-72 (PIMPL behind Solver,
+// registered by name in Solver.cpp:402-404). Integration steps: see INTEGRATION.md.
+
+#include <polysolve/linear/Solver.hpp>
+
+#include <memory>
+#include <string>
+
+namespace polysolve::linear
+{
+    class CUDASolver : public Solver
+    {
+    public:
+        CUDASolver();
+        ~CUDASolver() override;
+        POLYSOLVE_DELETE_MOVE_COPY(CUDASolver)
+
+    public:
+        // Reads params["CUDA"] (krylov, precond, tolerance, max_iter, amg{...}, ...) -- Solver.hpp:93
+        void set_parameters(const json &params) override;
+
+        // "solver_iter","solver_error" (EigenSolver.tpp:88-89) and "num_iterations","final_res_norm"
+        // (AMGCL.cpp:142-143) plus "solver_status" -- Solver.hpp:96
+        void get_info(json &params) const override;
+
+        // Index work only (CSC->CSR map, SpMV tiling); cached on an unchanged pattern -- Solver.hpp:99
+        void analyze_pattern(const StiffnessMatrix &A, const int precond_num) override;
+
+        // Values upload + preconditioner build (Jacobi / SA-AMG hierarchy) -- Solver.hpp:102
+        void factorize(const StiffnessMatrix &A) override;
+
+        // x is in/out: initial guess on entry -- Solver.hpp:119-128
+        void solve(const Ref<const VectorXd> b, Ref<VectorXd> x) override;
+
+        void set_block_size(int block_size) override; // Solver.hpp:110
+        void set_tolerance(const double tol) override; // Solver.hpp:116-117
+
+        std::string name() const override { return "CUDA"; } // Solver.hpp:131
+
+    private:
+        struct Impl;
+        std::unique_ptr<Impl> impl_;
+    };
+} // namespace polysolve::linear

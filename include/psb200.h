@@ -95,6 +95,8 @@ void *psb200_get_stream(psb200_handle h);
 int psb200_debug_set_aggregates(psb200_handle h, int level, const int32_t *agg, int64_t n);
 int psb200_debug_get_level(psb200_handle h, int level, int which, int64_t *rows, int64_t *cols,
                            int64_t *nnz, int32_t *row_ptr, int32_t *col_idx, double *vals);
+/* aggregate id of every row of `level` (int32[n], -2 = removed node) and the aggregate count. */
+int psb200_debug_get_aggregates(psb200_handle h, int level, int32_t *agg, int64_t n, int64_t *n_agg);
 /* z = M^-1 r : one application of the configured preconditioner (host buffers). */
 int psb200_precond_apply(psb200_handle h, const double *r, double *z, int64_t n);
 

@@ -535,7 +535,7 @@ void dense_lu_solve(const Level &L, const double *rhs, double *x)
 }
 
 // amgcl::amg::do_init (SURVEY A.3 "Hierarchy build")
-std::unique_ptr<Hierarchy> build(Csr A0, const Params &prm)
+std::unique_ptr<Hierarchy> build(Csr A0, const Params &prm, const std::vector<std::vector<int32_t>> &imposed = {})
 {
     auto H = std::make_unique<Hierarchy>();
     H->prm = prm;
@@ -554,7 +554,16 @@ std::unique_ptr<Hierarchy> build(Csr A0, const Params &prm)
         }
         // step_down: transfer operators + Galerkin coarse operator
         std::vector<char> strong;
-        const int64_t nc = plain_aggregates(L.A, eps_strong, strong, L.aggr);
+        int64_t nc = plain_aggregates(L.A, eps_strong, strong, L.aggr);
+        const size_t li = H->levels.size() - 1;
+        if (li < imposed.size() && !imposed[li].empty())
+        {
+            // aggregates imposed by the test (e.g. the GPU's parallel MIS-2 result): same strength flags
+            L.aggr = imposed[li];
+            nc = 0;
+            for (int32_t a : L.aggr)
+                nc = std::max<int64_t>(nc, (int64_t)a + 1);
+        }
         eps_strong *= 0.5;
         if (nc == 0)
         {
@@ -726,6 +735,34 @@ void *orc_amg_create(int64_t n, const int32_t *ptr, const int32_t *col, const do
     try
     {
         return build(std::move(A), prm).release();
+    }
+    catch (...)
+    {
+        return nullptr;
+    }
+}
+
+// Same, with aggregates imposed for the first n_imposed levels (agg[l] has lens[l] entries; lens[l] = 0 => not imposed).
+void *orc_amg_create_imposed(int64_t n, const int32_t *ptr, const int32_t *col, const double *val, const orc_amg_params *p,
+                             int n_imposed, const int32_t *const *agg, const int64_t *lens)
+{
+    Hierarchy *tmp = (Hierarchy *)orc_amg_create(0, ptr, col, val, p); // parse params only (n = 0 => empty hierarchy)
+    if (!tmp)
+        return nullptr;
+    Params prm = tmp->prm;
+    delete tmp;
+    std::vector<std::vector<int32_t>> imposed(n_imposed);
+    for (int l = 0; l < n_imposed; ++l)
+        if (lens[l] > 0)
+            imposed[l].assign(agg[l], agg[l] + lens[l]);
+    Csr A;
+    A.n = n;
+    A.ptr.assign(ptr, ptr + n + 1);
+    A.col.assign(col, col + ptr[n]);
+    A.val.assign(val, val + ptr[n]);
+    try
+    {
+        return build(std::move(A), prm, imposed).release();
     }
     catch (...)
     {

@@ -57,6 +57,9 @@ def lib():
     L.orc_amg_default_params.argtypes = [C.POINTER(AmgParams)]
     L.orc_amg_create.argtypes = [C.c_int64, i32p, i32p, f64p, C.POINTER(AmgParams)]
     L.orc_amg_create.restype = C.c_void_p
+    L.orc_amg_create_imposed.argtypes = [C.c_int64, i32p, i32p, f64p, C.POINTER(AmgParams), C.c_int,
+                                         C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.orc_amg_create_imposed.restype = C.c_void_p
     L.orc_amg_destroy.argtypes = [C.c_void_p]
     L.orc_amg_num_levels.argtypes = [C.c_void_p]
     L.orc_amg_level_info.argtypes = [C.c_void_p, C.c_int] + [C.POINTER(C.c_int64)] * 3 + [C.POINTER(C.c_double)] * 3
@@ -171,7 +174,7 @@ class Amg:
     """amgcl::make_solver<amg<builtin, smoothed_aggregation, chebyshev>, cg> restatement with
     polysolve's defaults (reference src/polysolve/linear/AMGCL.cpp:32-65)."""
 
-    def __init__(self, ptr, col, val, **kw):
+    def __init__(self, ptr, col, val, imposed=None, **kw):
         L = lib()
         self.prm = AmgParams()
         L.orc_amg_default_params(C.byref(self.prm))
@@ -179,7 +182,13 @@ class Amg:
             assert hasattr(self.prm, k), k
             setattr(self.prm, k, v)
         self.n = len(ptr) - 1
-        self.h = L.orc_amg_create(self.n, ptr, col, val, C.byref(self.prm))
+        if imposed:
+            arrs = [np.ascontiguousarray(a, np.int32) if a is not None else np.zeros(0, np.int32) for a in imposed]
+            ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+            lens = (C.c_int64 * len(arrs))(*[len(a) for a in arrs])
+            self.h = L.orc_amg_create_imposed(self.n, ptr, col, val, C.byref(self.prm), len(arrs), ptrs, lens)
+        else:
+            self.h = L.orc_amg_create(self.n, ptr, col, val, C.byref(self.prm))
         if not self.h:
             raise RuntimeError("oracle AMG setup failed")
 

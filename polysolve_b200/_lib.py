@@ -22,7 +22,7 @@ SYMBOLS = [
     "psb200_analyze_pattern_csc", "psb200_factorize_csc", "psb200_solve", "psb200_solve_device", "psb200_get_info",
     "psb200_name", "psb200_last_error", "psb200_dist_unique_id", "psb200_dist_init", "psb200_debug_get_csr",
     "psb200_spmv", "psb200_bench_spmv", "psb200_get_stream", "psb200_debug_set_aggregates", "psb200_debug_get_level",
-    "psb200_precond_apply",
+    "psb200_precond_apply", "psb200_debug_get_aggregates",
 ]
 
 
@@ -68,5 +68,6 @@ def lib():
     L.psb200_debug_get_level.argtypes = [H, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                          C.POINTER(C.c_int64), C.c_void_p, C.c_void_p, C.c_void_p]
     L.psb200_precond_apply.argtypes = [H, f64p, f64p, C.c_int64]
+    L.psb200_debug_get_aggregates.argtypes = [H, C.c_int, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
     _LIB = L
     return L

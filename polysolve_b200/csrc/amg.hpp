@@ -19,9 +19,11 @@ public:
     std::string info_json() const;
     const CsrDev &matrix(int level, int which) const; // 0 A, 1 P, 2 R
     int matrix_cols(int level, int which) const;
+    // aggregate id per row of `level` (device pointer, rows(level) entries; -2 = removed); n_agg out
+    const int *aggregates(int level, int *n_agg) const;
 
 private:
-    void cycle(int l, const double *rhs, double *x, bool x_is_zero, const int *done);
+    void cycle(int l, const double *rhs, double *&x, double *&x_alt, bool x_is_zero, const int *done);
     void relax(int l, const double *rhs, double *&x, double *&x_alt, bool x_is_zero, const int *done);
     Ctx &ctx_;
     AmgParams prm_;

@@ -213,6 +213,21 @@ int psb200_debug_get_level(psb200_handle h, int level, int which, int64_t *rows,
     });
 }
 
+int psb200_debug_get_aggregates(psb200_handle h, int level, int32_t *agg, int64_t n, int64_t *n_agg)
+{
+    return guarded(h, [&](psb::Solver &s) {
+        if (!s.amg || level < 0 || level >= s.amg->num_levels())
+            throw std::invalid_argument("psb200_debug_get_aggregates: no AMG hierarchy / bad level");
+        int na = 0;
+        const int *d = s.amg->aggregates(level, &na);
+        if (n_agg)
+            *n_agg = na;
+        PSB_CUDA(cudaStreamSynchronize(s.ctx.stream));
+        if (agg && d && n > 0)
+            PSB_CUDA(cudaMemcpy(agg, d, sizeof(int) * n, cudaMemcpyDeviceToHost));
+    });
+}
+
 int psb200_precond_apply(psb200_handle h, const double *r, double *z, int64_t n)
 {
     return guarded(h, [&](psb::Solver &s) { s.precond_apply_host(r, z, n); });

@@ -34,129 +34,6 @@ struct CsrView
     int n;
 };
 
-// ---------------------------------------------------------------------------------- SpMV epilogues
-// Called once per row by the lane that holds the row sum. NV = number of fused reduction values.
-struct EpiStore
-{
-    static constexpr int NV = 0;
-    double *y;
-    __device__ __forceinline__ void operator()(int row, double s, double (&)[1]) const { y[row] = s; }
-};
-// y = A x and u.y  (PCG: p.Ap; BiCGSTAB: r0.v)
-struct EpiDot
-{
-    static constexpr int NV = 1;
-    double *y;
-    const double *u;
-    __device__ __forceinline__ void operator()(int row, double s, double (&acc)[1]) const
-    {
-        y[row] = s;
-        acc[0] += u[row] * s;
-    }
-};
-// t = A z, t.t and t.s (BiCGSTAB omega)
-struct EpiDot2
-{
-    static constexpr int NV = 2;
-    double *y;
-    const double *u;
-    __device__ __forceinline__ void operator()(int row, double s, double (&acc)[2]) const
-    {
-        y[row] = s;
-        acc[0] += s * s;
-        acc[1] += s * u[row];
-    }
-};
-// r = b - A x with ||r||^2, ||b||^2 and r.(dinv r)
-struct EpiResidualNorms
-{
-    static constexpr int NV = 3;
-    double *r;
-    const double *b;
-    const double *dinv;
-    __device__ __forceinline__ void operator()(int row, double s, double (&acc)[3]) const
-    {
-        const double bi = b[row];
-        const double ri = bi - s;
-        r[row] = ri;
-        acc[0] += ri * ri;
-        acc[1] += bi * bi;
-        acc[2] += ri * ri * dinv[row];
-    }
-};
-// BiCGSTAB restart: r = b - A x, r0 = r, ||r||^2
-struct EpiResidualRestart
-{
-    static constexpr int NV = 1;
-    double *r, *r0;
-    const double *b;
-    __device__ __forceinline__ void operator()(int row, double s, double (&acc)[1]) const
-    {
-        const double ri = b[row] - s;
-        r[row] = ri;
-        r0[row] = ri;
-        acc[0] += ri * ri;
-    }
-};
-// r = b - A x (AMG residual before restriction)
-struct EpiResidual
-{
-    static constexpr int NV = 0;
-    double *r;
-    const double *b;
-    __device__ __forceinline__ void operator()(int row, double s, double (&)[1]) const { r[row] = b[row] - s; }
-};
-// One Chebyshev step fused into the SpMV (amgcl relaxation/chebyshev.hpp solve()):
-//   res = M (b - A x_in);  p = alpha res + beta p;  x_out = x_in + p.     x_in != x_out (ping-pong).
-struct EpiCheb
-{
-    static constexpr int NV = 0;
-    const double *b, *dinv, *xin;
-    double *p, *xout;
-    double alpha, beta;
-    __device__ __forceinline__ void operator()(int row, double s, double (&)[1]) const
-    {
-        const double res = dinv[row] * (b[row] - s);
-        double pn = alpha * res;
-        if (beta != 0.0)
-            pn += beta * p[row];
-        p[row] = pn;
-        xout[row] = xin[row] + pn;
-    }
-};
-// Damped Jacobi / generic diagonal relaxation: x_out = x_in + w[row] (b - A x_in)
-struct EpiRelaxDiag
-{
-    static constexpr int NV = 0;
-    const double *b, *w, *xin;
-    double *xout;
-    __device__ __forceinline__ void operator()(int row, double s, double (&)[1]) const
-    {
-        xout[row] = xin[row] + w[row] * (b[row] - s);
-    }
-};
-// x += P u  (prolongation-and-correct)
-struct EpiAddTo
-{
-    static constexpr int NV = 0;
-    double *x;
-    __device__ __forceinline__ void operator()(int row, double s, double (&)[1]) const { x[row] += s; }
-};
-// power iteration on D^-1 A : b1 = dinv (A b0); ||b1||^2 and |b1.b0|-sum (amgcl spectral_radius)
-struct EpiPower
-{
-    static constexpr int NV = 2;
-    double *b1;
-    const double *b0, *dinv;
-    __device__ __forceinline__ void operator()(int row, double s, double (&acc)[2]) const
-    {
-        const double v = s * dinv[row];
-        b1[row] = v;
-        acc[0] += v * v;
-        acc[1] += fabs(v * b0[row]);
-    }
-};
-
 // ---------------------------------------------------------------------------------- finalizers
 // Run by thread 0 of the last CTA with the grid totals.
 struct FinNone
@@ -380,211 +257,11 @@ struct FinBicgRestart
     }
 };
 
-// ---------------------------------------------------------------------------------- SpMV: vector schedule
-// LPR lanes cooperate on one row (LPR = 1 is the scalar thread-per-row schedule). Grid-stride over rows.
-template <class Epi, class Fin, int LPR, int THREADS>
-__global__ void __launch_bounds__(THREADS) spmv_vector_kernel(CsrView A, const double *__restrict__ x, Epi epi, RedCtx rc,
-                                                              Fin fin, const int *done, const int *only_if)
-{
-    if (done && *done)
-        return;
-    if (only_if && !*only_if)
-        return;
-    constexpr int NVA = Epi::NV > 0 ? Epi::NV : 1;
-    double acc[NVA];
-#pragma unroll
-    for (int i = 0; i < NVA; ++i)
-        acc[i] = 0;
-    const int lane = threadIdx.x % LPR;
-    const int rows_per_cta = THREADS / LPR;
-    for (long long base = (long long)blockIdx.x * rows_per_cta; base < A.n; base += (long long)gridDim.x * rows_per_cta)
-    {
-        const int row = (int)base + threadIdx.x / LPR;
-        double s = 0;
-        if (row < A.n)
-        {
-            const int kb = __ldg(A.rp + row), ke = __ldg(A.rp + row + 1);
-            for (int k = kb + lane; k < ke; k += LPR)
-                s += __ldg(A.va + k) * __ldg(x + __ldg(A.ci + k));
-        }
-#pragma unroll
-        for (int o = LPR / 2; o > 0; o >>= 1)
-            s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (row < A.n && lane == 0)
-            epi(row, s, acc);
-    }
-    double tot[NVA];
-    if (grid_reduce<Epi::NV, THREADS>(acc, rc, tot) && threadIdx.x == 0)
-        fin(tot);
-}
+} // namespace psb
 
-// ---------------------------------------------------------------------------------- SpMV: TMA-staged stream schedule
-// For short rows (stencils): a CTA walks tiles of THREADS consecutive rows. The tile's contiguous
-// val/col ranges are pulled into shared memory by 1-D TMA bulk copies (cp.async.bulk, completion on
-// an mbarrier) STAGES tiles ahead, so HBM streams the matrix at full line efficiency regardless of
-// row length; each thread then reduces its own row from shared memory, which makes the x gathers of
-// a warp hit consecutive addresses for banded matrices. Tiles whose nnz exceed CAP fall back to
-// direct global loads (correct for any matrix).
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar, unsigned long long policy)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
-                 : "memory");
-}
+#include "spmv.cuh"
 
-template <int CAP, int STAGES>
-struct StreamSmem
-{
-    static constexpr size_t val_bytes = (size_t)STAGES * CAP * sizeof(double);
-    static constexpr size_t col_bytes = (size_t)STAGES * CAP * sizeof(int);
-    static constexpr size_t bytes = val_bytes + col_bytes + 128;
-};
-
-template <class Epi, class Fin, int THREADS, int CAP, int STAGES>
-__global__ void __launch_bounds__(THREADS) spmv_stream_kernel(CsrView A, const double *__restrict__ x, Epi epi, RedCtx rc,
-                                                              Fin fin, const int *done, const int *only_if)
-{
-    if (done && *done)
-        return;
-    if (only_if && !*only_if)
-        return;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *sval = reinterpret_cast<double *>(smem_raw);
-    int *scol = reinterpret_cast<int *>(smem_raw + StreamSmem<CAP, STAGES>::val_bytes);
-    __shared__ __align__(8) unsigned long long bar[STAGES];
-
-    constexpr int NVA = Epi::NV > 0 ? Epi::NV : 1;
-    double acc[NVA];
-#pragma unroll
-    for (int i = 0; i < NVA; ++i)
-        acc[i] = 0;
-
-    const int ntiles = (A.n + THREADS - 1) / THREADS;
-    unsigned long long policy;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-
-    if (threadIdx.x == 0)
-    {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s)
-            mbar_init(&bar[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    auto issue = [&](int tile, int s) {
-        const int r0 = tile * THREADS;
-        const int r1 = min(A.n, r0 + THREADS);
-        const int k0 = __ldg(A.rp + r0), k1 = __ldg(A.rp + r1);
-        const int ka = k0 & ~3;
-        const int cnt4 = (k1 - ka + 3) & ~3;
-        if (cnt4 > 0 && cnt4 <= CAP)
-        {
-            mbar_expect_tx(&bar[s], (unsigned)cnt4 * 12u);
-            tma_bulk_g2s(sval + (size_t)s * CAP, A.va + ka, (unsigned)cnt4 * 8u, &bar[s], policy);
-            tma_bulk_g2s(scol + (size_t)s * CAP, A.ci + ka, (unsigned)cnt4 * 4u, &bar[s], policy);
-        }
-        else
-            mbar_arrive(&bar[s]);
-    };
-
-    if (threadIdx.x == 0)
-    {
-#pragma unroll
-        for (int s = 0; s < STAGES; ++s)
-        {
-            const int tile = blockIdx.x + s * gridDim.x;
-            if (tile < ntiles)
-                issue(tile, s);
-        }
-    }
-
-    int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it)
-    {
-        const int s = it % STAGES;
-        const unsigned parity = (it / STAGES) & 1;
-        const int r0 = tile * THREADS;
-        const int row = r0 + threadIdx.x;
-        int kb = 0, ke = 0;
-        if (row < A.n)
-        {
-            kb = __ldg(A.rp + row);
-            ke = __ldg(A.rp + row + 1);
-        }
-        const int k0 = __ldg(A.rp + r0);
-        const int k1 = __ldg(A.rp + min(A.n, r0 + THREADS));
-        const int ka = k0 & ~3;
-        const bool staged = ((k1 - ka + 3) & ~3) <= CAP;
-        mbar_wait(&bar[s], parity);
-        double sum = 0;
-        if (staged)
-        {
-            const double *sv = sval + (size_t)s * CAP - ka;
-            const int *sc = scol + (size_t)s * CAP - ka;
-            // 4 gathers in flight per trip; products are still added in k order
-            for (int k = kb; k < ke; k += 4)
-            {
-                double v[4], xx[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                {
-                    const bool ok = k + u < ke;
-                    const int c = ok ? sc[k + u] : 0;
-                    v[u] = ok ? sv[k + u] : 0.0;
-                    xx[u] = ok ? __ldg(x + c) : 0.0;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (k + u < ke)
-                        sum += v[u] * xx[u];
-            }
-        }
-        else
-        {
-            for (int k = kb; k < ke; ++k)
-                sum += __ldg(A.va + k) * __ldg(x + __ldg(A.ci + k));
-        }
-        if (row < A.n)
-            epi(row, sum, acc);
-        __syncthreads(); // every thread is done reading stage s
-        if (threadIdx.x == 0)
-        {
-            const int next = tile + STAGES * gridDim.x;
-            if (next < ntiles)
-                issue(next, s);
-        }
-    }
-    double tot[NVA];
-    if (grid_reduce<Epi::NV, THREADS>(acc, rc, tot) && threadIdx.x == 0)
-        fin(tot);
-}
+namespace psb {
 
 // ---------------------------------------------------------------------------------- fused vector kernels
 // Element-wise ops over double2 (128-bit) lanes with up to kMaxRed fused reductions. Vectors are

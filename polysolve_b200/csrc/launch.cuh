@@ -12,8 +12,8 @@ namespace psb {
 constexpr int kMaxBlocks = 4096;
 constexpr int kVecThreads = 256;
 constexpr int kSpmvThreads = 256;
-constexpr int kStreamCap = 2560; // nnz per 256-row tile staged in shared memory (<= 10 nnz/row on average)
-constexpr int kStreamStages = 3;
+// production tile shape of the stream schedule: rows per tile, staged nnz per tile, pipeline depth
+using StreamProd = StreamCfg<256, 2048, 2>;
 
 enum SpmvKind : int
 {
@@ -34,7 +34,8 @@ struct CsrDev
     void plan(const std::string &forced = "auto")
     {
         const double avg = n > 0 ? (double)nnz / n : 0;
-        if (forced == "stream" || (forced == "auto" && avg <= 9.5 && n >= 4 * kSpmvThreads))
+        if (forced.rfind("stream", 0) == 0 ||
+            (forced == "auto" && avg * StreamProd::threads + 16 <= StreamProd::cap && n >= 4 * StreamProd::threads))
         {
             kind = SPMV_STREAM;
             return;
@@ -188,6 +189,23 @@ void launch_spmv_vector(Ctx &c, const CsrDev &A, const double *x, Epi epi, Fin f
     spmv_vector_kernel<Epi, Fin, LPR, kSpmvThreads><<<grid, kSpmvThreads, 0, c.stream>>>(A.view(), x, epi, c.red(), fin, done, only_if);
 }
 
+template <class Epi, class Fin, class Cfg>
+void launch_spmv_stream(Ctx &c, const CsrDev &A, const double *x, Epi epi, Fin fin, const int *done, const int *only_if, int ctas_per_sm = 0)
+{
+    auto kern = spmv_stream_kernel<Epi, Fin, Cfg>;
+    static int max_ctas = 0;
+    if (!max_ctas)
+    {
+        PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::bytes));
+        PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas, kern, Cfg::threads, Cfg::bytes));
+        max_ctas = std::max(1, max_ctas);
+    }
+    const int ntiles = (A.n + Cfg::threads - 1) / Cfg::threads;
+    const int per_sm = ctas_per_sm > 0 ? std::min(ctas_per_sm, max_ctas) : max_ctas;
+    const int grid = std::min(ntiles, kSMs * per_sm); // persistent: every CTA resident, tiles dealt round-robin
+    kern<<<grid, Cfg::threads, Cfg::bytes, c.stream>>>(A.view(), x, epi, c.red(), fin, done, only_if);
+}
+
 template <class Epi, class Fin>
 void launch_spmv(Ctx &c, const char *name, const CsrDev &A, const double *x, Epi epi, Fin fin, const int *done = nullptr,
                  const int *only_if = nullptr)
@@ -196,19 +214,7 @@ void launch_spmv(Ctx &c, const char *name, const CsrDev &A, const double *x, Epi
         return;
     c.prof_begin(name);
     if (A.kind == SPMV_STREAM)
-    {
-        using SM = StreamSmem<kStreamCap, kStreamStages>;
-        auto kern = spmv_stream_kernel<Epi, Fin, kSpmvThreads, kStreamCap, kStreamStages>;
-        static bool attr_set = false;
-        if (!attr_set)
-        {
-            PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SM::bytes));
-            attr_set = true;
-        }
-        const int ntiles = (A.n + kSpmvThreads - 1) / kSpmvThreads;
-        const int grid = std::min(ntiles, kSMs * 2);
-        kern<<<grid, kSpmvThreads, SM::bytes, c.stream>>>(A.view(), x, epi, c.red(), fin, done, only_if);
-    }
+        launch_spmv_stream<Epi, Fin, StreamProd>(c, A, x, epi, fin, done, only_if);
     else
     {
         switch (A.lpr)

@@ -746,18 +746,47 @@ double Solver::bench_spmv(const std::string &kernel, int reps)
     ensure_vectors();
     cudaStream_t st = ctx.stream;
     const int kind0 = A.kind, lpr0 = A.lpr;
-    if (!kernel.empty())
+    // tile-shape exploration of the stream schedule: "stream:<threads>:<cap>:<stages>[:<ctas_per_sm>]"
+    std::function<void()> one = [&]() { launch_spmv(ctx, "spmv", A, vp.p, EpiStore{vq.p}, FinNone{}); };
+    if (kernel.rfind("stream:", 0) == 0)
+    {
+        int t = 0, cap = 0, stg = 0, ctas = 0;
+        if (std::sscanf(kernel.c_str(), "stream:%d:%d:%d:%d", &t, &cap, &stg, &ctas) < 3)
+            throw std::invalid_argument("psb200_bench_spmv: expected stream:<threads>:<cap>:<stages>[:<ctas>]");
+        bool found = false;
+#define PSB_STREAM_VARIANT(T, C, S)                                                                                          \
+    if (t == T && cap == C && stg == S)                                                                                      \
+    {                                                                                                                        \
+        found = true;                                                                                                        \
+        one = [&, ctas]() { launch_spmv_stream<EpiStore, FinNone, StreamCfg<T, C, S>>(ctx, A, vp.p, EpiStore{vq.p}, FinNone{}, nullptr, nullptr, ctas); }; \
+    }
+        PSB_STREAM_VARIANT(256, 2560, 3)
+        PSB_STREAM_VARIANT(256, 2048, 2)
+        PSB_STREAM_VARIANT(256, 2048, 3)
+        PSB_STREAM_VARIANT(256, 2048, 4)
+        PSB_STREAM_VARIANT(128, 1024, 2)
+        PSB_STREAM_VARIANT(128, 1024, 3)
+        PSB_STREAM_VARIANT(128, 1024, 4)
+        PSB_STREAM_VARIANT(512, 4096, 2)
+        PSB_STREAM_VARIANT(512, 4096, 3)
+        PSB_STREAM_VARIANT(64, 512, 4)
+#undef PSB_STREAM_VARIANT
+        if (!found)
+            throw std::invalid_argument("psb200_bench_spmv: stream variant not compiled: " + kernel);
+    }
+    else if (!kernel.empty())
         A.plan(kernel);
     // a non-trivial resident x
     launch_vec(ctx, "copy", n_pad, OpCopy{vp.p, dinv.p}, FinNone{});
     for (int i = 0; i < 3; ++i)
-        launch_spmv(ctx, "spmv", A, vp.p, EpiStore{vq.p}, FinNone{});
+        one();
+    check_launch();
     cudaEvent_t a, b;
     PSB_CUDA(cudaEventCreate(&a));
     PSB_CUDA(cudaEventCreate(&b));
     PSB_CUDA(cudaEventRecord(a, st));
     for (int i = 0; i < reps; ++i)
-        launch_spmv(ctx, "spmv", A, vp.p, EpiStore{vq.p}, FinNone{});
+        one();
     PSB_CUDA(cudaEventRecord(b, st));
     PSB_CUDA(cudaEventSynchronize(b));
     float ms = 0;

@@ -1,0 +1,397 @@
+// CSR SpMV kernels (fp64 values, int32 indices) with fused per-row epilogues and fused reductions.
+// Two schedules:
+//   * stream : TMA-staged tiles for short rows (stencils / FEM scalar problems, <= ~8 nnz per row)
+//   * vector : LPR lanes per row (LPR = 1 .. 32) for everything else (coarse AMG levels, R, dense rows)
+// Included from kernels.cuh (needs CsrView, RedCtx, grid_reduce).
+#pragma once
+
+namespace psb {
+
+// ---------------------------------------------------------------------------------- epilogues
+// An epilogue is applied once per row by the lane that holds the row sum:
+//   Pre  pre(row)                      -- loads the per-row side inputs; issued BEFORE the gathers so
+//                                         their latency overlaps with the x gathers
+//   void operator()(row, sum, pre, acc) -- stores outputs, accumulates NV fused reduction values
+struct NoPre
+{
+};
+struct EpiStore
+{
+    static constexpr int NV = 0;
+    using Pre = NoPre;
+    double *y;
+    __device__ __forceinline__ Pre pre(int) const { return {}; }
+    __device__ __forceinline__ void operator()(int row, double s, Pre, double (&)[1]) const { y[row] = s; }
+};
+// y = A x and u.y  (PCG: p.Ap; BiCGSTAB: r0.v)
+struct EpiDot
+{
+    static constexpr int NV = 1;
+    using Pre = double;
+    double *y;
+    const double *u;
+    __device__ __forceinline__ Pre pre(int row) const { return __ldg(u + row); }
+    __device__ __forceinline__ void operator()(int row, double s, Pre ur, double (&acc)[1]) const
+    {
+        y[row] = s;
+        acc[0] += ur * s;
+    }
+};
+// t = A z, t.t and t.s (BiCGSTAB omega)
+struct EpiDot2
+{
+    static constexpr int NV = 2;
+    using Pre = double;
+    double *y;
+    const double *u;
+    __device__ __forceinline__ Pre pre(int row) const { return __ldg(u + row); }
+    __device__ __forceinline__ void operator()(int row, double s, Pre ur, double (&acc)[2]) const
+    {
+        y[row] = s;
+        acc[0] += s * s;
+        acc[1] += s * ur;
+    }
+};
+struct Pre2
+{
+    double a, b;
+};
+struct Pre4
+{
+    double a, b, c, d;
+};
+// r = b - A x with ||r||^2, ||b||^2 and r.(dinv r)
+struct EpiResidualNorms
+{
+    static constexpr int NV = 3;
+    using Pre = Pre2;
+    double *r;
+    const double *b;
+    const double *dinv;
+    __device__ __forceinline__ Pre pre(int row) const { return {__ldg(b + row), __ldg(dinv + row)}; }
+    __device__ __forceinline__ void operator()(int row, double s, Pre p, double (&acc)[3]) const
+    {
+        const double ri = p.a - s;
+        r[row] = ri;
+        acc[0] += ri * ri;
+        acc[1] += p.a * p.a;
+        acc[2] += ri * ri * p.b;
+    }
+};
+// BiCGSTAB restart: r = b - A x, r0 = r, ||r||^2
+struct EpiResidualRestart
+{
+    static constexpr int NV = 1;
+    using Pre = double;
+    double *r, *r0;
+    const double *b;
+    __device__ __forceinline__ Pre pre(int row) const { return __ldg(b + row); }
+    __device__ __forceinline__ void operator()(int row, double s, Pre bi, double (&acc)[1]) const
+    {
+        const double ri = bi - s;
+        r[row] = ri;
+        r0[row] = ri;
+        acc[0] += ri * ri;
+    }
+};
+// r = b - A x (AMG residual before restriction)
+struct EpiResidual
+{
+    static constexpr int NV = 0;
+    using Pre = double;
+    double *r;
+    const double *b;
+    __device__ __forceinline__ Pre pre(int row) const { return __ldg(b + row); }
+    __device__ __forceinline__ void operator()(int row, double s, Pre bi, double (&)[1]) const { r[row] = bi - s; }
+};
+// One Chebyshev step fused into the SpMV (amgcl relaxation/chebyshev.hpp solve()):
+//   res = M (b - A x_in);  p = alpha res + beta p;  x_out = x_in + p.     x_in != x_out (ping-pong).
+struct EpiCheb
+{
+    static constexpr int NV = 0;
+    using Pre = Pre4;
+    const double *b, *dinv, *xin;
+    double *p, *xout;
+    double alpha, beta;
+    __device__ __forceinline__ Pre pre(int row) const
+    {
+        return {__ldg(b + row), __ldg(dinv + row), __ldg(xin + row), beta != 0.0 ? p[row] : 0.0};
+    }
+    __device__ __forceinline__ void operator()(int row, double s, Pre q, double (&)[1]) const
+    {
+        const double res = q.b * (q.a - s);
+        const double pn = alpha * res + beta * q.d;
+        p[row] = pn;
+        xout[row] = q.c + pn;
+    }
+};
+// Damped Jacobi / generic diagonal relaxation: x_out = x_in + w[row] (b - A x_in)
+struct EpiRelaxDiag
+{
+    static constexpr int NV = 0;
+    using Pre = Pre4;
+    const double *b, *w, *xin;
+    double *xout;
+    __device__ __forceinline__ Pre pre(int row) const { return {__ldg(b + row), __ldg(w + row), __ldg(xin + row), 0.0}; }
+    __device__ __forceinline__ void operator()(int row, double s, Pre q, double (&)[1]) const { xout[row] = q.c + q.b * (q.a - s); }
+};
+// x += P u  (prolongation-and-correct)
+struct EpiAddTo
+{
+    static constexpr int NV = 0;
+    using Pre = double;
+    double *x;
+    __device__ __forceinline__ Pre pre(int row) const { return x[row]; }
+    __device__ __forceinline__ void operator()(int row, double s, Pre xr, double (&)[1]) const { x[row] = xr + s; }
+};
+// power iteration on D^-1 A : b1 = dinv (A b0); ||b1||^2 and sum |b1_i b0_i| (amgcl spectral_radius)
+struct EpiPower
+{
+    static constexpr int NV = 2;
+    using Pre = Pre2;
+    double *b1;
+    const double *b0, *dinv;
+    __device__ __forceinline__ Pre pre(int row) const { return {__ldg(b0 + row), __ldg(dinv + row)}; }
+    __device__ __forceinline__ void operator()(int row, double s, Pre q, double (&acc)[2]) const
+    {
+        const double v = s * q.b;
+        b1[row] = v;
+        acc[0] += v * v;
+        acc[1] += fabs(v * q.a);
+    }
+};
+
+// ---------------------------------------------------------------------------------- vector schedule
+// LPR lanes cooperate on one row (LPR = 1 is the scalar thread-per-row schedule). Grid-stride over rows.
+template <class Epi, class Fin, int LPR, int THREADS>
+__global__ void __launch_bounds__(THREADS) spmv_vector_kernel(CsrView A, const double *__restrict__ x, Epi epi, RedCtx rc,
+                                                              Fin fin, const int *done, const int *only_if)
+{
+    if (done && *done)
+        return;
+    if (only_if && !*only_if)
+        return;
+    constexpr int NVA = Epi::NV > 0 ? Epi::NV : 1;
+    double acc[NVA];
+#pragma unroll
+    for (int i = 0; i < NVA; ++i)
+        acc[i] = 0;
+    const int lane = threadIdx.x % LPR;
+    const int rows_per_cta = THREADS / LPR;
+    for (long long base = (long long)blockIdx.x * rows_per_cta; base < A.n; base += (long long)gridDim.x * rows_per_cta)
+    {
+        const int row = (int)base + threadIdx.x / LPR;
+        double s = 0;
+        typename Epi::Pre pre{};
+        if (row < A.n)
+        {
+            const int kb = __ldg(A.rp + row), ke = __ldg(A.rp + row + 1);
+            if (lane == 0)
+                pre = epi.pre(row);
+            int k = kb + lane;
+            // two gathers in flight per lane
+            for (; k + LPR < ke; k += 2 * LPR)
+            {
+                const int c0 = __ldg(A.ci + k), c1 = __ldg(A.ci + k + LPR);
+                const double v0 = __ldg(A.va + k), v1 = __ldg(A.va + k + LPR);
+                const double x0 = __ldg(x + c0), x1 = __ldg(x + c1);
+                s += v0 * x0;
+                s += v1 * x1;
+            }
+            if (k < ke)
+                s += __ldg(A.va + k) * __ldg(x + __ldg(A.ci + k));
+        }
+#pragma unroll
+        for (int o = LPR / 2; o > 0; o >>= 1)
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (row < A.n && lane == 0)
+            epi(row, s, pre, acc);
+    }
+    double tot[NVA];
+    if (grid_reduce<Epi::NV, THREADS>(acc, rc, tot) && threadIdx.x == 0)
+        fin(tot);
+}
+
+// ---------------------------------------------------------------------------------- TMA-staged stream schedule
+// A CTA walks tiles of THREADS consecutive rows (tile t -> CTA t mod grid, so the CTAs that run
+// together work on neighbouring rows and share x through L2). For every tile one thread issues three
+// 1-D TMA bulk copies (cp.async.bulk -> SASS UBLKCP) STAGES tiles ahead: the tile's slice of row_ptr,
+// and its contiguous val / col ranges (16-byte aligned outward; the arrays are over-allocated).
+// Completion is tracked by one mbarrier per stage (expect_tx bytes). So HBM streams the matrix at
+// full line efficiency whatever the row length, nothing in the per-row dependency chain touches DRAM
+// except the x gathers, and those are issued 8 at a time; each thread owns one row, which makes the
+// gathers of a warp hit consecutive addresses for banded matrices.
+// Tiles whose nnz exceed CAP fall back to direct global loads (correct for any matrix).
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar, unsigned long long policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+
+template <int THREADS, int CAP, int STAGES>
+struct StreamCfg
+{
+    static constexpr int threads = THREADS, cap = CAP, stages = STAGES;
+    static constexpr int rp_ints = THREADS + 4; // THREADS + 1 row pointers, rounded to 16 bytes
+    static constexpr size_t val_bytes = (size_t)STAGES * CAP * sizeof(double);
+    static constexpr size_t col_bytes = (size_t)STAGES * CAP * sizeof(int);
+    static constexpr size_t rp_bytes = (size_t)STAGES * rp_ints * sizeof(int);
+    static constexpr size_t bytes = val_bytes + col_bytes + rp_bytes + 128;
+};
+
+template <class Epi, class Fin, class Cfg>
+__global__ void __launch_bounds__(Cfg::threads) spmv_stream_kernel(CsrView A, const double *__restrict__ x, Epi epi, RedCtx rc, Fin fin,
+                                                                   const int *done, const int *only_if)
+{
+    constexpr int THREADS = Cfg::threads, CAP = Cfg::cap, STAGES = Cfg::stages;
+    if (done && *done)
+        return;
+    if (only_if && !*only_if)
+        return;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sval = reinterpret_cast<double *>(smem_raw);
+    int *scol = reinterpret_cast<int *>(smem_raw + Cfg::val_bytes);
+    int *srp = reinterpret_cast<int *>(smem_raw + Cfg::val_bytes + Cfg::col_bytes);
+    __shared__ __align__(8) unsigned long long bar[STAGES];
+
+    constexpr int NVA = Epi::NV > 0 ? Epi::NV : 1;
+    double acc[NVA];
+#pragma unroll
+    for (int i = 0; i < NVA; ++i)
+        acc[i] = 0;
+
+    const int ntiles = (A.n + THREADS - 1) / THREADS;
+    unsigned long long policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+            mbar_init(&bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // one thread: launch the three bulk copies of `tile` into stage s
+    auto issue = [&](int tile, int s) {
+        const int r0 = tile * THREADS;
+        const int r1 = min(A.n, r0 + THREADS);
+        const int k0 = __ldg(A.rp + r0), k1 = __ldg(A.rp + r1);
+        const int ka = k0 & ~3;
+        const int cnt4 = (k1 - ka + 3) & ~3;
+        const unsigned rp_b = (unsigned)(((r1 - r0 + 1) + 3) & ~3) * 4u; // row_ptr array is over-allocated
+        unsigned bytes = rp_b;
+        const bool staged = cnt4 > 0 && cnt4 <= CAP;
+        if (staged)
+            bytes += (unsigned)cnt4 * 12u;
+        mbar_expect_tx(&bar[s], bytes);
+        tma_bulk_g2s(srp + (size_t)s * Cfg::rp_ints, A.rp + r0, rp_b, &bar[s], policy);
+        if (staged)
+        {
+            tma_bulk_g2s(sval + (size_t)s * CAP, A.va + ka, (unsigned)cnt4 * 8u, &bar[s], policy);
+            tma_bulk_g2s(scol + (size_t)s * CAP, A.ci + ka, (unsigned)cnt4 * 4u, &bar[s], policy);
+        }
+    };
+
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+        {
+            const int tile = blockIdx.x + s * gridDim.x;
+            if (tile < ntiles)
+                issue(tile, s);
+        }
+    }
+
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it)
+    {
+        const int s = it % STAGES;
+        const unsigned parity = (it / STAGES) & 1;
+        const int r0 = tile * THREADS;
+        const int nrow = min(A.n - r0, THREADS);
+        const int row = r0 + threadIdx.x;
+        const bool live = threadIdx.x < nrow;
+        typename Epi::Pre pre{};
+        if (live)
+            pre = epi.pre(row); // side inputs first: their latency hides behind the barrier wait and the gathers
+        mbar_wait(&bar[s], parity);
+        const int *rps = srp + (size_t)s * Cfg::rp_ints;
+        const int k0 = rps[0], k1 = rps[nrow];
+        const int ka = k0 & ~3;
+        const bool staged = ((k1 - ka + 3) & ~3) <= CAP;
+        int kb = 0, ke = 0;
+        if (live)
+        {
+            kb = rps[threadIdx.x];
+            ke = rps[threadIdx.x + 1];
+        }
+        double sum = 0;
+        if (staged)
+        {
+            const double *sv = sval + (size_t)s * CAP - ka;
+            const int *sc = scol + (size_t)s * CAP - ka;
+            // 8 gathers in flight per trip; products are still added in k order
+            for (int k = kb; k < ke; k += 8)
+            {
+                double v[8], xx[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                {
+                    const bool ok = k + u < ke;
+                    const int c = ok ? sc[k + u] : 0;
+                    v[u] = ok ? sv[k + u] : 0.0;
+                    xx[u] = ok ? __ldg(x + c) : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (k + u < ke)
+                        sum += v[u] * xx[u];
+            }
+        }
+        else
+        {
+            for (int k = kb; k < ke; ++k)
+                sum += __ldg(A.va + k) * __ldg(x + __ldg(A.ci + k));
+        }
+        if (live)
+            epi(row, sum, pre, acc);
+        __syncthreads(); // every thread is done reading stage s
+        if (threadIdx.x == 0)
+        {
+            const int next = tile + STAGES * gridDim.x;
+            if (next < ntiles)
+                issue(next, s);
+        }
+    }
+    double tot[NVA];
+    if (grid_reduce<Epi::NV, THREADS>(acc, rc, tot) && threadIdx.x == 0)
+        fin(tot);
+}
+
+} // namespace psb

@@ -177,6 +177,12 @@ class Solver:
         self._check(self._L.psb200_debug_get_level(self._h, level, w, None, None, None, rp.ctypes.data, ci.ctypes.data, va.ctypes.data))
         return rows.value, cols.value, rp, ci[:nnz.value], va[:nnz.value]
 
+    def debug_get_aggregates(self, level, n):
+        agg = np.empty(n, np.int32)
+        na = C.c_int64()
+        self._check(self._L.psb200_debug_get_aggregates(self._h, level, agg.ctypes.data, n, C.byref(na)))
+        return agg, na.value
+
     def precond_apply(self, r):
         r = np.ascontiguousarray(r, np.float64)
         z = np.empty_like(r)

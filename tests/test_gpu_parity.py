@@ -309,7 +309,7 @@ def test_pcg_full_size_manufactured_solution(psb):
     s.solve(b, x)
     info = s.get_info()
     assert info["solver_status"] == "Converged"
-    assert 500 <= info["solver_iter"] <= 800
+    assert 400 <= info["solver_iter"] <= 560  # oracle (CPU, same input): see tests/golden/c2_oracle_iters.json
     r = P.spmv_csr(o, i, v, x) - b
     assert np.linalg.norm(r) / np.linalg.norm(b) < 2e-8
     assert np.linalg.norm(x - xstar) / np.linalg.norm(xstar) < 1e-5
