@@ -154,6 +154,46 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def amg_leg(args, psb, P, local, hbm_peak):
+    """Config 3 of BASELINE.json (SA-AMG-PCG, polysolve's AMGCL defaults) next to the CPU restatement.
+    GPU: full 216^3 system. CPU (oracle/, OpenMP, all cores): a bounded sample on a smaller grid, with the
+    GPU timed on that same grid for a like-for-like ratio."""
+    out = {}
+    for tag, n in (("full", args.n), ("sample", args.amg_cpu_n)):
+        N, outer, inner, vals, b, _ = build_problem(n)
+        s = psb.Solver.create("CUDA", "")
+        s.set_parameters({"CUDA": {"precond": "amg", "tolerance": TOL, "max_iter": 1000, "device": local}})
+        s.analyze_pattern_raw(N, outer, inner, N)
+        s.factorize_raw(N, outer, inner, vals)  # warm-up (allocations, module load)
+        t0 = time.perf_counter()
+        s.factorize_raw(N, outer, inner, vals)
+        t_setup = time.perf_counter() - t0
+        x = np.zeros(N)
+        s.solve(b, x)
+        x[:] = 0
+        t0 = time.perf_counter()
+        s.solve(b, x)
+        t_solve = time.perf_counter() - t0
+        info = s.get_info()
+        rel = float(np.linalg.norm(P.spmv_csr(outer, inner, vals, x) - b) / np.linalg.norm(b))
+        out[tag] = {"n": N, "gpu_setup_s": t_setup, "gpu_solve_s": t_solve, "gpu_iters": info["num_iterations"], "rel_residual": rel,
+                    "levels": [lv["rows"] for lv in info["amg"]["levels"]], "operator_complexity": info["amg"]["operator_complexity"]}
+        del s
+        if tag == "sample" and not args.no_cpu:
+            from oracle import oracle as O
+            t0 = time.perf_counter()
+            H = O.Amg(outer, inner, vals)
+            c_setup = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            _, itc, relc = H.cg(b, tol=TOL)
+            c_solve = time.perf_counter() - t0
+            out[tag].update({"cpu_setup_s": c_setup, "cpu_solve_s": c_solve, "cpu_iters": itc, "cpu_rel_residual": relc,
+                             "cpu_cores": O.lib().orc_num_threads(), "cpu_kind": "port (oracle/ AMGCL restatement, OpenMP)",
+                             "speedup_setup_plus_solve": (c_setup + c_solve) / (t_setup + t_solve),
+                             "speedup_solve": c_solve / t_solve})
+    return out
+
+
 def run_ours(args):
     import torch
     import polysolve_b200 as psb
@@ -169,7 +209,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     n = args.n
-    # weak scaling: every rank owns a full C2-sized system (replicas until the row-partitioned path lands)
+    # strong scaling: ONE C2 system, row-range partitioned over the ranks (every rank builds the same
+    # synthetic matrix on its host and keeps its own rows)
     N, outer, inner, vals, b, xstar = build_problem(n)
     nnz = int(outer[-1])
     hbm_peak, peak_src = peaks()
@@ -177,16 +218,20 @@ def run_ours(args):
     s = psb.Solver.create("CUDA", "")
     s.set_parameters({"CUDA": {"krylov": "cg", "precond": "jacobi", "tolerance": TOL, "max_iter": MAX_ITER,
                                "check_every": args.check_every, "device": local}})
+    if world > 1:
+        s.dist_setup_torch(halo_cap=1 << 20)
     t0 = time.perf_counter()
     s.analyze_pattern_raw(N, outer, inner, N)
     t_analyze = time.perf_counter() - t0
     t0 = time.perf_counter()
     s.factorize_raw(N, outer, inner, vals)
     t_factorize = time.perf_counter() - t0
+    r0, r1 = s.dist_local_range() if world > 1 else (0, N)
+    nl = r1 - r0
 
     stream = torch.cuda.ExternalStream(s.stream())
-    db = torch.from_numpy(b).cuda()
-    dx = torch.zeros(N, dtype=torch.float64, device="cuda")
+    db = torch.from_numpy(b[r0:r1].copy()).cuda()
+    dx = torch.zeros(nl, dtype=torch.float64, device="cuda")
     torch.cuda.synchronize()
 
     def barrier():
@@ -198,7 +243,7 @@ def run_ours(args):
     def device_step():
         with torch.cuda.stream(stream):
             dx.zero_()
-        s.solve_device(db.data_ptr(), dx.data_ptr(), N)
+        s.solve_device(db.data_ptr(), dx.data_ptr(), nl)
         return s.get_info()["solver_iter"]
 
     # ---- device-resident timed region
@@ -219,8 +264,7 @@ def run_ours(args):
     clocks = sampler.stop()
     launches = s.get_info()["gpu_launches"] - launches0
     info = s.get_info()
-    x = dx.cpu().numpy()
-    rel_res = float(np.linalg.norm(P.spmv_csr(outer, inner, vals, x) - b) / np.linalg.norm(b))
+    xl = dx.cpu().numpy()
 
     # ---- e2e: host buffers through the C ABI (factorize values + solve), pinned host memory
     hv, hb = pinned_copy(vals), pinned_copy(b)
@@ -240,45 +284,54 @@ def run_ours(args):
     barrier()
     e2e_dt = time.perf_counter() - t0
 
-    # ---- max over ranks / whole-job aggregate
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([ms, e2e_dt], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_dt = float(t[0]), float(t[1])
-        c = torch.tensor([iters, e2e_iters, launches], dtype=torch.float64, device="cuda")
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        iters, e2e_iters, launches = int(c[0]), int(c[1]), int(c[2])
-
-    if rank != 0:
-        return
-    value = iters / (ms * 1e-3)
-    e2e_value = e2e_iters / e2e_dt
-
     # ---- roofline of the dominant kernel (fused SpMV + p.Ap), measured live: one extra solve with CUDA
     #      events around every launch on the solver's stream (graphs off), after the timed region.
     s.set_parameters({"CUDA": {"profile": True}})
     device_step()
     prof = s.get_info().get("profile", {})
     s.set_parameters({"CUDA": {"profile": False}})
+    plain_ms = s.bench_spmv(reps=50) if world == 1 else 0.0
+
+    # ---- max over ranks; the iteration count is a property of the one shared system (not summed)
+    x = np.zeros(N)
+    x[r0:r1] = xl
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms, e2e_dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_dt = float(t[0]), float(t[1])
+        c = torch.tensor([launches], dtype=torch.float64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        launches = int(c[0])
+        xt = torch.from_numpy(x).cuda()
+        dist.all_reduce(xt, op=dist.ReduceOp.SUM)
+        x = xt.cpu().numpy()
+    if rank != 0:
+        return
+    rel_res = float(np.linalg.norm(P.spmv_csr(outer, inner, vals, x) - b) / np.linalg.norm(b))
+    value = iters / (ms * 1e-3)
+    e2e_value = e2e_iters / e2e_dt
+
     total_prof_ms = sum(v["ms"] for v in prof.values()) or 1.0
     k = prof.get("spmv_dot", {"ms": 0.0, "launches": 1})
     spmv_ms = k["ms"] / max(1, k["launches"])
-    b_spmv = P.spmv_bytes(N, nnz)
+    # per-launch algorithmic bytes of THIS rank's kernel (rank 0's row range)
+    lnnz = info.get("dist", {}).get("local_nnz", nnz)
+    b_spmv = P.spmv_bytes(nl, lnnz)
     achieved = b_spmv / (spmv_ms * 1e-3) / 1e9 if spmv_ms > 0 else 0.0
-    plain_ms = s.bench_spmv(reps=50)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1:
         try:
             traffic = json.load(open(tp)).get("spmv_dot_dram_bytes_per_launch")
         except Exception:
             traffic = None
     iter_bytes = P.pcg_iter_bytes(N, nnz)
-    ms_per_iter = ms / max(1, iters) * world
+    ms_per_iter = ms / max(1, iters)
 
     # ---- CPU baseline on a bounded sample (rank 0, N == 1 only)
     cpu = None
+    amg = None
     if world == 1 and not args.no_cpu:
         from oracle import oracle as O
         threads = O.lib().orc_num_threads()
@@ -292,31 +345,39 @@ def run_ours(args):
         cpu = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{args.ref_iters} CG iterations on the full {N}-DoF system, OpenMP row-parallel CSR (oracle/)",
                "eigen_faithful_1thread": faithful}
+    if world == 1 and not args.no_amg:
+        del s
+        amg = amg_leg(args, psb, P, local, hbm_peak)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"poisson3d_{n}^3 ({N} DoF, 7-pt), Jacobi-PCG tol {TOL}", "n": N, "nnz": nnz,
-                   "per_gpu": "one full system per GPU (replicas)" if world > 1 else "single system",
-                   "l2_policy": "inputs_exceed_l2 (0.88 GB matrix + 0.4 GB vectors per iteration vs 126 MB L2)",
-                   "iters_per_solve": iters / args.steps / world, "rel_residual": rel_res,
+                   "partition": f"one system, contiguous row ranges over {world} GPU(s), NVLink peer-memory halo push + fused all-reduce"
+                   if world > 1 else "single GPU",
+                   "l2_policy": "inputs_exceed_l2 (0.88 GB matrix + 0.4 GB vectors per iteration vs 126 MB L2)"
+                   if world <= 2 else "per-GPU working set approaches L2 size at this rank count; no flush (strong scaling of the fixed system)",
+                   "iters_per_solve": iters / args.steps, "rel_residual": rel_res,
                    "spmv_kernel": info["spmv_kernel"], "check_every": args.check_every,
                    "analyze_s": t_analyze, "factorize_s": t_factorize},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8 * nnz + 16 * N, "d2h_bytes_per_step": 8 * N,
-                "what": "factorize_csc(host values) + solve(host b, x) per step, pinned host buffers"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (8 * nnz + 16 * N) // world, "d2h_bytes_per_step": 8 * N // world,
+                "what": "factorize_csc(host values) + solve(host b, x) per step, pinned host buffers; bytes are per rank"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "spmv_stream_kernel<EpiDot> (fused SpMV + p.Ap)", "achieved": achieved,
                      "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": b_spmv, "avg_launch_ms": spmv_ms,
                      "kernel_share_of_step": k["ms"] / total_prof_ms,
-                     "plain_spmv_gbs": b_spmv / (plain_ms * 1e-3) / 1e9,
-                     "pcg_iter_gbs": iter_bytes / (ms_per_iter * 1e-3) / 1e9, "pcg_iter_frac": iter_bytes / (ms_per_iter * 1e-3) / 1e9 / hbm_peak,
+                     "plain_spmv_gbs": (b_spmv / (plain_ms * 1e-3) / 1e9) if plain_ms > 0 else None,
+                     "pcg_iter_gbs_all_gpus": iter_bytes / (ms_per_iter * 1e-3) / 1e9,
+                     "pcg_iter_frac_of_n_gpu_peak": iter_bytes / (ms_per_iter * 1e-3) / 1e9 / (hbm_peak * world),
                      "profile_ms": {kk: vv["ms"] for kk, vv in prof.items()}},
     }
     if cpu:
         line["cpu_baseline"] = cpu
+    if amg:
+        line["amg_pcg"] = amg
     print(json.dumps(line), flush=True)
 
 
@@ -330,6 +391,8 @@ def main():
     ap.add_argument("--check-every", type=int, default=16)
     ap.add_argument("--ref-iters", type=int, default=40, help="CG iterations per CPU sample step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-amg", action="store_true", help="skip the AMG-PCG (config 3) leg")
+    ap.add_argument("--amg-cpu-n", type=int, default=128, help="grid side of the bounded CPU AMG sample")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

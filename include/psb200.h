@@ -72,12 +72,26 @@ int psb200_get_info(psb200_handle h, char *json_out, size_t cap, size_t *needed)
 const char *psb200_name(psb200_handle h);
 const char *psb200_last_error(psb200_handle h);
 
-/* ---- multi-GPU (one process per GPU). The unique id (128 bytes) is produced on rank 0
- * and distributed by the host application (torch.distributed / MPI); after psb200_dist_init the
- * handle owns rows [offsets[rank], offsets[rank+1]) of every system it is given: analyze/factorize
- * still receive the full CSC matrix on every rank, solve receives full-length b/x on every rank. */
-int psb200_dist_unique_id(char id128[128]);
-int psb200_dist_init(psb200_handle h, int rank, int world, const char id128[128]);
+/* ---- multi-GPU (one process per GPU, up to 8 GPUs of one node). No reference counterpart.
+ * The matrix is row-range partitioned (contiguous ranges balanced by nnz); halo x-entries and the
+ * dot-product all-reduce travel over NVLink peer memory, fused into the solver's kernels.
+ *   1. every rank: psb200_dist_prepare() -> a 64-byte CUDA IPC handle of its comm buffer
+ *   2. the host application all-gathers the handles (torch.distributed / MPI), rank order
+ *   3. every rank: psb200_dist_connect(all handles)
+ * Afterwards analyze_pattern / factorize still receive the FULL CSC matrix on every rank (each rank
+ * keeps its rows), psb200_solve receives full-length b / x (each rank reads and writes only its own
+ * rows [row_begin, row_end)), psb200_solve_device receives the local slices. Jacobi-PCG only. */
+int psb200_dist_prepare(psb200_handle h, int rank, int world, int64_t halo_cap_doubles, char handle_out[64]);
+int psb200_dist_connect(psb200_handle h, const char *handles /* world * 64 bytes */);
+int psb200_dist_local_range(psb200_handle h, int64_t *row_begin, int64_t *row_end);
+/* Host-only plan of one rank (no GPU needed; used by the CPU tests to check partition offsets and halo
+ * lists bit-exactly against the oracle). Caller-allocated arrays: offsets[world+1], counts[3] =
+ * {local rows, local nnz, halo columns}, local_rp[n+1], local_ci[nnz], local_perm[nnz],
+ * send_begin[world+1], send_rows[n], recv_count[world], halo_cols[n]. */
+int psb200_dist_plan_host(int64_t n, int64_t nnz, const int32_t *outer, const int32_t *inner, int rank, int world,
+                          int64_t halo_cap, int64_t *offsets, int64_t *counts, int32_t *local_rp, int32_t *local_ci,
+                          int32_t *local_perm, int32_t *send_begin, int32_t *send_rows, int32_t *recv_count,
+                          int32_t *halo_cols);
 
 /* ---- test / bench hooks (not part of the polysolve interface) */
 /* CSR produced by analyze_pattern: row_ptr int32[n+1], col_idx int32[nnz], perm int32[nnz] with

@@ -6,10 +6,7 @@
 #include <cstring>
 #include <new>
 
-struct psb200_solver
-{
-    psb::Solver s;
-};
+#include "capi_internal.hpp"
 
 namespace {
 thread_local std::string g_create_error;

@@ -91,11 +91,86 @@ private:
 // takes the last ticket sums the partials in a fixed order. No floating-point atomics, so results
 // are bit-reproducible for a fixed grid (contrast reference mas_utils/InnerProduct.cu:16-33, which
 // does one fp64 atomic per block).
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU communication over NVLink peer memory (one process per GPU; buffers exchanged as CUDA
+// IPC handles). Every rank owns one "comm buffer" with the same layout; kernels store straight into
+// the peers' buffers (st.global on mapped peer pointers) and poll their own.
+//   [0, 4096)     reduction slots  RedSlot[2 parity][8 source ranks]
+//   [4096, 8192)  halo flags       unsigned long long[8 source ranks]  (monotonic epoch)
+//   [8192, ...)   halo data        double[2 parity][8 source ranks][halo_cap]
+constexpr int kMaxRanks = 8;
+struct RedSlot
+{
+    double v[kMaxRed];
+    unsigned long long seq;
+    unsigned long long pad[3];
+};
+static_assert(sizeof(RedSlot) == 64, "RedSlot must be 64 bytes");
+constexpr size_t kCommFlagsOff = 4096, kCommHaloOff = 8192;
+
+struct CommDev
+{
+    int world = 1, rank = 0;
+    long long halo_cap = 0;           // doubles per (parity, source rank) region
+    unsigned char *peer[kMaxRanks];   // comm buffer base of every rank (peer[rank] is local)
+    unsigned long long *red_seq;      // local: number of all-reduces completed
+    unsigned long long *push_epoch;   // local: number of halo pushes completed
+    int *error;                       // local: set to 1 on a spin-wait timeout
+    __host__ __device__ RedSlot *slot(int owner, int parity, int src) const
+    {
+        return reinterpret_cast<RedSlot *>(peer[owner]) + parity * kMaxRanks + src;
+    }
+    __host__ __device__ unsigned long long *halo_flag(int owner, int src) const
+    {
+        return reinterpret_cast<unsigned long long *>(peer[owner] + kCommFlagsOff) + src;
+    }
+    __host__ __device__ double *halo(int owner, int parity, int src) const
+    {
+        return reinterpret_cast<double *>(peer[owner] + kCommHaloOff) + ((long long)parity * kMaxRanks + src) * halo_cap;
+    }
+};
+
+constexpr long long kSpinLimit = 6000000000ll; // ~3 s of SM clocks: a lost peer becomes an error, not a hang
+
+__device__ __forceinline__ unsigned long long ld_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_sys_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys_f64(double *p, double v)
+{
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+// spin until *p >= want (system scope); false on timeout
+__device__ __forceinline__ bool spin_ge(const unsigned long long *p, unsigned long long want)
+{
+    const long long t0 = clock64();
+    while (ld_sys(p) < want)
+    {
+        if (clock64() - t0 > kSpinLimit)
+            return false;
+        __nanosleep(20);
+    }
+    return true;
+}
+
 struct RedCtx
 {
     double *partials;      // [kMaxRed][max_blocks]
     unsigned int *counter; // ticket, self-resetting (atomicInc wraps)
     int stride;            // max_blocks
+    CommDev comm;          // world == 1: single GPU, no exchange
 };
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -130,6 +205,55 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double (*sm)[THREADS 
         }
     }
     __syncthreads();
+}
+
+// All-reduce (sum) of NV doubles across the ranks, fused into the reducing kernel: the last CTA of
+// every rank stores its totals into slot[parity][rank] of EVERY peer's comm buffer over NVLink,
+// then waits until all `world` slots of its own buffer carry this reduction's sequence number and
+// sums them in rank order (so every rank obtains the bit-identical result). Two slot parities are
+// enough: a rank cannot start reduction s+2 before every peer has finished reading reduction s.
+// Called by all threads of the last CTA; tot[] is valid in thread 0 on entry and on return.
+template <int NV>
+__device__ __forceinline__ void comm_allreduce(const CommDev &c, double (&tot)[NV])
+{
+    __shared__ double sh[kMaxRed];
+    __shared__ unsigned long long sseq;
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            sh[i] = tot[i];
+        sseq = *c.red_seq + 1;
+    }
+    __syncthreads();
+    const unsigned long long seq = sseq;
+    const int par = (int)(seq & 1);
+    if ((int)threadIdx.x < c.world)
+    {
+        RedSlot *dst = c.slot(threadIdx.x, par, c.rank);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            st_sys_f64(&dst->v[i], sh[i]);
+        __threadfence_system();
+        st_sys(&dst->seq, seq);
+        const RedSlot *src = c.slot(c.rank, par, threadIdx.x);
+        if (!spin_ge(&src->seq, seq))
+            *c.error = 1;
+        __threadfence_system();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+        {
+            double s = 0;
+            for (int q = 0; q < c.world; ++q)
+                s += ld_sys_f64(&c.slot(c.rank, par, q)->v[i]);
+            tot[i] = s;
+        }
+        *c.red_seq = seq;
+    }
 }
 
 // Returns true (for all threads of the CTA) in the CTA that finished last; then tot[] (thread 0) holds
@@ -175,6 +299,8 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV > 0 ? NV : 1], const 
 #pragma unroll
         for (int i = 0; i < NV; ++i)
             tot[i] = s[i];
+        if (rc.comm.world > 1)
+            comm_allreduce<NV>(rc.comm, tot);
     }
     return true;
 }

@@ -1,7 +1,517 @@
-// Multi-GPU plumbing (row-range partition, halo exchange, dot all-reduce). Placeholder entry points.
+// Row-partitioned multi-GPU Jacobi-PCG: one process per GPU, NVLink peer memory for everything that
+// crosses ranks. There is no reference counterpart (the reference is single-device, MASSolver.cu:193);
+// the partition / halo index arrays are checked bit-exactly against the host oracle.
+//
+//  * partition : contiguous row ranges balanced by nnz (offsets[g] = first row r with row_ptr[r] >= g nnz / world)
+//  * halo      : the owner PUSHES: the direction-update kernel recomputes the boundary entries of the new
+//                search direction and stores them straight into the consumers' comm buffers (st.global on
+//                IPC-mapped peer pointers), then raises a per-source epoch flag. The SpMV of the next
+//                iteration waits on the flags of its neighbours while its TMA prefetch is already running.
+//  * dots      : the last CTA of every reducing kernel writes its totals into every peer's slot and sums
+//                the `world` slots in rank order (comm_allreduce, common.cuh) -- no extra launch, no NCCL.
 #include "../../include/psb200.h"
+#include "dist.hpp"
+#include "capi_internal.hpp"
+#include "solver.hpp"
+
+#include <algorithm>
 #include <cstring>
-extern "C" {
-int psb200_dist_unique_id(char id128[128]) { std::memset(id128, 0, 128); return PSB200_ERR_COMM; }
-int psb200_dist_init(psb200_handle, int, int, const char *) { return PSB200_ERR_COMM; }
+#include <sstream>
+
+namespace psb {
+
+// ====================================================================================== host plan
+void DistPlanHost::build(long long n, long long nnz, const int *outer, const int *inner, int rank_, int world_, long long halo_cap_)
+{
+    if (world_ < 1 || world_ > kMaxRanks || rank_ < 0 || rank_ >= world_)
+        throw std::invalid_argument("psb200 dist: rank/world out of range (world <= 8)");
+    rank = rank_;
+    world = world_;
+    n_global = n;
+    nnz_global = nnz;
+    halo_cap = halo_cap_;
+    // CSR row pointer of the whole matrix (counting pass over the CSC row indices)
+    std::vector<int> row_ptr(n + 1, 0);
+    for (long long k = 0; k < nnz; ++k)
+    {
+        const int i = inner[k];
+        if (i < 0 || i >= n)
+            throw std::invalid_argument("psb200 dist: inner index out of range");
+        row_ptr[i + 1]++;
+    }
+    for (long long i = 0; i < n; ++i)
+        row_ptr[i + 1] += row_ptr[i];
+    // contiguous ranges balanced by nnz
+    offsets.assign(world + 1, 0);
+    for (int g = 1; g < world; ++g)
+    {
+        const long long target = (long long)(((__int128)nnz * g) / world);
+        long long r = std::lower_bound(row_ptr.begin(), row_ptr.end(), (int)std::min<long long>(target, 0x7fffffff)) - row_ptr.begin();
+        r = std::min(r, n);
+        r = std::max(r, offsets[g - 1]);
+        offsets[g] = r;
+    }
+    offsets[world] = n;
+    const long long a = offsets[rank], b = offsets[rank + 1];
+    const int nl = (int)(b - a);
+    auto owner = [&](int i) {
+        int q = 0;
+        while (i >= offsets[q + 1])
+            ++q;
+        return q;
+    };
+    // local rows by a counting transpose restricted to [a, b): columns come out ascending
+    rp.assign(nl + 1, 0);
+    for (int i = 0; i <= nl; ++i)
+        rp[i] = row_ptr[a + i] - row_ptr[a];
+    const int lnnz = rp[nl];
+    std::vector<int> gcol(lnnz);
+    perm.assign(lnnz, 0);
+    {
+        std::vector<int> cur(rp.begin(), rp.end() - 1);
+        for (long long c = 0; c < n; ++c)
+            for (int k = outer[c]; k < outer[c + 1]; ++k)
+            {
+                const int i = inner[k];
+                if (i >= a && i < b)
+                {
+                    const int pos = cur[i - a]++;
+                    gcol[pos] = (int)c;
+                    perm[pos] = k;
+                }
+            }
+    }
+    // halo columns: distinct off-range columns, ascending (=> grouped by owner)
+    halo_cols.clear();
+    for (int k = 0; k < lnnz; ++k)
+        if (gcol[k] < a || gcol[k] >= b)
+            halo_cols.push_back(gcol[k]);
+    std::sort(halo_cols.begin(), halo_cols.end());
+    halo_cols.erase(std::unique(halo_cols.begin(), halo_cols.end()), halo_cols.end());
+    recv_count.assign(world, 0);
+    std::vector<int> seg_start(world + 1, 0);
+    for (int c : halo_cols)
+        recv_count[owner(c)]++;
+    for (int q = 0; q < world; ++q)
+    {
+        seg_start[q + 1] = seg_start[q] + recv_count[q];
+        if (recv_count[q] > halo_cap)
+            throw std::runtime_error("psb200 dist: halo from rank " + std::to_string(q) + " needs " + std::to_string(recv_count[q]) +
+                                     " values, capacity is " + std::to_string(halo_cap) + " (raise halo_cap in psb200_dist_prepare)");
+    }
+    if ((long long)nl + (long long)world * halo_cap > 0x7fffffffLL)
+        throw std::runtime_error("psb200 dist: local rows + halo regions exceed the int32 column range");
+    // remap columns
+    ci.assign(lnnz, 0);
+    for (int k = 0; k < lnnz; ++k)
+    {
+        const int c = gcol[k];
+        if (c >= a && c < b)
+            ci[k] = (int)(c - a);
+        else
+        {
+            const int q = owner(c);
+            const int pos = (int)(std::lower_bound(halo_cols.begin(), halo_cols.end(), c) - halo_cols.begin()) - seg_start[q];
+            ci[k] = (int)(nl + (long long)q * halo_cap + pos);
+        }
+    }
+    // send lists: my column j is needed by rank q iff column j has a row owned by q (CSC gives this directly)
+    std::vector<std::vector<int>> send(world);
+    for (long long j = a; j < b; ++j)
+        for (int k = outer[j]; k < outer[j + 1]; ++k)
+        {
+            const int q = owner(inner[k]);
+            if (q != rank && (send[q].empty() || send[q].back() != (int)(j - a)))
+                send[q].push_back((int)(j - a)); // all rows of column j are visited consecutively, so back() dedups
+        }
+    send_begin.assign(world + 1, 0);
+    send_rows.clear();
+    for (int q = 0; q < world; ++q)
+    {
+        send_begin[q + 1] = send_begin[q] + (int)send[q].size();
+        send_rows.insert(send_rows.end(), send[q].begin(), send[q].end());
+    }
 }
+
+DistState::~DistState()
+{
+    for (int q = 0; q < world; ++q)
+        if (q != rank && peer[q])
+            cudaIpcCloseMemHandle(peer[q]);
+    if (comm_buf)
+        cudaFree(comm_buf);
+    if (counters)
+        cudaFree(counters);
+}
+
+// ====================================================================================== kernels
+struct PushList
+{
+    const int *rows, *peer, *off;
+    int n;
+    unsigned int *counter;
+    unsigned send_mask;
+    int push_blocks;
+};
+
+// the push part shared by both kernels below: value(row) -> halo region of the consumer, then flags
+template <class ValueFn>
+__device__ __forceinline__ void push_section(const PushList &pl, const CommDev &c, int first_push_block, ValueFn value)
+{
+    const unsigned long long epoch = *c.push_epoch + 1;
+    const int par = (int)(epoch & 1);
+    for (int e = (blockIdx.x - first_push_block) * blockDim.x + threadIdx.x; e < pl.n; e += pl.push_blocks * blockDim.x)
+    {
+        const int row = pl.rows[e];
+        c.halo(pl.peer[e], par, c.rank)[pl.off[e]] = value(row);
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int last_push;
+    if (threadIdx.x == 0)
+        last_push = atomicInc(pl.counter, pl.push_blocks - 1) == (unsigned)(pl.push_blocks - 1);
+    __syncthreads();
+    if (last_push)
+    {
+        __threadfence_system();
+        if ((int)threadIdx.x < c.world && ((pl.send_mask >> threadIdx.x) & 1u))
+            st_sys(c.halo_flag(threadIdx.x, c.rank), epoch);
+        if (threadIdx.x == 0)
+            *c.push_epoch = epoch;
+    }
+}
+
+// p_new = dinv r + beta p_old (Eigen CG direction update) with the halo push fused in:
+// CTAs [0, vec_blocks) update the local vector, CTAs [vec_blocks, grid) recompute the boundary entries
+// and store them into the neighbours' halo regions. p_new != p_old (ping-pong), so the two never race.
+template <bool FIRST, int THREADS>
+__global__ void __launch_bounds__(THREADS) cg_dir_dist_kernel(long long n2, double *__restrict__ p_new, const double *__restrict__ p_old,
+                                                              const double *__restrict__ r, const double *__restrict__ dinv, KState *st,
+                                                              RedCtx rc, PushList pl, int vec_blocks, const int *done)
+{
+    if (done && *done)
+        return;
+    const double beta = FIRST ? 0.0 : st->rz_new / st->rz;
+    if ((int)blockIdx.x < vec_blocks)
+    {
+        const long long stride = (long long)vec_blocks * THREADS;
+        for (long long j = (long long)blockIdx.x * THREADS + threadIdx.x; j < n2; j += stride)
+        {
+            const double2 rv = ld2(r, j), dv = ld2(dinv, j);
+            double2 o;
+            o.x = dv.x * rv.x;
+            o.y = dv.y * rv.y;
+            if (!FIRST)
+            {
+                const double2 pv = ld2(p_old, j);
+                o.x += beta * pv.x;
+                o.y += beta * pv.y;
+            }
+            st2(p_new, j, o);
+        }
+    }
+    else
+        push_section(pl, rc.comm, vec_blocks, [&](int row) { return FIRST ? dinv[row] * r[row] : dinv[row] * r[row] + beta * p_old[row]; });
+    double acc[1] = {0}, tot[1];
+    if (grid_reduce<0, THREADS>(acc, rc, tot) && threadIdx.x == 0 && !FIRST)
+    {
+        // FinCgDirEigen
+        st->rz = st->rz_new;
+        st->iter += 1;
+        if (st->iter >= st->max_iter)
+        {
+            st->done = 1;
+            st->status = ST_MAXITER;
+        }
+    }
+}
+
+// push the boundary entries of an arbitrary local vector (initial guess x0)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) halo_push_kernel(const double *__restrict__ v, RedCtx rc, PushList pl)
+{
+    push_section(pl, rc.comm, 0, [&](int row) { return v[row]; });
+}
+
+// ====================================================================================== Solver (dist mode)
+void Solver::dist_prepare(int rank, int world, long long halo_cap, char handle_out[64])
+{
+    if (analyzed)
+        throw std::runtime_error("psb200_dist_prepare: call before analyze_pattern");
+    if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world)
+        throw std::invalid_argument("psb200_dist_prepare: rank/world out of range (world <= 8)");
+    if (halo_cap <= 0)
+        halo_cap = 1 << 20;
+    ensure_ctx(*this);
+    dist = std::make_unique<DistState>();
+    DistState &d = *dist;
+    d.rank = rank;
+    d.world = world;
+    d.halo_cap = (halo_cap + 1) & ~1ll;
+    d.comm_bytes = kCommHaloOff + sizeof(double) * 2 * kMaxRanks * (size_t)d.halo_cap;
+    PSB_CUDA(cudaMalloc(&d.comm_buf, d.comm_bytes));
+    PSB_CUDA(cudaMemset(d.comm_buf, 0, d.comm_bytes));
+    PSB_CUDA(cudaMalloc(&d.counters, 64));
+    PSB_CUDA(cudaMemset(d.counters, 0, 64));
+    d.push_counter.alloc(4, true);
+    cudaIpcMemHandle_t hnd;
+    PSB_CUDA(cudaIpcGetMemHandle(&hnd, d.comm_buf));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    std::memcpy(handle_out, &hnd, 64);
+    PSB_CUDA(cudaDeviceSynchronize());
+}
+
+void Solver::dist_connect(const char *handles)
+{
+    if (!dist)
+        throw std::runtime_error("psb200_dist_connect: psb200_dist_prepare first");
+    DistState &d = *dist;
+    for (int q = 0; q < d.world; ++q)
+    {
+        if (q == d.rank)
+        {
+            d.peer[q] = d.comm_buf;
+            continue;
+        }
+        cudaIpcMemHandle_t hnd;
+        std::memcpy(&hnd, handles + 64 * q, 64);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+            throw CudaError(std::string("psb200_dist_connect: cudaIpcOpenMemHandle(rank ") + std::to_string(q) + "): " + cudaGetErrorString(e));
+        d.peer[q] = p;
+    }
+    CommDev c;
+    c.world = d.world;
+    c.rank = d.rank;
+    c.halo_cap = d.halo_cap;
+    for (int q = 0; q < kMaxRanks; ++q)
+        c.peer[q] = (unsigned char *)(q < d.world ? d.peer[q] : nullptr);
+    c.red_seq = d.counters;
+    c.push_epoch = d.counters + 1;
+    c.error = (int *)(d.counters + 2);
+    ctx.comm = c;
+    d.connected = true;
+}
+
+void Solver::analyze_pattern_dist(long long n_, long long nnz_, const int *outer, const int *inner)
+{
+    DistState &d = *dist;
+    if (!d.connected && d.world > 1)
+        throw std::runtime_error("psb200 dist: psb200_dist_connect has not been called");
+    if (prm.precond == "amg" || prm.krylov != "cg")
+        throw std::runtime_error("psb200 dist: the row-partitioned path provides Jacobi-PCG (krylov=cg, precond=jacobi|none) in this version");
+    d.plan.build(n_, nnz_, outer, inner, d.rank, d.world, d.halo_cap);
+    const DistPlanHost &P = d.plan;
+    cudaStream_t st = ctx.stream;
+    n = P.r1() - P.r0();
+    nnz = (long long)P.ci.size();
+    n_pad = (n + 3) & ~3ll;
+    sym_pattern = false;
+    A.n = (int)n;
+    A.ncols = (int)n;
+    A.nnz = nnz;
+    A.nl = (int)n;
+    A.rp.alloc(n + 1);
+    A.ci.alloc(std::max<long long>(nnz, 1), false, 64);
+    A.va.alloc(std::max<long long>(nnz, 1), false, 64);
+    PSB_CUDA(cudaMemcpyAsync(A.rp.p, P.rp.data(), sizeof(int) * (n + 1), cudaMemcpyHostToDevice, st));
+    if (nnz)
+        PSB_CUDA(cudaMemcpyAsync(A.ci.p, P.ci.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice, st));
+    d.recv_mask = 0;
+    d.send_mask = 0;
+    for (int q = 0; q < d.world; ++q)
+    {
+        if (P.recv_count[q] > 0)
+            d.recv_mask |= 1u << q;
+        if (P.send_begin[q + 1] > P.send_begin[q])
+            d.send_mask |= 1u << q;
+    }
+    A.halo_mask = d.recv_mask;
+    // device push list
+    d.n_push = (int)P.send_rows.size();
+    std::vector<int> peer(d.n_push), off(d.n_push);
+    for (int q = 0; q < d.world; ++q)
+        for (int e = P.send_begin[q]; e < P.send_begin[q + 1]; ++e)
+        {
+            peer[e] = q;
+            off[e] = e - P.send_begin[q];
+        }
+    d.push_rows.alloc(std::max(1, d.n_push));
+    d.push_peer.alloc(std::max(1, d.n_push));
+    d.push_off.alloc(std::max(1, d.n_push));
+    if (d.n_push)
+    {
+        PSB_CUDA(cudaMemcpyAsync(d.push_rows.p, P.send_rows.data(), sizeof(int) * d.n_push, cudaMemcpyHostToDevice, st));
+        PSB_CUDA(cudaMemcpyAsync(d.push_peer.p, peer.data(), sizeof(int) * d.n_push, cudaMemcpyHostToDevice, st));
+        PSB_CUDA(cudaMemcpyAsync(d.push_off.p, off.data(), sizeof(int) * d.n_push, cudaMemcpyHostToDevice, st));
+    }
+    A.plan(prm.spmv_kernel);
+    PSB_CUDA(cudaStreamSynchronize(st));
+}
+
+void Solver::factorize_values_dist(const double *vals)
+{
+    DistState &d = *dist;
+    const DistPlanHost &P = d.plan;
+    d.h_vals.resize(std::max<size_t>(1, P.perm.size()));
+    for (size_t k = 0; k < P.perm.size(); ++k)
+        d.h_vals[k] = vals[P.perm[k]];
+    if (nnz)
+        PSB_CUDA(cudaMemcpyAsync(A.va.p, d.h_vals.data(), sizeof(double) * nnz, cudaMemcpyHostToDevice, ctx.stream));
+    PSB_CUDA(cudaStreamSynchronize(ctx.stream));
+}
+
+void Solver::check_comm_error()
+{
+    if (!dist)
+        return;
+    int e = 0;
+    PSB_CUDA(cudaMemcpy(&e, dist->counters + 2, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e)
+    {
+        PSB_CUDA(cudaMemset(dist->counters + 2, 0, sizeof(int)));
+        throw std::runtime_error("psb200 dist: a peer did not answer within the spin limit (lost rank or mismatched call sequence)");
+    }
+}
+
+static PushList make_push(DistState &d, int push_blocks)
+{
+    return PushList{d.push_rows.p, d.push_peer.p, d.push_off.p, d.n_push, d.push_counter.p, d.send_mask, push_blocks};
+}
+
+// Jacobi-PCG in Eigen's ordering on the row partition. Same kernels as the single-GPU path for the
+// SpMV and the x/r update (their reductions all-reduce inside the kernel); the direction update is the
+// fused update + halo push. p ping-pongs between vp and vp2.
+void Solver::run_cg_eigen_dist(const double *d_b)
+{
+    DistState &d = *dist;
+    KState *S = d_state;
+    const int *done = &S->done;
+    d.vp2.alloc((size_t)n_pad, false);
+    init_state(*this, prm.tolerance, prm.max_iter);
+    const long long n2 = n_pad / 2;
+    const int vec_blocks = vec_grid(n2);
+    // every rank pushes at every push point (even an empty list) so the epochs advance in lockstep
+    const int push_blocks = d.world > 1 ? std::max(1, std::min(8, (d.n_push + kVecThreads - 1) / kVecThreads)) : 0;
+    PushList pl = make_push(d, std::max(1, push_blocks));
+    RedCtx rc = ctx.red();
+    if (push_blocks)
+    {
+        ctx.prof_begin("halo_push");
+        halo_push_kernel<kVecThreads><<<push_blocks, kVecThreads, 0, ctx.stream>>>(vx.p, rc, pl);
+        check_launch();
+        ctx.prof_end();
+    }
+    launch_spmv(ctx, "spmv_residual", A, vx.p, EpiResidualNorms{vr.p, d_b, dinv.p}, FinInitEigen{S});
+    ctx.prof_begin("cg_dir");
+    cg_dir_dist_kernel<true, kVecThreads><<<vec_blocks + push_blocks, kVecThreads, 0, ctx.stream>>>(n2, vp.p, vp.p, vr.p, dinv.p, S, rc, pl, vec_blocks, done);
+    check_launch();
+    ctx.prof_end();
+    const int batch_iters = std::max(2, prm.check_every & ~1);
+    auto batch = [&]() {
+        double *pc = vp.p, *pn = d.vp2.p;
+        for (int i = 0; i < batch_iters; ++i)
+        {
+            launch_spmv(ctx, "spmv_dot", A, pc, EpiDot{vq.p, pc}, FinPAp{S}, done);
+            launch_vec(ctx, "cg_update", n_pad, OpCgUpdateEigen{vx.p, vr.p, pc, vq.p, dinv.p, S, 0.0}, FinCgUpdateEigen{S}, done);
+            ctx.prof_begin("cg_dir");
+            cg_dir_dist_kernel<false, kVecThreads><<<vec_blocks + push_blocks, kVecThreads, 0, ctx.stream>>>(n2, pn, pc, vr.p, dinv.p, S, rc, pl, vec_blocks, done);
+            check_launch();
+            ctx.prof_end();
+            std::swap(pc, pn);
+        }
+    };
+    std::ostringstream key;
+    key << "cg_eigen_dist/" << A.kind << "/" << n << "/" << (void *)vx.p << "/" << (void *)A.va.p << "/" << (void *)d_b << "/" << batch_iters;
+    drive(batch, batch_iters, key.str());
+    finish_solve();
+    check_comm_error();
+}
+
+} // namespace psb
+
+// ====================================================================================== C ABI
+extern "C" {
+
+int psb200_dist_prepare(psb200_handle h, int rank, int world, int64_t halo_cap, char handle_out[64])
+{
+    if (!h || !handle_out)
+        return PSB200_ERR_INVALID;
+    try
+    {
+        h->s.err.clear();
+        h->s.dist_prepare(rank, world, halo_cap, handle_out);
+        return PSB200_OK;
+    }
+    catch (const std::invalid_argument &e)
+    {
+        h->s.err = e.what();
+        return PSB200_ERR_INVALID;
+    }
+    catch (const std::exception &e)
+    {
+        h->s.err = e.what();
+        return PSB200_ERR_COMM;
+    }
+}
+
+int psb200_dist_connect(psb200_handle h, const char *handles)
+{
+    if (!h || !handles)
+        return PSB200_ERR_INVALID;
+    try
+    {
+        h->s.err.clear();
+        h->s.dist_connect(handles);
+        return PSB200_OK;
+    }
+    catch (const std::exception &e)
+    {
+        h->s.err = e.what();
+        return PSB200_ERR_COMM;
+    }
+}
+
+int psb200_dist_local_range(psb200_handle h, int64_t *row_begin, int64_t *row_end)
+{
+    if (!h || !h->s.dist || !h->s.analyzed)
+        return PSB200_ERR_INVALID;
+    if (row_begin)
+        *row_begin = h->s.dist->plan.r0();
+    if (row_end)
+        *row_end = h->s.dist->plan.r1();
+    return PSB200_OK;
+}
+
+// Host-only (no GPU needed): the partition / halo plan of one rank. Arrays are caller-allocated:
+// offsets[world+1], local_rp[n+1], local_ci[nnz], local_perm[nnz], send_begin[world+1], send_rows[n],
+// recv_count[world], halo_cols[n]; counts[0..2] = {local rows, local nnz, halo columns}.
+int psb200_dist_plan_host(int64_t n, int64_t nnz, const int32_t *outer, const int32_t *inner, int rank, int world, int64_t halo_cap,
+                          int64_t *offsets, int64_t *counts, int32_t *local_rp, int32_t *local_ci, int32_t *local_perm,
+                          int32_t *send_begin, int32_t *send_rows, int32_t *recv_count, int32_t *halo_cols)
+{
+    try
+    {
+        psb::DistPlanHost P;
+        P.build(n, nnz, outer, inner, rank, world, halo_cap);
+        std::copy(P.offsets.begin(), P.offsets.end(), offsets);
+        counts[0] = P.r1() - P.r0();
+        counts[1] = (int64_t)P.ci.size();
+        counts[2] = (int64_t)P.halo_cols.size();
+        std::copy(P.rp.begin(), P.rp.end(), local_rp);
+        std::copy(P.ci.begin(), P.ci.end(), local_ci);
+        std::copy(P.perm.begin(), P.perm.end(), local_perm);
+        std::copy(P.send_begin.begin(), P.send_begin.end(), send_begin);
+        std::copy(P.send_rows.begin(), P.send_rows.end(), send_rows);
+        std::copy(P.recv_count.begin(), P.recv_count.end(), recv_count);
+        std::copy(P.halo_cols.begin(), P.halo_cols.end(), halo_cols);
+        return PSB200_OK;
+    }
+    catch (...)
+    {
+        return PSB200_ERR_INVALID;
+    }
+}
+
+} // extern "C"

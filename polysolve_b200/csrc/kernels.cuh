@@ -32,7 +32,34 @@ struct CsrView
     const int *ci;
     const double *va;
     int n;
+    // row-partitioned (multi-GPU) matrices: columns >= nl address the halo values the peers pushed
+    // into this rank's comm buffer instead of the local x. Single GPU: nl = INT_MAX, halo_mask = 0.
+    int nl;
+    unsigned halo_mask; // bit q set: rank q pushes halo values to this rank
 };
+
+// x[c] for a local column, xh[c - nl] for a halo column
+__device__ __forceinline__ double ldx(const double *__restrict__ x, const double *__restrict__ xh, int nl, int c)
+{
+    return c < nl ? __ldg(x + c) : xh[c - nl];
+}
+
+// Called by every thread at the start of a kernel that gathers halo columns: waits until every
+// neighbour's push of the current epoch has landed and returns the halo base pointer of that epoch.
+__device__ __forceinline__ const double *wait_halo(const CsrView &A, const CommDev &c)
+{
+    if (A.halo_mask == 0)
+        return nullptr;
+    const unsigned long long epoch = *c.push_epoch; // pushes completed locally == epoch of the vector being multiplied
+    if ((int)threadIdx.x < c.world && ((A.halo_mask >> threadIdx.x) & 1u))
+    {
+        if (!spin_ge(c.halo_flag(c.rank, threadIdx.x), epoch))
+            *c.error = 1;
+        __threadfence_system();
+    }
+    __syncthreads();
+    return c.halo(c.rank, (int)(epoch & 1), 0);
+}
 
 // ---------------------------------------------------------------------------------- finalizers
 // Run by thread 0 of the last CTA with the grid totals.

@@ -29,7 +29,9 @@ struct CsrDev
     DevBuf<double> va;
     int kind = SPMV_VECTOR;
     int lpr = 1; // lanes per row for the vector schedule
-    CsrView view() const { return CsrView{rp.p, ci.p, va.p, n}; }
+    int nl = 0x7fffffff;      // local columns (multi-GPU: columns >= nl are halo columns)
+    unsigned halo_mask = 0;   // ranks that push halo values to this one
+    CsrView view() const { return CsrView{rp.p, ci.p, va.p, n, nl, halo_mask}; }
     // choose the schedule from the average row length
     void plan(const std::string &forced = "auto")
     {
@@ -107,7 +109,8 @@ struct Ctx
             cudaStreamDestroy(stream);
         stream = nullptr;
     }
-    RedCtx red() const { return RedCtx{partials.p, counter.p, kMaxBlocks}; }
+    CommDev comm;             // world == 1 unless psb200_dist_connect() was called
+    RedCtx red() const { return RedCtx{partials.p, counter.p, kMaxBlocks, comm}; }
     cudaEvent_t get_event()
     {
         if (!ev_pool.empty())

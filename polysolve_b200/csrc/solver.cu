@@ -3,6 +3,7 @@
 // polysolve::linear::Solver (reference src/polysolve/linear/Solver.hpp:90-131) one method per virtual.
 #include "solver.hpp"
 #include "amg.hpp"
+#include "dist.hpp"
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -189,7 +190,7 @@ Solver::~Solver()
     ctx.destroy();
 }
 
-static void ensure_ctx(Solver &s)
+void ensure_ctx(Solver &s)
 {
     if (s.ctx.stream)
         return;
@@ -322,7 +323,7 @@ void Solver::analyze_pattern(long long n_, long long nnz_, const int *outer, con
     precond_num = precond_num_;
     unsigned long long h = hash_words(outer, sizeof(int) * (size_t)(n_ + 1), 0x5bd1e995ull + (unsigned long long)n_);
     h = hash_words(inner, sizeof(int) * (size_t)nnz_, h);
-    if (analyzed && n == n_ && nnz == nnz_ && h == pattern_hash)
+    if (analyzed && n_global == n_ && nnz_global == nnz_ && h == pattern_hash)
     {
         analyze_skipped = true; // Newton calls analyze_pattern every iteration with an unchanged pattern (Newton.cpp:189)
         t_analyze_ms = now_ms() - t0;
@@ -338,9 +339,19 @@ void Solver::analyze_pattern(long long n_, long long nnz_, const int *outer, con
         graph_exec = nullptr;
         graph_key.clear();
     }
+    n_global = n_;
+    nnz_global = nnz_;
+    pattern_hash = h;
+    if (dist)
+    {
+        // row-partitioned mode: build the local part on the host (dist.cu) and stop here
+        analyze_pattern_dist(n_, nnz_, outer, inner);
+        analyzed = true;
+        t_analyze_ms = now_ms() - t0;
+        return;
+    }
     n = n_;
     nnz = nnz_;
-    pattern_hash = h;
     n_pad = (n + 3) & ~3ll;
     cudaStream_t st = ctx.stream;
 
@@ -423,7 +434,7 @@ void Solver::factorize(long long n_, long long nnz_, const int *outer, const int
     ensure_ctx(*this);
     // factorize() without (or with a stale) analyze_pattern(): analyze now. The Eigen iterative wrappers
     // accept this order too (EigenSolver.tpp:100-105 only needs the matrix).
-    bool need = !analyzed || n != n_ || nnz != nnz_;
+    bool need = !analyzed || n_global != n_ || nnz_global != nnz_;
     if (!need && prm.verify_pattern && outer && inner)
     {
         // cheap guard against a silently changed pattern: outer fully, inner strided
@@ -439,12 +450,17 @@ void Solver::factorize(long long n_, long long nnz_, const int *outer, const int
     }
     const double t0 = now_ms();
     cudaStream_t st = ctx.stream;
-    csc_vals.alloc(std::max<long long>(nnz, 1));
-    if (nnz)
+    if (dist)
+        factorize_values_dist(vals);
+    else
     {
-        PSB_CUDA(cudaMemcpyAsync(csc_vals.p, vals, sizeof(double) * nnz, cudaMemcpyHostToDevice, st));
-        gather_vals_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(nnz, csc_vals.p, perm.p, A.va.p);
-        check_launch();
+        csc_vals.alloc(std::max<long long>(nnz, 1));
+        if (nnz)
+        {
+            PSB_CUDA(cudaMemcpyAsync(csc_vals.p, vals, sizeof(double) * nnz, cudaMemcpyHostToDevice, st));
+            gather_vals_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(nnz, csc_vals.p, perm.p, A.va.p);
+            check_launch();
+        }
     }
     dinv.alloc(n_pad, true);
     int *d_bad = (int *)ctx.counter.p + 3;
@@ -509,16 +525,22 @@ void Solver::solve_host(const double *b, double *x, long long n_)
 {
     if (!factorized)
         throw std::runtime_error("psb200_solve: factorize() has not been called");
-    if (n_ != n || !b || !x)
+    if (n_ != n_global || !b || !x)
         throw std::invalid_argument("psb200_solve: size mismatch or null vector");
     const double t0 = now_ms();
     cudaStream_t st = ctx.stream;
     ensure_vectors();
     if (prm.profile)
         ctx.prof.clear();
+    // row-partitioned mode: b and x are full-length on every rank; this rank reads / writes its own rows
+    const long long row0 = dist ? dist->plan.r0() : 0;
+    b += row0;
+    x += row0;
     PSB_CUDA(cudaMemcpyAsync(vb.p, b, sizeof(double) * n, cudaMemcpyHostToDevice, st));
     PSB_CUDA(cudaMemcpyAsync(vx.p, x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    if (prm.krylov == "bicgstab")
+    if (dist)
+        run_cg_eigen_dist(vb.p);
+    else if (prm.krylov == "bicgstab")
         run_bicgstab(vb.p);
     else if (prm.precond == "amg")
         run_cg_amgcl(vb.p);
@@ -543,7 +565,9 @@ void Solver::solve_device(const double *d_b, double *d_x, long long n_)
         ctx.prof.clear();
     // x lives in the solver's own buffer so captured graphs keep stable pointers
     PSB_CUDA(cudaMemcpyAsync(vx.p, d_x, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-    if (prm.krylov == "bicgstab")
+    if (dist)
+        run_cg_eigen_dist(d_b);
+    else if (prm.krylov == "bicgstab")
         run_bicgstab(d_b);
     else if (prm.precond == "amg")
         run_cg_amgcl(d_b);
@@ -637,7 +661,7 @@ void Solver::finish_solve()
         last_error = s.bn2 > 0 ? std::sqrt(s.rn2 / s.bn2) : 0.0;
 }
 
-static void init_state(Solver &s, double tol, int max_iter)
+void init_state(Solver &s, double tol, int max_iter)
 {
     KState &h = s.h_state[3];
     std::memset(&h, 0, sizeof(KState));
@@ -830,7 +854,11 @@ void Solver::build_info()
     o << ",\"num_iterations\":" << last_iters << ",\"final_res_norm\":" << jnum(last_error);
     o << ",\"solver_status\":" << jstr(status_str[std::min(std::max(last_status, 0), 4)]);
     o << ",\"krylov\":" << jstr(prm.krylov) << ",\"precond\":" << jstr(prm.precond);
-    o << ",\"n\":" << n << ",\"nnz\":" << nnz;
+    o << ",\"n\":" << n_global << ",\"nnz\":" << nnz_global;
+    if (dist)
+        o << ",\"dist\":{\"rank\":" << dist->rank << ",\"world\":" << dist->world << ",\"row_begin\":" << dist->plan.r0()
+          << ",\"row_end\":" << dist->plan.r1() << ",\"local_nnz\":" << nnz << ",\"halo_in\":" << dist->plan.halo_cols.size()
+          << ",\"halo_out\":" << dist->n_push << "}";
     o << ",\"symmetric_pattern\":" << (sym_pattern ? "true" : "false");
     o << ",\"analyze_skipped\":" << (analyze_skipped ? "true" : "false");
     o << ",\"spmv_kernel\":" << jstr(A.kind == SPMV_STREAM ? "stream" : ("vector" + std::to_string(A.lpr)));

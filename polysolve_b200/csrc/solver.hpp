@@ -48,7 +48,7 @@ struct Params
 
 class AmgHierarchy; // amg.cu
 
-struct DistComm; // dist.cu
+struct DistState; // dist.hpp / dist.cu
 
 struct Solver
 {
@@ -57,6 +57,17 @@ struct Solver
     std::string info_json = "{}";
     int device = 0;
     Ctx ctx;
+
+    // multi-GPU (row-partitioned) mode: set by dist_prepare/dist_connect. In this mode n, nnz, A and all
+    // vectors describe the LOCAL row range; n_global / nnz_global the whole system.
+    std::unique_ptr<DistState> dist;
+    long long n_global = 0, nnz_global = 0;
+    void dist_prepare(int rank, int world, long long halo_cap, char handle_out[64]);
+    void dist_connect(const char *handles);
+    void analyze_pattern_dist(long long n, long long nnz, const int *outer, const int *inner);
+    void factorize_values_dist(const double *vals);
+    void run_cg_eigen_dist(const double *d_b);
+    void check_comm_error();
 
     // pattern state (analyze_pattern)
     long long n = 0, nnz = 0;
@@ -101,7 +112,6 @@ struct Solver
     void precond_apply_host(const double *r, double *z, long long n);
     void build_info();
 
-private:
     void ensure_vectors();
     void run_cg_eigen(const double *d_b);
     void run_cg_amgcl(const double *d_b);
@@ -109,5 +119,8 @@ private:
     void drive(const std::function<void()> &enqueue_batch, int batch_iters, const std::string &key);
     void finish_solve();
 };
+
+void ensure_ctx(Solver &s);
+void init_state(Solver &s, double tol, int max_iter);
 
 } // namespace psb

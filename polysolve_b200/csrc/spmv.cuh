@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(THREADS) spmv_vector_kernel(CsrView A, const d
 #pragma unroll
     for (int i = 0; i < NVA; ++i)
         acc[i] = 0;
+    const double *xh = wait_halo(A, rc.comm);
     const int lane = threadIdx.x % LPR;
     const int rows_per_cta = THREADS / LPR;
     for (long long base = (long long)blockIdx.x * rows_per_cta; base < A.n; base += (long long)gridDim.x * rows_per_cta)
@@ -194,12 +195,12 @@ __global__ void __launch_bounds__(THREADS) spmv_vector_kernel(CsrView A, const d
             {
                 const int c0 = __ldg(A.ci + k), c1 = __ldg(A.ci + k + LPR);
                 const double v0 = __ldg(A.va + k), v1 = __ldg(A.va + k + LPR);
-                const double x0 = __ldg(x + c0), x1 = __ldg(x + c1);
+                const double x0 = ldx(x, xh, A.nl, c0), x1 = ldx(x, xh, A.nl, c1);
                 s += v0 * x0;
                 s += v1 * x1;
             }
             if (k < ke)
-                s += __ldg(A.va + k) * __ldg(x + __ldg(A.ci + k));
+                s += __ldg(A.va + k) * ldx(x, xh, A.nl, __ldg(A.ci + k));
         }
 #pragma unroll
         for (int o = LPR / 2; o > 0; o >>= 1)
@@ -328,6 +329,8 @@ __global__ void __launch_bounds__(Cfg::threads) spmv_stream_kernel(CsrView A, co
         }
     }
 
+    const double *xh = wait_halo(A, rc.comm); // the TMA prefetch above is already in flight
+
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it)
     {
@@ -366,7 +369,7 @@ __global__ void __launch_bounds__(Cfg::threads) spmv_stream_kernel(CsrView A, co
                     const bool ok = k + u < ke;
                     const int c = ok ? sc[k + u] : 0;
                     v[u] = ok ? sv[k + u] : 0.0;
-                    xx[u] = ok ? __ldg(x + c) : 0.0;
+                    xx[u] = ok ? ldx(x, xh, A.nl, c) : 0.0;
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
@@ -377,7 +380,7 @@ __global__ void __launch_bounds__(Cfg::threads) spmv_stream_kernel(CsrView A, co
         else
         {
             for (int k = kb; k < ke; ++k)
-                sum += __ldg(A.va + k) * __ldg(x + __ldg(A.ci + k));
+                sum += __ldg(A.va + k) * ldx(x, xh, A.nl, __ldg(A.ci + k));
         }
         if (live)
             epi(row, sum, pre, acc);

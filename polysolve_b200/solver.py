@@ -128,17 +128,55 @@ class Solver:
     def is_dense(self):
         return False
 
-    # ---- multi-GPU
-    @staticmethod
-    def dist_unique_id():
-        buf = C.create_string_buffer(128)
-        rc = _lib.lib().psb200_dist_unique_id(buf)
-        if rc:
-            raise RuntimeError("psb200_dist_unique_id failed")
+    # ---- multi-GPU (one process per GPU): row-partitioned Jacobi-PCG over NVLink peer memory
+    def dist_prepare(self, rank, world, halo_cap=1 << 20):
+        """Allocates this rank's comm buffer; returns its 64-byte CUDA IPC handle."""
+        buf = C.create_string_buffer(64)
+        self._check(self._L.psb200_dist_prepare(self._h, rank, world, halo_cap, buf))
         return buf.raw
 
-    def dist_init(self, rank, world, uid):
-        self._check(self._L.psb200_dist_init(self._h, rank, world, uid))
+    def dist_connect(self, handles):
+        """handles: the 64-byte handles of all ranks, concatenated in rank order."""
+        self._check(self._L.psb200_dist_connect(self._h, bytes(handles)))
+
+    def dist_setup_torch(self, halo_cap=1 << 20):
+        """Plumbing through torch.distributed (any backend): all-gather the IPC handles and connect."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        mine = self.dist_prepare(rank, world, halo_cap)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        self.dist_connect(b"".join(gathered))
+        dist.barrier()
+        return rank, world
+
+    def dist_local_range(self):
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self._L.psb200_dist_local_range(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    @staticmethod
+    def dist_plan_host(n, outer, inner, rank, world, halo_cap=1 << 20):
+        """Host-only partition / halo plan of one rank (no GPU needed)."""
+        L = _lib.lib()
+        nnz = int(outer[n])
+        offsets = np.zeros(world + 1, np.int64)
+        counts = np.zeros(3, np.int64)
+        rp = np.zeros(n + 1, np.int32)
+        ci = np.zeros(max(nnz, 1), np.int32)
+        perm = np.zeros(max(nnz, 1), np.int32)
+        send_begin = np.zeros(world + 1, np.int32)
+        send_rows = np.zeros(max(n, 1), np.int32)
+        recv_count = np.zeros(world, np.int32)
+        halo_cols = np.zeros(max(n, 1), np.int32)
+        rc = L.psb200_dist_plan_host(n, nnz, outer, inner, rank, world, halo_cap, offsets, counts, rp, ci, perm,
+                                     send_begin, send_rows, recv_count, halo_cols)
+        if rc:
+            raise RuntimeError("psb200_dist_plan_host failed")
+        nl, lnnz, nh = (int(c) for c in counts)
+        return dict(offsets=offsets, n_local=nl, rp=rp[:nl + 1], ci=ci[:lnnz], perm=perm[:lnnz], send_begin=send_begin,
+                    send_rows=send_rows[:int(send_begin[-1])], recv_count=recv_count, halo_cols=halo_cols[:nh])
 
     # ---- test / bench hooks
     def debug_get_csr(self, n, nnz):
