@@ -13,6 +13,7 @@
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <sstream>
 
@@ -587,6 +588,7 @@ struct AmgLevel
     double rho = 0, cheb_d = 0, cheb_c = 0, omega = 0;
     std::vector<double> alpha, beta;
     int mis_rounds = 0;
+    double t_relax = 0, t_agg = 0, t_prolong = 0, t_transpose = 0, t_ap = 0, t_rap = 0; // setup phase wall-clock, ms
 };
 
 AmgHierarchy::AmgHierarchy(Ctx &ctx, const AmgParams &prm) : ctx_(ctx), prm_(prm) {}
@@ -761,6 +763,12 @@ static int aggregate_mis2(Ctx &c, Temp &tmp, const CsrDev &A, const double *diag
     return n_agg;
 }
 
+static double wall_ms(cudaStream_t st)
+{
+    cudaStreamSynchronize(st);
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 // amgcl amg::do_init (SURVEY A.3 "Hierarchy build")
 void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &imposed)
 {
@@ -779,7 +787,9 @@ void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &
         AmgLevel &L = *levels_.back();
         const CsrDev &A = *L.A;
         const int li = (int)levels_.size() - 1;
+        double tp = wall_ms(st);
         setup_relaxation(ctx_, prm_, L, li);
+        L.t_relax = wall_ms(st) - tp;
         if ((int)levels_.size() >= prm_.max_levels)
             break; // last level is a plain smoothing-only level
         const long long n = A.n;
@@ -789,6 +799,7 @@ void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &
         diag_kernel<<<nblk(n), 256, 0, st>>>(A.view(), diag.p);
         check_launch();
         // ---- aggregates
+        tp = wall_ms(st);
         if (li < (int)imposed.size() && !imposed[li].empty())
         {
             if ((long long)imposed[li].size() != n)
@@ -802,6 +813,7 @@ void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &
         }
         else
             L.n_agg = aggregate_mis2(ctx_, tmp, A, diag.p, eps_strong, L.agg, L.mis_rounds);
+        L.t_agg = wall_ms(st) - tp;
         eps_strong *= 0.5; // amgcl halves eps_strong after every level
         if (L.n_agg <= 0)
             break;
@@ -813,6 +825,7 @@ void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &
             omega *= 2.0 / 3.0;
         L.omega = omega;
         // ---- smoothed prolongation
+        tp = wall_ms(st);
         {
             DevBuf<int> scol, cnt;
             DevBuf<double> sval;
@@ -832,15 +845,22 @@ void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &
             check_launch();
             PSB_CUDA(cudaStreamSynchronize(st));
         }
+        L.t_prolong = wall_ms(st) - tp;
+        tp = wall_ms(st);
         transpose(ctx_, tmp, L.P, L.R);
         L.P.plan("auto");
         L.R.plan("auto");
+        L.t_transpose = wall_ms(st) - tp;
         // ---- Galerkin coarse operator A_c = R (A P)
         auto next = std::make_unique<AmgLevel>();
         {
             CsrDev AP;
+            tp = wall_ms(st);
             spgemm(ctx_, tmp, A, L.P, L.n_agg, AP);
+            L.t_ap = wall_ms(st) - tp;
+            tp = wall_ms(st);
             spgemm(ctx_, tmp, L.R, AP, L.n_agg, next->Aown);
+            L.t_rap = wall_ms(st) - tp;
         }
         next->Aown.plan("auto");
         next->A = &next->Aown;
@@ -850,7 +870,9 @@ void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &
     {
         // coarsest level (rows <= coarse_enough): relaxation only (direct_coarse = false)
         levels_.push_back(std::move(cur));
+        const double tp = wall_ms(st);
         setup_relaxation(ctx_, prm_, *levels_.back(), (int)levels_.size() - 1);
+        levels_.back()->t_relax = wall_ms(st) - tp;
     }
     PSB_CUDA(cudaStreamSynchronize(st));
 }
@@ -970,7 +992,9 @@ std::string AmgHierarchy::info_json() const
         if (l)
             o << ",";
         o << "{\"rows\":" << L.A->n << ",\"nnz\":" << L.A->nnz << ",\"p_nnz\":" << L.P.nnz << ",\"aggregates\":" << L.n_agg
-          << ",\"rho\":" << jnum(L.rho) << ",\"omega\":" << jnum(L.omega) << ",\"mis_rounds\":" << L.mis_rounds
+          << ",\"rho\":" << jnum(L.rho) << ",\"omega\":" << jnum(L.omega) << ",\"mis_rounds\":" << L.mis_rounds << ",\"setup_ms\":{\"relax\":" << jnum(L.t_relax)
+          << ",\"aggregate\":" << jnum(L.t_agg) << ",\"prolong\":" << jnum(L.t_prolong) << ",\"transpose\":" << jnum(L.t_transpose)
+          << ",\"AP\":" << jnum(L.t_ap) << ",\"RAP\":" << jnum(L.t_rap) << "}"
           << ",\"spmv_kernel\":" << jstr(L.A->kind == SPMV_STREAM ? "stream" : "vector" + std::to_string(L.A->lpr)) << "}";
     }
     o << "],\"operator_complexity\":" << jnum(tot / fine_nnz) << ",\"ncycle\":" << prm_.ncycle << ",\"degree\":" << prm_.degree

@@ -182,8 +182,9 @@ __device__ __forceinline__ void push_section(const PushList &pl, const CommDev &
 }
 
 // p_new = dinv r + beta p_old (Eigen CG direction update) with the halo push fused in:
-// CTAs [0, vec_blocks) update the local vector, CTAs [vec_blocks, grid) recompute the boundary entries
-// and store them into the neighbours' halo regions. p_new != p_old (ping-pong), so the two never race.
+// CTAs [0, push_blocks) recompute the boundary entries and store them into the neighbours' halo regions
+// (scheduled first, so the halo is on the wire while the bulk of the vector is still being updated);
+// CTAs [push_blocks, grid) update the local vector. p_new != p_old (ping-pong), so the two never race.
 template <bool FIRST, int THREADS>
 __global__ void __launch_bounds__(THREADS) cg_dir_dist_kernel(long long n2, double *__restrict__ p_new, const double *__restrict__ p_old,
                                                               const double *__restrict__ r, const double *__restrict__ dinv, KState *st,
@@ -192,10 +193,11 @@ __global__ void __launch_bounds__(THREADS) cg_dir_dist_kernel(long long n2, doub
     if (done && *done)
         return;
     const double beta = FIRST ? 0.0 : st->rz_new / st->rz;
-    if ((int)blockIdx.x < vec_blocks)
+    const int push_blocks = (int)gridDim.x - vec_blocks;
+    if ((int)blockIdx.x >= push_blocks)
     {
         const long long stride = (long long)vec_blocks * THREADS;
-        for (long long j = (long long)blockIdx.x * THREADS + threadIdx.x; j < n2; j += stride)
+        for (long long j = (long long)(blockIdx.x - push_blocks) * THREADS + threadIdx.x; j < n2; j += stride)
         {
             const double2 rv = ld2(r, j), dv = ld2(dinv, j);
             double2 o;
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(THREADS) cg_dir_dist_kernel(long long n2, doub
         }
     }
     else
-        push_section(pl, rc.comm, vec_blocks, [&](int row) { return FIRST ? dinv[row] * r[row] : dinv[row] * r[row] + beta * p_old[row]; });
+        push_section(pl, rc.comm, 0, [&](int row) { return FIRST ? dinv[row] * r[row] : dinv[row] * r[row] + beta * p_old[row]; });
     double acc[1] = {0}, tot[1];
     if (grid_reduce<0, THREADS>(acc, rc, tot) && threadIdx.x == 0 && !FIRST)
     {
@@ -346,19 +348,49 @@ void Solver::analyze_pattern_dist(long long n_, long long nnz_, const int *outer
         PSB_CUDA(cudaMemcpyAsync(d.push_peer.p, peer.data(), sizeof(int) * d.n_push, cudaMemcpyHostToDevice, st));
         PSB_CUDA(cudaMemcpyAsync(d.push_off.p, off.data(), sizeof(int) * d.n_push, cudaMemcpyHostToDevice, st));
     }
+    // values window of this rank inside the CSC value array (banded matrices: ~ the local share)
+    d.val_lo = 0;
+    d.val_hi = 0;
+    if (nnz)
+    {
+        int lo = P.perm[0], hi = P.perm[0];
+        for (int v : P.perm)
+        {
+            lo = std::min(lo, v);
+            hi = std::max(hi, v);
+        }
+        d.val_lo = lo;
+        d.val_hi = (long long)hi + 1;
+        std::vector<int> rel(P.perm.size());
+        for (size_t k = 0; k < rel.size(); ++k)
+            rel[k] = P.perm[k] - lo;
+        d.d_perm.alloc(nnz);
+        PSB_CUDA(cudaMemcpyAsync(d.d_perm.p, rel.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice, st));
+        PSB_CUDA(cudaStreamSynchronize(st)); // rel is a stack-scoped staging vector
+    }
     A.plan(prm.spmv_kernel);
     PSB_CUDA(cudaStreamSynchronize(st));
 }
 
+__global__ void gather_window_kernel(long long n, const double *__restrict__ src, const int *__restrict__ perm, double *__restrict__ dst)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n)
+        dst[k] = src[perm[k]];
+}
+
+// values only: one contiguous H2D copy of this rank's CSC window + a device gather (no host-side gather)
 void Solver::factorize_values_dist(const double *vals)
 {
     DistState &d = *dist;
-    const DistPlanHost &P = d.plan;
-    d.h_vals.resize(std::max<size_t>(1, P.perm.size()));
-    for (size_t k = 0; k < P.perm.size(); ++k)
-        d.h_vals[k] = vals[P.perm[k]];
     if (nnz)
-        PSB_CUDA(cudaMemcpyAsync(A.va.p, d.h_vals.data(), sizeof(double) * nnz, cudaMemcpyHostToDevice, ctx.stream));
+    {
+        const long long w = d.val_hi - d.val_lo;
+        d.d_csc_window.alloc((size_t)w);
+        PSB_CUDA(cudaMemcpyAsync(d.d_csc_window.p, vals + d.val_lo, sizeof(double) * w, cudaMemcpyHostToDevice, ctx.stream));
+        gather_window_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, ctx.stream>>>(nnz, d.d_csc_window.p, d.d_perm.p, A.va.p);
+        check_launch();
+    }
     PSB_CUDA(cudaStreamSynchronize(ctx.stream));
 }
 
@@ -393,7 +425,8 @@ void Solver::run_cg_eigen_dist(const double *d_b)
     const long long n2 = n_pad / 2;
     const int vec_blocks = vec_grid(n2);
     // every rank pushes at every push point (even an empty list) so the epochs advance in lockstep
-    const int push_blocks = d.world > 1 ? std::max(1, std::min(8, (d.n_push + kVecThreads - 1) / kVecThreads)) : 0;
+    // enough push CTAs that every thread stores at most ~2 entries (the chain rows -> value -> remote store is latency-bound)
+    const int push_blocks = d.world > 1 ? std::max(1, std::min(128, (d.n_push + 2 * kVecThreads - 1) / (2 * kVecThreads))) : 0;
     PushList pl = make_push(d, std::max(1, push_blocks));
     RedCtx rc = ctx.red();
     if (push_blocks)

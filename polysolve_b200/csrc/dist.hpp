@@ -39,7 +39,11 @@ struct DistState
     int n_push = 0;
     unsigned send_mask = 0, recv_mask = 0;
     DevBuf<double> vp2; // second direction buffer (p ping-pongs so pushed values never race with the update)
-    std::vector<double> h_vals;
+    // values ingest: the CSC window [val_lo, val_hi) that holds every local entry is uploaded as one
+    // contiguous copy and gathered on the device (d_perm[k] = perm[k] - val_lo)
+    long long val_lo = 0, val_hi = 0;
+    DevBuf<int> d_perm;
+    DevBuf<double> d_csc_window;
     ~DistState();
 };
 

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <thread>
 #include <cstring>
 #include <functional>
 #include <sstream>
@@ -24,7 +25,7 @@ double now_ms()
 }
 
 // 64-bit hash of the pattern arrays (4 independent lanes so it runs at memory speed on one core).
-unsigned long long hash_words(const void *data, size_t bytes, unsigned long long seed)
+unsigned long long hash_chunk(const void *data, size_t bytes, unsigned long long seed)
 {
     const unsigned long long *w = (const unsigned long long *)data;
     const size_t nw = bytes / 8;
@@ -44,6 +45,33 @@ unsigned long long hash_words(const void *data, size_t bytes, unsigned long long
         r = (r ^ *tail++) * 0x100000001B3ull;
     r ^= r >> 29;
     return r * 0xBF58476D1CE4E5B9ull;
+}
+
+// Fixed 8 MiB chunks hashed by up to 8 host threads and combined in chunk order, so the result does not
+// depend on the thread count. Newton calls analyze_pattern + factorize every iteration (Newton.cpp:189-191):
+// the unchanged-pattern check must cost a few ms, not a pass of one core over 300 MB.
+unsigned long long hash_words(const void *data, size_t bytes, unsigned long long seed)
+{
+    constexpr size_t kChunk = 8u << 20;
+    const size_t nchunks = (bytes + kChunk - 1) / kChunk;
+    if (nchunks <= 1)
+        return hash_chunk(data, bytes, seed);
+    std::vector<unsigned long long> part(nchunks);
+    const unsigned nthreads = (unsigned)std::min<size_t>(nchunks, std::max(1u, std::min(8u, std::thread::hardware_concurrency())));
+    auto work = [&](unsigned t) {
+        for (size_t c = t; c < nchunks; c += nthreads)
+        {
+            const size_t off = c * kChunk;
+            part[c] = hash_chunk((const unsigned char *)data + off, std::min(kChunk, bytes - off), seed + 0x9E3779B97F4A7C15ull * (c + 1));
+        }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nthreads; ++t)
+        th.emplace_back(work, t);
+    work(0);
+    for (auto &t : th)
+        t.join();
+    return hash_chunk(part.data(), part.size() * 8, seed);
 }
 
 // ------------------------------------------------------------------ ingest kernels (analyze_pattern)
