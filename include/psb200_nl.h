@@ -1,0 +1,75 @@
+/* psb200_nl -- C ABI of the Newton / line-search driver that calls the psb200 linear solver the way
+ * polysolve::nonlinear::Solver does.
+ *
+ * It mirrors, call for call, the reference's nonlinear path that ends in the hot path:
+ *   nonlinear::Solver::create(solver_params, linear_solver_params, ...)   src/polysolve/nonlinear/Solver.cpp:124-186
+ *   nonlinear::Solver::minimize(Problem&, TVector&)                       src/polysolve/nonlinear/Solver.cpp:255-582
+ *   Newton / ProjectedNewton / RegularizedNewton (+ GradientDescent)      src/polysolve/nonlinear/descent_strategies/Newton.cpp:14-58,144-214,275-330
+ *   LineSearch::line_search + Backtracking / Armijo                       src/polysolve/nonlinear/line_search/LineSearch.cpp:73-254, Backtracking.cpp:15-83, Armijo.cpp:13-32
+ *   checkConvergence                                                      src/polysolve/nonlinear/Criteria.cpp:59-96
+ * A polysolve::nonlinear::Problem subclass (src/polysolve/nonlinear/Problem.hpp:22-143) becomes a
+ * table of callbacks. In a polysolve build nothing of this is needed -- nonlinear::Solver keeps calling
+ * linear::Solver::create("CUDA") -- it exists so that the Newton call site (config 5 of BASELINE.json)
+ * can be exercised and parity-tested in this repository, where polysolve itself cannot be built.
+ */
+#ifndef PSB200_NL_H
+#define PSB200_NL_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct psb200_nl_solver *psb200_nl_handle;
+
+/* polysolve::nonlinear::Problem as callbacks. value, gradient and hessian are required, the rest may be NULL
+ * (the defaults of Problem.hpp apply: steps are valid, max step size 1, no-ops). Vectors have length n. */
+typedef struct psb200_nl_problem
+{
+    void *user;
+    /* Problem::value(x) -- Problem.hpp:49 */
+    double (*value)(void *user, const double *x, int64_t n);
+    /* Problem::gradient(x, grad) -- Problem.hpp:54 */
+    void (*gradient)(void *user, const double *x, int64_t n, double *grad_out);
+    /* Problem::hessian(x, StiffnessMatrix&) -- Problem.hpp:67. The callee returns Eigen-style compressed-column
+     * arrays that stay valid until its next call. project_to_psd mirrors Problem::set_project_to_psd
+     * (Problem.hpp:97). Non-zero return = assembly failure (treated like a failed factorization). */
+    int (*hessian)(void *user, const double *x, int64_t n, int project_to_psd, int64_t *nnz, const int32_t **outer,
+                   const int32_t **inner, const double **vals);
+    /* Problem::solution_changed -- Problem.hpp:101 */
+    void (*solution_changed)(void *user, const double *x, int64_t n);
+    /* Problem::is_step_valid -- Problem.hpp:73 */
+    int (*is_step_valid)(void *user, const double *x0, const double *x1, int64_t n);
+    /* Problem::max_step_size -- Problem.hpp:79 */
+    double (*max_step_size)(void *user, const double *x0, const double *x1, int64_t n);
+    /* Problem::line_search_begin / line_search_end -- Problem.hpp:86-89 */
+    void (*line_search_begin)(void *user, const double *x0, const double *x1, int64_t n);
+    void (*line_search_end)(void *user);
+    /* Problem::post_step(PostStepData) -- Problem.hpp:93 */
+    void (*post_step)(void *user, int iteration, const double *x, const double *grad, int64_t n);
+    /* Problem::stop(x) -- Problem.hpp:114; non-zero stops with status "ObjectiveCustomStop" */
+    int (*stop)(void *user, const double *x, int64_t n);
+} psb200_nl_problem;
+
+/* nonlinear::Solver::create. solver_params: the reference's nonlinear JSON (keys and defaults of
+ * nonlinear-solver-spec.json: "solver": "Newton", "line_search": {"method": "Backtracking"|"Armijo"|"None", ...},
+ * "grad_norm_tol", "max_iterations", "Newton": {"residual_tolerance", "reg_weight_min", ...}, ...).
+ * linear_params: the linear-solver JSON handed to every strategy's linear::Solver ({"solver": "CUDA", "CUDA": {...}}).
+ * Either may be NULL for the defaults. */
+int psb200_nl_create(psb200_nl_handle *out, const char *solver_params_json, const char *linear_params_json);
+int psb200_nl_destroy(psb200_nl_handle h);
+/* nonlinear::Solver::minimize(problem, x): x is in/out. Returns 0 when the loop ended with a converged status;
+ * non-zero (message in psb200_nl_last_error) where the reference throws (NaN, iteration limit without
+ * allow_out_of_iterations, failure on the last strategy). x always holds the last iterate. */
+int psb200_nl_minimize(psb200_nl_handle h, const psb200_nl_problem *problem, double *x_inout, int64_t n);
+/* solver_info of the reference (Solver.cpp:615-637, Newton.cpp:333-340): "status", "iterations", "energy",
+ * "grad_norm", "line_search", "internal_solver": [get_info of every linear solve], timings. */
+int psb200_nl_get_info(psb200_nl_handle h, char *json_out, size_t cap, size_t *needed);
+const char *psb200_nl_last_error(psb200_nl_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSB200_NL_H */

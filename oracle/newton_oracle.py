@@ -1,0 +1,244 @@
+"""TEST INFRASTRUCTURE ONLY. PARITY UNPINNED (see oracle_core.hpp header).
+
+Python restatement of the reference's Newton + line-search control flow, used to check the C++ driver
+(polysolve_b200/csrc/newton.cpp) step for step on small problems:
+  nonlinear::Solver::minimize          reference src/polysolve/nonlinear/Solver.cpp:255-582
+  Newton chain + residual check        descent_strategies/Newton.cpp:14-58,144-214,275-291,326-330
+  LineSearch / Backtracking / Armijo   line_search/LineSearch.cpp:73-254, Backtracking.cpp:15-83, Armijo.cpp:13-32
+  checkConvergence                     Criteria.cpp:59-96
+The linear solve is pluggable (`linsolve(H_csc, rhs, x0) -> x`): the tests pass the oracle's Eigen-faithful
+Jacobi-PCG or a scipy direct solve."""
+import math
+
+import numpy as np
+import scipy.sparse as sp
+
+NaN = float("nan")
+
+
+def check_convergence(stop, cur):
+    if stop["iterations"] > 0 and cur["iterations"] > stop["iterations"]:
+        return "IterationLimit"
+    sg = stop["firstGradNorm"] if cur["iterations"] == 0 else stop["gradNorm"]
+    if sg > 0 and cur["gradNorm"] < sg:
+        return "GradNormTolerance"
+    if stop["relXDelta"] > 0 and cur["relXDelta"] < stop["relXDelta"]:
+        return "RelXDeltaTolerance"
+    if stop["relGradNorm"] > 0 and cur["relGradNorm"] < stop["relGradNorm"]:
+        return "RelGradNormTolerance"
+    if stop["xDelta"] > 0 and cur["xDelta"] < stop["xDelta"]:
+        return "XDeltaTolerance"
+    if stop["fDelta"] > 0 and cur["fDelta"] < stop["fDelta"] and cur["fDeltaCount"] >= stop["fDeltaCount"]:
+        return "FDeltaTolerance"
+    if stop["xDeltaDotGrad"] < 0 and cur["xDeltaDotGrad"] > stop["xDeltaDotGrad"]:
+        return "NotDescentDirection"
+    return "Continue"
+
+
+class LineSearch:
+    def __init__(self, p):
+        ls = p.get("line_search", {})
+        self.method = ls.get("method", "RobustArmijo")
+        if self.method == "RobustArmijo":
+            self.method = "Armijo"
+        self.min_step = ls.get("min_step_size", 1e-10)
+        self.max_iter = ls.get("max_step_size_iter", 30)
+        self.min_step_final = ls.get("min_step_size_final", 1e-20)
+        self.max_iter_final = ls.get("max_step_size_iter_final", 100)
+        self.init = ls.get("default_init_step_size", 1.0)
+        self.ratio = ls.get("step_ratio", 0.5)
+        self.use_grad_norm_tol = ls.get("use_grad_norm_tol", 1e-6)
+        self.c = ls.get("Armijo", {}).get("c", 1e-4)
+        self.final = False
+        self.total = 0
+
+    def lim(self):
+        return (self.min_step_final, self.max_iter_final) if self.final else (self.min_step, self.max_iter)
+
+    def line_search(self, x, dx, f):
+        it = 0
+        e0 = f.value(x)
+        if math.isnan(e0):
+            return NaN
+        g0 = np.asarray(f.gradient(x), float)
+        if not np.all(np.isfinite(g0)):
+            return NaN
+        step = self.init
+        mn, mx = self.lim()
+        while step > mn and it < mx:
+            nx = x + step * dx
+            if (not f.is_step_valid(x, nx)) or (not math.isfinite(f.value(nx))):
+                step *= self.ratio
+            else:
+                break
+            it += 1
+        if it >= mx or step <= mn:
+            return NaN
+        f.line_search_begin(x, x + step * dx)
+        ms = f.max_step_size(x, x + step * dx)
+        if ms == 0:
+            f.line_search_end()
+            return NaN
+        step = step * ms  # the reference rounds this product downward (LineSearch.cpp:243-248); exact for ms == 1
+        gn = float(np.linalg.norm(g0))
+        if gn < 1e-30:
+            self.total += it
+            return step
+        if self.method == "None":
+            f.line_search_end()
+            return step
+        use_gn = gn < self.use_grad_norm_tol
+        arm = self.c * float(dx @ g0)
+        while step > mn and it < mx:
+            nx = x + step * dx
+            f.solution_changed(nx)
+            ok = False
+            if f.is_step_valid(x, nx):
+                e = f.value(nx)
+                if math.isfinite(e):
+                    if self.method == "Armijo":
+                        ok = e <= e0 + step * arm
+                    elif use_gn:
+                        ok = np.linalg.norm(f.gradient(nx)) < gn
+                    else:
+                        ok = e < e0
+            if ok:
+                break
+            step *= self.ratio
+            it += 1
+        self.total += it
+        if it >= mx or step <= mn:
+            f.solution_changed(x)
+            f.line_search_end()
+            return NaN
+        f.line_search_end()
+        return step
+
+
+def minimize(problem, x, params, linsolve):
+    """Returns (x, info). Raises RuntimeError where the reference throws."""
+    adv = params.get("advanced", {})
+    stop = dict(xDelta=params.get("x_delta_tol", 0), fDelta=adv.get("f_delta_tol", 0), gradNorm=params.get("grad_norm_tol", 1e-10),
+                firstGradNorm=params.get("first_grad_norm_tol", 1e-12), xDeltaDotGrad=-adv.get("derivative_along_delta_x_tol", 0),
+                relGradNorm=params.get("rel_grad_norm_tol", 1e-10), relXDelta=params.get("rel_x_delta_tol", 0),
+                iterations=params.get("max_iterations", 500), fDeltaCount=adv.get("f_delta_step_tol", 100))
+    nw = params.get("Newton", {})
+    res_tol = nw.get("residual_tolerance", 1e-5)
+    wmin, wmax, winc = nw.get("reg_weight_min", 1e-8), nw.get("reg_weight_max", 1e8), nw.get("reg_weight_inc", 10)
+    strategies = []
+    if not nw.get("force_psd_projection", False):
+        strategies.append(["Newton", False, 0.0])
+    if nw.get("use_psd_projection", True):
+        strategies.append(["ProjectedNewton", True, 0.0])
+    if wmin > 0:
+        strategies.append(["RegularizedNewton", nw.get("use_psd_projection_in_regularized", True), wmin])
+    strategies.append(["GradientDescent", False, 0.0])
+    per = params.get("iterations_per_strategy", 5)
+    ls = LineSearch(params)
+    x = np.array(x, float)
+    n = x.size
+    cur = dict(iterations=0, xDelta=0.0, fDelta=0.0, gradNorm=0.0, xDeltaDotGrad=0.0, relGradNorm=0.0, relXDelta=0.0, fDeltaCount=0)
+    strategy = prev = 0
+    cur_iter = 0
+    dx = np.zeros(n)
+    old_energy = NaN
+    status = "NotStarted"
+    lin_iters = []
+    problem.solution_changed(x)
+    g0n = dx0n = NaN
+
+    def handle_error(s):
+        if s[0] != "RegularizedNewton":
+            return False
+        s[2] *= winc
+        return s[2] < wmax
+
+    def reset():
+        for s in strategies:
+            if s[0] == "RegularizedNewton":
+                s[2] = wmin
+
+    while True:
+        ls.final = strategy == len(strategies) - 1
+        energy = problem.value(x)
+        if not math.isfinite(energy):
+            raise RuntimeError("f(x) is nan or inf; stopping")
+        cur["fDelta"] = abs(old_energy - energy)
+        grad = np.asarray(problem.gradient(x), float)
+        cur["gradNorm"] = float(np.linalg.norm(grad))
+        if cur["iterations"] == 0:
+            g0n = cur["gradNorm"]
+            cur["relGradNorm"] = NaN
+        else:
+            cur["relGradNorm"] = cur["gradNorm"] / g0n
+        cur["xDelta"] = cur["xDeltaDotGrad"] = cur["relXDelta"] = NaN
+        status = check_convergence(stop, cur)
+        if status != "Continue":
+            break
+        s = strategies[strategy]
+        ok = True
+        if s[0] == "GradientDescent":
+            dx = -grad
+        else:
+            H = sp.csc_matrix(problem.hessian(x, s[1]))
+            if s[0] == "RegularizedNewton" and s[2] > 0:
+                H = (H + s[2] * sp.identity(n, format="csc")).tocsc()
+            try:
+                dx, it = linsolve(H, -grad, dx.copy())
+                lin_iters.append(it)
+                r = float(np.linalg.norm(H @ dx + grad))
+                ok = not (math.isnan(r) or r > res_tol)
+            except ArithmeticError:
+                ok = False
+        cur["xDelta"] = float(np.linalg.norm(dx))
+        if cur["iterations"] == 0:
+            dx0n = cur["xDelta"]
+            cur["relXDelta"] = NaN
+        else:
+            cur["relXDelta"] = cur["xDelta"] / dx0n
+        if (not ok) or math.isnan(cur["xDelta"]):
+            if not handle_error(s):
+                strategy += 1
+            if strategy >= len(strategies):
+                raise RuntimeError("Update direction could not be computed on last strategy; stopping")
+            continue
+        cur["xDeltaDotGrad"] = float(dx @ grad)
+        if cur["gradNorm"] != 0 and cur["xDeltaDotGrad"] >= 0:
+            if not handle_error(s):
+                strategy += 1
+            if strategy >= len(strategies):
+                raise RuntimeError("Search direction not a descent direction on last strategy; stopping")
+            continue
+        status = check_convergence(stop, cur)
+        if status != "Continue":
+            break
+        rate = ls.line_search(x, dx, problem)
+        if math.isnan(rate):
+            if not handle_error(s):
+                strategy += 1
+            if strategy >= len(strategies):
+                raise RuntimeError("Line search failed on last strategy; stopping")
+            continue
+        x = x + rate * dx
+        old_energy = energy
+        if strategy != prev:
+            cur_iter = 0
+        if strategy != 0 and cur_iter >= per:
+            strategy = 0
+            reset()
+        prev = strategy
+        cur_iter += 1
+        problem.post_step(cur["iterations"], x, grad)
+        if problem.stop(x):
+            status = "ObjectiveCustomStop"
+        cur["fDeltaCount"] = cur["fDeltaCount"] + 1 if cur["fDelta"] < stop["fDelta"] else 0
+        cur["iterations"] += 1
+        if cur["iterations"] >= stop["iterations"]:
+            status = "IterationLimit"
+        if status != "Continue":
+            break
+    if status == "IterationLimit" and not params.get("allow_out_of_iterations", False):
+        raise RuntimeError("Reached iteration limit")
+    return x, dict(status=status, iterations=cur["iterations"], energy=problem.value(x), grad_norm=cur["gradNorm"],
+                   linear_iterations=lin_iters, final_strategy=strategies[min(strategy, len(strategies) - 1)][0],
+                   line_search_iterations=ls.total)

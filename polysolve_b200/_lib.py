@@ -24,6 +24,8 @@ SYMBOLS = [
     "psb200_dist_plan_host", "psb200_debug_get_csr",
     "psb200_spmv", "psb200_bench_spmv", "psb200_get_stream", "psb200_debug_set_aggregates", "psb200_debug_get_level",
     "psb200_precond_apply", "psb200_debug_get_aggregates",
+    # include/psb200_nl.h
+    "psb200_nl_create", "psb200_nl_destroy", "psb200_nl_minimize", "psb200_nl_get_info", "psb200_nl_last_error",
 ]
 
 

@@ -1,0 +1,192 @@
+"""Host-side mirror of polysolve::nonlinear::Solver (Newton + line search) for the "CUDA" linear backend.
+
+Same names and argument meaning as the reference (reference src/polysolve/nonlinear/Solver.hpp:37-66,
+Problem.hpp:22-143); every call forwards to the C ABI of include/psb200_nl.h, whose driver
+(polysolve_b200/csrc/newton.cpp) issues analyze_pattern -> factorize -> solve -> get_info on the
+GPU linear solver exactly as Newton.cpp:189-211 does."""
+import ctypes as C
+import json
+
+import numpy as np
+
+from . import _lib
+
+
+class Problem:
+    """polysolve::nonlinear::Problem (reference Problem.hpp:22-143). Subclasses implement value, gradient and
+    hessian (scipy.sparse CSC, the layout of StiffnessMatrix); the other hooks default as in the reference."""
+
+    def value(self, x):
+        raise NotImplementedError
+
+    def gradient(self, x):
+        raise NotImplementedError
+
+    def hessian(self, x, project_to_psd=False):
+        raise NotImplementedError
+
+    def solution_changed(self, x):
+        pass
+
+    def is_step_valid(self, x0, x1):
+        return True
+
+    def max_step_size(self, x0, x1):
+        return 1.0
+
+    def line_search_begin(self, x0, x1):
+        pass
+
+    def line_search_end(self):
+        pass
+
+    def post_step(self, iteration, x, grad):
+        pass
+
+    def stop(self, x):
+        return False
+
+
+_f64p = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_VALUE = C.CFUNCTYPE(C.c_double, C.c_void_p, _f64p, C.c_int64)
+_GRAD = C.CFUNCTYPE(None, C.c_void_p, _f64p, C.c_int64, _f64p)
+_HESS = C.CFUNCTYPE(C.c_int, C.c_void_p, _f64p, C.c_int64, C.c_int, C.POINTER(C.c_int64), C.POINTER(_i32p), C.POINTER(_i32p),
+                    C.POINTER(_f64p))
+_VOIDX = C.CFUNCTYPE(None, C.c_void_p, _f64p, C.c_int64)
+_STEPV = C.CFUNCTYPE(C.c_int, C.c_void_p, _f64p, _f64p, C.c_int64)
+_MAXST = C.CFUNCTYPE(C.c_double, C.c_void_p, _f64p, _f64p, C.c_int64)
+_LSBEG = C.CFUNCTYPE(None, C.c_void_p, _f64p, _f64p, C.c_int64)
+_LSEND = C.CFUNCTYPE(None, C.c_void_p)
+_POST = C.CFUNCTYPE(None, C.c_void_p, C.c_int, _f64p, _f64p, C.c_int64)
+_STOP = C.CFUNCTYPE(C.c_int, C.c_void_p, _f64p, C.c_int64)
+
+
+class _CProblem(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("value", _VALUE), ("gradient", _GRAD), ("hessian", _HESS),
+                ("solution_changed", _VOIDX), ("is_step_valid", _STEPV), ("max_step_size", _MAXST),
+                ("line_search_begin", _LSBEG), ("line_search_end", _LSEND), ("post_step", _POST), ("stop", _STOP)]
+
+
+def _vec(p, n):
+    return np.ctypeslib.as_array(p, shape=(n,))
+
+
+class NonlinearSolver:
+    """polysolve::nonlinear::Solver. create(solver_params, linear_solver_params) mirrors Solver.cpp:124-186."""
+
+    @staticmethod
+    def create(solver_params=None, linear_solver_params=None):
+        return NonlinearSolver(solver_params or {}, linear_solver_params or {"solver": "CUDA"})
+
+    def __init__(self, solver_params, linear_solver_params):
+        self._L = _lib.lib()
+        L = self._L
+        L.psb200_nl_create.argtypes = [C.POINTER(C.c_void_p), C.c_char_p, C.c_char_p]
+        L.psb200_nl_destroy.argtypes = [C.c_void_p]
+        L.psb200_nl_minimize.argtypes = [C.c_void_p, C.POINTER(_CProblem), np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS"), C.c_int64]
+        L.psb200_nl_get_info.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.psb200_nl_last_error.argtypes = [C.c_void_p]
+        L.psb200_nl_last_error.restype = C.c_char_p
+        self._h = C.c_void_p()
+        rc = L.psb200_nl_create(C.byref(self._h), json.dumps(solver_params).encode(), json.dumps(linear_solver_params).encode())
+        if rc:
+            raise RuntimeError(L.psb200_nl_last_error(None).decode())
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.psb200_nl_destroy(h)
+            self._h = None
+
+    def minimize(self, problem, x):
+        """x is in/out (float64, contiguous). Raises RuntimeError where the reference throws."""
+        if not (isinstance(x, np.ndarray) and x.dtype == np.float64 and x.flags.c_contiguous):
+            raise TypeError("x must be a contiguous float64 numpy array (it is updated in place)")
+        n = x.shape[0]
+        keep = {}
+        errors = []
+
+        def guard(default):
+            def deco(fn):
+                def wrapped(*a):
+                    try:
+                        return fn(*a)
+                    except Exception as e:  # noqa: BLE001 -- exceptions must not cross the C frame
+                        errors.append(e)
+                        return default
+                return wrapped
+            return deco
+
+        @guard(float("nan"))
+        def value(_, xp, nn):
+            return float(problem.value(_vec(xp, nn)))
+
+        @guard(None)
+        def gradient(_, xp, nn, gp):
+            _vec(gp, nn)[:] = problem.gradient(_vec(xp, nn))
+
+        @guard(1)
+        def hessian(_, xp, nn, psd, nnz, outer, inner, vals):
+            import scipy.sparse as sp
+            H = problem.hessian(_vec(xp, nn), bool(psd))
+            if not sp.isspmatrix_csc(H):
+                H = sp.csc_matrix(H)
+            H.sort_indices()
+            o = np.ascontiguousarray(H.indptr, np.int32)
+            i = np.ascontiguousarray(H.indices, np.int32)
+            v = np.ascontiguousarray(H.data, np.float64)
+            keep["h"] = (o, i, v)  # valid until the next hessian() call
+            nnz[0] = int(o[-1])
+            outer[0] = o.ctypes.data_as(_i32p)
+            inner[0] = i.ctypes.data_as(_i32p)
+            vals[0] = v.ctypes.data_as(_f64p)
+            return 0
+
+        @guard(None)
+        def solution_changed(_, xp, nn):
+            problem.solution_changed(_vec(xp, nn))
+
+        @guard(0)
+        def is_step_valid(_, x0, x1, nn):
+            return 1 if problem.is_step_valid(_vec(x0, nn), _vec(x1, nn)) else 0
+
+        @guard(0.0)
+        def max_step_size(_, x0, x1, nn):
+            return float(problem.max_step_size(_vec(x0, nn), _vec(x1, nn)))
+
+        @guard(None)
+        def ls_begin(_, x0, x1, nn):
+            problem.line_search_begin(_vec(x0, nn), _vec(x1, nn))
+
+        @guard(None)
+        def ls_end(_):
+            problem.line_search_end()
+
+        @guard(None)
+        def post_step(_, it, xp, gp, nn):
+            problem.post_step(it, _vec(xp, nn), _vec(gp, nn))
+
+        @guard(1)
+        def stop(_, xp, nn):
+            return 1 if problem.stop(_vec(xp, nn)) else 0
+
+        cp = _CProblem(None, _VALUE(value), _GRAD(gradient), _HESS(hessian), _VOIDX(solution_changed), _STEPV(is_step_valid),
+                       _MAXST(max_step_size), _LSBEG(ls_begin), _LSEND(ls_end), _POST(post_step), _STOP(stop))
+        rc = self._L.psb200_nl_minimize(self._h, C.byref(cp), x, n)
+        if errors:
+            raise errors[0]
+        if rc:
+            raise RuntimeError(self._L.psb200_nl_last_error(self._h).decode())
+        return x
+
+    def get_info(self):
+        need = C.c_size_t()
+        buf = C.create_string_buffer(1 << 16)
+        rc = self._L.psb200_nl_get_info(self._h, buf, len(buf), C.byref(need))
+        if rc and need.value > len(buf):
+            buf = C.create_string_buffer(need.value)
+            rc = self._L.psb200_nl_get_info(self._h, buf, len(buf), C.byref(need))
+        if rc:
+            raise RuntimeError("psb200_nl_get_info failed")
+        return json.loads(buf.value.decode())

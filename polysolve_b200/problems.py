@@ -76,3 +76,103 @@ def spmv_bytes(n, nnz):
 def pcg_iter_bytes(n, nnz):
     """Compulsory traffic of one fused Jacobi-PCG iteration: B_spmv + 88 N."""
     return spmv_bytes(n, nnz) + 88 * n
+
+
+class QuarticSpringGrid3D:
+    """A polysolve::nonlinear::Problem on the C2 grid: nodes of an n^3 Dirichlet grid joined by nonlinear springs,
+        E(u) = sum_edges phi(u_i - u_j) - f.u,   phi(d) = d^2/2 + kappa d^4/4   (edges to the boundary use u = 0).
+    Convex, so the Hessian is SPD with the 7-point pattern of poisson3d(n) and values that change every Newton step --
+    the analyze-once / factorize-many protocol of Newton.cpp:189-204 at any size (n = 100 -> 1,000,000 DoF).
+    Duck-types polysolve_b200.nonlinear.Problem."""
+
+    def __init__(self, n, kappa=10.0, seed=3):
+        self.n, self.kappa = n, float(kappa)
+        self.N = n ** 3
+        self.outer, self.inner, _ = poisson3d(n)
+        idx = np.arange(self.N, dtype=np.int64)
+        strides = [1, n, n * n]
+        coords = [(idx // s) % n for s in strides]
+        # same column order as _stencil: -s2, -s1, -s0, 0, +s0, +s1, +s2
+        self.dirs = [(-s, c > 0) for s, c in reversed(list(zip(strides, coords)))] + [(0, None)] + \
+                    [(s, c < n - 1) for s, c in zip(strides, coords)]
+        counts = np.zeros(self.N, np.int64)
+        for off, m in self.dirs:
+            counts += 1 if m is None else m
+        pos = np.zeros(self.N + 1, np.int64)
+        np.cumsum(counts, out=pos[1:])
+        assert int(pos[-1]) == int(self.outer[-1])
+        cur = pos[:-1].copy()
+        self.slots = []
+        for off, m in self.dirs:
+            mm = np.ones(self.N, bool) if m is None else m
+            self.slots.append(cur[mm].copy())
+            cur[mm] += 1
+        self.f = 0.5 + 0.5 * splitmix64(seed, self.N)
+
+    def _diffs(self, x):
+        """d[k][i] = u_i - u_neighbour for the 6 directions (neighbour value 0 outside the grid)."""
+        out = []
+        for off, m in self.dirs:
+            if off == 0:
+                continue
+            nb = np.zeros(self.N)
+            nb[m] = x[np.nonzero(m)[0] + off]
+            out.append(x - nb)
+        return out
+
+    def value(self, x):
+        e = 0.0
+        for (off, m), d in zip([d for d in self.dirs if d[0] != 0], self._diffs(x)):
+            w = np.where(m, 0.5, 1.0)  # interior edges are seen from both ends
+            e += float(np.sum(w * (0.5 * d * d + 0.25 * self.kappa * d ** 4)))
+        return e - float(self.f @ x)
+
+    def gradient(self, x):
+        g = -self.f.copy()
+        for d in self._diffs(x):
+            g += d + self.kappa * d ** 3
+        return g
+
+    def hessian(self, x, project_to_psd=False):
+        import scipy.sparse as sp
+        vals = np.zeros(int(self.outer[-1]))
+        diag = np.zeros(self.N)
+        k = 0
+        for (off, m), slot in zip(self.dirs, self.slots):
+            if off == 0:
+                diag_slot = slot
+                continue
+            d = self._diffs_one(x, off, m)
+            h = 1.0 + 3.0 * self.kappa * d * d
+            diag += h
+            vals[slot] = -h[m]
+            k += 1
+        vals[diag_slot] = diag
+        return sp.csc_matrix((vals, self.inner, self.outer), shape=(self.N, self.N))
+
+    def _diffs_one(self, x, off, m):
+        nb = np.zeros(self.N)
+        nb[m] = x[np.nonzero(m)[0] + off]
+        return x - nb
+
+    # hooks of Problem.hpp with their default behaviour
+    def solution_changed(self, x):
+        pass
+
+    def is_step_valid(self, x0, x1):
+        return True
+
+    def max_step_size(self, x0, x1):
+        return 1.0
+
+    def line_search_begin(self, x0, x1):
+        pass
+
+    def line_search_end(self):
+        pass
+
+    def post_step(self, iteration, x, grad):
+        pass
+
+    def stop(self, x):
+        return False

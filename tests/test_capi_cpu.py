@@ -22,7 +22,7 @@ def _has_gpu():
 
 def test_library_exports_every_declared_symbol(psb):
     L = psb._lib.lib()
-    header = open(os.path.join(ROOT, "include", "psb200.h")).read()
+    header = "".join(open(os.path.join(ROOT, "include", h)).read() for h in sorted(os.listdir(os.path.join(ROOT, "include"))) if h.endswith(".h"))
     declared = sorted(set(re.findall(r"\b(psb200_[a-z0-9_]+)\s*\(", header)))
     assert declared, "no declarations parsed"
     assert sorted(psb._lib.SYMBOLS) == declared
