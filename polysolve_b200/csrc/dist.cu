@@ -13,6 +13,9 @@
 #include "dist.hpp"
 #include "capi_internal.hpp"
 #include "solver.hpp"
+#include "amg.hpp"
+
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cstring>
@@ -301,8 +304,8 @@ void Solver::analyze_pattern_dist(long long n_, long long nnz_, const int *outer
     DistState &d = *dist;
     if (!d.connected && d.world > 1)
         throw std::runtime_error("psb200 dist: psb200_dist_connect has not been called");
-    if (prm.precond == "amg" || prm.krylov != "cg")
-        throw std::runtime_error("psb200 dist: the row-partitioned path provides Jacobi-PCG (krylov=cg, precond=jacobi|none) in this version");
+    if (prm.krylov != "cg")
+        throw std::runtime_error("psb200 dist: the row-partitioned path provides PCG (krylov=cg) with precond = jacobi | none | amg");
     d.plan.build(n_, nnz_, outer, inner, d.rank, d.world, d.halo_cap);
     const DistPlanHost &P = d.plan;
     cudaStream_t st = ctx.stream;
@@ -410,6 +413,153 @@ void Solver::check_comm_error()
 static PushList make_push(DistState &d, int push_blocks)
 {
     return PushList{d.push_rows.p, d.push_peer.p, d.push_off.p, d.n_push, d.push_counter.p, d.send_mask, push_blocks};
+}
+
+// ---------------------------------------------------------------------------------- rank-local AMG
+__global__ void diag_count_kernel(int n, int nl, const int *__restrict__ rp, const int *__restrict__ ci, int *__restrict__ cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n)
+        return;
+    int c = 0;
+    if (i < n)
+        for (int k = rp[i]; k < rp[i + 1]; ++k)
+            c += ci[k] < nl;
+    cnt[i] = c;
+}
+__global__ void diag_fill_kernel(int n, int nl, const int *__restrict__ rp, const int *__restrict__ ci, const int *__restrict__ drp,
+                                 int *__restrict__ dci, int *__restrict__ src)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    int o = drp[i];
+    for (int k = rp[i]; k < rp[i + 1]; ++k)
+        if (ci[k] < nl)
+        {
+            dci[o] = ci[k];
+            src[o] = k;
+            ++o;
+        }
+}
+__global__ void diag_vals_kernel(long long nnz, const double *__restrict__ va, const int *__restrict__ src, double *__restrict__ out)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < nnz)
+        out[k] = va[src[k]];
+}
+
+// A_diag = A[local rows, local columns]: pattern once per analysis, values on every factorize
+void Solver::build_diag_block_dist()
+{
+    DistState &d = *dist;
+    cudaStream_t st = ctx.stream;
+    CsrDev &D = d.A_diag;
+    if (D.n != (int)n || D.rp.p == nullptr || d.diag_src.n == 0)
+    {
+        DevBuf<int> cnt;
+        cnt.alloc((size_t)n + 1, true);
+        D.n = (int)n;
+        D.ncols = (int)n;
+        D.rp.alloc((size_t)n + 1);
+        const unsigned blocks = (unsigned)((n + 256) / 256);
+        diag_count_kernel<<<blocks, 256, 0, st>>>((int)n, (int)n, A.rp.p, A.ci.p, cnt.p);
+        size_t bytes = 0;
+        PSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt.p, D.rp.p, (int)n + 1, st));
+        DevBuf<unsigned char> tmp;
+        tmp.alloc(bytes);
+        PSB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, cnt.p, D.rp.p, (int)n + 1, st));
+        int dn = 0;
+        PSB_CUDA(cudaMemcpyAsync(&dn, D.rp.p + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PSB_CUDA(cudaStreamSynchronize(st));
+        D.nnz = dn;
+        D.ci.alloc(std::max(1, dn), false, 64);
+        D.va.alloc(std::max(1, dn), false, 64);
+        d.diag_src.alloc(std::max(1, dn));
+        diag_fill_kernel<<<blocks, 256, 0, st>>>((int)n, (int)n, A.rp.p, A.ci.p, D.rp.p, D.ci.p, d.diag_src.p);
+        check_launch();
+        D.plan("auto");
+    }
+    if (D.nnz)
+        diag_vals_kernel<<<(unsigned)((D.nnz + 255) / 256), 256, 0, st>>>(D.nnz, A.va.p, d.diag_src.p, D.va.p);
+    check_launch();
+    PSB_CUDA(cudaStreamSynchronize(st));
+}
+
+// p_new = s + beta p_old (amgcl cg direction update) with the halo push fused in (same layout as
+// cg_dir_dist_kernel: push CTAs first).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) cg_dir_amgcl_dist_kernel(long long n2, double *__restrict__ p_new, const double *__restrict__ p_old,
+                                                                    const double *__restrict__ s, const KState *st, RedCtx rc, PushList pl,
+                                                                    int vec_blocks, const int *done)
+{
+    if (done && *done)
+        return;
+    const double beta = st->iter ? st->rho / st->rho_old : 0.0;
+    const int push_blocks = (int)gridDim.x - vec_blocks;
+    if ((int)blockIdx.x >= push_blocks)
+    {
+        const long long stride = (long long)vec_blocks * THREADS;
+        for (long long j = (long long)(blockIdx.x - push_blocks) * THREADS + threadIdx.x; j < n2; j += stride)
+        {
+            const double2 sv = ld2(s, j), pv = ld2(p_old, j);
+            double2 o;
+            o.x = sv.x + (beta != 0.0 ? beta * pv.x : 0.0);
+            o.y = sv.y + (beta != 0.0 ? beta * pv.y : 0.0);
+            st2(p_new, j, o);
+        }
+    }
+    else
+        push_section(pl, rc.comm, 0, [&](int row) { return s[row] + (beta != 0.0 ? beta * p_old[row] : 0.0); });
+}
+
+// AMG-PCG on the row partition (amgcl cg ordering). The preconditioner is rank-local: every rank
+// applies the SA-AMG cycle of its own diagonal block (block-Jacobi across ranks, no communication inside the
+// cycle); the outer CG is the global one -- halo push of p, three fused all-reduces per iteration.
+void Solver::run_cg_amgcl_dist(const double *d_b)
+{
+    if (!amg)
+        throw std::runtime_error("psb200_solve: AMG hierarchy missing (factorize with precond=amg first)");
+    DistState &d = *dist;
+    KState *S = d_state;
+    const int *done = &S->done;
+    d.vp2.alloc((size_t)n_pad, true);
+    init_state(*this, prm.tolerance, prm.max_iter);
+    const long long n2 = n_pad / 2;
+    const int vec_blocks = vec_grid(n2);
+    const int push_blocks = d.world > 1 ? std::max(1, std::min(128, (d.n_push + 2 * kVecThreads - 1) / (2 * kVecThreads))) : 0;
+    PushList pl = make_push(d, std::max(1, push_blocks));
+    RedCtx rc = ctx.red();
+    PSB_CUDA(cudaMemsetAsync(vp.p, 0, sizeof(double) * n_pad, ctx.stream));
+    if (push_blocks)
+    {
+        halo_push_kernel<kVecThreads><<<push_blocks, kVecThreads, 0, ctx.stream>>>(vx.p, rc, pl);
+        check_launch();
+    }
+    launch_spmv(ctx, "spmv_residual", A, vx.p, EpiResidualNorms{vr.p, d_b, dinv.p}, FinInitAmgcl{S});
+    auto batch = [&]() {
+        double *pc = vp.p, *pn = d.vp2.p;
+        for (int i = 0; i < 2; ++i)
+        {
+            {
+                LocalScope local(ctx);
+                amg->apply(vr.p, vz.p, done);
+            }
+            launch_vec(ctx, "dot", n_pad, OpDot{vr.p, vz.p}, FinRhoAmgcl{S}, done);
+            ctx.prof_begin("cg_dir");
+            cg_dir_amgcl_dist_kernel<kVecThreads><<<vec_blocks + push_blocks, kVecThreads, 0, ctx.stream>>>(n2, pn, pc, vz.p, S, rc, pl, vec_blocks, done);
+            check_launch();
+            ctx.prof_end();
+            launch_spmv(ctx, "spmv_dot", A, pn, EpiDot{vq.p, pn}, FinPAp{S}, done);
+            launch_vec(ctx, "cg_update", n_pad, OpCgUpdateAmgcl{vx.p, vr.p, pn, vq.p, S, 0.0}, FinCgUpdateAmgcl{S}, done);
+            std::swap(pc, pn);
+        }
+    };
+    std::ostringstream key;
+    key << "cg_amgcl_dist/" << n << "/" << (void *)vx.p << "/" << (void *)amg.get() << "/" << (void *)d_b;
+    drive(batch, 2, key.str());
+    finish_solve();
+    check_comm_error();
 }
 
 // Jacobi-PCG in Eigen's ordering on the row partition. Same kernels as the single-GPU path for the

@@ -44,6 +44,9 @@ struct DistState
     long long val_lo = 0, val_hi = 0;
     DevBuf<int> d_perm;
     DevBuf<double> d_csc_window;
+    // rank-local diagonal block A[r0:r1, r0:r1] (halo columns dropped): the operator the rank-local AMG is built on
+    CsrDev A_diag;
+    DevBuf<int> diag_src; // A_diag.va[k] = A.va[diag_src[k]]
     ~DistState();
 };
 

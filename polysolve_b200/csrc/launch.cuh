@@ -110,7 +110,14 @@ struct Ctx
         stream = nullptr;
     }
     CommDev comm;             // world == 1 unless psb200_dist_connect() was called
-    RedCtx red() const { return RedCtx{partials.p, counter.p, kMaxBlocks, comm}; }
+    bool comm_local = false;  // true while rank-local work runs (AMG setup / cycle): reductions stay on this GPU
+    RedCtx red() const
+    {
+        RedCtx r{partials.p, counter.p, kMaxBlocks, comm};
+        if (comm_local)
+            r.comm.world = 1;
+        return r;
+    }
     cudaEvent_t get_event()
     {
         if (!ev_pool.empty())
@@ -154,6 +161,14 @@ struct Ctx
         }
         pending.clear();
     }
+};
+
+struct LocalScope
+{
+    Ctx &c;
+    bool prev;
+    explicit LocalScope(Ctx &ctx) : c(ctx), prev(ctx.comm_local) { c.comm_local = true; }
+    ~LocalScope() { c.comm_local = prev; }
 };
 
 inline void check_launch()

@@ -509,7 +509,15 @@ void Solver::factorize(long long n_, long long nnz_, const int *outer, const int
     {
         const double t1 = now_ms();
         amg = std::make_unique<AmgHierarchy>(ctx, prm.amg);
-        amg->setup(A, imposed_aggregates);
+        if (dist)
+        {
+            // multi-GPU: every rank builds the hierarchy of its own diagonal block (no communication in the cycle)
+            LocalScope local(ctx);
+            build_diag_block_dist();
+            amg->setup(dist->A_diag, imposed_aggregates);
+        }
+        else
+            amg->setup(A, imposed_aggregates);
         PSB_CUDA(cudaStreamSynchronize(st));
         t_setup_precond_ms = now_ms() - t1;
         if (graph_exec)
@@ -567,7 +575,7 @@ void Solver::solve_host(const double *b, double *x, long long n_)
     PSB_CUDA(cudaMemcpyAsync(vb.p, b, sizeof(double) * n, cudaMemcpyHostToDevice, st));
     PSB_CUDA(cudaMemcpyAsync(vx.p, x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
     if (dist)
-        run_cg_eigen_dist(vb.p);
+        prm.precond == "amg" ? run_cg_amgcl_dist(vb.p) : run_cg_eigen_dist(vb.p);
     else if (prm.krylov == "bicgstab")
         run_bicgstab(vb.p);
     else if (prm.precond == "amg")
@@ -594,7 +602,7 @@ void Solver::solve_device(const double *d_b, double *d_x, long long n_)
     // x lives in the solver's own buffer so captured graphs keep stable pointers
     PSB_CUDA(cudaMemcpyAsync(vx.p, d_x, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     if (dist)
-        run_cg_eigen_dist(d_b);
+        prm.precond == "amg" ? run_cg_amgcl_dist(d_b) : run_cg_eigen_dist(d_b);
     else if (prm.krylov == "bicgstab")
         run_bicgstab(d_b);
     else if (prm.precond == "amg")

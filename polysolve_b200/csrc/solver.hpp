@@ -67,6 +67,8 @@ struct Solver
     void analyze_pattern_dist(long long n, long long nnz, const int *outer, const int *inner);
     void factorize_values_dist(const double *vals);
     void run_cg_eigen_dist(const double *d_b);
+    void run_cg_amgcl_dist(const double *d_b);
+    void build_diag_block_dist();
     void check_comm_error();
 
     // pattern state (analyze_pattern)

@@ -26,7 +26,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, tol, q):
+def _worker(rank, world, port, n, tol, q, precond="jacobi"):
     import torch
     import torch.distributed as dist
 
@@ -41,7 +41,7 @@ def _worker(rank, world, port, n, tol, q):
         N = n ** 3
         b = P.spmv_csr(o, i, v, P.splitmix64(42, N))
         s = psb.Solver.create("CUDA", "")
-        s.set_parameters({"CUDA": {"tolerance": tol, "max_iter": 10000, "device": rank, "check_every": 8}})
+        s.set_parameters({"CUDA": {"tolerance": tol, "max_iter": 10000, "device": rank, "check_every": 8, "precond": precond}})
         s.dist_setup_torch(halo_cap=1 << 16)
         s.analyze_pattern_raw(N, o, i, N)
         s.factorize_raw(N, o, i, v)
@@ -59,12 +59,12 @@ def _worker(rank, world, port, n, tol, q):
         dist.destroy_process_group()
 
 
-def _run(world, n, tol):
+def _run(world, n, tol, precond="jacobi"):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     port = _free_port()
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, tol, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, tol, q, precond)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
@@ -96,5 +96,28 @@ def test_dist_pcg_matches_oracle(orc, world):
         assert err < tol
         assert it2 == 0
         assert dinfo["world"] == world
+    assert np.linalg.norm(x - x0) / np.linalg.norm(x0) < 10 * tol
+    assert np.linalg.norm(orc.spmv_csc(o, i, v, x) - b) / np.linalg.norm(b) < 2 * tol
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_dist_amg_pcg(orc, world):
+    """AMG-PCG on the row partition: rank-local SA-AMG (block-Jacobi across ranks) inside the global CG. The solution
+    must equal the single-GPU / oracle solution to the solver tolerance; the iteration count may grow with the rank count."""
+    if world > max(1, _ngpu()):
+        pytest.skip(f"needs {world} GPUs")
+    n, tol = 40, 1e-8
+    N = n ** 3
+    o, i, v = orc.poisson3d(n)
+    b = orc.spmv_csc(o, i, v, orc.splitmix64(42, N))
+    x0, _, _, _ = orc.eigen_cg(o, i, v, b, tol=1e-12, max_iters=10000)
+    res = _run(world, n, tol, "amg")
+    x = np.zeros(N)
+    for rank, a, e, xs, it, err, status, it2, dinfo in res:
+        x[a:e] = xs
+        assert status == "Converged"
+        assert it == res[0][4] and 1 <= it <= 40
+        assert err < tol
+        assert it2 == 0
     assert np.linalg.norm(x - x0) / np.linalg.norm(x0) < 10 * tol
     assert np.linalg.norm(orc.spmv_csc(o, i, v, x) - b) / np.linalg.norm(b) < 2 * tol
