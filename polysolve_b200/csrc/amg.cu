@@ -82,6 +82,189 @@ __global__ void splitmix_kernel(long long n, unsigned long long seed, double *ou
     out[i] = 2.0 * (double)(z >> 11) * (1.0 / 9007199254740992.0) - 1.0;
 }
 
+
+// ------------------------------------------------------------------------------ block mode (AMGCL_Block<B>, reference AMGCL.cpp:246-298)
+// AMGCL's block value type (static_matrix<double,B,B>) is realised on the scalar CSR by its scalar expansion: the B rows of
+// a node share one column list of full B x B blocks (made explicit by analyze_pattern, preserved by P, R and the Galerkin
+// product), aggregation acts on nodes with Frobenius block norms, and every D^-1 of the scalar algorithm becomes the
+// inverse of the B x B diagonal block, applied once to the matrix: Ahat = Dblk^-1 A is what the smoother, the
+// prolongation smoothing and the spectral-radius estimate multiply with (and bhat = Dblk^-1 b per application).
+template <int B>
+__device__ __forceinline__ bool invert_small(const double *m, double *inv)
+{
+    if (B == 1)
+    {
+        inv[0] = 1.0 / m[0];
+        return m[0] != 0.0;
+    }
+    if (B == 2)
+    {
+        const double det = m[0] * m[3] - m[1] * m[2];
+        const double id = 1.0 / det;
+        inv[0] = m[3] * id;
+        inv[1] = -m[1] * id;
+        inv[2] = -m[2] * id;
+        inv[3] = m[0] * id;
+        return det != 0.0 && det == det;
+    }
+    const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+    const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+    const double id = 1.0 / det;
+    inv[0] = c00 * id;
+    inv[1] = (m[2] * m[7] - m[1] * m[8]) * id;
+    inv[2] = (m[1] * m[5] - m[2] * m[4]) * id;
+    inv[3] = c01 * id;
+    inv[4] = (m[0] * m[8] - m[2] * m[6]) * id;
+    inv[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+    inv[6] = c02 * id;
+    inv[7] = (m[1] * m[6] - m[0] * m[7]) * id;
+    inv[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+    return det != 0.0 && det == det;
+}
+// dinvb[node] = inverse of the diagonal block; bad is raised for a missing / singular block or a broken block pattern
+template <int B>
+__global__ void block_diag_inv_kernel(CsrView A, double *__restrict__ dinvb, int *bad)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nb = A.n / B;
+    if (i >= nb)
+        return;
+    double m[B * B];
+    bool found = false;
+    const int k0 = A.rp[B * i], len = A.rp[B * i + 1] - k0;
+    for (int q = 0; q < len; q += B)
+        if (A.ci[k0 + q] == B * i)
+        {
+            found = true;
+            for (int r = 0; r < B; ++r)
+                for (int c = 0; c < B; ++c)
+                    m[r * B + c] = A.va[A.rp[B * i + r] + q + c];
+        }
+    for (int r = 1; r < B; ++r)
+        if (A.rp[B * i + r + 1] - A.rp[B * i + r] != len)
+            found = false;
+    double inv[B * B];
+    if (!found || !invert_small<B>(m, inv))
+    {
+        *bad = 1;
+        for (int e = 0; e < B * B; ++e)
+            inv[e] = (e % (B + 1) == 0) ? 1.0 : 0.0;
+    }
+    for (int e = 0; e < B * B; ++e)
+        dinvb[(size_t)i * B * B + e] = inv[e];
+}
+// Ahat = Dblk^-1 A : entry k of row B i + c is sum_d Dinv[c][d] A[B i + d][same slot]
+template <int B>
+__global__ void block_scale_rows_kernel(CsrView A, const double *__restrict__ dinvb, double *__restrict__ out)
+{
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= A.n)
+        return;
+    const int i = (int)(row / B), c = (int)(row % B);
+    const int kb = A.rp[row], len = A.rp[row + 1] - kb;
+    double w[B];
+    int base[B];
+    for (int d = 0; d < B; ++d)
+    {
+        w[d] = dinvb[(size_t)i * B * B + c * B + d];
+        base[d] = A.rp[B * i + d];
+    }
+    for (int q = 0; q < len; ++q)
+    {
+        double s = 0;
+        for (int d = 0; d < B; ++d)
+            s += w[d] * A.va[base[d] + q];
+        out[kb + q] = s;
+    }
+}
+// out_node = Dinv_node in_node
+template <int B>
+__global__ void block_diag_apply_kernel(long long nb, const double *__restrict__ dinvb, const double *__restrict__ in, double *__restrict__ out,
+                                        const int *done)
+{
+    if (done && *done)
+        return;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb)
+        return;
+    double v[B];
+    for (int d = 0; d < B; ++d)
+        v[d] = in[i * B + d];
+    for (int c = 0; c < B; ++c)
+    {
+        double s = 0;
+        for (int d = 0; d < B; ++d)
+            s += dinvb[i * B * B + c * B + d] * v[d];
+        out[i * B + c] = s;
+    }
+}
+// node graph S: S.rp[i] = A.rp[B i] / B^2, S.ci = block columns, S.va = Frobenius norm of the block (math::norm of amgcl)
+template <int B>
+__global__ void block_norm_matrix_kernel(CsrView A, int *__restrict__ srp, int *__restrict__ sci, double *__restrict__ sva)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nb = A.n / B;
+    if (i > nb)
+        return;
+    srp[i] = A.rp[B * i] / (B * B);
+    if (i == nb)
+        return;
+    const int k0 = A.rp[B * i], len = (A.rp[B * i + 1] - k0) / B, o = k0 / (B * B);
+    for (int q = 0; q < len; ++q)
+    {
+        double s = 0;
+        for (int r = 0; r < B; ++r)
+            for (int c = 0; c < B; ++c)
+            {
+                const double v = A.va[A.rp[B * i + r] + B * q + c];
+                s += v * v;
+            }
+        sci[o + q] = A.ci[k0 + B * q] / B;
+        sva[o + q] = sqrt(s);
+    }
+}
+// amgcl spectral_radius<true> with power_iters = 0 on block values: max_i (sum_j ||A_ij||) ||D_i^-1||
+template <int B>
+__global__ void block_gershgorin_kernel(CsrView S, const double *__restrict__ dinvb, unsigned long long *out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0;
+    if (i < S.n)
+    {
+        for (int k = S.rp[i]; k < S.rp[i + 1]; ++k)
+            s += S.va[k];
+        double d = 0;
+        for (int e = 0; e < B * B; ++e)
+            d += dinvb[i * B * B + e] * dinvb[i * B * B + e];
+        s *= sqrt(d);
+    }
+    for (int o = 16; o > 0; o >>= 1)
+        s = fmax(s, __shfl_xor_sync(0xffffffffu, s, o));
+    if ((threadIdx.x & 31) == 0 && s > 0)
+        atomicMax(out, (unsigned long long)__double_as_longlong(s));
+}
+// amgcl spectral_radius power iteration, block values: radius = sum_nodes |<b1_node, b0_node>|
+__global__ void block_radius_terms_kernel(int B, long long nb, const double *__restrict__ b1, const double *__restrict__ b0, double *__restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb)
+        return;
+    double s = 0;
+    for (int c = 0; c < B; ++c)
+        s += b1[i * B + c] * b0[i * B + c];
+    out[i] = fabs(s);
+}
+// scalar aggregate ids from node aggregates: agg[B i + c] = B agg_node[i] + c (negative states are kept)
+__global__ void block_expand_agg_kernel(int B, long long nb, const int *__restrict__ agg_node, int *__restrict__ agg)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nb)
+        return;
+    const int g = agg_node[i];
+    for (int c = 0; c < B; ++c)
+        agg[i * B + c] = g >= 0 ? B * g + c : g;
+}
+
 // ------------------------------------------------------------------------------ strength + MIS-2 aggregation
 // strong(i,j) <=> j != i and eps^2 a_ii a_jj < a_ij^2   (amgcl plain_aggregates; eps = 0 => every stored off-diagonal non-zero)
 __device__ __forceinline__ bool is_strong(int i, int j, double aij, double eps2, const double *diag)
@@ -242,8 +425,9 @@ __global__ void agg_assign2_kernel(CsrView A, const double *__restrict__ diag, d
 // P = (I - omega D_f^-1 A_f) P_tent, P_tent(i, agg(i)) = 1 (amgcl smoothed_aggregation::transfer_operators).
 // Each row is built in place inside the slot [A.rp[i], A.rp[i+1]) of scratch arrays (a row of P never has
 // more entries than the row of A), merged by aggregate id and sorted by column; cnt[i] = entries.
+// all_strong (block mode, eps_strong = 0): every stored entry takes part, so the B rows of a node keep one pattern.
 __global__ void prolong_rows_kernel(CsrView A, const double *__restrict__ diagv, double eps2, const int *__restrict__ agg, double omega,
-                                    int *__restrict__ scol, double *__restrict__ sval, int *__restrict__ cnt)
+                                    int *__restrict__ scol, double *__restrict__ sval, int *__restrict__ cnt, bool all_strong)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= A.n)
@@ -254,7 +438,7 @@ __global__ void prolong_rows_kernel(CsrView A, const double *__restrict__ diagv,
     for (int k = kb; k < ke; ++k)
     {
         const int j = A.ci[k];
-        if (j == (int)i || !is_strong((int)i, j, A.va[k], eps2, diagv))
+        if (j == (int)i || (!all_strong && !is_strong((int)i, j, A.va[k], eps2, diagv)))
             dia += A.va[k];
     }
     dia = -omega * (1.0 / dia);
@@ -262,7 +446,7 @@ __global__ void prolong_rows_kernel(CsrView A, const double *__restrict__ diagv,
     for (int k = kb; k < ke; ++k)
     {
         const int j = A.ci[k];
-        if (j != (int)i && !is_strong((int)i, j, A.va[k], eps2, diagv))
+        if (j != (int)i && !all_strong && !is_strong((int)i, j, A.va[k], eps2, diagv))
             continue;
         const int g = agg[j];
         if (g < 0)
@@ -585,6 +769,11 @@ struct AmgLevel
     DevBuf<double> dinv, w, f, u, ualt, t, cp;
     DevBuf<int> agg;
     int n_agg = 0;
+    // block mode: Ahat = Dblk^-1 A is the smoother's operator (Asm), dinvb the inverted diagonal blocks, bh = Dblk^-1 rhs
+    CsrDev Ahat;
+    const CsrDev *Asm = nullptr;
+    DevBuf<double> dinvb, bh;
+    DevBuf<int> agg_node;
     double rho = 0, cheb_d = 0, cheb_c = 0, omega = 0;
     std::vector<double> alpha, beta;
     int mis_rounds = 0;
@@ -640,9 +829,51 @@ static void setup_relaxation(Ctx &c, const AmgParams &prm, AmgLevel &L, int leve
     L.cp.alloc(np, true);
     DevBuf<double> diag;
     diag.alloc(np, true);
-    diag_kernel<<<nblk(A.n), 256, 0, st>>>(A.view(), diag.p);
-    inv_kernel<<<nblk(A.n), 256, 0, st>>>(A.n, diag.p, L.dinv.p, 1.0);
+    const int B = std::max(1, prm.block_size);
+    L.Asm = &A;
+    if (B > 1)
+    {
+        // Dblk^-1 once, Ahat = Dblk^-1 A; from here on the scalar code runs on Ahat with a unit diagonal scaling
+        if (A.n % B)
+            throw std::runtime_error("psb200 amg: level size is not a multiple of the block size");
+        const long long nb = A.n / B;
+        L.dinvb.alloc((size_t)nb * B * B);
+        L.bh.alloc(np, true);
+        int *d_bad = (int *)c.counter.p + 3;
+        PSB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+        if (B == 2)
+            block_diag_inv_kernel<2><<<nblk(nb), 256, 0, st>>>(A.view(), L.dinvb.p, d_bad);
+        else
+            block_diag_inv_kernel<3><<<nblk(nb), 256, 0, st>>>(A.view(), L.dinvb.p, d_bad);
+        check_launch();
+        if (d2h(c, d_bad))
+            throw std::runtime_error("psb200 amg: singular or missing diagonal block (block_size " + std::to_string(B) + ")");
+        L.Ahat.n = A.n;
+        L.Ahat.ncols = A.ncols;
+        L.Ahat.nnz = A.nnz;
+        L.Ahat.rp.alloc((size_t)A.n + 1);
+        L.Ahat.ci.alloc(std::max<long long>(1, A.nnz), false, 64);
+        L.Ahat.va.alloc(std::max<long long>(1, A.nnz), false, 64);
+        PSB_CUDA(cudaMemcpyAsync(L.Ahat.rp.p, A.rp.p, sizeof(int) * ((size_t)A.n + 1), cudaMemcpyDeviceToDevice, st));
+        PSB_CUDA(cudaMemcpyAsync(L.Ahat.ci.p, A.ci.p, sizeof(int) * (size_t)A.nnz, cudaMemcpyDeviceToDevice, st));
+        if (B == 2)
+            block_scale_rows_kernel<2><<<nblk(A.n), 256, 0, st>>>(A.view(), L.dinvb.p, L.Ahat.va.p);
+        else
+            block_scale_rows_kernel<3><<<nblk(A.n), 256, 0, st>>>(A.view(), L.dinvb.p, L.Ahat.va.p);
+        check_launch();
+        L.Ahat.kind = A.kind;
+        L.Ahat.lpr = A.lpr;
+        L.Asm = &L.Ahat;
+        fill_kernel<<<nblk(A.n), 256, 0, st>>>(A.n, L.dinv.p, 1.0);
+        fill_kernel<<<nblk(A.n), 256, 0, st>>>(A.n, diag.p, 1.0);
+    }
+    else
+    {
+        diag_kernel<<<nblk(A.n), 256, 0, st>>>(A.view(), diag.p);
+        inv_kernel<<<nblk(A.n), 256, 0, st>>>(A.n, diag.p, L.dinv.p, 1.0);
+    }
     check_launch();
+    const CsrDev &As = *L.Asm;
     if (prm.relax_type == "chebyshev")
     {
         // amgcl relaxation::chebyshev ctor: rho(D^-1 A) by power iteration (or Gershgorin), hi = higher rho, lo = lower rho
@@ -650,7 +881,7 @@ static void setup_relaxation(Ctx &c, const AmgParams &prm, AmgLevel &L, int leve
             throw std::runtime_error("psb200 amg: chebyshev with scale=false is not supported");
         double rho;
         if (prm.power_iters <= 0)
-            rho = gershgorin(c, A);
+            rho = gershgorin(c, As);
         else
         {
             // b0 = the same counter-based splitmix64 stream the CPU restatement starts from
@@ -664,9 +895,18 @@ static void setup_relaxation(Ctx &c, const AmgParams &prm, AmgLevel &L, int leve
             launch_vec(c, "amg_setup", L.n_pad, OpScale{b0.p, b0.p, scal.p, 0.0}, FinNone{});
             for (int it = 0; it < prm.power_iters; ++it)
             {
-                launch_spmv(c, "amg_setup", A, b0.p, EpiPower{b1.p, b0.p, L.dinv.p}, FinStore{scal.p, 2});
+                launch_spmv(c, "amg_setup", As, b0.p, EpiPower{b1.p, b0.p, L.dinv.p}, FinStore{scal.p, 2});
                 if (it + 1 < prm.power_iters)
                     launch_vec(c, "amg_setup", L.n_pad, OpScale{b0.p, b1.p, scal.p, 0.0}, FinNone{});
+            }
+            if (B > 1)
+            {
+                // the block algorithm takes |.| of the per-node inner product, not of every scalar product
+                DevBuf<double> terms;
+                terms.alloc(np, true);
+                block_radius_terms_kernel<<<nblk(A.n / B), 256, 0, st>>>(B, A.n / B, b1.p, b0.p, terms.p);
+                check_launch();
+                launch_vec(c, "amg_setup", L.n_pad, OpDot{terms.p, L.dinv.p}, FinStore{scal.p + 1, 1});
             }
             double h[2];
             PSB_CUDA(cudaMemcpyAsync(h, scal.p, 16, cudaMemcpyDeviceToHost, st));
@@ -794,25 +1034,63 @@ void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &
             break; // last level is a plain smoothing-only level
         const long long n = A.n;
         const double eps2 = eps_strong * eps_strong;
+        const int B = std::max(1, prm_.block_size);
+        if (B > 1 && eps_strong != 0.0)
+            throw std::runtime_error("psb200 amg: block_size > 1 supports eps_strong = 0 only (polysolve's default, AMGCL.cpp:52)");
+        const CsrDev &Asm = *L.Asm; // Dblk^-1 A in block mode, A otherwise
         DevBuf<double> diag;
         diag.alloc(n);
-        diag_kernel<<<nblk(n), 256, 0, st>>>(A.view(), diag.p);
+        if (B > 1)
+            fill_kernel<<<nblk(n), 256, 0, st>>>(n, diag.p, 1.0);
+        else
+            diag_kernel<<<nblk(n), 256, 0, st>>>(A.view(), diag.p);
         check_launch();
+        const double *pdiag = diag.p;
         // ---- aggregates
         tp = wall_ms(st);
+        CsrDev S; // block mode: node graph with Frobenius block norms
+        DevBuf<double> sdiag;
+        if (B > 1)
+        {
+            const long long nb = n / B;
+            S.n = (int)nb;
+            S.ncols = (int)nb;
+            S.nnz = A.nnz / (B * B);
+            S.rp.alloc((size_t)nb + 1);
+            S.ci.alloc(std::max<long long>(1, S.nnz), false, 64);
+            S.va.alloc(std::max<long long>(1, S.nnz), false, 64);
+            if (B == 2)
+                block_norm_matrix_kernel<2><<<nblk(nb + 1), 256, 0, st>>>(A.view(), S.rp.p, S.ci.p, S.va.p);
+            else
+                block_norm_matrix_kernel<3><<<nblk(nb + 1), 256, 0, st>>>(A.view(), S.rp.p, S.ci.p, S.va.p);
+            sdiag.alloc((size_t)nb);
+            diag_kernel<<<nblk(nb), 256, 0, st>>>(S.view(), sdiag.p);
+            check_launch();
+        }
         if (li < (int)imposed.size() && !imposed[li].empty())
         {
-            if ((long long)imposed[li].size() != n)
+            // imposed ids are per node in block mode, per row otherwise
+            if ((long long)imposed[li].size() != n / B)
                 throw std::invalid_argument("psb200 amg: imposed aggregate array has the wrong length");
-            L.agg.alloc(n);
-            PSB_CUDA(cudaMemcpyAsync(L.agg.p, imposed[li].data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+            DevBuf<int> &dst = B > 1 ? L.agg_node : L.agg;
+            dst.alloc(n / B);
+            PSB_CUDA(cudaMemcpyAsync(dst.p, imposed[li].data(), sizeof(int) * (n / B), cudaMemcpyHostToDevice, st));
             int mx = -1;
             for (int a : imposed[li])
                 mx = std::max(mx, a);
             L.n_agg = mx + 1;
         }
+        else if (B > 1)
+            L.n_agg = aggregate_mis2(ctx_, tmp, S, sdiag.p, eps_strong, L.agg_node, L.mis_rounds);
         else
             L.n_agg = aggregate_mis2(ctx_, tmp, A, diag.p, eps_strong, L.agg, L.mis_rounds);
+        if (B > 1)
+        {
+            L.agg.alloc(n);
+            block_expand_agg_kernel<<<nblk(n / B), 256, 0, st>>>(B, n / B, L.agg_node.p, L.agg.p);
+            check_launch();
+            L.n_agg *= B;
+        }
         L.t_agg = wall_ms(st) - tp;
         eps_strong *= 0.5; // amgcl halves eps_strong after every level
         if (L.n_agg <= 0)
@@ -820,7 +1098,23 @@ void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &
         // ---- omega = relax * (4/3) / rho_Gershgorin(D^-1 A)
         double omega = prm_.sa_relax;
         if (prm_.estimate_spectral_radius)
-            omega *= (4.0 / 3.0) / gershgorin(ctx_, A);
+        {
+            double rho_g;
+            if (B > 1)
+            {
+                unsigned long long *d_max = (unsigned long long *)ctx_.partials.p;
+                PSB_CUDA(cudaMemsetAsync(d_max, 0, 8, st));
+                if (B == 2)
+                    block_gershgorin_kernel<2><<<nblk(S.n), 256, 0, st>>>(S.view(), L.dinvb.p, d_max);
+                else
+                    block_gershgorin_kernel<3><<<nblk(S.n), 256, 0, st>>>(S.view(), L.dinvb.p, d_max);
+                check_launch();
+                rho_g = bits_to_double(d2h(ctx_, d_max));
+            }
+            else
+                rho_g = gershgorin(ctx_, A);
+            omega *= (4.0 / 3.0) / rho_g;
+        }
         else
             omega *= 2.0 / 3.0;
         L.omega = omega;
@@ -832,7 +1126,7 @@ void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &
             scol.alloc(std::max<long long>(1, A.nnz));
             sval.alloc(std::max<long long>(1, A.nnz));
             cnt.alloc(n + 1, true);
-            prolong_rows_kernel<<<nblk(n), 256, 0, st>>>(A.view(), diag.p, eps2, L.agg.p, omega, scol.p, sval.p, cnt.p);
+            prolong_rows_kernel<<<nblk(n), 256, 0, st>>>(Asm.view(), pdiag, eps2, L.agg.p, omega, scol.p, sval.p, cnt.p, B > 1);
             check_launch();
             L.P.n = (int)n;
             L.P.ncols = L.n_agg;
@@ -884,7 +1178,21 @@ void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &
 void AmgHierarchy::relax(int l, const double *rhs, double *&x, double *&x_alt, bool x_is_zero, const int *done)
 {
     AmgLevel &L = *levels_[l];
-    const CsrDev &A = *L.A;
+    const CsrDev &A = *L.Asm;
+    const int B = std::max(1, prm_.block_size);
+    if (B > 1)
+    {
+        // M (b - A x) = Dblk^-1 b - Ahat x : scale the right-hand side once per application
+        const long long nb = L.n / B;
+        ctx_.prof_begin("block_diag_apply");
+        if (B == 2)
+            block_diag_apply_kernel<2><<<nblk(nb), 256, 0, ctx_.stream>>>(nb, L.dinvb.p, rhs, L.bh.p, done);
+        else
+            block_diag_apply_kernel<3><<<nblk(nb), 256, 0, ctx_.stream>>>(nb, L.dinvb.p, rhs, L.bh.p, done);
+        check_launch();
+        ctx_.prof_end();
+        rhs = L.bh.p;
+    }
     if (prm_.relax_type == "chebyshev")
     {
         for (int k = 0; k < prm_.degree; ++k)
@@ -997,7 +1305,7 @@ std::string AmgHierarchy::info_json() const
           << ",\"AP\":" << jnum(L.t_ap) << ",\"RAP\":" << jnum(L.t_rap) << "}"
           << ",\"spmv_kernel\":" << jstr(L.A->kind == SPMV_STREAM ? "stream" : "vector" + std::to_string(L.A->lpr)) << "}";
     }
-    o << "],\"operator_complexity\":" << jnum(tot / fine_nnz) << ",\"ncycle\":" << prm_.ncycle << ",\"degree\":" << prm_.degree
+    o << "],\"block_size\":" << std::max(1, prm_.block_size) << ",\"operator_complexity\":" << jnum(tot / fine_nnz) << ",\"ncycle\":" << prm_.ncycle << ",\"degree\":" << prm_.degree
       << ",\"relax\":" << jstr(prm_.relax_type) << "}";
     return o.str();
 }

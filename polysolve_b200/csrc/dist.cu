@@ -304,6 +304,8 @@ void Solver::analyze_pattern_dist(long long n_, long long nnz_, const int *outer
     DistState &d = *dist;
     if (!d.connected && d.world > 1)
         throw std::runtime_error("psb200 dist: psb200_dist_connect has not been called");
+    if (prm.block_size > 1)
+        throw std::runtime_error("psb200 dist: block_size > 1 is not available on the row-partitioned path in this version");
     if (prm.krylov != "cg")
         throw std::runtime_error("psb200 dist: the row-partitioned path provides PCG (krylov=cg) with precond = jacobi | none | amg");
     d.plan.build(n_, nnz_, outer, inner, d.rank, d.world, d.halo_cap);

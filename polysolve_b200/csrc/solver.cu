@@ -6,6 +6,7 @@
 #include "dist.hpp"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <chrono>
@@ -154,13 +155,90 @@ __global__ void gather_int_kernel(long long n, const int *__restrict__ src, cons
         dst[i] = src[idx[i]];
 }
 
+// ------------------------------------------------------------------ block expansion (block_size B > 1)
+// amgcl::adapter::block_matrix (reference AMGCL.cpp:270-272) views the scalar matrix as B x B blocks: block row I holds
+// rows B I .. B I + B - 1 and the union of their block columns, missing scalar entries being zero. The same view is
+// made explicit here once per pattern: every block row gets the full B x B pattern (perm = -1 marks the fill-in), so
+// all B rows of a node share one column list -- the invariant the block AMG kernels rely on.
+// Walks the B sorted rows of node `node` in merged order; calls f(q, jb) for the q-th distinct block column jb.
+template <class F>
+__device__ __forceinline__ int merged_block_cols(int B, int node, const int *__restrict__ rp, const int *__restrict__ ci, F f)
+{
+    int head[4];
+    for (int r = 0; r < B; ++r)
+        head[r] = rp[B * node + r];
+    int q = 0;
+    for (;;)
+    {
+        int jb = 0x7fffffff;
+        for (int r = 0; r < B; ++r)
+            if (head[r] < rp[B * node + r + 1])
+                jb = min(jb, ci[head[r]] / B);
+        if (jb == 0x7fffffff)
+            break;
+        f(q, jb);
+        for (int r = 0; r < B; ++r)
+            while (head[r] < rp[B * node + r + 1] && ci[head[r]] / B == jb)
+                ++head[r];
+        ++q;
+    }
+    return q;
+}
+__global__ void block_count_kernel(int B, int nb, const int *__restrict__ rp, const int *__restrict__ ci, int *__restrict__ cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nb)
+        return;
+    cnt[i] = i < nb ? merged_block_cols(B, i, rp, ci, [](int, int) {}) : 0;
+}
+__global__ void block_fill_kernel(int B, int nb, const int *__restrict__ rp, const int *__restrict__ ci, const int *__restrict__ perm,
+                                  const int *__restrict__ boff, int *__restrict__ nrp, int *__restrict__ nci, int *__restrict__ nperm)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nb)
+        return;
+    if (i == nb)
+    {
+        nrp[B * nb] = B * B * boff[nb];
+        return;
+    }
+    const int len = boff[i + 1] - boff[i];
+    const int base = B * B * boff[i];
+    for (int r = 0; r < B; ++r)
+        nrp[B * i + r] = base + r * B * len;
+    merged_block_cols(B, i, rp, ci, [&](int q, int jb) {
+        for (int r = 0; r < B; ++r)
+            for (int c = 0; c < B; ++c)
+            {
+                nci[base + r * B * len + B * q + c] = B * jb + c;
+                nperm[base + r * B * len + B * q + c] = -1;
+            }
+    });
+    // scatter the existing entries: both lists are sorted, so one forward walk per row finds the block slot
+    for (int r = 0; r < B; ++r)
+    {
+        int q = 0;
+        const int rowbase = base + r * B * len;
+        for (int k = rp[B * i + r]; k < rp[B * i + r + 1]; ++k)
+        {
+            const int j = ci[k];
+            while (nci[rowbase + B * q] / B != j / B)
+                ++q;
+            nperm[rowbase + B * q + j % B] = perm[k];
+        }
+    }
+}
+
 // ------------------------------------------------------------------ factorize kernels
 // vals_csr[k] = vals_csc[perm[k]]
 __global__ void gather_vals_kernel(long long n, const double *__restrict__ src, const int *__restrict__ perm, double *__restrict__ dst)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n)
-        dst[i] = __ldg(src + __ldg(perm + i));
+    {
+        const int p = __ldg(perm + i);
+        dst[i] = p >= 0 ? __ldg(src + p) : 0.0; // p < 0: explicit zero added by the block expansion
+    }
 }
 // Eigen::DiagonalPreconditioner::factorize: invdiag = (A_ii != 0) ? 1/A_ii : 1. mode 0: ones.
 __global__ void inv_diag_kernel(CsrView A, double *__restrict__ dinv, int mode, int *bad)
@@ -351,7 +429,7 @@ void Solver::analyze_pattern(long long n_, long long nnz_, const int *outer, con
     precond_num = precond_num_;
     unsigned long long h = hash_words(outer, sizeof(int) * (size_t)(n_ + 1), 0x5bd1e995ull + (unsigned long long)n_);
     h = hash_words(inner, sizeof(int) * (size_t)nnz_, h);
-    if (analyzed && n_global == n_ && nnz_global == nnz_ && h == pattern_hash)
+    if (analyzed && n_global == n_ && nnz_global == nnz_ && h == pattern_hash && pattern_block == std::max(1, prm.block_size))
     {
         analyze_skipped = true; // Newton calls analyze_pattern every iteration with an unchanged pattern (Newton.cpp:189)
         t_analyze_ms = now_ms() - t0;
@@ -448,6 +526,47 @@ void Solver::analyze_pattern(long long n_, long long nnz_, const int *outer, con
     {
         PSB_CUDA(cudaMemsetAsync(A.rp.p, 0, sizeof(int) * (n + 1), st));
     }
+    pattern_block = 1;
+    if (prm.block_size > 1 && n > 0)
+    {
+        const int B = prm.block_size;
+        if (B > 3)
+            throw std::invalid_argument("psb200: block_size must be 1, 2 or 3 (reference AMGCL.cpp:111-123)");
+        if (n % B != 0)
+            throw std::invalid_argument("psb200: the matrix size is not a multiple of block_size");
+        const int nb = (int)(n / B);
+        DevBuf<int> cnt, boff;
+        cnt.alloc((size_t)nb + 1, true);
+        boff.alloc((size_t)nb + 1);
+        block_count_kernel<<<blocks_for(nb + 1, 256), 256, 0, st>>>(B, nb, A.rp.p, A.ci.p, cnt.p);
+        check_launch();
+        size_t tmp_bytes = 0;
+        PSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt.p, boff.p, nb + 1, st));
+        DevBuf<unsigned char> tmp;
+        tmp.alloc(tmp_bytes);
+        PSB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, cnt.p, boff.p, nb + 1, st));
+        int nblocks = 0;
+        PSB_CUDA(cudaMemcpyAsync(&nblocks, boff.p + nb, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PSB_CUDA(cudaStreamSynchronize(st));
+        const long long nnz_full = (long long)nblocks * B * B;
+        if (nnz_full > 0x7fffffffLL - 1024)
+            throw std::invalid_argument("psb200: int32 index range exceeded after block expansion");
+        DevBuf<int> nrp, nci, nperm;
+        nrp.alloc(n + 1);
+        nci.alloc(std::max<long long>(nnz_full, 1), false, 64);
+        nperm.alloc(std::max<long long>(nnz_full, 1));
+        block_fill_kernel<<<blocks_for(nb + 1, 256), 256, 0, st>>>(B, nb, A.rp.p, A.ci.p, perm.p, boff.p, nrp.p, nci.p, nperm.p);
+        check_launch();
+        PSB_CUDA(cudaStreamSynchronize(st));
+        A.rp = std::move(nrp);
+        A.ci = std::move(nci);
+        perm = std::move(nperm);
+        nnz = nnz_full;
+        A.nnz = nnz;
+        A.va.alloc(std::max<long long>(nnz, 1), false, 64);
+        pattern_block = B;
+        sym_pattern = false; // CSR arrays no longer alias the CSC arrays
+    }
     A.plan(prm.spmv_kernel);
     PSB_CUDA(cudaStreamSynchronize(st));
     analyzed = true;
@@ -462,7 +581,7 @@ void Solver::factorize(long long n_, long long nnz_, const int *outer, const int
     ensure_ctx(*this);
     // factorize() without (or with a stale) analyze_pattern(): analyze now. The Eigen iterative wrappers
     // accept this order too (EigenSolver.tpp:100-105 only needs the matrix).
-    bool need = !analyzed || n_global != n_ || nnz_global != nnz_;
+    bool need = !analyzed || n_global != n_ || nnz_global != nnz_ || pattern_block != std::max(1, prm.block_size);
     if (!need && prm.verify_pattern && outer && inner)
     {
         // cheap guard against a silently changed pattern: outer fully, inner strided
@@ -482,10 +601,10 @@ void Solver::factorize(long long n_, long long nnz_, const int *outer, const int
         factorize_values_dist(vals);
     else
     {
-        csc_vals.alloc(std::max<long long>(nnz, 1));
+        csc_vals.alloc(std::max<long long>(nnz_global, 1));
         if (nnz)
         {
-            PSB_CUDA(cudaMemcpyAsync(csc_vals.p, vals, sizeof(double) * nnz, cudaMemcpyHostToDevice, st));
+            PSB_CUDA(cudaMemcpyAsync(csc_vals.p, vals, sizeof(double) * nnz_global, cudaMemcpyHostToDevice, st));
             gather_vals_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(nnz, csc_vals.p, perm.p, A.va.p);
             check_launch();
         }
@@ -508,7 +627,9 @@ void Solver::factorize(long long n_, long long nnz_, const int *outer, const int
     if (prm.precond == "amg")
     {
         const double t1 = now_ms();
-        amg = std::make_unique<AmgHierarchy>(ctx, prm.amg);
+        AmgParams ap = prm.amg;
+        ap.block_size = pattern_block;
+        amg = std::make_unique<AmgHierarchy>(ctx, ap);
         if (dist)
         {
             // multi-GPU: every rank builds the hierarchy of its own diagonal block (no communication in the cycle)

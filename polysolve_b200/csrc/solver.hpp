@@ -27,6 +27,7 @@ struct AmgParams
     double sa_relax = 1.0;
     bool estimate_spectral_radius = true;
     double eps_strong = 0.0;
+    int block_size = 1; // AMGCL_Block<B> (reference AMGCL.cpp:246-298): B x B value type
     std::string aggregation = "mis2"; // mis2 (parallel, deterministic) | imposed via debug hook
 };
 
@@ -76,6 +77,8 @@ struct Solver
     unsigned long long pattern_hash = 0;
     bool analyzed = false, factorized = false;
     bool sym_pattern = false;
+    int pattern_block = 1;   // block size the stored CSR pattern was expanded for (analyze_pattern)
+    long long nnz_input = 0; // nnz of the matrix as received (nnz counts the expanded pattern in block mode)
     int precond_num = 0;
     DevBuf<int> csc_outer, csc_inner, perm;
     DevBuf<double> csc_vals;

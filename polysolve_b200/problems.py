@@ -176,3 +176,107 @@ class QuarticSpringGrid3D:
 
     def stop(self, x):
         return False
+
+
+# ----------------------------------------------------------------------------------------- elasticity (C4 / C5 family)
+def _kuhn_tets():
+    """The 6 tetrahedra of the Kuhn split of the unit cube: paths 000 -> 111 along a permutation of the axes."""
+    import itertools
+    tets = []
+    for perm in itertools.permutations(range(3)):
+        v = [np.zeros(3, int)]
+        for ax in perm:
+            w = v[-1].copy()
+            w[ax] += 1
+            v.append(w)
+        tets.append(np.array(v))
+    return tets
+
+
+def _p1_elastic_element(X, E, nu):
+    """12 x 12 stiffness of a P1 tetrahedron with vertices X (4 x 3), isotropic linear elasticity (Voigt)."""
+    M = np.hstack([np.ones((4, 1)), X.astype(float)])
+    G = np.linalg.inv(M)[1:, :]          # G[:, a] = grad of the a-th barycentric function
+    vol = abs(np.linalg.det(M)) / 6.0
+    Bm = np.zeros((6, 12))
+    for a in range(4):
+        gx, gy, gz = G[:, a]
+        Bm[:, 3 * a:3 * a + 3] = [[gx, 0, 0], [0, gy, 0], [0, 0, gz], [gy, gx, 0], [0, gz, gy], [gz, 0, gx]]
+    lam = E * nu / ((1 + nu) * (1 - 2 * nu))
+    mu = E / (2 * (1 + nu))
+    D = np.zeros((6, 6))
+    D[:3, :3] = lam
+    D[:3, :3] += 2 * mu * np.eye(3)
+    D[3:, 3:] = mu * np.eye(3)
+    return vol * Bm.T @ D @ Bm
+
+
+def elasticity3d(m, E=1.0, nu=0.3):
+    """C4: P1-tet (Kuhn 6-tet split) linear elasticity on an m^3-node unit-spacing grid, node-major 3-dof ordering,
+    face x = 0 clamped as identity rows/columns (cf. reference FEMSolver.cpp:136-161). Returns the scalar CSC triple
+    (symmetric, so CSC == CSR) and the right-hand side b = unit body force in -z on the free nodes.
+    Assembled stencil-wise: for every (tet type, local vertex pair) one 3 x 3 block is added to a slab of nodes."""
+    N = m ** 3
+    tets = _kuhn_tets()
+    blocks = {}   # offset (dx,dy,dz) -> [values (m,m,m,3,3) indexed [k,j,i], present (m,m,m) bool]
+
+    def slab(o):  # nodes cell_origin + o over all cells, as slices of the (k, j, i) grid
+        return tuple(slice(o[ax], o[ax] + m - 1) for ax in (2, 1, 0))
+
+    for T in tets:
+        K = _p1_elastic_element(T, E, nu)
+        for a in range(4):
+            for b in range(4):
+                d = tuple(int(t) for t in (T[b] - T[a]))
+                if d not in blocks:
+                    blocks[d] = [np.zeros((m, m, m, 3, 3)), np.zeros((m, m, m), bool)]
+                sl = slab(T[a])
+                blocks[d][0][sl] += K[3 * a:3 * a + 3, 3 * b:3 * b + 3]
+                blocks[d][1][sl] = True
+    # clamp x = 0: rows and columns of those nodes become identity
+    offs = sorted(blocks, key=lambda d: d[0] + m * d[1] + m * m * d[2])
+    ii = np.arange(m)
+    for d in offs:
+        V, Pm = blocks[d]
+        row_clamped = np.zeros((m, m, m), bool)
+        row_clamped[:, :, 0] = True
+        col_clamped = np.zeros((m, m, m), bool)
+        col_i = ii + d[0]
+        col_clamped[:, :, (col_i == 0)] = True
+        kill = row_clamped | col_clamped
+        if d == (0, 0, 0):
+            V[row_clamped] = np.eye(3)
+        else:
+            Pm &= ~kill
+            V[kill] = 0.0
+    # block CSR in ascending column order
+    present = np.stack([blocks[d][1].reshape(N) for d in offs], axis=1)            # N x noff
+    cnt = present.sum(axis=1)
+    brp = np.zeros(N + 1, np.int64)
+    np.cumsum(cnt, out=brp[1:])
+    node = np.arange(N, dtype=np.int64)
+    coloff = np.array([d[0] + m * d[1] + m * m * d[2] for d in offs], np.int64)
+    rows_idx, off_idx = np.nonzero(present)                                        # row-major: ascending offsets per row
+    bci = node[rows_idx] + coloff[off_idx]
+    allv = np.stack([blocks[d][0].reshape(N, 3, 3) for d in offs], axis=1)          # N x noff x 3 x 3
+    bva = allv[rows_idx, off_idx]                                                   # nnzb x 3 x 3
+    del allv
+    nnzb = bci.shape[0]
+    # scalar CSR: row 3 I + r = blocks of I in order, each contributing columns 3 J .. 3 J + 2
+    len3 = 3 * cnt
+    ptr = np.zeros(3 * N + 1, np.int64)
+    np.cumsum(np.repeat(len3, 3), out=ptr[1:])
+    col = np.empty(9 * nnzb, np.int32)
+    val = np.empty(9 * nnzb, np.float64)
+    blk_row = rows_idx                                                              # block -> node
+    q = np.arange(nnzb, dtype=np.int64) - brp[blk_row]                              # position of the block inside its row
+    for r in range(3):
+        base = ptr[3 * blk_row + r] + 3 * q
+        for c in range(3):
+            col[base + c] = (3 * bci + c).astype(np.int32)
+            val[base + c] = bva[:, r, c]
+    b = np.zeros(3 * N)
+    free = np.ones((m, m, m), bool)
+    free[:, :, 0] = False
+    b[2::3][free.reshape(N)] = -1.0
+    return ptr.astype(np.int32), col, val, b

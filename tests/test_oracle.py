@@ -167,3 +167,47 @@ def test_amg_galerkin_and_transfer_properties(orc):
     np.testing.assert_allclose(np.asarray(P.sum(axis=1)).ravel()[rows_interior], 1.0, atol=1e-13)
     agg = H.aggregates(0)
     assert agg.min() >= 0 and agg.max() == nc - 1 and len(np.unique(agg)) == nc
+
+
+def test_block_oracle_reduces_to_scalar_oracle(orc):
+    """The block-arithmetic AMG oracle with B = 1 is the scalar AMGCL restatement (same hierarchy, same iterates)."""
+    from oracle import amg_block_oracle as BO
+    o, i, v = orc.poisson3d(20)
+    b = orc.spmv_csc(o, i, v, orc.splitmix64(42, 8000))
+    H1, Hc = BO.BlockAmg(o, i, v, 1), orc.Amg(o, i, v)
+    assert [r for r, _ in H1.level_sizes()] == [Hc.level_info(l)["rows"] for l in range(Hc.num_levels)]
+    assert [z for _, z in H1.level_sizes()] == [Hc.level_info(l)["nnz"] for l in range(Hc.num_levels)]
+    x1, it1, _ = H1.cg(b, tol=1e-8)
+    xc, itc, _ = Hc.cg(b, tol=1e-8)
+    assert it1 == itc and np.abs(x1 - xc).max() < 1e-13
+
+
+def test_elasticity_generator_matches_element_assembly():
+    """C4 generator (stencil-wise assembly) against a brute-force element loop; SPD; block oracle converges on it."""
+    import scipy.sparse as sp
+    from polysolve_b200 import problems as P
+    from oracle import amg_block_oracle as BO
+    m = 5
+    o, i, v, b = P.elasticity3d(m)
+    N = len(b)
+    A = sp.csr_matrix((v, i, o), shape=(N, N))
+    nid = lambda p: int(p[0] + m * p[1] + m * m * p[2])  # noqa: E731
+    ref = np.zeros((N, N))
+    for cz in range(m - 1):
+        for cy in range(m - 1):
+            for cx in range(m - 1):
+                for T in P._kuhn_tets():
+                    K = P._p1_elastic_element(T, 1.0, 0.3)
+                    ids = [nid(T[a] + np.array([cx, cy, cz])) for a in range(4)]
+                    dof = np.array([3 * q + c for q in ids for c in range(3)])
+                    ref[np.ix_(dof, dof)] += K
+    cl = np.array([3 * nid((0, j, k)) + c for j in range(m) for k in range(m) for c in range(3)])
+    ref[cl, :] = 0
+    ref[:, cl] = 0
+    ref[cl, cl] = 1
+    assert np.abs(ref - A.toarray()).max() < 1e-14
+    assert np.linalg.eigvalsh(ref).min() > 0
+    o, i, v, b = P.elasticity3d(12)
+    H = BO.BlockAmg(o, i, v, 3)
+    x, it, rel = H.cg(b, tol=1e-8)
+    assert len(H.levels) == 2 and 0 < it < 30 and rel < 1e-8
