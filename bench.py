@@ -220,7 +220,7 @@ def run_ours(args):
 
     s = psb.Solver.create("CUDA", "")
     s.set_parameters({"CUDA": {"krylov": "cg", "precond": "jacobi", "tolerance": TOL, "max_iter": MAX_ITER,
-                               "check_every": args.check_every, "device": local}})
+                               "check_every": args.check_every, "device": local, "cg_kernel": args.cg_kernel}})
     if world > 1:
         s.dist_setup_torch(halo_cap=1 << 20)
     t0 = time.perf_counter()
@@ -362,7 +362,8 @@ def run_ours(args):
                    "l2_policy": "inputs_exceed_l2 (0.88 GB matrix + 0.4 GB vectors per iteration vs 126 MB L2)"
                    if world <= 2 else "per-GPU working set approaches L2 size at this rank count; no flush (strong scaling of the fixed system)",
                    "iters_per_solve": iters / args.steps, "rel_residual": rel_res,
-                   "spmv_kernel": info["spmv_kernel"], "check_every": args.check_every,
+                   "spmv_kernel": info["spmv_kernel"], "cg_kernel": info.get("cg_kernel"), "check_every": args.check_every,
+                   "persist_phase_us_per_iter": [round(c / 1.965e3 / max(1, info["solver_iter"]), 2) for c in info.get("persist_cycles", [])],
                    "analyze_s": t_analyze, "factorize_s": t_factorize},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (8 * nnz + 16 * N) // world, "d2h_bytes_per_step": 8 * N // world,
                 "what": "factorize_csc(host values) + solve(host b, x) per step, pinned host buffers; bytes are per rank"},
@@ -393,6 +394,7 @@ def main():
     ap.add_argument("--n", type=int, default=216, help="grid points per side (216 -> 10,077,696 DoF)")
     ap.add_argument("--check-every", type=int, default=16)
     ap.add_argument("--ref-iters", type=int, default=40, help="CG iterations per CPU sample step")
+    ap.add_argument("--cg-kernel", default="auto", choices=["auto", "persistent", "split"])
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-amg", action="store_true", help="skip the AMG-PCG (config 3) leg")
     ap.add_argument("--amg-cpu-n", type=int, default=0, help="grid side of the CPU AMG leg (0 = the full --n system)")

@@ -95,24 +95,27 @@ private:
 // Multi-GPU communication over NVLink peer memory (one process per GPU; buffers exchanged as CUDA
 // IPC handles). Every rank owns one "comm buffer" with the same layout; kernels store straight into
 // the peers' buffers (st.global on mapped peer pointers) and poll their own.
-//   [0, 4096)     reduction slots  RedSlot[2 parity][8 source ranks]
-//   [4096, 8192)  halo flags       unsigned long long[8 source ranks]  (monotonic epoch)
+//   [0, 4096)     reduction slots  RedSlot[2 parity][8 source ranks]   (flag-in-data words, no fences)
+//   [4096, 8192)  halo flags       unsigned long long[8 source ranks]  (monotonic count of landed push chunks)
 //   [8192, ...)   halo data        double[2 parity][8 source ranks][halo_cap]
 constexpr int kMaxRanks = 8;
+// One fp64 travels as two 8-byte words {32 payload bits, 32-bit sequence tag}: an aligned 8-byte store is
+// single-copy atomic over NVLink, so a word whose tag matches carries valid payload -- the reader needs no
+// fence and the writer no flag store behind a fence (the "LL" idea of NCCL's low-latency protocol).
 struct RedSlot
 {
-    double v[kMaxRed];
-    unsigned long long seq;
-    unsigned long long pad[3];
+    uint4 w[kMaxRed]; // {lo, tag, hi, tag}
 };
 static_assert(sizeof(RedSlot) == 64, "RedSlot must be 64 bytes");
 constexpr size_t kCommFlagsOff = 4096, kCommHaloOff = 8192;
+constexpr int kPushChunk = 512; // halo entries per push chunk (one release-add on the consumer's flag per chunk)
 
 struct CommDev
 {
     int world = 1, rank = 0;
     long long halo_cap = 0;           // doubles per (parity, source rank) region
     unsigned char *peer[kMaxRanks];   // comm buffer base of every rank (peer[rank] is local)
+    int in_chunks[kMaxRanks];         // push chunks per epoch this rank receives from every source (0: none)
     unsigned long long *red_seq;      // local: number of all-reduces completed
     unsigned long long *push_epoch;   // local: number of halo pushes completed
     int *error;                       // local: set to 1 on a spin-wait timeout
@@ -142,15 +145,34 @@ __device__ __forceinline__ void st_sys(unsigned long long *p, unsigned long long
 {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ double ld_sys_f64(const double *p)
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+// flag += v on a (peer) counter with release semantics at system scope: every store this thread has observed
+// (its own and, through the preceding bar.sync, its CTA's) is visible before the increment
+__device__ __forceinline__ void red_release_sys_add(unsigned long long *p, unsigned long long v)
 {
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_sys_f64(double *p, double v)
+__device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v)
 {
-    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_ll(uint4 *p, double v, unsigned tag)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.relaxed.sys.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)b), "r"(tag), "r"((unsigned)(b >> 32)), "r"(tag)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 ld_ll(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
 }
 // spin until *p >= want (system scope); false on timeout
 __device__ __forceinline__ bool spin_ge(const unsigned long long *p, unsigned long long want)
@@ -208,38 +230,50 @@ __device__ __forceinline__ void block_sum(double (&v)[NV], double (*sm)[THREADS 
 }
 
 // All-reduce (sum) of NV doubles across the ranks, fused into the reducing kernel: the last CTA of
-// every rank stores its totals into slot[parity][rank] of EVERY peer's comm buffer over NVLink,
-// then waits until all `world` slots of its own buffer carry this reduction's sequence number and
-// sums them in rank order (so every rank obtains the bit-identical result). Two slot parities are
-// enough: a rank cannot start reduction s+2 before every peer has finished reading reduction s.
-// Called by all threads of the last CTA; tot[] is valid in thread 0 on entry and on return.
+// every rank stores its totals as tagged words into slot[parity][rank] of EVERY peer's comm buffer over
+// NVLink, then polls the `world` slots of its own buffer until their tags carry this reduction's sequence
+// number and sums them in rank order (so every rank obtains the bit-identical result). One NVLink store
+// latency per all-reduce; no fence on either side. Two slot parities are enough: a rank cannot start
+// reduction s+2 before every peer has finished reading reduction s.
+// Called by all threads of the reducing CTA (>= 32 threads); tot[] is valid in thread 0 on entry and on
+// return. seq = index of this reduction (1-based, identical on every rank).
 template <int NV>
-__device__ __forceinline__ void comm_allreduce(const CommDev &c, double (&tot)[NV])
+__device__ __forceinline__ void comm_allreduce_seq(const CommDev &c, double (&tot)[NV], unsigned long long seq)
 {
     __shared__ double sh[kMaxRed];
-    __shared__ unsigned long long sseq;
+    __shared__ double got[kMaxRed][kMaxRanks];
     if (threadIdx.x == 0)
     {
 #pragma unroll
         for (int i = 0; i < NV; ++i)
             sh[i] = tot[i];
-        sseq = *c.red_seq + 1;
     }
     __syncthreads();
-    const unsigned long long seq = sseq;
     const int par = (int)(seq & 1);
+    const unsigned tag = (unsigned)seq;
     if ((int)threadIdx.x < c.world)
     {
         RedSlot *dst = c.slot(threadIdx.x, par, c.rank);
 #pragma unroll
         for (int i = 0; i < NV; ++i)
-            st_sys_f64(&dst->v[i], sh[i]);
-        __threadfence_system();
-        st_sys(&dst->seq, seq);
+            st_ll(&dst->w[i], sh[i], tag);
         const RedSlot *src = c.slot(c.rank, par, threadIdx.x);
-        if (!spin_ge(&src->seq, seq))
-            *c.error = 1;
-        __threadfence_system();
+        const long long t0 = clock64();
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+        {
+            uint4 v = ld_ll(&src->w[i]);
+            while (v.y != tag || v.w != tag)
+            {
+                if (clock64() - t0 > kSpinLimit)
+                {
+                    *c.error = 1;
+                    break;
+                }
+                v = ld_ll(&src->w[i]);
+            }
+            got[i][threadIdx.x] = __longlong_as_double((long long)(((unsigned long long)v.z << 32) | v.x));
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0)
@@ -249,11 +283,21 @@ __device__ __forceinline__ void comm_allreduce(const CommDev &c, double (&tot)[N
         {
             double s = 0;
             for (int q = 0; q < c.world; ++q)
-                s += ld_sys_f64(&c.slot(c.rank, par, q)->v[i]);
+                s += got[i][q];
             tot[i] = s;
         }
-        *c.red_seq = seq;
     }
+}
+template <int NV>
+__device__ __forceinline__ void comm_allreduce(const CommDev &c, double (&tot)[NV])
+{
+    __shared__ unsigned long long sseq;
+    if (threadIdx.x == 0)
+        sseq = *c.red_seq + 1;
+    __syncthreads();
+    comm_allreduce_seq<NV>(c, tot, sseq);
+    if (threadIdx.x == 0)
+        *c.red_seq = sseq;
 }
 
 // Returns true (for all threads of the CTA) in the CTA that finished last; then tot[] (thread 0) holds

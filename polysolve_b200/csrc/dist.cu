@@ -148,39 +148,23 @@ DistState::~DistState()
 }
 
 // ====================================================================================== kernels
-struct PushList
-{
-    const int *rows, *peer, *off;
-    int n;
-    unsigned int *counter;
-    unsigned send_mask;
-    int push_blocks;
-};
-
-// the push part shared by both kernels below: value(row) -> halo region of the consumer, then flags
+// The push part shared by the kernels below: value(row) -> halo region of the consumer. The send list is cut
+// into chunks of kPushChunk entries per destination; a CTA stores a chunk and then adds 1 to the consumer's
+// flag with release semantics (no grid-level ticket, no second fence). push_no = number of this push (1-based).
 template <class ValueFn>
-__device__ __forceinline__ void push_section(const PushList &pl, const CommDev &c, int first_push_block, ValueFn value)
+__device__ __forceinline__ void push_section(const PushList &pl, const CommDev &c, unsigned long long push_no, int first_block, int nblocks,
+                                             ValueFn value)
 {
-    const unsigned long long epoch = *c.push_epoch + 1;
-    const int par = (int)(epoch & 1);
-    for (int e = (blockIdx.x - first_push_block) * blockDim.x + threadIdx.x; e < pl.n; e += pl.push_blocks * blockDim.x)
+    const int par = (int)(push_no & 1);
+    for (int ch = (int)blockIdx.x - first_block; ch < pl.nchunks; ch += nblocks)
     {
-        const int row = pl.rows[e];
-        c.halo(pl.peer[e], par, c.rank)[pl.off[e]] = value(row);
-    }
-    __threadfence_system();
-    __syncthreads();
-    __shared__ int last_push;
-    if (threadIdx.x == 0)
-        last_push = atomicInc(pl.counter, pl.push_blocks - 1) == (unsigned)(pl.push_blocks - 1);
-    __syncthreads();
-    if (last_push)
-    {
-        __threadfence_system();
-        if ((int)threadIdx.x < c.world && ((pl.send_mask >> threadIdx.x) & 1u))
-            st_sys(c.halo_flag(threadIdx.x, c.rank), epoch);
+        const int peer = pl.chunk_peer[ch], start = pl.chunk_start[ch], cnt = pl.chunk_cnt[ch];
+        double *dst = c.halo(peer, par, c.rank) + pl.chunk_off[ch];
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x)
+            dst[e] = value(pl.rows[start + e]);
+        __syncthreads();
         if (threadIdx.x == 0)
-            *c.push_epoch = epoch;
+            red_release_sys_add(c.halo_flag(peer, c.rank), 1ull);
     }
 }
 
@@ -197,6 +181,7 @@ __global__ void __launch_bounds__(THREADS) cg_dir_dist_kernel(long long n2, doub
         return;
     const double beta = FIRST ? 0.0 : st->rz_new / st->rz;
     const int push_blocks = (int)gridDim.x - vec_blocks;
+    const unsigned long long push_no = *rc.comm.push_epoch + 1;
     if ((int)blockIdx.x >= push_blocks)
     {
         const long long stride = (long long)vec_blocks * THREADS;
@@ -216,17 +201,22 @@ __global__ void __launch_bounds__(THREADS) cg_dir_dist_kernel(long long n2, doub
         }
     }
     else
-        push_section(pl, rc.comm, 0, [&](int row) { return FIRST ? dinv[row] * r[row] : dinv[row] * r[row] + beta * p_old[row]; });
+        push_section(pl, rc.comm, push_no, 0, push_blocks, [&](int row) { return FIRST ? dinv[row] * r[row] : dinv[row] * r[row] + beta * p_old[row]; });
     double acc[1] = {0}, tot[1];
-    if (grid_reduce<0, THREADS>(acc, rc, tot) && threadIdx.x == 0 && !FIRST)
+    if (grid_reduce<0, THREADS>(acc, rc, tot) && threadIdx.x == 0)
     {
-        // FinCgDirEigen
-        st->rz = st->rz_new;
-        st->iter += 1;
-        if (st->iter >= st->max_iter)
+        if (push_blocks > 0)
+            *rc.comm.push_epoch = push_no;
+        if (!FIRST)
         {
-            st->done = 1;
-            st->status = ST_MAXITER;
+            // FinCgDirEigen
+            st->rz = st->rz_new;
+            st->iter += 1;
+            if (st->iter >= st->max_iter)
+            {
+                st->done = 1;
+                st->status = ST_MAXITER;
+            }
         }
     }
 }
@@ -235,7 +225,11 @@ __global__ void __launch_bounds__(THREADS) cg_dir_dist_kernel(long long n2, doub
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) halo_push_kernel(const double *__restrict__ v, RedCtx rc, PushList pl)
 {
-    push_section(pl, rc.comm, 0, [&](int row) { return v[row]; });
+    const unsigned long long push_no = *rc.comm.push_epoch + 1;
+    push_section(pl, rc.comm, push_no, 0, (int)gridDim.x, [&](int row) { return v[row]; });
+    double acc[1] = {0}, tot[1];
+    if (grid_reduce<0, THREADS>(acc, rc, tot) && threadIdx.x == 0)
+        *rc.comm.push_epoch = push_no;
 }
 
 // ====================================================================================== Solver (dist mode)
@@ -258,7 +252,6 @@ void Solver::dist_prepare(int rank, int world, long long halo_cap, char handle_o
     PSB_CUDA(cudaMemset(d.comm_buf, 0, d.comm_bytes));
     PSB_CUDA(cudaMalloc(&d.counters, 64));
     PSB_CUDA(cudaMemset(d.counters, 0, 64));
-    d.push_counter.alloc(4, true);
     cudaIpcMemHandle_t hnd;
     PSB_CUDA(cudaIpcGetMemHandle(&hnd, d.comm_buf));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -335,23 +328,35 @@ void Solver::analyze_pattern_dist(long long n_, long long nnz_, const int *outer
             d.send_mask |= 1u << q;
     }
     A.halo_mask = d.recv_mask;
-    // device push list
+    // device push list: the send rows of every destination cut into chunks of kPushChunk entries; the consumer
+    // derives the number of chunks it will see from its own recv_count (same formula on both sides)
     d.n_push = (int)P.send_rows.size();
-    std::vector<int> peer(d.n_push), off(d.n_push);
+    std::vector<int> cpeer, cstart, ccnt, coff;
     for (int q = 0; q < d.world; ++q)
-        for (int e = P.send_begin[q]; e < P.send_begin[q + 1]; ++e)
+    {
+        const int cnt = P.send_begin[q + 1] - P.send_begin[q];
+        for (int o = 0; o < cnt; o += kPushChunk)
         {
-            peer[e] = q;
-            off[e] = e - P.send_begin[q];
+            cpeer.push_back(q);
+            cstart.push_back(P.send_begin[q] + o);
+            ccnt.push_back(std::min(kPushChunk, cnt - o));
+            coff.push_back(o);
         }
+        ctx.comm.in_chunks[q] = (P.recv_count[q] + kPushChunk - 1) / kPushChunk;
+    }
+    d.n_chunks = (int)cpeer.size();
     d.push_rows.alloc(std::max(1, d.n_push));
-    d.push_peer.alloc(std::max(1, d.n_push));
-    d.push_off.alloc(std::max(1, d.n_push));
+    d.chunk_tab.alloc(std::max(1, 4 * d.n_chunks));
     if (d.n_push)
     {
+        std::vector<int> tab;
+        tab.insert(tab.end(), cpeer.begin(), cpeer.end());
+        tab.insert(tab.end(), cstart.begin(), cstart.end());
+        tab.insert(tab.end(), ccnt.begin(), ccnt.end());
+        tab.insert(tab.end(), coff.begin(), coff.end());
         PSB_CUDA(cudaMemcpyAsync(d.push_rows.p, P.send_rows.data(), sizeof(int) * d.n_push, cudaMemcpyHostToDevice, st));
-        PSB_CUDA(cudaMemcpyAsync(d.push_peer.p, peer.data(), sizeof(int) * d.n_push, cudaMemcpyHostToDevice, st));
-        PSB_CUDA(cudaMemcpyAsync(d.push_off.p, off.data(), sizeof(int) * d.n_push, cudaMemcpyHostToDevice, st));
+        PSB_CUDA(cudaMemcpyAsync(d.chunk_tab.p, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, st));
+        PSB_CUDA(cudaStreamSynchronize(st)); // tab is a stack-scoped staging vector
     }
     // values window of this rank inside the CSC value array (banded matrices: ~ the local share)
     d.val_lo = 0;
@@ -374,6 +379,28 @@ void Solver::analyze_pattern_dist(long long n_, long long nnz_, const int *outer
         PSB_CUDA(cudaStreamSynchronize(st)); // rel is a stack-scoped staging vector
     }
     A.plan(prm.spmv_kernel);
+    // interior-first tile order of the stream schedule: tiles of kSpmvThreads rows that touch no halo column come
+    // first, so the persistent CG kernel multiplies them while the neighbours' pushes are still on the wire
+    {
+        const int T = StreamProd::threads;
+        const int ntiles = (int)((n + T - 1) / T);
+        std::vector<int> order, boundary;
+        order.reserve(ntiles);
+        for (int t = 0; t < ntiles; ++t)
+        {
+            const int k0 = P.rp[(size_t)t * T], k1 = P.rp[std::min<long long>(n, (long long)(t + 1) * T)];
+            bool halo = false;
+            for (int k = k0; k < k1 && !halo; ++k)
+                halo = P.ci[k] >= (int)n;
+            (halo ? boundary : order).push_back(t);
+        }
+        d.n_interior_tiles = (int)order.size();
+        order.insert(order.end(), boundary.begin(), boundary.end());
+        d.tile_order.alloc(std::max(1, ntiles));
+        if (ntiles)
+            PSB_CUDA(cudaMemcpyAsync(d.tile_order.p, order.data(), sizeof(int) * ntiles, cudaMemcpyHostToDevice, st));
+        PSB_CUDA(cudaStreamSynchronize(st)); // order is a stack-scoped staging vector
+    }
     PSB_CUDA(cudaStreamSynchronize(st));
 }
 
@@ -412,10 +439,15 @@ void Solver::check_comm_error()
     }
 }
 
-static PushList make_push(DistState &d, int push_blocks)
+PushList make_push(DistState &d)
 {
-    return PushList{d.push_rows.p, d.push_peer.p, d.push_off.p, d.n_push, d.push_counter.p, d.send_mask, push_blocks};
+    const int *t = d.chunk_tab.p;
+    const int nc = d.n_chunks;
+    return PushList{d.push_rows.p, t, t + nc, t + 2 * nc, t + 3 * nc, nc};
 }
+// CTAs that push: one per chunk up to 128 (a CTA loops over chunks beyond that); 0 on a single rank. Every rank
+// of a multi-rank run launches at least one so the epochs advance in lockstep.
+static int push_ctas(const DistState &d) { return d.world > 1 ? std::max(1, std::min(128, d.n_chunks)) : 0; }
 
 // ---------------------------------------------------------------------------------- rank-local AMG
 __global__ void diag_count_kernel(int n, int nl, const int *__restrict__ rp, const int *__restrict__ ci, int *__restrict__ cnt)
@@ -499,6 +531,7 @@ __global__ void __launch_bounds__(THREADS) cg_dir_amgcl_dist_kernel(long long n2
         return;
     const double beta = st->iter ? st->rho / st->rho_old : 0.0;
     const int push_blocks = (int)gridDim.x - vec_blocks;
+    const unsigned long long push_no = *rc.comm.push_epoch + 1;
     if ((int)blockIdx.x >= push_blocks)
     {
         const long long stride = (long long)vec_blocks * THREADS;
@@ -512,7 +545,10 @@ __global__ void __launch_bounds__(THREADS) cg_dir_amgcl_dist_kernel(long long n2
         }
     }
     else
-        push_section(pl, rc.comm, 0, [&](int row) { return s[row] + (beta != 0.0 ? beta * p_old[row] : 0.0); });
+        push_section(pl, rc.comm, push_no, 0, push_blocks, [&](int row) { return s[row] + (beta != 0.0 ? beta * p_old[row] : 0.0); });
+    double acc[1] = {0}, tot[1];
+    if (grid_reduce<0, THREADS>(acc, rc, tot) && threadIdx.x == 0 && push_blocks > 0)
+        *rc.comm.push_epoch = push_no;
 }
 
 // AMG-PCG on the row partition (amgcl cg ordering). The preconditioner is rank-local: every rank
@@ -529,8 +565,8 @@ void Solver::run_cg_amgcl_dist(const double *d_b)
     init_state(*this, prm.tolerance, prm.max_iter);
     const long long n2 = n_pad / 2;
     const int vec_blocks = vec_grid(n2);
-    const int push_blocks = d.world > 1 ? std::max(1, std::min(128, (d.n_push + 2 * kVecThreads - 1) / (2 * kVecThreads))) : 0;
-    PushList pl = make_push(d, std::max(1, push_blocks));
+    const int push_blocks = push_ctas(d);
+    PushList pl = make_push(d);
     RedCtx rc = ctx.red();
     PSB_CUDA(cudaMemsetAsync(vp.p, 0, sizeof(double) * n_pad, ctx.stream));
     if (push_blocks)
@@ -577,9 +613,8 @@ void Solver::run_cg_eigen_dist(const double *d_b)
     const long long n2 = n_pad / 2;
     const int vec_blocks = vec_grid(n2);
     // every rank pushes at every push point (even an empty list) so the epochs advance in lockstep
-    // enough push CTAs that every thread stores at most ~2 entries (the chain rows -> value -> remote store is latency-bound)
-    const int push_blocks = d.world > 1 ? std::max(1, std::min(128, (d.n_push + 2 * kVecThreads - 1) / (2 * kVecThreads))) : 0;
-    PushList pl = make_push(d, std::max(1, push_blocks));
+    const int push_blocks = push_ctas(d);
+    PushList pl = make_push(d);
     RedCtx rc = ctx.red();
     if (push_blocks)
     {
@@ -594,6 +629,18 @@ void Solver::run_cg_eigen_dist(const double *d_b)
     check_launch();
     ctx.prof_end();
     const int batch_iters = std::max(2, prm.check_every & ~1);
+    if (use_persist())
+    {
+        persist_reset();
+        auto pbatch = [&]() { launch_cg_persist(vp.p, d.vp2.p, batch_iters); };
+        std::ostringstream pkey;
+        pkey << "cg_persist_dist/" << n << "/" << (void *)vx.p << "/" << (void *)A.va.p << "/" << (void *)d.vp2.p << "/" << batch_iters;
+        drive(pbatch, batch_iters, pkey.str());
+        finish_solve();
+        persist_collect();
+        check_comm_error();
+        return;
+    }
     auto batch = [&]() {
         double *pc = vp.p, *pn = d.vp2.p;
         for (int i = 0; i < batch_iters; ++i)

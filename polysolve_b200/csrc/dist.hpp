@@ -23,6 +23,14 @@ struct DistPlanHost
     void build(long long n, long long nnz, const int *outer, const int *inner, int rank_, int world_, long long halo_cap_);
 };
 
+// Device view of the send side of the halo exchange (see push_section, dist.cu)
+struct PushList
+{
+    const int *rows;                                          // local row ids, grouped by destination
+    const int *chunk_peer, *chunk_start, *chunk_cnt, *chunk_off; // per chunk: destination, first entry in rows, entries, offset in the destination's region
+    int nchunks;
+};
+
 struct DistState
 {
     int rank = 0, world = 1;
@@ -33,10 +41,12 @@ struct DistState
     bool connected = false;
     unsigned long long *counters = nullptr; // device: [0] red_seq, [1] push_epoch, [2] error (int)
     DistPlanHost plan;
-    // device push list (all destinations concatenated)
-    DevBuf<int> push_rows, push_peer, push_off;
-    DevBuf<unsigned int> push_counter;
-    int n_push = 0;
+    // device push list: send rows of all destinations concatenated + the chunk table [peer | start | count | offset]
+    DevBuf<int> push_rows, chunk_tab;
+    int n_push = 0, n_chunks = 0;
+    // interior-first tile order of the stream schedule (persistent CG kernel): tiles without halo columns first
+    DevBuf<int> tile_order;
+    int n_interior_tiles = 0;
     unsigned send_mask = 0, recv_mask = 0;
     DevBuf<double> vp2; // second direction buffer (p ping-pongs so pushed values never race with the update)
     // values ingest: the CSC window [val_lo, val_hi) that holds every local entry is uploaded as one
@@ -49,5 +59,7 @@ struct DistState
     DevBuf<int> diag_src; // A_diag.va[k] = A.va[diag_src[k]]
     ~DistState();
 };
+
+PushList make_push(DistState &d);
 
 } // namespace psb

@@ -23,7 +23,8 @@ enum : int
     ST_CONVERGED = 1,
     ST_MAXITER = 2,
     ST_BREAKDOWN = 3,
-    ST_ZERO_RHS = 4
+    ST_ZERO_RHS = 4,
+    ST_COMM = 5 // a grid-wide or cross-GPU wait timed out (persistent kernel)
 };
 
 struct CsrView
@@ -38,27 +39,33 @@ struct CsrView
     unsigned halo_mask; // bit q set: rank q pushes halo values to this rank
 };
 
-// x[c] for a local column, xh[c - nl] for a halo column
+// x[c] for a local column, xh[c - nl] for a halo column. Halo values were written by a peer GPU: they are
+// read at L2 (ld.global.cg), never through the non-coherent L1.
 __device__ __forceinline__ double ldx(const double *__restrict__ x, const double *__restrict__ xh, int nl, int c)
 {
-    return c < nl ? __ldg(x + c) : xh[c - nl];
+    return c < nl ? __ldg(x + c) : __ldcg(xh + (c - nl));
 }
 
-// Called by every thread at the start of a kernel that gathers halo columns: waits until every
-// neighbour's push of the current epoch has landed and returns the halo base pointer of that epoch.
+// Waits until every neighbour's push number `epoch` has landed completely: the consumer's flag of source q
+// counts landed push chunks, so push `epoch` is complete once it reaches epoch * in_chunks[q]. Called by all
+// threads of a CTA; returns the halo base pointer of that epoch.
+__device__ __forceinline__ const double *wait_halo_epoch(unsigned halo_mask, const CommDev &c, unsigned long long epoch)
+{
+    if ((int)threadIdx.x < c.world && ((halo_mask >> threadIdx.x) & 1u))
+    {
+        if (!spin_ge(c.halo_flag(c.rank, threadIdx.x), epoch * (unsigned long long)c.in_chunks[threadIdx.x]))
+            *c.error = 1;
+        fence_acq_rel_sys();
+    }
+    __syncthreads();
+    return c.halo(c.rank, (int)(epoch & 1), 0);
+}
+// Kernel-start form: pushes completed locally == epoch of the vector being multiplied.
 __device__ __forceinline__ const double *wait_halo(const CsrView &A, const CommDev &c)
 {
     if (A.halo_mask == 0)
         return nullptr;
-    const unsigned long long epoch = *c.push_epoch; // pushes completed locally == epoch of the vector being multiplied
-    if ((int)threadIdx.x < c.world && ((A.halo_mask >> threadIdx.x) & 1u))
-    {
-        if (!spin_ge(c.halo_flag(c.rank, threadIdx.x), epoch))
-            *c.error = 1;
-        __threadfence_system();
-    }
-    __syncthreads();
-    return c.halo(c.rank, (int)(epoch & 1), 0);
+    return wait_halo_epoch(A.halo_mask, c, *c.push_epoch);
 }
 
 // ---------------------------------------------------------------------------------- finalizers

@@ -386,6 +386,8 @@ void Solver::set_parameters(const std::string &json)
         np.use_graph = j.at("use_graph").as_bool();
     if (j.contains("spmv_kernel"))
         np.spmv_kernel = j.at("spmv_kernel").as_str();
+    if (j.contains("cg_kernel"))
+        np.cg_kernel = j.at("cg_kernel").as_str();
     if (j.contains("device"))
         np.device = (int)j.at("device").as_num();
     if (j.contains("block_size"))
@@ -400,6 +402,8 @@ void Solver::set_parameters(const std::string &json)
         throw std::runtime_error("psb200: unknown krylov '" + np.krylov + "' (cg | bicgstab)");
     if (np.precond != "jacobi" && np.precond != "amg" && np.precond != "none")
         throw std::runtime_error("psb200: unknown precond '" + np.precond + "' (jacobi | amg | none)");
+    if (np.cg_kernel != "auto" && np.cg_kernel != "persistent" && np.cg_kernel != "split")
+        throw std::runtime_error("psb200: unknown cg_kernel '" + np.cg_kernel + "' (auto | persistent | split)");
     if (np.krylov == "bicgstab" && np.precond == "amg")
         throw std::runtime_error("psb200: bicgstab + amg is not available yet");
     prm = np;
@@ -804,6 +808,8 @@ void Solver::finish_solve()
     if (prm.profile)
         ctx.prof_collect();
     const KState &s = h_state[2];
+    if (s.status == ST_COMM)
+        throw std::runtime_error("psb200_solve: a grid-wide or cross-GPU wait timed out inside the persistent CG kernel");
     last_iters = s.iter;
     last_status = s.done ? s.status : ST_MAXITER;
     if (s.status == ST_ZERO_RHS)
@@ -834,6 +840,15 @@ void init_state(Solver &s, double tol, int max_iter)
 // Jacobi-PCG in Eigen's ordering (reference path EigenSolver.tpp:108-114 -> Eigen
 // conjugate_gradient()). Per iteration: 1 fused SpMV+dot, 1 fused x/r update + ||r||^2 + r.z,
 // 1 direction update = B_spmv + 88 N bytes of compulsory traffic.
+// The persistent kernel implements the TMA stream schedule only; per-launch profiling needs the split kernels.
+// auto = split: measured on B200 (profiles/r01_persist_vs_split.txt) the kernel-per-phase path is faster at 1 and 2
+// GPUs (at 4 CTAs / SM the vector phases of the fused kernel lose ~15 % of the HBM bandwidth to load imbalance
+// between SMs); the persistent kernel stays selectable for latency-bound partitions (many ranks, small systems).
+bool Solver::use_persist() const
+{
+    return prm.cg_kernel == "persistent" && A.kind == SPMV_STREAM && !prm.profile && n > 0;
+}
+
 void Solver::run_cg_eigen(const double *d_b)
 {
     KState *S = d_state;
@@ -841,6 +856,19 @@ void Solver::run_cg_eigen(const double *d_b)
     init_state(*this, prm.tolerance, prm.max_iter);
     launch_spmv(ctx, "spmv_residual", A, vx.p, EpiResidualNorms{vr.p, d_b, dinv.p}, FinInitEigen{S});
     launch_vec(ctx, "cg_dir", n_pad, OpCgDirEigen<true>{vp.p, vr.p, dinv.p, S, 0.0}, FinNone{}, done);
+    if (use_persist())
+    {
+        const int batch_iters = std::max(2, prm.check_every & ~1);
+        vp2.alloc((size_t)n_pad, false);
+        persist_reset();
+        auto batch = [&]() { launch_cg_persist(vp.p, vp2.p, batch_iters); };
+        std::ostringstream key;
+        key << "cg_persist/" << n << "/" << (void *)vx.p << "/" << (void *)A.va.p << "/" << (void *)vp2.p << "/" << batch_iters;
+        drive(batch, batch_iters, key.str());
+        finish_solve();
+        persist_collect();
+        return;
+    }
     auto batch = [&]() {
         for (int i = 0; i < prm.check_every; ++i)
         {
@@ -1003,13 +1031,14 @@ void Solver::precond_apply_host(const double *r, double *z, long long n_)
 
 void Solver::build_info()
 {
-    static const char *status_str[] = {"Running", "Converged", "Reach max iterations", "Breakdown (non-finite residual)", "Zero right-hand side"};
+    static const char *status_str[] = {"Running", "Converged", "Reach max iterations", "Breakdown (non-finite residual)", "Zero right-hand side",
+                                       "Communication timeout"};
     std::ostringstream o;
     o << "{";
     // both conventions: Eigen/MAS (EigenSolver.tpp:88-89, MASSolver.cu:214-219) and AMGCL/Hypre (AMGCL.cpp:142-143)
     o << "\"solver_iter\":" << last_iters << ",\"solver_error\":" << jnum(last_error);
     o << ",\"num_iterations\":" << last_iters << ",\"final_res_norm\":" << jnum(last_error);
-    o << ",\"solver_status\":" << jstr(status_str[std::min(std::max(last_status, 0), 4)]);
+    o << ",\"solver_status\":" << jstr(status_str[std::min(std::max(last_status, 0), 5)]);
     o << ",\"krylov\":" << jstr(prm.krylov) << ",\"precond\":" << jstr(prm.precond);
     o << ",\"n\":" << n_global << ",\"nnz\":" << nnz_global;
     if (dist)
@@ -1019,6 +1048,14 @@ void Solver::build_info()
     o << ",\"symmetric_pattern\":" << (sym_pattern ? "true" : "false");
     o << ",\"analyze_skipped\":" << (analyze_skipped ? "true" : "false");
     o << ",\"spmv_kernel\":" << jstr(A.kind == SPMV_STREAM ? "stream" : ("vector" + std::to_string(A.lpr)));
+    o << ",\"cg_kernel\":" << jstr(use_persist() ? "persistent" : "split");
+    if (use_persist())
+    {
+        o << ",\"persist_cycles\":[";
+        for (int i = 0; i < 6; ++i)
+            o << (i ? "," : "") << jnum(persist_cycles[i]);
+        o << "]";
+    }
     o << ",\"time_analyze_ms\":" << jnum(t_analyze_ms) << ",\"time_factorize_ms\":" << jnum(t_factorize_ms);
     o << ",\"time_precond_setup_ms\":" << jnum(t_setup_precond_ms) << ",\"time_solve_ms\":" << jnum(t_solve_ms);
     o << ",\"gpu_launches\":" << ctx.launches;

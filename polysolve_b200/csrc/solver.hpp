@@ -40,6 +40,7 @@ struct Params
     int check_every = 16;
     bool use_graph = true;
     std::string spmv_kernel = "auto";
+    std::string cg_kernel = "auto"; // Jacobi-PCG: persistent (one cooperative launch per batch) | split (one kernel per phase) | auto
     int device = -1; // -1: current device
     int block_size = 1;
     bool profile = false;
@@ -88,6 +89,14 @@ struct Solver
 
     // work vectors (padded, zero tails)
     DevBuf<double> vb, vx, vr, vp, vq, vz, vy, vv, vt, vr0;
+    DevBuf<double> vp2;               // ping-pong partner of vp (persistent CG kernel)
+    DevBuf<unsigned long long> gbar;  // grid-sync state of the persistent CG kernel (cg_persist.cu)
+    bool use_persist() const;
+    int persist_grid();
+    void persist_reset();
+    void persist_collect();
+    double persist_cycles[6] = {0, 0, 0, 0, 0, 0}; // CTA 0: spmv, sync, update, sync, dir+push, sync (SM cycles, last solve)
+    void launch_cg_persist(double *p_cur, double *p_other, int iters);
     KState *d_state = nullptr;
     KState *h_state = nullptr; // pinned, 4 slots
     cudaEvent_t ev[2] = {nullptr, nullptr};

@@ -177,6 +177,52 @@ def test_pcg_iteration_parity_3d(psb, orc, n, tol):
     assert np.linalg.norm(csc(o, i, v) @ x - b) / np.linalg.norm(b) < 2 * tol
 
 
+@pytest.mark.parametrize("n,check_every", [(20, 16), (48, 6), (37, 2)])
+def test_persistent_kernel_matches_split_kernels(psb, orc, n, check_every):
+    """The cooperative one-launch-per-batch kernel (cg_persist.cu) and the kernel-per-phase path run the same
+    algorithm in the same order: same iteration count (+-1 from the summation order of the reductions), same x."""
+    o, i, v = orc.poisson3d(n)
+    N = n ** 3
+    v = v * (1.0 + 0.05 * orc.splitmix64(13, len(v)))
+    v = 0.5 * (v + v[orc.csc_to_csr(N, o, i)[2]])  # keep it symmetric
+    b = orc.splitmix64(42, N)
+    out = {}
+    for mode in ("persistent", "split"):
+        s = make(psb, tolerance=1e-9, max_iter=5000, cg_kernel=mode, check_every=check_every)
+        s.factorize_raw(N, o, i, v)
+        x = np.zeros(N)
+        s.solve(b, x)
+        info = s.get_info()
+        assert info["cg_kernel"] == mode and info["solver_status"] == "Converged"
+        out[mode] = (x, info["solver_iter"], info["solver_error"])
+        x2 = x.copy()
+        s.solve(b, x2)  # warm start => 0 iterations on both paths
+        assert s.get_info()["solver_iter"] == 0 and np.array_equal(x2, x)
+    assert abs(out["persistent"][1] - out["split"][1]) <= 1
+    assert np.linalg.norm(out["persistent"][0] - out["split"][0]) / np.linalg.norm(out["split"][0]) < 1e-8
+    x0, it0, _, _ = orc.eigen_cg(o, i, v, b, tol=1e-9, max_iters=5000)
+    assert abs(out["persistent"][1] - it0) <= max(1, 0.02 * it0)
+    assert np.linalg.norm(out["persistent"][0] - x0) / np.linalg.norm(x0) < 1e-8
+
+
+def test_persistent_kernel_max_iter_and_odd_counts(psb, orc):
+    """max_iter that is not a multiple of the batch length: the kernel stops inside a batch exactly like Eigen."""
+    o, i, v = orc.poisson2d(40)
+    N = 1600
+    b = orc.splitmix64(5, N)
+    for mi in (1, 7, 10):
+        s = make(psb, tolerance=1e-14, max_iter=mi, check_every=4, cg_kernel="persistent")
+        s.factorize_raw(N, o, i, v)
+        x = np.zeros(N)
+        s.solve(b, x)
+        info = s.get_info()
+        assert info["cg_kernel"] == "persistent"
+        assert info["solver_iter"] == mi and info["solver_status"] == "Reach max iterations"
+        x0, it0, err0, _ = orc.eigen_cg(o, i, v, b, tol=1e-14, max_iters=mi)
+        assert it0 == mi
+        np.testing.assert_allclose(x, x0, rtol=0, atol=1e-12)
+
+
 def test_pcg_identity_precond_and_max_iter(psb, orc):
     o, i, v = orc.poisson2d(32)
     b = orc.splitmix64(42, 1024)
