@@ -71,6 +71,9 @@ int psb200_get_info(psb200_handle h, char *json_out, size_t cap, size_t *needed)
 /* Solver::name() -- Solver.hpp:131. Returns "CUDA". */
 const char *psb200_name(psb200_handle h);
 const char *psb200_last_error(psb200_handle h);
+/* Device buffers come from the GPU's stream-ordered memory pool and stay cached there between factorize() calls
+ * (policy precedent: one pool per solver, MASSolver.cu:154-156). This returns the cached, unused part to the driver. */
+int psb200_release_cached_memory(psb200_handle h);
 
 /* ---- multi-GPU (one process per GPU, up to 8 GPUs of one node). No reference counterpart.
  * The matrix is row-range partitioned (contiguous ranges balanced by nnz); halo x-entries and the

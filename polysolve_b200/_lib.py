@@ -20,7 +20,7 @@ f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 SYMBOLS = [
     "psb200_create", "psb200_destroy", "psb200_set_parameters", "psb200_set_tolerance", "psb200_set_block_size",
     "psb200_analyze_pattern_csc", "psb200_factorize_csc", "psb200_solve", "psb200_solve_device", "psb200_get_info",
-    "psb200_name", "psb200_last_error", "psb200_dist_prepare", "psb200_dist_connect", "psb200_dist_local_range",
+    "psb200_name", "psb200_last_error", "psb200_release_cached_memory", "psb200_dist_prepare", "psb200_dist_connect", "psb200_dist_local_range",
     "psb200_dist_plan_host", "psb200_debug_get_csr",
     "psb200_spmv", "psb200_bench_spmv", "psb200_get_stream", "psb200_debug_set_aggregates", "psb200_debug_get_level",
     "psb200_precond_apply", "psb200_debug_get_aggregates",
@@ -54,6 +54,7 @@ def lib():
     L.psb200_analyze_pattern_csc.argtypes = [H, C.c_int64, C.c_int64, i32p, i32p, C.c_int]
     L.psb200_factorize_csc.argtypes = [H, C.c_int64, C.c_int64, i32p, i32p, f64p]
     L.psb200_solve.argtypes = [H, f64p, f64p, C.c_int64]
+    L.psb200_release_cached_memory.argtypes = [H]
     L.psb200_solve_device.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int64]
     L.psb200_get_info.argtypes = [H, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.psb200_name.argtypes = [H]

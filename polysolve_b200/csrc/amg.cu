@@ -1142,8 +1142,8 @@ void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &
         L.t_prolong = wall_ms(st) - tp;
         tp = wall_ms(st);
         transpose(ctx_, tmp, L.P, L.R);
-        L.P.plan("auto");
-        L.R.plan("auto");
+        L.P.plan("auto", st);
+        L.R.plan("auto", st);
         L.t_transpose = wall_ms(st) - tp;
         // ---- Galerkin coarse operator A_c = R (A P)
         auto next = std::make_unique<AmgLevel>();
@@ -1156,7 +1156,7 @@ void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &
             spgemm(ctx_, tmp, L.R, AP, L.n_agg, next->Aown);
             L.t_rap = wall_ms(st) - tp;
         }
-        next->Aown.plan("auto");
+        next->Aown.plan("auto", st);
         next->A = &next->Aown;
         cur = std::move(next);
     }
@@ -1303,7 +1303,7 @@ std::string AmgHierarchy::info_json() const
           << ",\"rho\":" << jnum(L.rho) << ",\"omega\":" << jnum(L.omega) << ",\"mis_rounds\":" << L.mis_rounds << ",\"setup_ms\":{\"relax\":" << jnum(L.t_relax)
           << ",\"aggregate\":" << jnum(L.t_agg) << ",\"prolong\":" << jnum(L.t_prolong) << ",\"transpose\":" << jnum(L.t_transpose)
           << ",\"AP\":" << jnum(L.t_ap) << ",\"RAP\":" << jnum(L.t_rap) << "}"
-          << ",\"spmv_kernel\":" << jstr(L.A->kind == SPMV_STREAM ? "stream" : "vector" + std::to_string(L.A->lpr)) << "}";
+          << ",\"spmv_kernel\":" << jstr(L.A->kernel_name()) << "}";
     }
     o << "],\"block_size\":" << std::max(1, prm_.block_size) << ",\"operator_complexity\":" << jnum(tot / fine_nnz) << ",\"ncycle\":" << prm_.ncycle << ",\"degree\":" << prm_.degree
       << ",\"relax\":" << jstr(prm_.relax_type) << "}";

@@ -19,6 +19,7 @@ int guarded(psb200_handle h, F &&f)
     try
     {
         h->s.err.clear();
+        psb::AllocScope alloc_scope(h->s.ctx.stream); // buffers are allocated / freed in order on the solver's stream
         f(h->s);
         return PSB200_OK;
     }
@@ -134,6 +135,19 @@ int psb200_get_info(psb200_handle h, char *json_out, size_t cap, size_t *needed)
     }
     std::memcpy(json_out, j.c_str(), j.size() + 1);
     return PSB200_OK;
+}
+
+// Returns the memory cached in the device's stream-ordered pool to the driver (buffers in use are unaffected).
+int psb200_release_cached_memory(psb200_handle h)
+{
+    return guarded(h, [&](psb::Solver &s) {
+        if (!s.ctx.stream)
+            return;
+        PSB_CUDA(cudaStreamSynchronize(s.ctx.stream));
+        cudaMemPool_t pool = nullptr;
+        PSB_CUDA(cudaDeviceGetDefaultMemPool(&pool, s.device));
+        PSB_CUDA(cudaMemPoolTrimTo(pool, 0));
+    });
 }
 
 const char *psb200_name(psb200_handle) { return "CUDA"; }

@@ -27,8 +27,30 @@ struct CudaError : std::runtime_error
 constexpr int kSMs = 148; // B200: 2 dies x 74 SMs
 constexpr int kMaxRed = 4; // max simultaneous reduction values per kernel
 
-// Owning device buffer (cudaMalloc). Over-allocates `pad` elements so 16-byte TMA bulk copies that
-// round a range outward never leave the allocation.
+// Stream the calling thread's device allocations are ordered on (set by the C-ABI entry points for the duration
+// of a call: every buffer of a solver is produced and consumed on that solver's stream). nullptr: plain cudaMalloc.
+inline cudaStream_t &alloc_stream()
+{
+    static thread_local cudaStream_t s = nullptr;
+    return s;
+}
+struct AllocScope
+{
+    cudaStream_t prev;
+    explicit AllocScope(cudaStream_t s) : prev(alloc_stream())
+    {
+        if (s)
+            alloc_stream() = s;
+    }
+    ~AllocScope() { alloc_stream() = prev; }
+};
+
+// Owning device buffer. Memory comes from the device's stream-ordered pool (cudaMallocAsync on the solver's stream;
+// the pool's release threshold is raised in ensure_ctx so freed blocks stay cached): a factorize that rebuilds an AMG
+// hierarchy -- dozens of buffers, GBs of temporaries -- never pays cudaMalloc / cudaFree after the first time
+// (reference precedent: one stream + one pool per solver, MASSolver.cu:154-156,193-195). Outside an AllocScope, or
+// while the stream is being captured, it falls back to cudaMalloc. Over-allocates `pad` elements so 16-byte TMA
+// bulk copies that round a range outward never leave the allocation.
 template <typename T>
 struct DevBuf
 {
@@ -45,8 +67,12 @@ struct DevBuf
             release();
             p = o.p;
             n = o.n;
+            cap_ = o.cap_;
+            st_ = o.st_;
+            pooled_ = o.pooled_;
             o.p = nullptr;
             o.n = 0;
+            o.cap_ = 0;
         }
         return *this;
     }
@@ -54,36 +80,57 @@ struct DevBuf
     void release()
     {
         if (p)
-            cudaFree(p);
+        {
+            if (pooled_)
+                cudaFreeAsync(p, st_); // ordered after every use: all of them were enqueued on st_
+            else
+                cudaFree(p);
+        }
         p = nullptr;
         n = 0;
+        cap_ = 0;
     }
-    // Grow-only (re)allocation; contents are zeroed when `zero`.
+    // Grow-only (re)allocation; contents are zeroed when `zero` (always after a fresh allocation).
     void alloc(size_t count, bool zero = false, size_t pad = 16)
     {
+        cudaStream_t st = alloc_stream();
         if (count + pad > cap_)
         {
             release();
-            cudaError_t e = cudaMalloc(&p, (count + pad) * sizeof(T));
+            const size_t bytes = (count + pad) * sizeof(T);
+            cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+            if (st)
+                cudaStreamIsCapturing(st, &cs);
+            pooled_ = st != nullptr && cs == cudaStreamCaptureStatusNone;
+            cudaError_t e = pooled_ ? cudaMallocAsync(&p, bytes, st) : cudaMalloc(&p, bytes);
             if (e != cudaSuccess)
             {
                 size_t fr = 0, tot = 0;
                 cudaMemGetInfo(&fr, &tot);
                 p = nullptr;
-                throw CudaError("CUDA out of memory: requested " + std::to_string((count + pad) * sizeof(T) >> 20) +
-                                " MiB, free " + std::to_string(fr >> 20) + " MiB of " + std::to_string(tot >> 20) + " MiB");
+                cudaGetLastError();
+                throw CudaError("CUDA out of memory: requested " + std::to_string(bytes >> 20) + " MiB, free " + std::to_string(fr >> 20) +
+                                " MiB of " + std::to_string(tot >> 20) + " MiB");
             }
+            st_ = st;
             cap_ = count + pad;
             zero = true;
         }
         n = count;
         if (zero)
-            PSB_CUDA(cudaMemset(p, 0, cap_ * sizeof(T)));
+        {
+            if (pooled_)
+                PSB_CUDA(cudaMemsetAsync(p, 0, cap_ * sizeof(T), st_));
+            else
+                PSB_CUDA(cudaMemset(p, 0, cap_ * sizeof(T)));
+        }
     }
     size_t capacity() const { return cap_; }
 
 private:
     size_t cap_ = 0;
+    cudaStream_t st_ = nullptr;
+    bool pooled_ = false;
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -378,7 +378,8 @@ void Solver::analyze_pattern_dist(long long n_, long long nnz_, const int *outer
         PSB_CUDA(cudaMemcpyAsync(d.d_perm.p, rel.data(), sizeof(int) * nnz, cudaMemcpyHostToDevice, st));
         PSB_CUDA(cudaStreamSynchronize(st)); // rel is a stack-scoped staging vector
     }
-    A.plan(prm.spmv_kernel);
+    PSB_CUDA(cudaStreamSynchronize(st));
+    A.plan(prm.spmv_kernel, st);
     // interior-first tile order of the stream schedule: tiles of kSpmvThreads rows that touch no halo column come
     // first, so the persistent CG kernel multiplies them while the neighbours' pushes are still on the wire
     {
@@ -512,7 +513,8 @@ void Solver::build_diag_block_dist()
         d.diag_src.alloc(std::max(1, dn));
         diag_fill_kernel<<<blocks, 256, 0, st>>>((int)n, (int)n, A.rp.p, A.ci.p, D.rp.p, D.ci.p, d.diag_src.p);
         check_launch();
-        D.plan("auto");
+        PSB_CUDA(cudaStreamSynchronize(st));
+        D.plan("auto", st);
     }
     if (D.nnz)
         diag_vals_kernel<<<(unsigned)((D.nnz + 255) / 256), 256, 0, st>>>(D.nnz, A.va.p, d.diag_src.p, D.va.p);
@@ -673,6 +675,7 @@ int psb200_dist_prepare(psb200_handle h, int rank, int world, int64_t halo_cap, 
     try
     {
         h->s.err.clear();
+        psb::AllocScope alloc_scope(h->s.ctx.stream);
         h->s.dist_prepare(rank, world, halo_cap, handle_out);
         return PSB200_OK;
     }
@@ -695,6 +698,7 @@ int psb200_dist_connect(psb200_handle h, const char *handles)
     try
     {
         h->s.err.clear();
+        psb::AllocScope alloc_scope(h->s.ctx.stream);
         h->s.dist_connect(handles);
         return PSB200_OK;
     }

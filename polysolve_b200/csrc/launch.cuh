@@ -14,6 +14,23 @@ constexpr int kVecThreads = 256;
 constexpr int kSpmvThreads = 256;
 // production tile shape of the stream schedule: rows per tile, staged nnz per tile, pipeline depth
 using StreamProd = StreamCfg<256, 2048, 2>;
+// long rows (30-80 nnz: Galerkin coarse levels, 3-dof elasticity): LPR lanes per row, 256 / LPR rows per tile
+template <int LPR>
+using StreamWide = StreamCfg<256, 3072, 2, LPR>;
+
+// number of tiles of `rows` rows whose staged nnz range would not fit `cap` entries
+template <int DUMMY>
+__global__ void tile_overflow_kernel(int n, const int *__restrict__ rp, int rows, int cap, int *count)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ntiles = (n + rows - 1) / rows;
+    if (t >= ntiles)
+        return;
+    const int r0 = t * rows, r1 = min(n, r0 + rows);
+    const int ka = rp[r0] & ~3;
+    if (((rp[r1] - ka + 3) & ~3) > cap)
+        atomicAdd(count, 1);
+}
 
 enum SpmvKind : int
 {
@@ -32,15 +49,52 @@ struct CsrDev
     int nl = 0x7fffffff;      // local columns (multi-GPU: columns >= nl are halo columns)
     unsigned halo_mask = 0;   // ranks that push halo values to this one
     CsrView view() const { return CsrView{rp.p, ci.p, va.p, n, nl, halo_mask}; }
-    // choose the schedule from the average row length
-    void plan(const std::string &forced = "auto")
+    // Chooses the schedule. auto: the TMA stream schedule with the smallest lanes-per-row whose tiles fit the staging
+    // buffers (checked on the device against the actual row pointer: at most 2 % of the tiles may overflow to the
+    // direct-load path), else the plain vector schedule. `st` is the stream the row pointer was produced on.
+    DevBuf<int> plan_scratch;
+    double overflow_frac(int rows, int cap, cudaStream_t st)
+    {
+        if (n <= 0 || rp.p == nullptr)
+            return 0.0;
+        plan_scratch.alloc(4, false);
+        PSB_CUDA(cudaMemsetAsync(plan_scratch.p, 0, sizeof(int), st));
+        const int ntiles = (n + rows - 1) / rows;
+        tile_overflow_kernel<0><<<(ntiles + 255) / 256, 256, 0, st>>>(n, rp.p, rows, cap, plan_scratch.p);
+        int h = 0;
+        PSB_CUDA(cudaMemcpyAsync(&h, plan_scratch.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PSB_CUDA(cudaStreamSynchronize(st));
+        return (double)h / ntiles;
+    }
+    void plan(const std::string &forced = "auto", cudaStream_t st = nullptr)
     {
         const double avg = n > 0 ? (double)nnz / n : 0;
-        if (forced.rfind("stream", 0) == 0 ||
-            (forced == "auto" && avg * StreamProd::threads + 16 <= StreamProd::cap && n >= 4 * StreamProd::threads))
+        const bool want_stream = forced.rfind("stream", 0) == 0;
+        if (want_stream && forced.size() > 6 && forced[6] != ':')
         {
             kind = SPMV_STREAM;
+            lpr = std::stoi(forced.substr(6));
             return;
+        }
+        if (want_stream || (forced == "auto" && n >= 4 * StreamProd::threads))
+        {
+            for (int L : {1, 2, 4, 8, 16})
+            {
+                const int rows = StreamProd::threads / L, cap = L == 1 ? StreamProd::cap : StreamWide<2>::cap;
+                if (avg * rows + 16 > cap)
+                    continue;
+                if (overflow_frac(rows, cap, st) > 0.02)
+                    continue;
+                kind = SPMV_STREAM;
+                lpr = L;
+                return;
+            }
+            if (want_stream)
+            {
+                kind = SPMV_STREAM; // forced: correct for any matrix (overflowing tiles use direct loads)
+                lpr = 1;
+                return;
+            }
         }
         kind = SPMV_VECTOR;
         if (forced == "scalar")
@@ -60,6 +114,7 @@ struct CsrDev
         if (forced.rfind("vector", 0) == 0 && forced.size() > 6)
             lpr = std::stoi(forced.substr(6));
     }
+    std::string kernel_name() const { return kind == SPMV_STREAM ? (lpr == 1 ? "stream" : "stream" + std::to_string(lpr)) : "vector" + std::to_string(lpr); }
 };
 
 struct ProfEntry
@@ -91,6 +146,7 @@ struct Ctx
     void init()
     {
         PSB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        alloc_stream() = stream; // restored by the AllocScope of the C-ABI call we are in
         partials.alloc((size_t)kMaxRed * kMaxBlocks, true);
         counter.alloc(4, true);
     }
@@ -105,8 +161,22 @@ struct Ctx
         for (auto e : ev_pool)
             cudaEventDestroy(e);
         ev_pool.clear();
+    }
+    Ctx() = default;
+    Ctx(const Ctx &) = delete;
+    Ctx &operator=(const Ctx &) = delete;
+    // The stream outlives every buffer that was allocated on it: Ctx is declared before all buffers of a Solver, so
+    // this runs after their destructors have queued their cudaFreeAsync on it.
+    ~Ctx()
+    {
+        destroy();
+        partials.release();
+        counter.release();
         if (stream)
+        {
+            cudaStreamSynchronize(stream);
             cudaStreamDestroy(stream);
+        }
         stream = nullptr;
     }
     CommDev comm;             // world == 1 unless psb200_dist_connect() was called
@@ -218,7 +288,7 @@ void launch_spmv_stream(Ctx &c, const CsrDev &A, const double *x, Epi epi, Fin f
         PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas, kern, Cfg::threads, Cfg::bytes));
         max_ctas = std::max(1, max_ctas);
     }
-    const int ntiles = (A.n + Cfg::threads - 1) / Cfg::threads;
+    const int ntiles = (A.n + Cfg::rows - 1) / Cfg::rows;
     const int per_sm = ctas_per_sm > 0 ? std::min(ctas_per_sm, max_ctas) : max_ctas;
     const int grid = std::min(ntiles, kSMs * per_sm); // persistent: every CTA resident, tiles dealt round-robin
     kern<<<grid, Cfg::threads, Cfg::bytes, c.stream>>>(A.view(), x, epi, c.red(), fin, done, only_if);
@@ -232,7 +302,16 @@ void launch_spmv(Ctx &c, const char *name, const CsrDev &A, const double *x, Epi
         return;
     c.prof_begin(name);
     if (A.kind == SPMV_STREAM)
-        launch_spmv_stream<Epi, Fin, StreamProd>(c, A, x, epi, fin, done, only_if);
+    {
+        switch (A.lpr)
+        {
+        case 2: launch_spmv_stream<Epi, Fin, StreamWide<2>>(c, A, x, epi, fin, done, only_if); break;
+        case 4: launch_spmv_stream<Epi, Fin, StreamWide<4>>(c, A, x, epi, fin, done, only_if); break;
+        case 8: launch_spmv_stream<Epi, Fin, StreamWide<8>>(c, A, x, epi, fin, done, only_if); break;
+        case 16: launch_spmv_stream<Epi, Fin, StreamWide<16>>(c, A, x, epi, fin, done, only_if); break;
+        default: launch_spmv_stream<Epi, Fin, StreamProd>(c, A, x, epi, fin, done, only_if); break;
+        }
+    }
     else
     {
         switch (A.lpr)

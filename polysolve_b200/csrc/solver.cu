@@ -293,7 +293,7 @@ Solver::~Solver()
         cudaFree(d_state);
     if (h_state)
         cudaFreeHost(h_state);
-    ctx.destroy();
+    // the stream is destroyed by ~Ctx, after the buffers declared below it have been returned to the pool
 }
 
 void ensure_ctx(Solver &s)
@@ -308,6 +308,17 @@ void ensure_ctx(Solver &s)
     if (s.prm.device >= 0)
         PSB_CUDA(cudaSetDevice(s.prm.device));
     PSB_CUDA(cudaGetDevice(&s.device));
+    {
+        // keep freed blocks cached in the device's stream-ordered pool (DevBuf allocates from it)
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, s.device) == cudaSuccess && pool)
+        {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        else
+            cudaGetLastError();
+    }
     s.ctx.init();
     PSB_CUDA(cudaMalloc(&s.d_state, sizeof(KState)));
     PSB_CUDA(cudaMemset(s.d_state, 0, sizeof(KState)));
@@ -415,7 +426,7 @@ void Solver::set_parameters(const std::string &json)
         graph_key.clear();
     }
     if (analyzed)
-        A.plan(prm.spmv_kernel);
+        A.plan(prm.spmv_kernel, ctx.stream);
     ctx.profile = prm.profile;
 }
 
@@ -571,7 +582,7 @@ void Solver::analyze_pattern(long long n_, long long nnz_, const int *outer, con
         pattern_block = B;
         sym_pattern = false; // CSR arrays no longer alias the CSC arrays
     }
-    A.plan(prm.spmv_kernel);
+    A.plan(prm.spmv_kernel, st);
     PSB_CUDA(cudaStreamSynchronize(st));
     analyzed = true;
     t_analyze_ms = now_ms() - t0;
@@ -846,7 +857,7 @@ void init_state(Solver &s, double tol, int max_iter)
 // between SMs); the persistent kernel stays selectable for latency-bound partitions (many ranks, small systems).
 bool Solver::use_persist() const
 {
-    return prm.cg_kernel == "persistent" && A.kind == SPMV_STREAM && !prm.profile && n > 0;
+    return prm.cg_kernel == "persistent" && A.kind == SPMV_STREAM && A.lpr == 1 && !prm.profile && n > 0;
 }
 
 void Solver::run_cg_eigen(const double *d_b)
@@ -984,7 +995,7 @@ double Solver::bench_spmv(const std::string &kernel, int reps)
             throw std::invalid_argument("psb200_bench_spmv: stream variant not compiled: " + kernel);
     }
     else if (!kernel.empty())
-        A.plan(kernel);
+        A.plan(kernel, st);
     // a non-trivial resident x
     launch_vec(ctx, "copy", n_pad, OpCopy{vp.p, dinv.p}, FinNone{});
     for (int i = 0; i < 3; ++i)
@@ -1047,7 +1058,7 @@ void Solver::build_info()
           << ",\"halo_out\":" << dist->n_push << "}";
     o << ",\"symmetric_pattern\":" << (sym_pattern ? "true" : "false");
     o << ",\"analyze_skipped\":" << (analyze_skipped ? "true" : "false");
-    o << ",\"spmv_kernel\":" << jstr(A.kind == SPMV_STREAM ? "stream" : ("vector" + std::to_string(A.lpr)));
+    o << ",\"spmv_kernel\":" << jstr(A.kernel_name());
     o << ",\"cg_kernel\":" << jstr(use_persist() ? "persistent" : "split");
     if (use_persist())
     {

@@ -252,11 +252,14 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, unsigne
                  : "memory");
 }
 
-template <int THREADS, int CAP, int STAGES>
+// LPR lanes cooperate on one row, so a tile holds THREADS / LPR rows: LPR = 1 for stencil-like rows (<= ~8 nnz),
+// LPR = 2 .. 16 for the 30-80 nnz rows of Galerkin coarse levels and vector-valued FEM (the staged nnz per tile
+// stays within CAP while every lane still has several gathers in flight).
+template <int THREADS, int CAP, int STAGES, int LPR = 1>
 struct StreamCfg
 {
-    static constexpr int threads = THREADS, cap = CAP, stages = STAGES;
-    static constexpr int rp_ints = THREADS + 4; // THREADS + 1 row pointers, rounded to 16 bytes
+    static constexpr int threads = THREADS, cap = CAP, stages = STAGES, lpr = LPR, rows = THREADS / LPR;
+    static constexpr int rp_ints = rows + 4; // rows + 1 row pointers, rounded to 16 bytes
     static constexpr size_t val_bytes = (size_t)STAGES * CAP * sizeof(double);
     static constexpr size_t col_bytes = (size_t)STAGES * CAP * sizeof(int);
     static constexpr size_t rp_bytes = (size_t)STAGES * rp_ints * sizeof(int);
@@ -267,7 +270,7 @@ template <class Epi, class Fin, class Cfg>
 __global__ void __launch_bounds__(Cfg::threads) spmv_stream_kernel(CsrView A, const double *__restrict__ x, Epi epi, RedCtx rc, Fin fin,
                                                                    const int *done, const int *only_if)
 {
-    constexpr int THREADS = Cfg::threads, CAP = Cfg::cap, STAGES = Cfg::stages;
+    constexpr int THREADS = Cfg::threads, CAP = Cfg::cap, STAGES = Cfg::stages, LPR = Cfg::lpr, ROWS = Cfg::rows;
     if (done && *done)
         return;
     if (only_if && !*only_if)
@@ -284,7 +287,7 @@ __global__ void __launch_bounds__(Cfg::threads) spmv_stream_kernel(CsrView A, co
     for (int i = 0; i < NVA; ++i)
         acc[i] = 0;
 
-    const int ntiles = (A.n + THREADS - 1) / THREADS;
+    const int ntiles = (A.n + ROWS - 1) / ROWS;
     unsigned long long policy;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
 
@@ -299,8 +302,8 @@ __global__ void __launch_bounds__(Cfg::threads) spmv_stream_kernel(CsrView A, co
 
     // one thread: launch the three bulk copies of `tile` into stage s
     auto issue = [&](int tile, int s) {
-        const int r0 = tile * THREADS;
-        const int r1 = min(A.n, r0 + THREADS);
+        const int r0 = tile * ROWS;
+        const int r1 = min(A.n, r0 + ROWS);
         const int k0 = __ldg(A.rp + r0), k1 = __ldg(A.rp + r1);
         const int ka = k0 & ~3;
         const int cnt4 = (k1 - ka + 3) & ~3;
@@ -336,12 +339,13 @@ __global__ void __launch_bounds__(Cfg::threads) spmv_stream_kernel(CsrView A, co
     {
         const int s = it % STAGES;
         const unsigned parity = (it / STAGES) & 1;
-        const int r0 = tile * THREADS;
-        const int nrow = min(A.n - r0, THREADS);
-        const int row = r0 + threadIdx.x;
-        const bool live = threadIdx.x < nrow;
+        const int r0 = tile * ROWS;
+        const int nrow = min(A.n - r0, ROWS);
+        const int trow = threadIdx.x / LPR, lane = threadIdx.x % LPR;
+        const int row = r0 + trow;
+        const bool live = trow < nrow;
         typename Epi::Pre pre{};
-        if (live)
+        if (live && lane == 0)
             pre = epi.pre(row); // side inputs first: their latency hides behind the barrier wait and the gathers
         mbar_wait(&bar[s], parity);
         const int *rps = srp + (size_t)s * Cfg::rp_ints;
@@ -351,38 +355,67 @@ __global__ void __launch_bounds__(Cfg::threads) spmv_stream_kernel(CsrView A, co
         int kb = 0, ke = 0;
         if (live)
         {
-            kb = rps[threadIdx.x];
-            ke = rps[threadIdx.x + 1];
+            kb = rps[trow];
+            ke = rps[trow + 1];
         }
         double sum = 0;
         if (staged)
         {
             const double *sv = sval + (size_t)s * CAP - ka;
             const int *sc = scol + (size_t)s * CAP - ka;
-            // 8 gathers in flight per trip; products are still added in k order
-            for (int k = kb; k < ke; k += 8)
+            if constexpr (LPR == 1)
             {
-                double v[8], xx[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u)
+                // 8 gathers in flight per trip; products are still added in k order
+                for (int k = kb; k < ke; k += 8)
                 {
-                    const bool ok = k + u < ke;
-                    const int c = ok ? sc[k + u] : 0;
-                    v[u] = ok ? sv[k + u] : 0.0;
-                    xx[u] = ok ? ldx(x, xh, A.nl, c) : 0.0;
-                }
+                    double v[8], xx[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    if (k + u < ke)
-                        sum += v[u] * xx[u];
+                    for (int u = 0; u < 8; ++u)
+                    {
+                        const bool ok = k + u < ke;
+                        const int c = ok ? sc[k + u] : 0;
+                        v[u] = ok ? sv[k + u] : 0.0;
+                        xx[u] = ok ? ldx(x, xh, A.nl, c) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (k + u < ke)
+                            sum += v[u] * xx[u];
+                }
+            }
+            else
+            {
+                // lane l takes entries kb + l, kb + l + LPR, ...: conflict-free shared-memory reads, 4 gathers in flight
+                for (int k = kb + lane; k < ke; k += 4 * LPR)
+                {
+                    double v[4], xx[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                    {
+                        const bool ok = k + u * LPR < ke;
+                        const int c = ok ? sc[k + u * LPR] : 0;
+                        v[u] = ok ? sv[k + u * LPR] : 0.0;
+                        xx[u] = ok ? ldx(x, xh, A.nl, c) : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (k + u * LPR < ke)
+                            sum += v[u] * xx[u];
+                }
             }
         }
         else
         {
-            for (int k = kb; k < ke; ++k)
+            for (int k = kb + lane; k < ke; k += LPR)
                 sum += __ldg(A.va + k) * ldx(x, xh, A.nl, __ldg(A.ci + k));
         }
-        if (live)
+        if constexpr (LPR > 1)
+        {
+#pragma unroll
+            for (int o = LPR / 2; o > 0; o >>= 1)
+                sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        }
+        if (live && lane == 0)
             epi(row, sum, pre, acc);
         __syncthreads(); // every thread is done reading stage s
         if (threadIdx.x == 0)

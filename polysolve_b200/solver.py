@@ -125,6 +125,10 @@ class Solver:
     def name(self):
         return self._L.psb200_name(self._h).decode()
 
+    def release_cached_memory(self):
+        """Returns the unused part of the GPU's stream-ordered memory pool to the driver."""
+        self._check(self._L.psb200_release_cached_memory(self._h))
+
     def is_dense(self):
         return False
 

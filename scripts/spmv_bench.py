@@ -1,0 +1,50 @@
+"""SpMV GB/s (algorithmic bytes 12 nnz + 20 n + 4) of every schedule on three matrix families:
+poisson3d (7 nnz/row), its Galerkin-like square (25 nnz/row, stands for AMG level 1) and P1 elasticity (45 nnz/row).
+    python scripts/spmv_bench.py [poisson_n] [elasticity_m]"""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np  # noqa: E402
+import scipy.sparse as sp  # noqa: E402
+
+import polysolve_b200 as psb  # noqa: E402
+
+P = psb.problems
+pn = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+em = int(sys.argv[2]) if len(sys.argv) > 2 else 72
+peak = 6538.6
+try:
+    peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+
+
+def run(tag, o, i, v, kernels):
+    n = len(o) - 1
+    nnz = int(o[-1])
+    s = psb.Solver.create("CUDA", "")
+    s.factorize_raw(n, o, i, v)
+    auto = s.get_info()["spmv_kernel"]
+    x = P.splitmix64(3, n)
+    y_ref = sp.csr_matrix((v, i, o), shape=(n, n)) @ x
+    for k in ["auto"] + kernels:
+        ms = s.bench_spmv(reps=30, kernel="" if k == "auto" else k)
+        y = s.spmv(x) if k == "auto" else None
+        err = float(np.max(np.abs(y - y_ref)) / np.max(np.abs(y_ref))) if y is not None else None
+        gbs = P.spmv_bytes(n, nnz) / (ms * 1e-3) / 1e9
+        print(json.dumps({"matrix": tag, "n": n, "nnz": nnz, "nnz_per_row": round(nnz / n, 1), "kernel": k if k != "auto" else "auto=" + auto,
+                          "ms": round(ms, 4), "GB/s": round(gbs, 1), "frac_of_measured_peak": round(gbs / peak, 3), "max_rel_err": err}), flush=True)
+
+
+o, i, v = P.poisson3d(pn)
+run(f"poisson3d_{pn}", o, i, v, ["vector2", "vector4"])
+A = sp.csr_matrix((v, i, o), shape=(pn ** 3, pn ** 3))
+A2 = (A @ A).tocsr()
+A2.sort_indices()
+run(f"poisson3d_{pn}_squared", A2.indptr.astype(np.int32), A2.indices.astype(np.int32), A2.data.astype(np.float64),
+    ["stream2", "stream4", "stream8", "stream16", "vector8", "vector16", "vector32"])
+del A, A2
+o, i, v, _ = P.elasticity3d(em)
+run(f"elasticity3d_{em}", o, i, v, ["stream4", "stream8", "stream16", "vector16", "vector32"])

@@ -101,6 +101,38 @@ def test_spmv_schedules_match_oracle(psb, orc, kernel):
     assert np.max(np.abs(y - y0) / scale) < 4 * np.finfo(float).eps
 
 
+@pytest.mark.parametrize("kernel", ["auto", "stream2", "stream4", "stream8", "stream16", "vector16"])
+def test_spmv_wide_stream_long_rows(psb, orc, kernel):
+    """Rows of ~25 nnz (a Galerkin-like operator): the TMA stream schedule with several lanes per row, every
+    lane count, against scipy; auto must pick a multi-lane stream schedule."""
+    o, i, v = orc.poisson3d(24)
+    n = 24 ** 3
+    A = csc(o, i, v * (1.0 + 0.1 * orc.splitmix64(11, len(v))))
+    A2 = sp.csc_matrix(A @ A.T)
+    A2.sort_indices()
+    o2, i2, v2 = A2.indptr.astype(np.int32), A2.indices.astype(np.int32), A2.data.astype(np.float64)
+    s = make(psb, spmv_kernel=kernel)
+    s.factorize_raw(n, o2, i2, v2)
+    name = s.get_info()["spmv_kernel"]
+    if kernel == "auto":
+        assert name.startswith("stream") and name != "stream", name
+    else:
+        assert name == kernel
+    x = orc.splitmix64(5, n)
+    y0 = A2 @ x
+    scale = abs(A2) @ np.abs(x)
+    assert np.max(np.abs(s.spmv(x) - y0) / scale) < 8 * np.finfo(float).eps
+    # a ragged variant: every 7th row emptied, one very long row (tile overflow => direct-load path)
+    L = sp.lil_matrix(A2)
+    L[::7, :] = 0
+    L[100, :] = 1.0
+    B = sp.csc_matrix(L)
+    B.eliminate_zeros()
+    B.sort_indices()
+    s.factorize_raw(n, B.indptr.astype(np.int32), B.indices.astype(np.int32), B.data.astype(np.float64))
+    np.testing.assert_allclose(s.spmv(x), B @ x, rtol=1e-12, atol=1e-10)
+
+
 def test_spmv_stream_falls_back_on_dense_tiles(psb, orc):
     """Tiles whose nnz exceed the shared-memory stage take the direct-load path."""
     rng = np.random.default_rng(5)
