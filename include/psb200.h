@@ -95,6 +95,12 @@ int psb200_dist_plan_host(int64_t n, int64_t nnz, const int32_t *outer, const in
                           int64_t halo_cap, int64_t *offsets, int64_t *counts, int32_t *local_rp, int32_t *local_ci,
                           int32_t *local_perm, int32_t *send_begin, int32_t *send_rows, int32_t *recv_count,
                           int32_t *halo_cols);
+/* Same, with the row offsets rounded up to multiples of `align`: block problems (set_block_size(B), SURVEY 8e "for
+ * block problems aligned to 3") keep the B rows of a node on one rank; align = 1 is psb200_dist_plan_host. */
+int psb200_dist_plan_host_aligned(int64_t n, int64_t nnz, const int32_t *outer, const int32_t *inner, int rank, int world,
+                                  int64_t halo_cap, int align, int64_t *offsets, int64_t *counts, int32_t *local_rp,
+                                  int32_t *local_ci, int32_t *local_perm, int32_t *send_begin, int32_t *send_rows,
+                                  int32_t *recv_count, int32_t *halo_cols);
 
 /* ---- test / bench hooks (not part of the polysolve interface) */
 /* CSR produced by analyze_pattern: row_ptr int32[n+1], col_idx int32[nnz], perm int32[nnz] with

@@ -21,7 +21,7 @@ SYMBOLS = [
     "psb200_create", "psb200_destroy", "psb200_set_parameters", "psb200_set_tolerance", "psb200_set_block_size",
     "psb200_analyze_pattern_csc", "psb200_factorize_csc", "psb200_solve", "psb200_solve_device", "psb200_get_info",
     "psb200_name", "psb200_last_error", "psb200_release_cached_memory", "psb200_dist_prepare", "psb200_dist_connect", "psb200_dist_local_range",
-    "psb200_dist_plan_host", "psb200_debug_get_csr",
+    "psb200_dist_plan_host", "psb200_dist_plan_host_aligned", "psb200_debug_get_csr",
     "psb200_spmv", "psb200_bench_spmv", "psb200_get_stream", "psb200_debug_set_aggregates", "psb200_debug_get_level",
     "psb200_precond_apply", "psb200_debug_get_aggregates",
     # include/psb200_nl.h
@@ -67,6 +67,8 @@ def lib():
     i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
     L.psb200_dist_plan_host.argtypes = [C.c_int64, C.c_int64, i32p, i32p, C.c_int, C.c_int, C.c_int64, i64p, i64p,
                                         i32p, i32p, i32p, i32p, i32p, i32p, i32p]
+    L.psb200_dist_plan_host_aligned.argtypes = [C.c_int64, C.c_int64, i32p, i32p, C.c_int, C.c_int, C.c_int64, C.c_int, i64p, i64p,
+                                                i32p, i32p, i32p, i32p, i32p, i32p, i32p]
     L.psb200_debug_get_csr.argtypes = [H, i32p, i32p, i32p]
     L.psb200_spmv.argtypes = [H, f64p, f64p, C.c_int64]
     L.psb200_bench_spmv.argtypes = [H, C.c_char_p, C.c_int, C.POINTER(C.c_double)]

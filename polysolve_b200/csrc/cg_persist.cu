@@ -416,18 +416,13 @@ void Solver::launch_cg_persist(double *p_cur, double *p_other, int iters)
 {
     PersistArgs a{};
     a.A = A.view();
-    a.order = nullptr;
-    a.n_interior = 0x7fffffff;
+    a.order = a.A.tile_order;
+    a.n_interior = a.A.tile_order ? a.A.n_interior : 0x7fffffff;
     a.push = PushList{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
     a.comm = ctx.comm;
     if (dist)
     {
         a.push = make_push(*dist);
-        if (dist->world > 1 && dist->tile_order.n > 0)
-        {
-            a.order = dist->tile_order.p;
-            a.n_interior = dist->n_interior_tiles;
-        }
     }
     else
         a.comm.world = 1;

@@ -24,8 +24,10 @@
 namespace psb {
 
 // ====================================================================================== host plan
-void DistPlanHost::build(long long n, long long nnz, const int *outer, const int *inner, int rank_, int world_, long long halo_cap_)
+void DistPlanHost::build(long long n, long long nnz, const int *outer, const int *inner, int rank_, int world_, long long halo_cap_, int align)
 {
+    if (align < 1 || n % align != 0)
+        throw std::invalid_argument("psb200 dist: the matrix size is not a multiple of the block size");
     if (world_ < 1 || world_ > kMaxRanks || rank_ < 0 || rank_ >= world_)
         throw std::invalid_argument("psb200 dist: rank/world out of range (world <= 8)");
     rank = rank_;
@@ -50,6 +52,7 @@ void DistPlanHost::build(long long n, long long nnz, const int *outer, const int
     {
         const long long target = (long long)(((__int128)nnz * g) / world);
         long long r = std::lower_bound(row_ptr.begin(), row_ptr.end(), (int)std::min<long long>(target, 0x7fffffff)) - row_ptr.begin();
+        r = ((r + align - 1) / align) * align;
         r = std::min(r, n);
         r = std::max(r, offsets[g - 1]);
         offsets[g] = r;
@@ -297,11 +300,14 @@ void Solver::analyze_pattern_dist(long long n_, long long nnz_, const int *outer
     DistState &d = *dist;
     if (!d.connected && d.world > 1)
         throw std::runtime_error("psb200 dist: psb200_dist_connect has not been called");
-    if (prm.block_size > 1)
-        throw std::runtime_error("psb200 dist: block_size > 1 is not available on the row-partitioned path in this version");
+    const int B = std::max(1, prm.block_size);
+    if (B > 3)
+        throw std::invalid_argument("psb200: block_size must be 1, 2 or 3 (reference AMGCL.cpp:111-123)");
     if (prm.krylov != "cg")
         throw std::runtime_error("psb200 dist: the row-partitioned path provides PCG (krylov=cg) with precond = jacobi | none | amg");
-    d.plan.build(n_, nnz_, outer, inner, d.rank, d.world, d.halo_cap);
+    d.plan.build(n_, nnz_, outer, inner, d.rank, d.world, d.halo_cap, B);
+    d.A_diag.n = 0; // new pattern: the rank-local diagonal block is rebuilt at the next AMG factorize
+    pattern_block = B; // the Krylov loop works on the scalar rows; the rank-local AMG sees B x B blocks (build_diag_block_dist)
     const DistPlanHost &P = d.plan;
     cudaStream_t st = ctx.stream;
     n = P.r1() - P.r0();
@@ -380,10 +386,11 @@ void Solver::analyze_pattern_dist(long long n_, long long nnz_, const int *outer
     }
     PSB_CUDA(cudaStreamSynchronize(st));
     A.plan(prm.spmv_kernel, st);
-    // interior-first tile order of the stream schedule: tiles of kSpmvThreads rows that touch no halo column come
-    // first, so the persistent CG kernel multiplies them while the neighbours' pushes are still on the wire
+    // interior-first tile order of the stream schedule: tiles that touch no halo column come first, so the SpMV
+    // multiplies them while the neighbours' pushes are still on the wire (both the split and the persistent path)
+    if (A.kind == SPMV_STREAM)
     {
-        const int T = StreamProd::threads;
+        const int T = A.stream_rows();
         const int ntiles = (int)((n + T - 1) / T);
         std::vector<int> order, boundary;
         order.reserve(ntiles);
@@ -395,11 +402,12 @@ void Solver::analyze_pattern_dist(long long n_, long long nnz_, const int *outer
                 halo = P.ci[k] >= (int)n;
             (halo ? boundary : order).push_back(t);
         }
-        d.n_interior_tiles = (int)order.size();
+        A.n_interior = (int)order.size();
+        A.order_rows = T;
         order.insert(order.end(), boundary.begin(), boundary.end());
-        d.tile_order.alloc(std::max(1, ntiles));
+        A.tile_order.alloc(std::max(1, ntiles));
         if (ntiles)
-            PSB_CUDA(cudaMemcpyAsync(d.tile_order.p, order.data(), sizeof(int) * ntiles, cudaMemcpyHostToDevice, st));
+            PSB_CUDA(cudaMemcpyAsync(A.tile_order.p, order.data(), sizeof(int) * ntiles, cudaMemcpyHostToDevice, st));
         PSB_CUDA(cudaStreamSynchronize(st)); // order is a stack-scoped staging vector
     }
     PSB_CUDA(cudaStreamSynchronize(st));
@@ -481,7 +489,7 @@ __global__ void diag_vals_kernel(long long nnz, const double *__restrict__ va, c
 {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k < nnz)
-        out[k] = va[src[k]];
+        out[k] = src[k] >= 0 ? va[src[k]] : 0.0;
 }
 
 // A_diag = A[local rows, local columns]: pattern once per analysis, values on every factorize
@@ -513,6 +521,13 @@ void Solver::build_diag_block_dist()
         d.diag_src.alloc(std::max(1, dn));
         diag_fill_kernel<<<blocks, 256, 0, st>>>((int)n, (int)n, A.rp.p, A.ci.p, D.rp.p, D.ci.p, d.diag_src.p);
         check_launch();
+        if (pattern_block > 1 && n > 0)
+        {
+            // block mode: the B rows of a node get the full B x B block pattern (diag_src = -1 marks the fill-in),
+            // the invariant the block AMG kernels rely on (same expansion as the single-GPU analyze_pattern)
+            D.nnz = expand_block_pattern(ctx, pattern_block, n, D.rp, D.ci, d.diag_src);
+            D.va.alloc(std::max<long long>(1, D.nnz), false, 64);
+        }
         PSB_CUDA(cudaStreamSynchronize(st));
         D.plan("auto", st);
     }
@@ -727,10 +742,19 @@ int psb200_dist_plan_host(int64_t n, int64_t nnz, const int32_t *outer, const in
                           int64_t *offsets, int64_t *counts, int32_t *local_rp, int32_t *local_ci, int32_t *local_perm,
                           int32_t *send_begin, int32_t *send_rows, int32_t *recv_count, int32_t *halo_cols)
 {
+    return psb200_dist_plan_host_aligned(n, nnz, outer, inner, rank, world, halo_cap, 1, offsets, counts, local_rp, local_ci, local_perm,
+                                         send_begin, send_rows, recv_count, halo_cols);
+}
+
+// Same with the row offsets rounded up to multiples of `align` (block problems: align = block size).
+int psb200_dist_plan_host_aligned(int64_t n, int64_t nnz, const int32_t *outer, const int32_t *inner, int rank, int world,
+                                  int64_t halo_cap, int align, int64_t *offsets, int64_t *counts, int32_t *local_rp, int32_t *local_ci,
+                                  int32_t *local_perm, int32_t *send_begin, int32_t *send_rows, int32_t *recv_count, int32_t *halo_cols)
+{
     try
     {
         psb::DistPlanHost P;
-        P.build(n, nnz, outer, inner, rank, world, halo_cap);
+        P.build(n, nnz, outer, inner, rank, world, halo_cap, align);
         std::copy(P.offsets.begin(), P.offsets.end(), offsets);
         counts[0] = P.r1() - P.r0();
         counts[1] = (int64_t)P.ci.size();

@@ -20,7 +20,8 @@ struct DistPlanHost
     std::vector<int> halo_cols;     // global ids of the halo columns, ascending (grouped by owner automatically)
     long long r0() const { return offsets[rank]; }
     long long r1() const { return offsets[rank + 1]; }
-    void build(long long n, long long nnz, const int *outer, const int *inner, int rank_, int world_, long long halo_cap_);
+    // align: row offsets are rounded up to a multiple of `align` (block problems keep the rows of a node together)
+    void build(long long n, long long nnz, const int *outer, const int *inner, int rank_, int world_, long long halo_cap_, int align = 1);
 };
 
 // Device view of the send side of the halo exchange (see push_section, dist.cu)
@@ -44,9 +45,6 @@ struct DistState
     // device push list: send rows of all destinations concatenated + the chunk table [peer | start | count | offset]
     DevBuf<int> push_rows, chunk_tab;
     int n_push = 0, n_chunks = 0;
-    // interior-first tile order of the stream schedule (persistent CG kernel): tiles without halo columns first
-    DevBuf<int> tile_order;
-    int n_interior_tiles = 0;
     unsigned send_mask = 0, recv_mask = 0;
     DevBuf<double> vp2; // second direction buffer (p ping-pongs so pushed values never race with the update)
     // values ingest: the CSC window [val_lo, val_hi) that holds every local entry is uploaded as one

@@ -37,6 +37,10 @@ struct CsrView
     // into this rank's comm buffer instead of the local x. Single GPU: nl = INT_MAX, halo_mask = 0.
     int nl;
     unsigned halo_mask; // bit q set: rank q pushes halo values to this rank
+    // stream schedule on a row partition: sequence position -> tile with the tiles that touch no halo column first
+    // (positions < n_interior), so the multiplication starts while the neighbours' pushes are still on the wire
+    const int *tile_order;
+    int n_interior;
 };
 
 // x[c] for a local column, xh[c - nl] for a halo column. Halo values were written by a peer GPU: they are

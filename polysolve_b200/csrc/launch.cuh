@@ -48,7 +48,14 @@ struct CsrDev
     int lpr = 1; // lanes per row for the vector schedule
     int nl = 0x7fffffff;      // local columns (multi-GPU: columns >= nl are halo columns)
     unsigned halo_mask = 0;   // ranks that push halo values to this one
-    CsrView view() const { return CsrView{rp.p, ci.p, va.p, n, nl, halo_mask}; }
+    DevBuf<int> tile_order;   // interior-first tile order of the stream schedule (row partitions only)
+    int n_interior = 0, order_rows = 0; // order_rows: rows per tile the order was built for
+    int stream_rows() const { return kSpmvThreads / std::max(1, lpr); }
+    CsrView view() const
+    {
+        const bool ord = kind == SPMV_STREAM && halo_mask != 0 && tile_order.p != nullptr && order_rows == stream_rows();
+        return CsrView{rp.p, ci.p, va.p, n, nl, halo_mask, ord ? tile_order.p : nullptr, ord ? n_interior : 0};
+    }
     // Chooses the schedule. auto: the TMA stream schedule with the smallest lanes-per-row whose tiles fit the staging
     // buffers (checked on the device against the actual row pointer: at most 2 % of the tiles may overflow to the
     // direct-load path), else the plain vector schedule. `st` is the stream the row pointer was produced on.

@@ -278,6 +278,45 @@ inline int blocks_for(long long n, int threads) { return (int)std::max<long long
 
 } // namespace
 
+// Full-block expansion of a sorted scalar CSR pattern (see the comment above merged_block_cols): rp / ci / perm are
+// replaced by the expanded arrays (perm = -1 marks fill-in); returns the new nnz. n must be a multiple of B.
+long long expand_block_pattern(Ctx &ctx, int B, long long n, DevBuf<int> &rp, DevBuf<int> &ci, DevBuf<int> &perm)
+{
+    cudaStream_t st = ctx.stream;
+    if (B > 3)
+        throw std::invalid_argument("psb200: block_size must be 1, 2 or 3 (reference AMGCL.cpp:111-123)");
+    if (n % B != 0)
+        throw std::invalid_argument("psb200: the matrix size is not a multiple of block_size");
+    const int nb = (int)(n / B);
+    DevBuf<int> cnt, boff;
+    cnt.alloc((size_t)nb + 1, true);
+    boff.alloc((size_t)nb + 1);
+    block_count_kernel<<<blocks_for(nb + 1, 256), 256, 0, st>>>(B, nb, rp.p, ci.p, cnt.p);
+    check_launch();
+    size_t tmp_bytes = 0;
+    PSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt.p, boff.p, nb + 1, st));
+    DevBuf<unsigned char> tmp;
+    tmp.alloc(tmp_bytes);
+    PSB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, cnt.p, boff.p, nb + 1, st));
+    int nblocks = 0;
+    PSB_CUDA(cudaMemcpyAsync(&nblocks, boff.p + nb, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PSB_CUDA(cudaStreamSynchronize(st));
+    const long long nnz_full = (long long)nblocks * B * B;
+    if (nnz_full > 0x7fffffffLL - 1024)
+        throw std::invalid_argument("psb200: int32 index range exceeded after block expansion");
+    DevBuf<int> nrp, nci, nperm;
+    nrp.alloc(n + 1);
+    nci.alloc(std::max<long long>(nnz_full, 1), false, 64);
+    nperm.alloc(std::max<long long>(nnz_full, 1));
+    block_fill_kernel<<<blocks_for(nb + 1, 256), 256, 0, st>>>(B, nb, rp.p, ci.p, perm.p, boff.p, nrp.p, nci.p, nperm.p);
+    check_launch();
+    PSB_CUDA(cudaStreamSynchronize(st));
+    rp = std::move(nrp);
+    ci = std::move(nci);
+    perm = std::move(nperm);
+    return nnz_full;
+}
+
 // ==================================================================================== lifecycle
 Solver::Solver() {}
 
@@ -545,38 +584,7 @@ void Solver::analyze_pattern(long long n_, long long nnz_, const int *outer, con
     if (prm.block_size > 1 && n > 0)
     {
         const int B = prm.block_size;
-        if (B > 3)
-            throw std::invalid_argument("psb200: block_size must be 1, 2 or 3 (reference AMGCL.cpp:111-123)");
-        if (n % B != 0)
-            throw std::invalid_argument("psb200: the matrix size is not a multiple of block_size");
-        const int nb = (int)(n / B);
-        DevBuf<int> cnt, boff;
-        cnt.alloc((size_t)nb + 1, true);
-        boff.alloc((size_t)nb + 1);
-        block_count_kernel<<<blocks_for(nb + 1, 256), 256, 0, st>>>(B, nb, A.rp.p, A.ci.p, cnt.p);
-        check_launch();
-        size_t tmp_bytes = 0;
-        PSB_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt.p, boff.p, nb + 1, st));
-        DevBuf<unsigned char> tmp;
-        tmp.alloc(tmp_bytes);
-        PSB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, cnt.p, boff.p, nb + 1, st));
-        int nblocks = 0;
-        PSB_CUDA(cudaMemcpyAsync(&nblocks, boff.p + nb, sizeof(int), cudaMemcpyDeviceToHost, st));
-        PSB_CUDA(cudaStreamSynchronize(st));
-        const long long nnz_full = (long long)nblocks * B * B;
-        if (nnz_full > 0x7fffffffLL - 1024)
-            throw std::invalid_argument("psb200: int32 index range exceeded after block expansion");
-        DevBuf<int> nrp, nci, nperm;
-        nrp.alloc(n + 1);
-        nci.alloc(std::max<long long>(nnz_full, 1), false, 64);
-        nperm.alloc(std::max<long long>(nnz_full, 1));
-        block_fill_kernel<<<blocks_for(nb + 1, 256), 256, 0, st>>>(B, nb, A.rp.p, A.ci.p, perm.p, boff.p, nrp.p, nci.p, nperm.p);
-        check_launch();
-        PSB_CUDA(cudaStreamSynchronize(st));
-        A.rp = std::move(nrp);
-        A.ci = std::move(nci);
-        perm = std::move(nperm);
-        nnz = nnz_full;
+        nnz = expand_block_pattern(ctx, B, n, A.rp, A.ci, perm);
         A.nnz = nnz;
         A.va.alloc(std::max<long long>(nnz, 1), false, 64);
         pattern_block = B;
@@ -597,9 +605,17 @@ void Solver::factorize(long long n_, long long nnz_, const int *outer, const int
     // factorize() without (or with a stale) analyze_pattern(): analyze now. The Eigen iterative wrappers
     // accept this order too (EigenSolver.tpp:100-105 only needs the matrix).
     bool need = !analyzed || n_global != n_ || nnz_global != nnz_ || pattern_block != std::max(1, prm.block_size);
+    // The raw CSC values go to the device first (valid whatever the pattern turns out to be): with pinned host
+    // memory the copy runs while the host hashes the index arrays below.
+    if (!dist)
+    {
+        csc_vals.alloc(std::max<long long>(nnz_, 1));
+        if (nnz_)
+            PSB_CUDA(cudaMemcpyAsync(csc_vals.p, vals, sizeof(double) * nnz_, cudaMemcpyHostToDevice, ctx.stream));
+    }
     if (!need && prm.verify_pattern && outer && inner)
     {
-        // cheap guard against a silently changed pattern: outer fully, inner strided
+        // guard against a silently changed pattern (Newton re-assembles every iteration, Newton.cpp:189-191)
         unsigned long long h = hash_words(outer, sizeof(int) * (size_t)(n_ + 1), 0x5bd1e995ull + (unsigned long long)n_);
         h = hash_words(inner, sizeof(int) * (size_t)nnz_, h);
         need = h != pattern_hash;
@@ -614,15 +630,10 @@ void Solver::factorize(long long n_, long long nnz_, const int *outer, const int
     cudaStream_t st = ctx.stream;
     if (dist)
         factorize_values_dist(vals);
-    else
+    else if (nnz)
     {
-        csc_vals.alloc(std::max<long long>(nnz_global, 1));
-        if (nnz)
-        {
-            PSB_CUDA(cudaMemcpyAsync(csc_vals.p, vals, sizeof(double) * nnz_global, cudaMemcpyHostToDevice, st));
-            gather_vals_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(nnz, csc_vals.p, perm.p, A.va.p);
-            check_launch();
-        }
+        gather_vals_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(nnz, csc_vals.p, perm.p, A.va.p);
+        check_launch();
     }
     dinv.alloc(n_pad, true);
     int *d_bad = (int *)ctx.counter.p + 3;

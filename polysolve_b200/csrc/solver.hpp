@@ -135,6 +135,7 @@ struct Solver
 };
 
 void ensure_ctx(Solver &s);
+long long expand_block_pattern(Ctx &ctx, int B, long long n, DevBuf<int> &rp, DevBuf<int> &ci, DevBuf<int> &perm);
 void init_state(Solver &s, double tol, int max_iter);
 
 } // namespace psb

@@ -321,22 +321,37 @@ __global__ void __launch_bounds__(Cfg::threads) spmv_stream_kernel(CsrView A, co
         }
     };
 
+    auto tile_at = [&](int pos) { return A.tile_order ? __ldg(A.tile_order + pos) : pos; };
     if (threadIdx.x == 0)
     {
 #pragma unroll
         for (int s = 0; s < STAGES; ++s)
         {
-            const int tile = blockIdx.x + s * gridDim.x;
-            if (tile < ntiles)
-                issue(tile, s);
+            const int pos = blockIdx.x + s * gridDim.x;
+            if (pos < ntiles)
+                issue(tile_at(pos), s);
         }
     }
 
-    const double *xh = wait_halo(A, rc.comm); // the TMA prefetch above is already in flight
+    // Row partitions: the halo values are needed by the boundary tiles only. With an interior-first order the wait
+    // happens right before this CTA's first boundary tile; otherwise here (the TMA prefetch is already in flight).
+    const double *xh = nullptr;
+    bool halo_ready = A.halo_mask == 0;
+    if (!halo_ready && A.tile_order == nullptr)
+    {
+        xh = wait_halo(A, rc.comm);
+        halo_ready = true;
+    }
 
     int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it)
+    for (int pos = blockIdx.x; pos < ntiles; pos += gridDim.x, ++it)
     {
+        const int tile = tile_at(pos);
+        if (!halo_ready && pos >= A.n_interior)
+        {
+            xh = wait_halo(A, rc.comm);
+            halo_ready = true;
+        }
         const int s = it % STAGES;
         const unsigned parity = (it / STAGES) & 1;
         const int r0 = tile * ROWS;
@@ -420,9 +435,9 @@ __global__ void __launch_bounds__(Cfg::threads) spmv_stream_kernel(CsrView A, co
         __syncthreads(); // every thread is done reading stage s
         if (threadIdx.x == 0)
         {
-            const int next = tile + STAGES * gridDim.x;
+            const int next = pos + STAGES * gridDim.x;
             if (next < ntiles)
-                issue(next, s);
+                issue(tile_at(next), s);
         }
     }
     double tot[NVA];

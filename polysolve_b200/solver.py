@@ -161,7 +161,7 @@ class Solver:
         return a.value, b.value
 
     @staticmethod
-    def dist_plan_host(n, outer, inner, rank, world, halo_cap=1 << 20):
+    def dist_plan_host(n, outer, inner, rank, world, halo_cap=1 << 20, align=1):
         """Host-only partition / halo plan of one rank (no GPU needed)."""
         L = _lib.lib()
         nnz = int(outer[n])
@@ -174,7 +174,7 @@ class Solver:
         send_rows = np.zeros(max(n, 1), np.int32)
         recv_count = np.zeros(world, np.int32)
         halo_cols = np.zeros(max(n, 1), np.int32)
-        rc = L.psb200_dist_plan_host(n, nnz, outer, inner, rank, world, halo_cap, offsets, counts, rp, ci, perm,
+        rc = L.psb200_dist_plan_host_aligned(n, nnz, outer, inner, rank, world, halo_cap, align, offsets, counts, rp, ci, perm,
                                      send_begin, send_rows, recv_count, halo_cols)
         if rc:
             raise RuntimeError("psb200_dist_plan_host failed")

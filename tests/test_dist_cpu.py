@@ -61,6 +61,28 @@ def test_plan_matches_oracle_bit_exact(psb, orc, world):
                     assert len(sent) == 0
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_plan_block_aligned_offsets(psb, orc, world):
+    """Block problems (set_block_size(3)): offsets are multiples of the block size, equal to the oracle's
+    aligned partition, and every other index array still matches the oracle for those offsets."""
+    o, i, v, _ = psb.problems.elasticity3d(6)
+    n = len(o) - 1
+    rp, ci, perm = orc.csc_to_csr(n, o, i)
+    off0 = orc.partition_rows(rp, world, align=3)
+    assert np.all(off0 % 3 == 0)
+    for r in range(world):
+        P = psb.Solver.dist_plan_host(n, o, i, r, world, HALO_CAP, align=3)
+        assert np.array_equal(P["offsets"], off0)
+        a, b = int(off0[r]), int(off0[r + 1])
+        lc0, halo0 = orc.halo_for_rank(rp, ci, a, b)
+        assert np.array_equal(P["rp"], rp[a:b + 1] - rp[a])
+        assert np.array_equal(P["halo_cols"], halo0)
+        assert np.array_equal(compact_cols(P, world), lc0)
+        assert np.array_equal(P["perm"], perm[rp[a]:rp[b]])
+    with pytest.raises(RuntimeError):
+        psb.Solver.dist_plan_host(n, o, i, 0, world, HALO_CAP, align=7)  # 648 is not a multiple of 7
+
+
 def test_plan_halo_capacity_error(psb, orc):
     o, i, v = orc.poisson3d(12)
     with pytest.raises(RuntimeError):

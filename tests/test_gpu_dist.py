@@ -26,7 +26,16 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, tol, q, precond="jacobi"):
+def _problem(P, n, block):
+    if block > 1:
+        o, i, v, b = P.elasticity3d(n)
+        return o, i, v, b, 3 * n ** 3
+    o, i, v = P.poisson3d(n)
+    N = n ** 3
+    return o, i, v, P.spmv_csr(o, i, v, P.splitmix64(42, N)), N
+
+
+def _worker(rank, world, port, n, tol, q, precond="jacobi", block=1):
     import torch
     import torch.distributed as dist
 
@@ -37,11 +46,10 @@ def _worker(rank, world, port, n, tol, q, precond="jacobi"):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         P = psb.problems
-        o, i, v = P.poisson3d(n)
-        N = n ** 3
-        b = P.spmv_csr(o, i, v, P.splitmix64(42, N))
+        o, i, v, b, N = _problem(P, n, block)
         s = psb.Solver.create("CUDA", "")
-        s.set_parameters({"CUDA": {"tolerance": tol, "max_iter": 10000, "device": rank, "check_every": 8, "precond": precond}})
+        s.set_parameters({"CUDA": {"tolerance": tol, "max_iter": 10000, "device": rank, "check_every": 8, "precond": precond,
+                                   "block_size": block}})
         s.dist_setup_torch(halo_cap=1 << 16)
         s.analyze_pattern_raw(N, o, i, N)
         s.factorize_raw(N, o, i, v)
@@ -59,12 +67,12 @@ def _worker(rank, world, port, n, tol, q, precond="jacobi"):
         dist.destroy_process_group()
 
 
-def _run(world, n, tol, precond="jacobi"):
+def _run(world, n, tol, precond="jacobi", block=1):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     port = _free_port()
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, tol, q, precond)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, tol, q, precond, block)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
@@ -121,3 +129,31 @@ def test_dist_amg_pcg(orc, world):
         assert it2 == 0
     assert np.linalg.norm(x - x0) / np.linalg.norm(x0) < 10 * tol
     assert np.linalg.norm(orc.spmv_csc(o, i, v, x) - b) / np.linalg.norm(b) < 2 * tol
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_dist_block3_amg_pcg_elasticity(psb, orc, world):
+    """C4-shaped (BASELINE config 4): P1 linear elasticity, block-3 SA-AMG-PCG on the row partition. Offsets are
+    multiples of 3 and equal the oracle's aligned partition; the solution equals a direct solve."""
+    if world > max(1, _ngpu()):
+        pytest.skip(f"needs {world} GPUs")
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    m, tol = 16, 1e-8
+    o, i, v, b = psb.problems.elasticity3d(m)
+    N = 3 * m ** 3
+    A = sp.csc_matrix((v, i, o), shape=(N, N))
+    x0 = spla.spsolve(A, b)
+    res = _run(world, m, tol, "amg", 3)
+    rp, ci, _ = orc.csc_to_csr(N, o, i)
+    off0 = orc.partition_rows(rp, world, align=3)
+    x = np.zeros(N)
+    for rank, a, e, xs, it, err, status, it2, dinfo in res:
+        assert (a, e) == (off0[rank], off0[rank + 1]) and a % 3 == 0
+        x[a:e] = xs
+        assert status == "Converged"
+        assert it == res[0][4] and 1 <= it <= 80
+        assert err < tol
+        assert it2 == 0
+    assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) < 2 * tol
+    assert np.linalg.norm(x - x0) / np.linalg.norm(x0) < 1e-5
