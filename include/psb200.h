@@ -63,6 +63,17 @@ int psb200_solve(psb200_handle h, const double *b, double *x_inout, int64_t n);
 /* Same, with b and x resident in device memory of the solver's GPU. */
 int psb200_solve_device(psb200_handle h, const double *d_b, double *d_x_inout, int64_t n);
 
+/* Device-resident Newton step (reference call site Newton::solve_sparse_linear_system,
+ * Newton.cpp:173-214): the Hessian values are already in GPU memory, in the CSC order of the pattern given to
+ * psb200_analyze_pattern_csc (which Newton re-submits unchanged every iteration, Newton.cpp:189). diag_shift is added
+ * to every diagonal entry (RegularizedNewton: hessian += reg_weight * I, Newton.cpp:287-290; the diagonal must be
+ * structurally present). Row partitions: d_vals is the full CSC value array on every rank. */
+int psb200_factorize_csc_device(psb200_handle h, int64_t n, int64_t nnz, const double *d_vals, double diag_shift);
+/* ||A x - b||_2 with x and b in device memory: the residual Newton checks after the solve
+ * (objFunc.grad_norm(hessian * direction + grad), Newton.cpp:207, with b = -grad). Row partitions: local slices in,
+ * the global norm out on every rank. */
+int psb200_residual_norm_device(psb200_handle h, const double *d_x, const double *d_b, int64_t n, double *norm_out);
+
 /* Solver::get_info(json&) -- Solver.hpp:96. Writes a JSON object with both key conventions:
  * "solver_iter","solver_error" (EigenSolver.tpp:88-89) and "num_iterations","final_res_norm"
  * (AMGCL.cpp:142-143), plus "solver_status" (MASSolver.cu:214-219) and timing/hierarchy details.
@@ -74,6 +85,25 @@ const char *psb200_last_error(psb200_handle h);
 /* Device buffers come from the GPU's stream-ordered memory pool and stay cached there between factorize() calls
  * (policy precedent: one pool per solver, MASSolver.cu:154-156). This returns the cached, unused part to the driver. */
 int psb200_release_cached_memory(psb200_handle h);
+
+/* ---- Dirichlet pre-processing on the GPU: the reference's FEMSolver helpers, the step right before
+ * the hot path in PolyFEM. N = diag(1 iff i is a Dirichlet dof).
+ * psb200_dirichlet_solve = dirichlet_solve(solver, A, f, dirichlet_nodes, u, precond_num) with remove_zero_cols =
+ * false (FEMSolver.cpp:97-300): A~ = A with the rows and columns of the Dirichlet dofs set to identity,
+ * g = f - (I - N) A N f, analyze_pattern + factorize(A~) + solve(g, u); on return f holds g (":282 f = g") and u the
+ * solution (u is also the initial guess). The host matrix is not modified (the reference rewrites A in place to save
+ * host memory; here the masked copy lives in HBM). Single GPU. */
+int psb200_dirichlet_solve(psb200_handle h, int64_t n, int64_t nnz, const int32_t *outer, const int32_t *inner,
+                           const double *vals, double *f_inout, const int32_t *dirichlet_nodes, int64_t n_nodes,
+                           double *u_inout, int precond_num);
+/* prefactorize(solver, A, dirichlet_nodes, precond_num) -- FEMSolver.cpp:303-343. */
+int psb200_dirichlet_prefactorize(psb200_handle h, int64_t n, int64_t nnz, const int32_t *outer, const int32_t *inner,
+                                  const double *vals, const int32_t *dirichlet_nodes, int64_t n_nodes, int precond_num);
+/* dirichlet_solve_prefactorized(solver, A, f, dirichlet_nodes, u) -- FEMSolver.cpp:345-372: g is computed with the
+ * matrix values the caller passes (vals, CSC order of the prefactorized pattern); NULL = the resident masked matrix,
+ * which is what the reference multiplies with when the caller hands back the A that prefactorize rewrote. */
+int psb200_dirichlet_solve_prefactorized(psb200_handle h, const double *vals_or_null, double *f_inout, double *u_inout,
+                                         int64_t n);
 
 /* ---- multi-GPU (one process per GPU, up to 8 GPUs of one node). No reference counterpart.
  * The matrix is row-range partitioned (contiguous ranges balanced by nnz); halo x-entries and the

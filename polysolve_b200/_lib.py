@@ -20,10 +20,14 @@ f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 SYMBOLS = [
     "psb200_create", "psb200_destroy", "psb200_set_parameters", "psb200_set_tolerance", "psb200_set_block_size",
     "psb200_analyze_pattern_csc", "psb200_factorize_csc", "psb200_solve", "psb200_solve_device", "psb200_get_info",
-    "psb200_name", "psb200_last_error", "psb200_release_cached_memory", "psb200_dist_prepare", "psb200_dist_connect", "psb200_dist_local_range",
+    "psb200_name", "psb200_last_error", "psb200_release_cached_memory", "psb200_factorize_csc_device", "psb200_residual_norm_device",
+    "psb200_dirichlet_solve", "psb200_dirichlet_prefactorize", "psb200_dirichlet_solve_prefactorized", "psb200_dist_prepare", "psb200_dist_connect", "psb200_dist_local_range",
     "psb200_dist_plan_host", "psb200_dist_plan_host_aligned", "psb200_debug_get_csr",
     "psb200_spmv", "psb200_bench_spmv", "psb200_get_stream", "psb200_debug_set_aggregates", "psb200_debug_get_level",
     "psb200_precond_apply", "psb200_debug_get_aggregates",
+    # include/psb200_io.h
+    "psb200_market_load", "psb200_market_get_csc", "psb200_market_free", "psb200_market_save", "psb200_market_load_vector",
+    "psb200_market_save_vector", "psb200_market_last_error",
     # include/psb200_nl.h
     "psb200_nl_create", "psb200_nl_destroy", "psb200_nl_minimize", "psb200_nl_get_info", "psb200_nl_last_error",
 ]
@@ -55,6 +59,18 @@ def lib():
     L.psb200_factorize_csc.argtypes = [H, C.c_int64, C.c_int64, i32p, i32p, f64p]
     L.psb200_solve.argtypes = [H, f64p, f64p, C.c_int64]
     L.psb200_release_cached_memory.argtypes = [H]
+    L.psb200_market_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.psb200_market_get_csc.argtypes = [C.c_void_p, i32p, i32p, f64p]
+    L.psb200_market_free.argtypes = [C.c_void_p]
+    L.psb200_market_save.argtypes = [C.c_char_p, C.c_int64, C.c_int64, i32p, i32p, f64p, C.c_int]
+    L.psb200_market_load_vector.argtypes = [C.c_char_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+    L.psb200_market_save_vector.argtypes = [C.c_char_p, f64p, C.c_int64]
+    L.psb200_market_last_error.restype = C.c_char_p
+    L.psb200_dirichlet_solve.argtypes = [H, C.c_int64, C.c_int64, i32p, i32p, f64p, f64p, i32p, C.c_int64, f64p, C.c_int]
+    L.psb200_dirichlet_prefactorize.argtypes = [H, C.c_int64, C.c_int64, i32p, i32p, f64p, i32p, C.c_int64, C.c_int]
+    L.psb200_dirichlet_solve_prefactorized.argtypes = [H, C.c_void_p, f64p, f64p, C.c_int64]
+    L.psb200_factorize_csc_device.argtypes = [H, C.c_int64, C.c_int64, C.c_void_p, C.c_double]
+    L.psb200_residual_norm_device.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_double)]
     L.psb200_solve_device.argtypes = [H, C.c_void_p, C.c_void_p, C.c_int64]
     L.psb200_get_info.argtypes = [H, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
     L.psb200_name.argtypes = [H]

@@ -110,6 +110,20 @@ int psb200_factorize_csc(psb200_handle h, int64_t n, int64_t nnz, const int32_t 
     return guarded(h, [&](psb::Solver &s) { s.factorize(n, nnz, outer, inner, vals); });
 }
 
+int psb200_factorize_csc_device(psb200_handle h, int64_t n, int64_t nnz, const double *d_vals, double diag_shift)
+{
+    return guarded(h, [&](psb::Solver &s) { s.factorize_device(n, nnz, d_vals, diag_shift); });
+}
+
+int psb200_residual_norm_device(psb200_handle h, const double *d_x, const double *d_b, int64_t n, double *norm_out)
+{
+    return guarded(h, [&](psb::Solver &s) {
+        const double r = s.residual_norm_device(d_x, d_b, n);
+        if (norm_out)
+            *norm_out = r;
+    });
+}
+
 int psb200_solve(psb200_handle h, const double *b, double *x, int64_t n)
 {
     return guarded(h, [&](psb::Solver &s) { s.solve_host(b, x, n); });

@@ -458,6 +458,16 @@ PushList make_push(DistState &d)
 // of a multi-rank run launches at least one so the epochs advance in lockstep.
 static int push_ctas(const DistState &d) { return d.world > 1 ? std::max(1, std::min(128, d.n_chunks)) : 0; }
 
+void Solver::push_halo_of(const double *d_v)
+{
+    DistState &d = *dist;
+    const int push_blocks = push_ctas(d);
+    if (!push_blocks)
+        return;
+    halo_push_kernel<kVecThreads><<<push_blocks, kVecThreads, 0, ctx.stream>>>(d_v, ctx.red(), make_push(d));
+    check_launch();
+}
+
 // ---------------------------------------------------------------------------------- rank-local AMG
 __global__ void diag_count_kernel(int n, int nl, const int *__restrict__ rp, const int *__restrict__ ci, int *__restrict__ cnt)
 {

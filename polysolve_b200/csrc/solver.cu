@@ -274,6 +274,26 @@ __global__ void inv_diag_kernel(CsrView A, double *__restrict__ dinv, int mode, 
     }
 }
 
+// A_ii += shift (8 lanes per row; rows of a row partition hold their diagonal at local column i)
+__global__ void shift_diag_kernel(CsrView A, double *__restrict__ va, double shift, int *missing)
+{
+    const int lane = threadIdx.x & 7;
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    if (row >= A.n)
+        return;
+    bool found = false;
+    for (int k = A.rp[row] + lane; k < A.rp[row + 1]; k += 8)
+        if (A.ci[k] == (int)row)
+        {
+            va[k] += shift;
+            found = true;
+        }
+    for (int o = 4; o > 0; o >>= 1)
+        found |= (bool)__shfl_xor_sync(0xffffffffu, (int)found, o);
+    if (lane == 0 && !found)
+        atomicExch(missing, 1);
+}
+
 inline int blocks_for(long long n, int threads) { return (int)std::max<long long>(1, (n + threads - 1) / threads); }
 
 } // namespace
@@ -635,6 +655,50 @@ void Solver::factorize(long long n_, long long nnz_, const int *outer, const int
         gather_vals_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(nnz, csc_vals.p, perm.p, A.va.p);
         check_launch();
     }
+    factorize_tail(t0);
+}
+
+// Newton step with the Hessian values already on the device (reference call site Newton.cpp:173-214):
+// d_vals holds the values in the CSC order of the analyzed pattern, nothing crosses PCIe. diag_shift is added to the
+// diagonal after the gather (RegularizedNewton: hessian += reg_weight * I, Newton.cpp:287-290).
+void Solver::factorize_device(long long n_, long long nnz_, const double *d_vals, double diag_shift)
+{
+    if (!analyzed)
+        throw std::invalid_argument("psb200_factorize_csc_device: analyze_pattern() first (the device path has no index arrays to analyze)");
+    if (n_ != n_global || nnz_ != nnz_global || pattern_block != std::max(1, prm.block_size))
+        throw std::invalid_argument("psb200_factorize_csc_device: size differs from the analyzed pattern");
+    if (!d_vals && nnz_ > 0)
+        throw std::invalid_argument("psb200_factorize_csc_device: null values");
+    ensure_ctx(*this);
+    const double t0 = now_ms();
+    cudaStream_t st = ctx.stream;
+    if (nnz)
+    {
+        if (dist)
+            gather_vals_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(nnz, d_vals + dist->val_lo, dist->d_perm.p, A.va.p);
+        else
+            gather_vals_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(nnz, d_vals, perm.p, A.va.p);
+        check_launch();
+    }
+    if (diag_shift != 0.0 && n > 0)
+    {
+        int *d_missing = (int *)ctx.counter.p + 3;
+        PSB_CUDA(cudaMemsetAsync(d_missing, 0, sizeof(int), st));
+        shift_diag_kernel<<<blocks_for(n * 8, 256), 256, 0, st>>>(A.view(), A.va.p, diag_shift, d_missing);
+        check_launch();
+        int missing = 0;
+        PSB_CUDA(cudaMemcpyAsync(&missing, d_missing, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PSB_CUDA(cudaStreamSynchronize(st));
+        if (missing)
+            throw std::runtime_error("psb200_factorize_csc_device: diag_shift needs a structurally present diagonal");
+    }
+    factorize_tail(t0);
+}
+
+// preconditioner setup on the values now in A.va (shared by the host and the device entry)
+void Solver::factorize_tail(double t0)
+{
+    cudaStream_t st = ctx.stream;
     dinv.alloc(n_pad, true);
     int *d_bad = (int *)ctx.counter.p + 3;
     PSB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
@@ -680,8 +744,28 @@ void Solver::factorize(long long n_, long long nnz_, const int *outer, const int
     last_iters = 0;
     last_error = 0;
     last_status = 0;
-    t_factorize_ms = now_ms() - t0;
+    t_factorize_ms = t0 > 0 ? now_ms() - t0 : 0.0;
     build_info();
+}
+
+void Solver::gather_values_to_csr(const double *d_csc_vals)
+{
+    if (!nnz)
+        return;
+    gather_vals_kernel<<<blocks_for(nnz, 256), 256, 0, ctx.stream>>>(nnz, d_csc_vals, perm.p, A.va.p);
+    check_launch();
+}
+
+void Solver::run_solver(const double *d_b)
+{
+    if (dist)
+        prm.precond == "amg" ? run_cg_amgcl_dist(d_b) : run_cg_eigen_dist(d_b);
+    else if (prm.krylov == "bicgstab")
+        run_bicgstab(d_b);
+    else if (prm.precond == "amg")
+        run_cg_amgcl(d_b);
+    else
+        run_cg_eigen(d_b);
 }
 
 void Solver::ensure_vectors()
@@ -721,14 +805,7 @@ void Solver::solve_host(const double *b, double *x, long long n_)
     x += row0;
     PSB_CUDA(cudaMemcpyAsync(vb.p, b, sizeof(double) * n, cudaMemcpyHostToDevice, st));
     PSB_CUDA(cudaMemcpyAsync(vx.p, x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-    if (dist)
-        prm.precond == "amg" ? run_cg_amgcl_dist(vb.p) : run_cg_eigen_dist(vb.p);
-    else if (prm.krylov == "bicgstab")
-        run_bicgstab(vb.p);
-    else if (prm.precond == "amg")
-        run_cg_amgcl(vb.p);
-    else
-        run_cg_eigen(vb.p);
+    run_solver(vb.p);
     PSB_CUDA(cudaMemcpyAsync(x, vx.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     PSB_CUDA(cudaStreamSynchronize(st));
     t_solve_ms = now_ms() - t0;
@@ -748,18 +825,35 @@ void Solver::solve_device(const double *d_b, double *d_x, long long n_)
         ctx.prof.clear();
     // x lives in the solver's own buffer so captured graphs keep stable pointers
     PSB_CUDA(cudaMemcpyAsync(vx.p, d_x, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-    if (dist)
-        prm.precond == "amg" ? run_cg_amgcl_dist(d_b) : run_cg_eigen_dist(d_b);
-    else if (prm.krylov == "bicgstab")
-        run_bicgstab(d_b);
-    else if (prm.precond == "amg")
-        run_cg_amgcl(d_b);
-    else
-        run_cg_eigen(d_b);
+    run_solver(d_b);
     PSB_CUDA(cudaMemcpyAsync(d_x, vx.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     PSB_CUDA(cudaStreamSynchronize(st));
     t_solve_ms = now_ms() - t0;
     build_info();
+}
+
+// ||A x - b||_2 with x, b resident on the device (the Newton residual check H dx + g, Newton.cpp:207, with b = -g)
+double Solver::residual_norm_device(const double *d_x, const double *d_b, long long n_)
+{
+    if (!factorized)
+        throw std::runtime_error("psb200_residual_norm_device: factorize() has not been called");
+    if (n_ != n || !d_x || !d_b)
+        throw std::invalid_argument("psb200_residual_norm_device: size mismatch or null vector");
+    ensure_vectors();
+    cudaStream_t st = ctx.stream;
+    // the solver's own buffers: padded (zero tails) and, on a row partition, the ones the halo push reads
+    PSB_CUDA(cudaMemcpyAsync(vx.p, d_x, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    if (dist)
+        push_halo_of(vx.p);
+    DevBuf<double> out;
+    out.alloc(4, true);
+    launch_spmv(ctx, "spmv_residual", A, vx.p, EpiResidualNorms{vr.p, d_b, dinv.p}, FinStore{out.p, 3});
+    double h[3] = {0, 0, 0};
+    PSB_CUDA(cudaMemcpyAsync(h, out.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    PSB_CUDA(cudaStreamSynchronize(st));
+    if (dist)
+        check_comm_error();
+    return std::sqrt(h[0]);
 }
 
 // Launches batches of iterations until the device-side `done` flag is seen. Two batches are kept in

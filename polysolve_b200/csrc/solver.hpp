@@ -119,6 +119,23 @@ struct Solver
     void set_parameters(const std::string &json);
     void analyze_pattern(long long n, long long nnz, const int *outer, const int *inner, int precond_num);
     void factorize(long long n, long long nnz, const int *outer, const int *inner, const double *vals);
+    void factorize_device(long long n, long long nnz, const double *d_vals, double diag_shift);
+    void factorize_tail(double t0);
+    double residual_norm_device(const double *d_x, const double *d_b, long long n);
+    void push_halo_of(const double *d_v); // row partition: push the boundary entries of a local vector (dist.cu)
+    // Dirichlet pre-processing (fem.cu; reference FEMSolver.cpp:97-372)
+    DevBuf<unsigned char> dmask; // N: 1 for a Dirichlet dof
+    void dirichlet_set_nodes(const int *nodes, long long count);
+    void dirichlet_upload(long long n, long long nnz, const int *outer, const int *inner, const double *vals, int precond_num);
+    void dirichlet_lift(const double *d_f, double *d_g);
+    void dirichlet_mask_matrix();
+    void dirichlet_solve(long long n, long long nnz, const int *outer, const int *inner, const double *vals, double *f, const int *nodes,
+                         long long n_nodes, double *u, int precond_num);
+    void dirichlet_prefactorize(long long n, long long nnz, const int *outer, const int *inner, const double *vals, const int *nodes,
+                                long long n_nodes, int precond_num);
+    void dirichlet_solve_prefactorized(const double *vals, double *f, double *u, long long n);
+    void gather_values_to_csr(const double *d_csc_vals); // A.va[k] = d_csc_vals[perm[k]] on the solver's stream
+    void run_solver(const double *d_b);                  // the configured Krylov method on vx (in/out) and d_b
     void solve_host(const double *b, double *x, long long n);
     void solve_device(const double *d_b, double *d_x, long long n);
     void spmv_host(const double *x, double *y, long long n);

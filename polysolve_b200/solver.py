@@ -98,6 +98,17 @@ class Solver:
     def factorize_raw(self, n, outer, inner, vals):
         self._check(self._L.psb200_factorize_csc(self._h, n, int(outer[n]), outer, inner, vals))
 
+    def factorize_device(self, n, nnz, vals_ptr, diag_shift=0.0):
+        """factorize() with the values already in GPU memory (CSC order of the analyzed pattern); diag_shift is
+        RegularizedNewton's reg_weight (reference Newton.cpp:287-290)."""
+        self._check(self._L.psb200_factorize_csc_device(self._h, int(n), int(nnz), vals_ptr, float(diag_shift)))
+
+    def residual_norm_device(self, x_ptr, b_ptr, n):
+        """||A x - b||_2 for device-resident x, b (reference Newton.cpp:207)."""
+        out = C.c_double()
+        self._check(self._L.psb200_residual_norm_device(self._h, x_ptr, b_ptr, int(n), C.byref(out)))
+        return out.value
+
     def solve(self, b, x):
         """x is in/out (initial guess), as in the reference (Solver.hpp:119-128)."""
         b = np.ascontiguousarray(b, np.float64)
@@ -111,6 +122,33 @@ class Solver:
     def solve_device(self, b_ptr, x_ptr, n):
         """b, x resident on the solver's GPU (raw device pointers, e.g. torch.Tensor.data_ptr())."""
         self._check(self._L.psb200_solve_device(self._h, b_ptr, x_ptr, n))
+
+    # ---- FEMSolver helpers (reference src/polysolve/linear/FEMSolver.cpp:97-372), Dirichlet masking + lifting on the GPU
+    @staticmethod
+    def _nodes(nodes):
+        nodes = np.ascontiguousarray(nodes, np.int32)
+        return nodes if nodes.size else np.zeros(1, np.int32), int(nodes.size)
+
+    def dirichlet_solve(self, A, f, dirichlet_nodes, u, precond_num):
+        """dirichlet_solve(solver, A, f, dirichlet_nodes, u, precond_num): f becomes g, u the solution (both in place)."""
+        n, outer, inner, vals = self._csc(A)
+        nodes, cnt = self._nodes(dirichlet_nodes)
+        for v in (f, u):
+            if not (isinstance(v, np.ndarray) and v.dtype == np.float64 and v.flags.c_contiguous and v.shape == (n,)):
+                raise TypeError("f and u must be contiguous float64 arrays of length n (they are updated in place)")
+        self._check(self._L.psb200_dirichlet_solve(self._h, n, int(outer[n]), outer, inner, vals, f, nodes, cnt, u, int(precond_num)))
+
+    def prefactorize(self, A, dirichlet_nodes, precond_num):
+        n, outer, inner, vals = self._csc(A)
+        nodes, cnt = self._nodes(dirichlet_nodes)
+        self._check(self._L.psb200_dirichlet_prefactorize(self._h, n, int(outer[n]), outer, inner, vals, nodes, cnt, int(precond_num)))
+
+    def dirichlet_solve_prefactorized(self, A, f, u):
+        """A: the matrix to lift with (None = the resident masked matrix)."""
+        vals = None
+        if A is not None:
+            vals = self._csc(A)[3]
+        self._check(self._L.psb200_dirichlet_solve_prefactorized(self._h, None if vals is None else vals.ctypes.data, f, u, f.shape[0]))
 
     def get_info(self):
         need = C.c_size_t()

@@ -330,6 +330,46 @@ def test_solve_device_pointers(psb, orc):
     assert np.linalg.norm(x - g["x"]) / np.linalg.norm(g["x"]) < 1e-7
 
 
+def test_device_resident_newton_step(psb, orc):
+    """the Newton call sequence (Newton.cpp:173-214) with H, g and dx in GPU memory -- analyze once,
+    factorize_csc_device(values, reg_weight), solve_device, residual_norm_device -- equals the host path."""
+    import torch
+    o, i, v = orc.poisson3d(20)
+    N, nnz = 20 ** 3, len(v)
+    v = v * (1.0 + 0.2 * orc.splitmix64(4, nnz))
+    v = 0.5 * (v + v[orc.csc_to_csr(N, o, i)[2]])
+    g = orc.splitmix64(8, N)
+    s = make(psb, tolerance=1e-10, max_iter=5000)
+    with pytest.raises(RuntimeError):
+        s.factorize_device(N, nnz, 0, 0.0)  # no pattern yet
+    s.analyze_pattern_raw(N, o, i, N)
+    dv = torch.from_numpy(v).cuda()
+    db = torch.from_numpy(-g).cuda()
+    for shift in (0.0, 0.75):
+        s.analyze_pattern_raw(N, o, i, N)            # Newton re-submits the pattern every iteration: skipped by hash
+        assert s.get_info()["analyze_skipped"]
+        s.factorize_device(N, nnz, dv.data_ptr(), shift)
+        dx = torch.zeros(N, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        s.solve_device(db.data_ptr(), dx.data_ptr(), N)
+        res = s.residual_norm_device(dx.data_ptr(), db.data_ptr(), N)
+        x = dx.cpu().numpy()
+        H = csc(o, i, v) + shift * sp.identity(N, format="csc")
+        assert abs(res - np.linalg.norm(H @ x + g)) < 1e-12 * np.linalg.norm(g) + 1e-14
+        assert res < 1e-9 * np.linalg.norm(g)
+        # same iterates as the host entry points on the shifted matrix
+        Hs = sp.csc_matrix(H)
+        Hs.sort_indices()
+        s2 = make(psb, tolerance=1e-10, max_iter=5000)
+        s2.factorize_raw(N, Hs.indptr.astype(np.int32), Hs.indices.astype(np.int32), Hs.data.astype(np.float64))
+        x2 = np.zeros(N)
+        s2.solve(-g, x2)
+        assert s2.get_info()["solver_iter"] == s.get_info()["solver_iter"]
+        np.testing.assert_allclose(x, x2, rtol=0, atol=1e-13)
+    with pytest.raises(RuntimeError):
+        s.factorize_device(N, nnz - 1, dv.data_ptr(), 0.0)  # size differs from the analyzed pattern
+
+
 # ------------------------------------------------------------------ BiCGSTAB (Eigen ordering)
 def test_bicgstab_golden_unsymmetric(psb, orc):
     g = np.load(os.path.join(GOLD, "convdiff2d_32.npz"))
