@@ -95,6 +95,58 @@ namespace polysolve::linear
         impl_->check(psb200_solve(impl_->h, b.data(), x.data(), b.size()), "solve");
     }
 
+    void CUDASolver::dirichlet_solve(const StiffnessMatrix &A, Eigen::VectorXd &f, const std::vector<int> &dirichlet_nodes, Eigen::VectorXd &u,
+                                     const int precond_num)
+    {
+        if (!A.isCompressed())
+            throw std::runtime_error("[CUDA] dirichlet_solve: the matrix must be compressed");
+        if (u.size() != A.rows())
+        {
+            u.resize(A.rows()); // FEMSolver.cpp:268-272
+            u.setZero();
+        }
+        impl_->check(psb200_dirichlet_solve(impl_->h, A.rows(), A.nonZeros(), A.outerIndexPtr(), A.innerIndexPtr(), A.valuePtr(), f.data(),
+                                            dirichlet_nodes.data(), (int64_t)dirichlet_nodes.size(), u.data(), precond_num),
+                     "dirichlet_solve");
+    }
+
+    void CUDASolver::prefactorize(const StiffnessMatrix &A, const std::vector<int> &dirichlet_nodes, const int precond_num)
+    {
+        if (!A.isCompressed())
+            throw std::runtime_error("[CUDA] prefactorize: the matrix must be compressed");
+        impl_->check(psb200_dirichlet_prefactorize(impl_->h, A.rows(), A.nonZeros(), A.outerIndexPtr(), A.innerIndexPtr(), A.valuePtr(),
+                                                   dirichlet_nodes.data(), (int64_t)dirichlet_nodes.size(), precond_num),
+                     "prefactorize");
+    }
+
+    void CUDASolver::dirichlet_solve_prefactorized(const StiffnessMatrix *A_or_null, Eigen::VectorXd &f, Eigen::VectorXd &u)
+    {
+        if (u.size() != f.size())
+        {
+            u.resize(f.size()); // FEMSolver.cpp:363-367
+            u.setZero();
+        }
+        impl_->check(psb200_dirichlet_solve_prefactorized(impl_->h, A_or_null ? A_or_null->valuePtr() : nullptr, f.data(), u.data(), f.size()),
+                     "dirichlet_solve_prefactorized");
+    }
+
+    void CUDASolver::factorize_device(const long n, const long nnz, const double *d_vals, const double reg_weight)
+    {
+        impl_->check(psb200_factorize_csc_device(impl_->h, n, nnz, d_vals, reg_weight), "factorize_device");
+    }
+
+    void CUDASolver::solve_device(const double *d_b, double *d_x, const long n)
+    {
+        impl_->check(psb200_solve_device(impl_->h, d_b, d_x, n), "solve_device");
+    }
+
+    double CUDASolver::residual_norm_device(const double *d_x, const double *d_b, const long n)
+    {
+        double r = 0;
+        impl_->check(psb200_residual_norm_device(impl_->h, d_x, d_b, n, &r), "residual_norm_device");
+        return r;
+    }
+
     void CUDASolver::set_block_size(int block_size)
     {
         impl_->check(psb200_set_block_size(impl_->h, block_size), "set_block_size");

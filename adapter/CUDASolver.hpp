@@ -9,6 +9,7 @@
 
 #include <memory>
 #include <string>
+#include <vector>
 
 namespace polysolve::linear
 {
@@ -40,6 +41,21 @@ namespace polysolve::linear
         void set_tolerance(const double tol) override; // Solver.hpp:116-117
 
         std::string name() const override { return "CUDA"; } // Solver.hpp:131
+
+    public:
+        // ---- beyond the Solver virtuals (optional). The reference's FEMSolver free functions
+        // (FEMSolver.cpp:97-372) call these instead of their host-side triplet rebuild when `solver` is a CUDASolver
+        // (see INTEGRATION.md section 5): masking and rhs lifting run on the GPU, A is not rewritten on the host.
+        void dirichlet_solve(const StiffnessMatrix &A, Eigen::VectorXd &f, const std::vector<int> &dirichlet_nodes, Eigen::VectorXd &u,
+                             const int precond_num);
+        void prefactorize(const StiffnessMatrix &A, const std::vector<int> &dirichlet_nodes, const int precond_num);
+        void dirichlet_solve_prefactorized(const StiffnessMatrix *A_or_null, Eigen::VectorXd &f, Eigen::VectorXd &u);
+
+        // Newton step with device-resident data (Newton.cpp:173-214): values in the CSC order of the analyzed pattern,
+        // reg_weight of RegularizedNewton (Newton.cpp:287-290), the residual ||H dx + g|| (Newton.cpp:207) with b = -g.
+        void factorize_device(const long n, const long nnz, const double *d_vals, const double reg_weight = 0.0);
+        void solve_device(const double *d_b, double *d_x, const long n);
+        double residual_norm_device(const double *d_x, const double *d_b, const long n);
 
     private:
         struct Impl;
