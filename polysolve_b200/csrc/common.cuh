@@ -234,6 +234,13 @@ __device__ __forceinline__ bool spin_ge(const unsigned long long *p, unsigned lo
     return true;
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may become
+// resident while its predecessor drains; everything it does before griddep_wait() must be independent of the
+// predecessor (barrier init, TMA prefetch of the constant matrix), everything after sees the predecessor's memory.
+// Both are no-ops for an ordinary launch.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 struct RedCtx
 {
     double *partials;      // [kMaxRed][max_blocks]

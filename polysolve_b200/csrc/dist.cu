@@ -180,6 +180,8 @@ __global__ void __launch_bounds__(THREADS) cg_dir_dist_kernel(long long n2, doub
                                                               const double *__restrict__ r, const double *__restrict__ dinv, KState *st,
                                                               RedCtx rc, PushList pl, int vec_blocks, const int *done)
 {
+    griddep_launch_dependents();
+    griddep_wait();
     if (done && *done)
         return;
     const double beta = FIRST ? 0.0 : st->rz_new / st->rz;
@@ -228,6 +230,8 @@ __global__ void __launch_bounds__(THREADS) cg_dir_dist_kernel(long long n2, doub
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) halo_push_kernel(const double *__restrict__ v, RedCtx rc, PushList pl)
 {
+    griddep_launch_dependents();
+    griddep_wait();
     const unsigned long long push_no = *rc.comm.push_epoch + 1;
     push_section(pl, rc.comm, push_no, 0, (int)gridDim.x, [&](int row) { return v[row]; });
     double acc[1] = {0}, tot[1];
@@ -464,7 +468,7 @@ void Solver::push_halo_of(const double *d_v)
     const int push_blocks = push_ctas(d);
     if (!push_blocks)
         return;
-    halo_push_kernel<kVecThreads><<<push_blocks, kVecThreads, 0, ctx.stream>>>(d_v, ctx.red(), make_push(d));
+    launch_chain(ctx, halo_push_kernel<kVecThreads>, push_blocks, kVecThreads, 0, d_v, ctx.red(), make_push(d));
     check_launch();
 }
 
@@ -554,6 +558,8 @@ __global__ void __launch_bounds__(THREADS) cg_dir_amgcl_dist_kernel(long long n2
                                                                     const double *__restrict__ s, const KState *st, RedCtx rc, PushList pl,
                                                                     int vec_blocks, const int *done)
 {
+    griddep_launch_dependents();
+    griddep_wait();
     if (done && *done)
         return;
     const double beta = st->iter ? st->rho / st->rho_old : 0.0;
@@ -598,7 +604,7 @@ void Solver::run_cg_amgcl_dist(const double *d_b)
     PSB_CUDA(cudaMemsetAsync(vp.p, 0, sizeof(double) * n_pad, ctx.stream));
     if (push_blocks)
     {
-        halo_push_kernel<kVecThreads><<<push_blocks, kVecThreads, 0, ctx.stream>>>(vx.p, rc, pl);
+        launch_chain(ctx, halo_push_kernel<kVecThreads>, push_blocks, kVecThreads, 0, vx.p, rc, pl);
         check_launch();
     }
     launch_spmv(ctx, "spmv_residual", A, vx.p, EpiResidualNorms{vr.p, d_b, dinv.p}, FinInitAmgcl{S});
@@ -612,7 +618,7 @@ void Solver::run_cg_amgcl_dist(const double *d_b)
             }
             launch_vec(ctx, "dot", n_pad, OpDot{vr.p, vz.p}, FinRhoAmgcl{S}, done);
             ctx.prof_begin("cg_dir");
-            cg_dir_amgcl_dist_kernel<kVecThreads><<<vec_blocks + push_blocks, kVecThreads, 0, ctx.stream>>>(n2, pn, pc, vz.p, S, rc, pl, vec_blocks, done);
+            launch_chain(ctx, cg_dir_amgcl_dist_kernel<kVecThreads>, vec_blocks + push_blocks, kVecThreads, 0, n2, pn, pc, vz.p, S, rc, pl, vec_blocks, done);
             check_launch();
             ctx.prof_end();
             launch_spmv(ctx, "spmv_dot", A, pn, EpiDot{vq.p, pn}, FinPAp{S}, done);
@@ -646,13 +652,13 @@ void Solver::run_cg_eigen_dist(const double *d_b)
     if (push_blocks)
     {
         ctx.prof_begin("halo_push");
-        halo_push_kernel<kVecThreads><<<push_blocks, kVecThreads, 0, ctx.stream>>>(vx.p, rc, pl);
+        launch_chain(ctx, halo_push_kernel<kVecThreads>, push_blocks, kVecThreads, 0, vx.p, rc, pl);
         check_launch();
         ctx.prof_end();
     }
     launch_spmv(ctx, "spmv_residual", A, vx.p, EpiResidualNorms{vr.p, d_b, dinv.p}, FinInitEigen{S});
     ctx.prof_begin("cg_dir");
-    cg_dir_dist_kernel<true, kVecThreads><<<vec_blocks + push_blocks, kVecThreads, 0, ctx.stream>>>(n2, vp.p, vp.p, vr.p, dinv.p, S, rc, pl, vec_blocks, done);
+    launch_chain(ctx, cg_dir_dist_kernel<true, kVecThreads>, vec_blocks + push_blocks, kVecThreads, 0, n2, vp.p, vp.p, vr.p, dinv.p, S, rc, pl, vec_blocks, done);
     check_launch();
     ctx.prof_end();
     const int batch_iters = std::max(2, prm.check_every & ~1);
@@ -675,7 +681,7 @@ void Solver::run_cg_eigen_dist(const double *d_b)
             launch_spmv(ctx, "spmv_dot", A, pc, EpiDot{vq.p, pc}, FinPAp{S}, done);
             launch_vec(ctx, "cg_update", n_pad, OpCgUpdateEigen{vx.p, vr.p, pc, vq.p, dinv.p, S, 0.0}, FinCgUpdateEigen{S}, done);
             ctx.prof_begin("cg_dir");
-            cg_dir_dist_kernel<false, kVecThreads><<<vec_blocks + push_blocks, kVecThreads, 0, ctx.stream>>>(n2, pn, pc, vr.p, dinv.p, S, rc, pl, vec_blocks, done);
+            launch_chain(ctx, cg_dir_dist_kernel<false, kVecThreads>, vec_blocks + push_blocks, kVecThreads, 0, n2, pn, pc, vr.p, dinv.p, S, rc, pl, vec_blocks, done);
             check_launch();
             ctx.prof_end();
             std::swap(pc, pn);

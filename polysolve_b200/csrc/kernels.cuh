@@ -307,6 +307,8 @@ namespace psb {
 template <class Op, class Fin, int THREADS>
 __global__ void __launch_bounds__(THREADS) vec_kernel(long long n2, Op op, RedCtx rc, Fin fin, const int *done, const int *only_if)
 {
+    griddep_launch_dependents();
+    griddep_wait();
     if (done && *done)
         return;
     if (only_if && !*only_if)

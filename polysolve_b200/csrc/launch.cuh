@@ -141,6 +141,7 @@ struct Ctx
     // profiling (events around every launch; only when enabled, never inside graph capture)
     bool profile = false;
     bool capturing = false;
+    bool pdl = false; // programmatic dependent launch between the kernels of the Krylov chain (Params::pdl)
     std::map<std::string, ProfEntry> prof;
     struct Pending
     {
@@ -248,6 +249,25 @@ struct LocalScope
     ~LocalScope() { c.comm_local = prev; }
 };
 
+// Launch on the context's stream; with c.pdl the kernel may overlap its independent prologue with the tail of its
+// predecessor (programmatic stream serialization; captured as a programmatic edge inside CUDA graphs). Every kernel
+// launched through this helper executes griddep_wait() before it touches anything a predecessor produced.
+template <class... KArgs, class... Args>
+void launch_chain(Ctx &c, void (*kern)(KArgs...), int grid, int block, size_t smem, Args &&...args)
+{
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = c.pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PSB_CUDA(cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...));
+}
+
 inline void check_launch()
 {
     cudaError_t e = cudaGetLastError();
@@ -270,7 +290,7 @@ void launch_vec(Ctx &c, const char *name, long long n_pad, Op op, Fin fin, const
     if (n2 == 0)
         return;
     c.prof_begin(name);
-    vec_kernel<Op, Fin, kVecThreads><<<vec_grid(n2), kVecThreads, 0, c.stream>>>(n2, op, c.red(), fin, done, only_if);
+    launch_chain(c, vec_kernel<Op, Fin, kVecThreads>, vec_grid(n2), kVecThreads, 0, n2, op, c.red(), fin, done, only_if);
     check_launch();
     c.prof_end();
 }
@@ -281,7 +301,7 @@ void launch_spmv_vector(Ctx &c, const CsrDev &A, const double *x, Epi epi, Fin f
     const int rows_per_cta = kSpmvThreads / LPR;
     long long need = ((long long)A.n + rows_per_cta - 1) / rows_per_cta;
     const int grid = (int)std::max<long long>(1, std::min<long long>(need, (long long)kSMs * 16));
-    spmv_vector_kernel<Epi, Fin, LPR, kSpmvThreads><<<grid, kSpmvThreads, 0, c.stream>>>(A.view(), x, epi, c.red(), fin, done, only_if);
+    launch_chain(c, spmv_vector_kernel<Epi, Fin, LPR, kSpmvThreads>, grid, kSpmvThreads, 0, A.view(), x, epi, c.red(), fin, done, only_if);
 }
 
 template <class Epi, class Fin, class Cfg>
@@ -298,7 +318,7 @@ void launch_spmv_stream(Ctx &c, const CsrDev &A, const double *x, Epi epi, Fin f
     const int ntiles = (A.n + Cfg::rows - 1) / Cfg::rows;
     const int per_sm = ctas_per_sm > 0 ? std::min(ctas_per_sm, max_ctas) : max_ctas;
     const int grid = std::min(ntiles, kSMs * per_sm); // persistent: every CTA resident, tiles dealt round-robin
-    kern<<<grid, Cfg::threads, Cfg::bytes, c.stream>>>(A.view(), x, epi, c.red(), fin, done, only_if);
+    launch_chain(c, kern, grid, Cfg::threads, Cfg::bytes, A.view(), x, epi, c.red(), fin, done, only_if);
 }
 
 template <class Epi, class Fin>

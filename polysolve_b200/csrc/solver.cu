@@ -454,6 +454,8 @@ void Solver::set_parameters(const std::string &json)
         np.check_every = std::max(1, (int)j.at("check_every").as_num());
     if (j.contains("use_graph"))
         np.use_graph = j.at("use_graph").as_bool();
+    if (j.contains("pdl"))
+        np.pdl = j.at("pdl").as_bool();
     if (j.contains("spmv_kernel"))
         np.spmv_kernel = j.at("spmv_kernel").as_str();
     if (j.contains("cg_kernel"))
@@ -487,6 +489,7 @@ void Solver::set_parameters(const std::string &json)
     if (analyzed)
         A.plan(prm.spmv_kernel, ctx.stream);
     ctx.profile = prm.profile;
+    ctx.pdl = prm.pdl;
 }
 
 // ==================================================================================== analyze_pattern

@@ -39,6 +39,10 @@ struct Params
     int max_iter = 1000;
     int check_every = 16;
     bool use_graph = true;
+    // programmatic dependent launch between the kernels of the Krylov chain. Off by default: measured on B200
+    // (profiles/r01_pdl.txt) it gains nothing at 1.26 M rows and loses 9 % at 10 M rows (dependents that become
+    // resident while the predecessor drains land unevenly on the SMs, and the vector kernels are statically partitioned)
+    bool pdl = false;
     std::string spmv_kernel = "auto";
     std::string cg_kernel = "auto"; // Jacobi-PCG: persistent (one cooperative launch per batch) | split (one kernel per phase) | auto
     int device = -1; // -1: current device

@@ -167,6 +167,8 @@ template <class Epi, class Fin, int LPR, int THREADS>
 __global__ void __launch_bounds__(THREADS) spmv_vector_kernel(CsrView A, const double *__restrict__ x, Epi epi, RedCtx rc,
                                                               Fin fin, const int *done, const int *only_if)
 {
+    griddep_launch_dependents();
+    griddep_wait();
     if (done && *done)
         return;
     if (only_if && !*only_if)
@@ -271,10 +273,7 @@ __global__ void __launch_bounds__(Cfg::threads) spmv_stream_kernel(CsrView A, co
                                                                    const int *done, const int *only_if)
 {
     constexpr int THREADS = Cfg::threads, CAP = Cfg::cap, STAGES = Cfg::stages, LPR = Cfg::lpr, ROWS = Cfg::rows;
-    if (done && *done)
-        return;
-    if (only_if && !*only_if)
-        return;
+    griddep_launch_dependents();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *sval = reinterpret_cast<double *>(smem_raw);
     int *scol = reinterpret_cast<int *>(smem_raw + Cfg::val_bytes);
@@ -331,6 +330,19 @@ __global__ void __launch_bounds__(Cfg::threads) spmv_stream_kernel(CsrView A, co
             if (pos < ntiles)
                 issue(tile_at(pos), s);
         }
+    }
+
+    // Everything above touches only the matrix, which no kernel of the chain writes: under a programmatic dependent
+    // launch it overlaps with the tail of the predecessor. From here on its results (x, the `done` flag) are needed.
+    griddep_wait();
+    if ((done && *done) || (only_if && !*only_if))
+    {
+        // the solve is over (or this launch is predicated off): drain the copies already in flight, then leave
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+            if ((int)blockIdx.x + s * (int)gridDim.x < ntiles)
+                mbar_wait(&bar[s], 0);
+        return;
     }
 
     // Row partitions: the halo values are needed by the boundary tiles only. With an interior-first order the wait
