@@ -45,10 +45,14 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi during the timed region (B200_PROFILING.md 'clocks line')."""
+    """Samples nvidia-smi (B200_PROFILING.md 'clocks line'). Started before the warm-up steps -- nvidia-smi needs a few
+    hundred ms to come up, longer than the timed region of a multi-GPU run -- and marked at the edges of the timed
+    region: the reported median is over the samples inside it, or, when none fell inside, over the samples taken
+    under the same load during warm-up (the count of both is reported)."""
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = self.tl = None
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -56,7 +60,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -65,7 +69,16 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def mark_load(self):
+        self.tl = time.perf_counter()
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
@@ -75,19 +88,26 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for nm, val in zip(names, r[3:7]):
-                    if val.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
+
+        def digest(rows):
+            sm, mx, reasons = [], [], set()
+            for _, r in rows:
+                try:
+                    sm.append(float(r[0]))
+                    mx.append(float(r[1]))
+                    for nm, val in zip(names, r[3:7]):
+                        if val.lower().startswith("active"):
+                            reasons.add(nm)
+                except Exception:
+                    continue
+            return sm, mx, reasons
+        inside = [x for x in self.rows if self.t0 is not None and self.t1 is not None and self.t0 <= x[0] <= self.t1]
+        loaded = [x for x in self.rows if self.tl is not None and self.t1 is not None and self.tl <= x[0] <= self.t1]
+        sm, mx, reasons = digest(inside if inside else (loaded if loaded else self.rows))
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "samples_in_timed_region": len(digest(inside)[0]), "samples_under_load": len(digest(loaded)[0]),
+                "samples_total": len(self.rows)}
 
 
 def build_problem(n):
@@ -255,6 +275,10 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun for --gpus > 1 (one process per GPU)")
     torch.cuda.set_device(local)
+    # nvidia-smi needs a few hundred ms to deliver its first sample: start it now, filter by time stamps later
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -298,12 +322,12 @@ def run_ours(args):
         return s.get_info()["solver_iter"]
 
     # ---- device-resident timed region
+    sampler.mark_load()
     for _ in range(args.warmup):
         device_step()
     launches0 = s.get_info()["gpu_launches"]
-    sampler = ClockSampler(local)
-    sampler.start()
     barrier()
+    sampler.mark_begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     iters = 0
@@ -311,6 +335,7 @@ def run_ours(args):
         iters += device_step()
     e1.record(stream)
     barrier()
+    sampler.mark_end()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     launches = s.get_info()["gpu_launches"] - launches0

@@ -69,6 +69,24 @@ int psb200_nl_minimize(psb200_nl_handle h, const psb200_nl_problem *problem, dou
 int psb200_nl_get_info(psb200_nl_handle h, char *json_out, size_t cap, size_t *needed);
 const char *psb200_nl_last_error(psb200_nl_handle h);
 
+/* ---- L-BFGS memory on device vectors. Mirrors what the reference's LBFGS strategy does with
+ * LBFGSpp::BFGSMat (src/polysolve/nonlinear/descent_strategies/LBFGS.cpp:22-61): the first call after create / reset
+ * returns -grad; every later call adds the correction (x - x_prev, grad - grad_prev) to a memory of history_size pairs
+ * ("/L-BFGS/history_size", default 6, nonlinear-solver-spec.json) and returns direction = -H grad by the two-loop
+ * recursion. psb200_nl_create with {"solver": "L-BFGS"} uses it as the first strategy, followed by GradientDescent
+ * (Solver.cpp:83-85,175-181). device < 0: the current device. */
+typedef struct psb200_lbfgs *psb200_lbfgs_handle;
+int psb200_lbfgs_create(psb200_lbfgs_handle *out, int64_t n, int history_size, int device);
+int psb200_lbfgs_destroy(psb200_lbfgs_handle h);
+/* LBFGS::reset -- LBFGS.cpp:22-28 */
+int psb200_lbfgs_reset(psb200_lbfgs_handle h);
+/* LBFGS::compute_update_direction -- LBFGS.cpp:30-61; host vectors of length n */
+int psb200_lbfgs_direction(psb200_lbfgs_handle h, const double *x, const double *grad, double *direction, int64_t n);
+/* same with x, grad, direction resident on the GPU */
+int psb200_lbfgs_direction_device(psb200_lbfgs_handle h, const double *d_x, const double *d_grad, double *d_direction,
+                                  int64_t n);
+const char *psb200_lbfgs_last_error(psb200_lbfgs_handle h);
+
 #ifdef __cplusplus
 }
 #endif

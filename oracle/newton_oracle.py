@@ -115,6 +115,61 @@ class LineSearch:
         return step
 
 
+class BFGSMat:
+    """LBFGSpp::BFGSMat as the reference's LBFGS strategy uses it (descent_strategies/LBFGS.hpp:38, LBFGS.cpp:48-51;
+    LBFGSpp is un-vendored, cmake/recipes/LBFGSpp.cmake -- restated from its published algorithm):
+    add_correction stores (s, y), ys = s.y, theta = y.y / s.y in a ring of m pairs; apply_Hv is the two-loop recursion
+    with H0 = I / theta."""
+
+    def __init__(self, n, m):
+        self.m, self.S, self.Y = m, np.zeros((m, n)), np.zeros((m, n))
+        self.ys, self.alpha = np.zeros(m), np.zeros(m)
+        self.theta, self.ncorr, self.ptr = 1.0, 0, 0
+
+    def add_correction(self, s, y):
+        loc = self.ptr % self.m
+        self.S[loc], self.Y[loc] = s, y
+        self.ys[loc] = float(s @ y)
+        self.theta = float(y @ y) / self.ys[loc]
+        if self.ncorr < self.m:
+            self.ncorr += 1
+        self.ptr = loc + 1
+
+    def apply_Hv(self, v, a):
+        res = a * v
+        j = self.ptr % self.m
+        for _ in range(self.ncorr):
+            j = (j + self.m - 1) % self.m
+            self.alpha[j] = float(self.S[j] @ res) / self.ys[j]
+            res = res - self.alpha[j] * self.Y[j]
+        res = res / self.theta
+        for _ in range(self.ncorr):
+            beta = float(self.Y[j] @ res) / self.ys[j]
+            res = res + (self.alpha[j] - beta) * self.S[j]
+            j = (j + 1) % self.m
+        return res
+
+
+class LbfgsStrategy:
+    """LBFGS::reset / compute_update_direction (LBFGS.cpp:22-61)."""
+
+    def __init__(self, history):
+        self.history, self.mat, self.prev_x, self.prev_g = history, None, None, None
+
+    def reset(self):
+        self.mat, self.prev_x, self.prev_g = None, None, None
+
+    def direction(self, x, grad):
+        if self.prev_x is None:
+            d = -grad
+            self.mat = BFGSMat(x.size, self.history)
+        else:
+            self.mat.add_correction(x - self.prev_x, grad - self.prev_g)
+            d = self.mat.apply_Hv(grad, -1.0)
+        self.prev_x, self.prev_g = x.copy(), grad.copy()
+        return d
+
+
 def minimize(problem, x, params, linsolve):
     """Returns (x, info). Raises RuntimeError where the reference throws."""
     adv = params.get("advanced", {})
@@ -126,12 +181,17 @@ def minimize(problem, x, params, linsolve):
     res_tol = nw.get("residual_tolerance", 1e-5)
     wmin, wmax, winc = nw.get("reg_weight_min", 1e-8), nw.get("reg_weight_max", 1e8), nw.get("reg_weight_inc", 10)
     strategies = []
-    if not nw.get("force_psd_projection", False):
-        strategies.append(["Newton", False, 0.0])
-    if nw.get("use_psd_projection", True):
-        strategies.append(["ProjectedNewton", True, 0.0])
-    if wmin > 0:
-        strategies.append(["RegularizedNewton", nw.get("use_psd_projection_in_regularized", True), wmin])
+    lbfgs = None
+    if params.get("solver", "Newton") in ("L-BFGS", "LBFGS"):       # Solver.cpp:83-85
+        lbfgs = LbfgsStrategy(params.get("L-BFGS", {}).get("history_size", 6))
+        strategies.append(["L-BFGS", False, 0.0])
+    else:
+        if not nw.get("force_psd_projection", False):
+            strategies.append(["Newton", False, 0.0])
+        if nw.get("use_psd_projection", True):
+            strategies.append(["ProjectedNewton", True, 0.0])
+        if wmin > 0:
+            strategies.append(["RegularizedNewton", nw.get("use_psd_projection_in_regularized", True), wmin])
     strategies.append(["GradientDescent", False, 0.0])
     per = params.get("iterations_per_strategy", 5)
     ls = LineSearch(params)
@@ -157,6 +217,8 @@ def minimize(problem, x, params, linsolve):
         for s in strategies:
             if s[0] == "RegularizedNewton":
                 s[2] = wmin
+        if lbfgs is not None:
+            lbfgs.reset()
 
     while True:
         ls.final = strategy == len(strategies) - 1
@@ -179,6 +241,8 @@ def minimize(problem, x, params, linsolve):
         ok = True
         if s[0] == "GradientDescent":
             dx = -grad
+        elif s[0] == "L-BFGS":
+            dx = lbfgs.direction(x, grad)
         else:
             H = sp.csc_matrix(problem.hessian(x, s[1]))
             if s[0] == "RegularizedNewton" and s[2] > 0:

@@ -4,4 +4,4 @@
 hand-written sm_100a CUDA behind the C ABI of include/psb200.h."""
 from . import _lib, io, problems  # noqa: F401
 from .solver import Solver  # noqa: F401
-from .nonlinear import NonlinearSolver, Problem  # noqa: F401
+from .nonlinear import Lbfgs, NonlinearSolver, Problem  # noqa: F401

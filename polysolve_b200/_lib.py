@@ -30,6 +30,8 @@ SYMBOLS = [
     "psb200_market_save_vector", "psb200_market_last_error",
     # include/psb200_nl.h
     "psb200_nl_create", "psb200_nl_destroy", "psb200_nl_minimize", "psb200_nl_get_info", "psb200_nl_last_error",
+    "psb200_lbfgs_create", "psb200_lbfgs_destroy", "psb200_lbfgs_reset", "psb200_lbfgs_direction", "psb200_lbfgs_direction_device",
+    "psb200_lbfgs_last_error",
 ]
 
 
@@ -59,6 +61,13 @@ def lib():
     L.psb200_factorize_csc.argtypes = [H, C.c_int64, C.c_int64, i32p, i32p, f64p]
     L.psb200_solve.argtypes = [H, f64p, f64p, C.c_int64]
     L.psb200_release_cached_memory.argtypes = [H]
+    L.psb200_lbfgs_create.argtypes = [C.POINTER(C.c_void_p), C.c_int64, C.c_int, C.c_int]
+    L.psb200_lbfgs_destroy.argtypes = [C.c_void_p]
+    L.psb200_lbfgs_reset.argtypes = [C.c_void_p]
+    L.psb200_lbfgs_direction.argtypes = [C.c_void_p, f64p, f64p, f64p, C.c_int64]
+    L.psb200_lbfgs_direction_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    L.psb200_lbfgs_last_error.argtypes = [C.c_void_p]
+    L.psb200_lbfgs_last_error.restype = C.c_char_p
     L.psb200_market_load.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.psb200_market_get_csc.argtypes = [C.c_void_p, i32p, i32p, f64p]
     L.psb200_market_free.argtypes = [C.c_void_p]

@@ -505,6 +505,45 @@ struct NewtonStrategy : Strategy
     }
 };
 
+// LBFGS.cpp:22-61: the memory lives on the GPU (lbfgs.cu), created on first use for the problem size at hand
+struct LbfgsStrategy : Strategy
+{
+    int history = 6;
+    int device = -1;
+    psb200_lbfgs_handle h = nullptr;
+    long long n_alloc = -1;
+    explicit LbfgsStrategy(int history_size, int dev) : history(history_size), device(dev) {}
+    ~LbfgsStrategy() override
+    {
+        if (h)
+            psb200_lbfgs_destroy(h);
+    }
+    std::string name() const override { return "L-BFGS"; }
+    void reset() override
+    {
+        if (h)
+            psb200_lbfgs_reset(h);
+    }
+    bool direction(const Problem &, const std::vector<double> &x, const std::vector<double> &g, std::vector<double> &dx, std::string &err) override
+    {
+        if (!h || n_alloc != (long long)x.size())
+        {
+            if (h)
+                psb200_lbfgs_destroy(h);
+            h = nullptr;
+            if (psb200_lbfgs_create(&h, (int64_t)x.size(), history, device) != PSB200_OK)
+                throw std::runtime_error(std::string("L-BFGS: ") + psb200_lbfgs_last_error(nullptr)); // no device: never "recoverable"
+            n_alloc = (long long)x.size();
+        }
+        dx.resize(x.size());
+        if (psb200_lbfgs_direction(h, x.data(), g.data(), dx.data(), (int64_t)x.size()) != PSB200_OK)
+            throw std::runtime_error(std::string("L-BFGS: ") + psb200_lbfgs_last_error(h));
+        (void)err;
+        return true;
+    }
+    void info(std::ostringstream &o) const override { o << ",\"history_size\":" << history; }
+};
+
 struct GradientDescent : Strategy
 {
     std::string name() const override { return "GradientDescent"; }
@@ -597,10 +636,26 @@ void build(psb200_nl_solver &S, const std::string &solver_json, const std::strin
             throw std::runtime_error("Newton needs to have at least one of force_psd_projection=false, reg_weight_min>0, or use_psd_projection=true");
         S.strategies.push_back(std::make_unique<GradientDescent>()); // Solver.cpp:175-181
     }
+    else if (S.solver_name == "LBFGS" || S.solver_name == "L-BFGS")
+    {
+        // Solver.cpp:83-85 + the GradientDescent fallback every non-GD solver gets (:175-181)
+        const int history = (int)jget(jsub(j, "L-BFGS"), "history_size", 6);
+        if (history <= 0)
+            throw std::runtime_error("L-BFGS history_size must be >=1, instead got " + std::to_string(history)); // LBFGS.cpp:17-18
+        int device = -1;
+        if (!linear_json.empty())
+        {
+            const JValue lj = psb::JParser::parse(linear_json);
+            if (lj.is_obj() && lj.contains("CUDA") && lj.at("CUDA").is_obj() && lj.at("CUDA").contains("device"))
+                device = (int)lj.at("CUDA").at("device").as_num();
+        }
+        S.strategies.push_back(std::make_unique<LbfgsStrategy>(history, device));
+        S.strategies.push_back(std::make_unique<GradientDescent>());
+    }
     else if (S.solver_name == "GradientDescent" || S.solver_name == "gradient_descent")
         S.strategies.push_back(std::make_unique<GradientDescent>());
     else
-        throw std::runtime_error("Unrecognized solver type: " + S.solver_name + " (this driver provides Newton and GradientDescent)");
+        throw std::runtime_error("Unrecognized solver type: " + S.solver_name + " (this driver provides Newton, L-BFGS and GradientDescent)");
     // Solver.cpp:232-245
     S.iter_per_strategy.assign(S.strategies.size() + 1, (int)jget(j, "iterations_per_strategy", 5));
 }

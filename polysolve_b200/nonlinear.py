@@ -190,3 +190,40 @@ class NonlinearSolver:
         if rc:
             raise RuntimeError("psb200_nl_get_info failed")
         return json.loads(buf.value.decode())
+
+
+class Lbfgs:
+    """The L-BFGS memory of the reference's LBFGS strategy (LBFGS.cpp:22-61, LBFGSpp::BFGSMat) on device vectors
+    (include/psb200_nl.h, polysolve_b200/csrc/lbfgs.cu)."""
+
+    def __init__(self, n, history_size=6, device=-1):
+        self._L = _lib.lib()
+        self._h = C.c_void_p()
+        self.n = int(n)
+        if self._L.psb200_lbfgs_create(C.byref(self._h), self.n, int(history_size), int(device)):
+            raise RuntimeError(self._L.psb200_lbfgs_last_error(None).decode())
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.psb200_lbfgs_destroy(h)
+            self._h = None
+
+    def _check(self, rc):
+        if rc:
+            raise RuntimeError(self._L.psb200_lbfgs_last_error(self._h).decode())
+
+    def reset(self):
+        self._check(self._L.psb200_lbfgs_reset(self._h))
+
+    def compute_update_direction(self, x, grad):
+        x = np.ascontiguousarray(x, np.float64)
+        grad = np.ascontiguousarray(grad, np.float64)
+        if x.shape != grad.shape:
+            raise RuntimeError("psb200_lbfgs_direction: x and grad differ in size")
+        d = np.empty(max(x.shape[0], 1), np.float64)
+        self._check(self._L.psb200_lbfgs_direction(self._h, x if x.size else d, grad if grad.size else d, d, x.shape[0]))
+        return d[:x.shape[0]]
+
+    def compute_update_direction_device(self, x_ptr, grad_ptr, dir_ptr):
+        self._check(self._L.psb200_lbfgs_direction_device(self._h, x_ptr, grad_ptr, dir_ptr, self.n))

@@ -171,3 +171,92 @@ def test_newton_amg_million_dof(psb):
     assert np.linalg.norm(prob.gradient(x)) < 1e-8
     assert 2 <= info["iterations"] <= 30
     assert all(i["precond"] == "amg" and i["solver_status"] == "Converged" for i in info["internal_solver"])
+
+
+# ------------------------------------------------------------------------------------------ L-BFGS
+def test_lbfgs_oracle_two_loop_equals_explicit_bfgs_matrix():
+    """The restated BFGSMat (LBFGSpp, un-vendored) against the textbook definition it implements: with H0 = I / theta,
+    H_{k+1} = (I - rho s y^T) H_k (I - rho y s^T) + rho s s^T over the stored pairs, oldest first."""
+    from oracle import newton_oracle as NO
+    rng = np.random.default_rng(2)
+    n, m = 9, 4
+    B = NO.BFGSMat(n, m)
+    pairs = []
+    for k in range(7):  # more corrections than the memory holds: the ring wraps
+        s = rng.standard_normal(n)
+        y = s * rng.uniform(0.5, 2.0, n) + 0.05 * rng.standard_normal(n)
+        B.add_correction(s, y)
+        pairs = (pairs + [(s, y)])[-m:]
+        H = np.eye(n) / B.theta
+        for s_, y_ in pairs:
+            rho = 1.0 / (s_ @ y_)
+            V = np.eye(n) - rho * np.outer(y_, s_)
+            H = V.T @ H @ V + rho * np.outer(s_, s_)
+        v = rng.standard_normal(n)
+        np.testing.assert_allclose(B.apply_Hv(v, -1.0), -H @ v, rtol=1e-11, atol=1e-12)
+
+
+def test_lbfgs_oracle_converges_on_reference_problems():
+    """tests/test_nonlinear_solver.cpp:422-426 with solver = L-BFGS (the restatement alone, no GPU)."""
+    from oracle import newton_oracle as NO
+    rng = np.random.default_rng(3)
+    p = dict(PARAMS, solver="L-BFGS", max_iterations=2000)
+    for prob in (Rosenbrock(10), Sphere(10), Quadratic(12)):
+        x, info = NO.minimize(prob, rng.uniform(-1, 1, prob.n), p, direct)
+        assert min(np.linalg.norm(x - sol) for sol in prob.solutions()) < 1e-6 or info["grad_norm"] < 1e-7, (type(prob), info)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,m", [(1, 3), (10, 6), (1003, 4), (40000, 6)])
+def test_lbfgs_device_direction_matches_oracle(psb, n, m):
+    """Every direction of a sequence longer than the memory (ring wrap-around), sizes that are not multiples of the
+    vector width, reset, and the device-pointer entry: equal to the oracle to rounding (different summation order)."""
+    import torch
+    from oracle import newton_oracle as NO
+    rng = np.random.default_rng(n + m)
+    L = psb.Lbfgs(n, m)
+    O = NO.LbfgsStrategy(m)
+    A = rng.uniform(0.5, 2.0, n)           # gradients of a convex quadratic keep s.y > 0
+    x = rng.standard_normal(n)
+    for k in range(2 * m + 3):
+        if k == m + 2:
+            L.reset()
+            O.reset()
+        g = A * x + 0.01 * np.sin(x)
+        d0 = O.direction(x, g)
+        d = L.compute_update_direction(x, g) if k % 2 == 0 else None
+        if d is None:
+            dx, dg, dd = torch.from_numpy(x).cuda(), torch.from_numpy(g).cuda(), torch.zeros(n, dtype=torch.float64, device="cuda")
+            torch.cuda.synchronize()
+            L.compute_update_direction_device(dx.data_ptr(), dg.data_ptr(), dd.data_ptr())
+            d = dd.cpu().numpy()
+        assert np.linalg.norm(d - d0) <= 1e-11 * np.linalg.norm(d0), (k, np.linalg.norm(d - d0), np.linalg.norm(d0))
+        assert d @ g < 0
+        x = x + 0.5 * d
+    with pytest.raises(RuntimeError):
+        L.compute_update_direction(np.zeros(n + 1), np.zeros(n + 1))
+    with pytest.raises(RuntimeError):
+        psb.Lbfgs(5, 0)   # LBFGS.cpp:17-18: history_size must be >= 1
+
+
+@pytest.mark.gpu
+def test_lbfgs_driver_matches_oracle(psb):
+    """solver = "L-BFGS" through the nonlinear driver: strategy chain [L-BFGS, GradientDescent] (Solver.cpp:83-85,175-181),
+    same iteration count and minimiser as the restatement; the reference problems converge from random starts."""
+    from oracle import newton_oracle as NO
+    rng = np.random.default_rng(4)
+    p = dict(PARAMS, solver="L-BFGS", max_iterations=2000)
+    p["L-BFGS"] = {"history_size": 5}
+    for prob in (Quadratic(12), Sphere(10), Rosenbrock(10)):
+        x0 = rng.uniform(-1, 1, prob.n)
+        xo, io = NO.minimize(prob, x0, p, direct)
+        x = x0.copy()
+        s = psb.NonlinearSolver.create(p, _lin())
+        s.minimize(prob, x)
+        info = s.get_info()
+        assert info["succeeded"], info
+        assert info["solver"] == "L-BFGS"
+        assert min(np.linalg.norm(x - sol) for sol in prob.solutions()) < 1e-6 or info["grad_norm"] < 1e-7
+        if not isinstance(prob, Rosenbrock):  # chaotic line-search path on Rosenbrock: only convergence is compared
+            assert abs(info["iterations"] - io["iterations"]) <= 1
+            assert np.abs(x - xo).max() < 1e-8
