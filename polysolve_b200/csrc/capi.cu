@@ -19,6 +19,7 @@ int guarded(psb200_handle h, F &&f)
     try
     {
         h->s.err.clear();
+        psb::DeviceScope device_scope(h->s.device, h->s.ctx.stream != nullptr);
         psb::AllocScope alloc_scope(h->s.ctx.stream); // buffers are allocated / freed in order on the solver's stream
         f(h->s);
         return PSB200_OK;
@@ -77,7 +78,11 @@ int psb200_create(psb200_handle *out, const char *json_params)
 
 int psb200_destroy(psb200_handle h)
 {
-    delete h;
+    if (h)
+    {
+        psb::DeviceScope device_scope(h->s.device, h->s.ctx.stream != nullptr);
+        delete h;
+    }
     return PSB200_OK;
 }
 

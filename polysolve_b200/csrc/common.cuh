@@ -45,6 +45,27 @@ struct AllocScope
     ~AllocScope() { alloc_stream() = prev; }
 };
 
+// Makes `device` current for the duration of a C-ABI call and restores the caller's device afterwards: solver
+// instances on different GPUs may be driven from one host thread (the reference keeps several solver instances alive
+// at once, Newton.cpp:32-52), and streams / pool allocations are only valid with their own device current.
+struct DeviceScope
+{
+    int prev = -1;
+    bool active = false;
+    explicit DeviceScope(int device, bool enable)
+    {
+        if (!enable)
+            return;
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != device)
+            active = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceScope()
+    {
+        if (active)
+            cudaSetDevice(prev);
+    }
+};
+
 // Owning device buffer. Memory comes from the device's stream-ordered pool (cudaMallocAsync on the solver's stream;
 // the pool's release threshold is raised in ensure_ctx so freed blocks stay cached): a factorize that rebuilds an AMG
 // hierarchy -- dozens of buffers, GBs of temporaries -- never pays cudaMalloc / cudaFree after the first time

@@ -706,6 +706,7 @@ int psb200_dist_prepare(psb200_handle h, int rank, int world, int64_t halo_cap, 
     try
     {
         h->s.err.clear();
+        psb::DeviceScope device_scope(h->s.device, h->s.ctx.stream != nullptr);
         psb::AllocScope alloc_scope(h->s.ctx.stream);
         h->s.dist_prepare(rank, world, halo_cap, handle_out);
         return PSB200_OK;
@@ -729,6 +730,7 @@ int psb200_dist_connect(psb200_handle h, const char *handles)
     try
     {
         h->s.err.clear();
+        psb::DeviceScope device_scope(h->s.device, h->s.ctx.stream != nullptr);
         psb::AllocScope alloc_scope(h->s.ctx.stream);
         h->s.dist_connect(handles);
         return PSB200_OK;

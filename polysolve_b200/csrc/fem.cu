@@ -230,6 +230,7 @@ int fem_guarded(psb200_handle h, F &&f)
     try
     {
         h->s.err.clear();
+        psb::DeviceScope device_scope(h->s.device, h->s.ctx.stream != nullptr);
         psb::AllocScope alloc_scope(h->s.ctx.stream);
         f(h->s);
         return PSB200_OK;

@@ -170,6 +170,7 @@ struct Lbfgs
     std::string err;
     Ctx ctx;
     long long n = 0, n_pad = 0;
+    int device = 0;
     int m = 6, ncorr = 0, ptr = 0;
     bool has_prev = false;
     DevBuf<double> S, Y, xp, gp, res, x, g, scal;
@@ -183,6 +184,7 @@ struct Lbfgs
             throw CudaError("psb200: no CUDA device available; the CUDA backend has no CPU fallback");
         if (device >= 0)
             PSB_CUDA(cudaSetDevice(device));
+        PSB_CUDA(cudaGetDevice(&this->device));
         n = n_;
         m = m_;
         n_pad = (n + 3) & ~3ll;
@@ -289,6 +291,7 @@ int lbfgs_guarded(psb200_lbfgs_handle h, F &&f)
     try
     {
         h->l.err.clear();
+        psb::DeviceScope device_scope(h->l.device, h->l.ctx.stream != nullptr);
         psb::AllocScope scope(h->l.ctx.stream);
         f(h->l);
         return PSB200_OK;
@@ -333,7 +336,11 @@ int psb200_lbfgs_create(psb200_lbfgs_handle *out, int64_t n, int history_size, i
 
 int psb200_lbfgs_destroy(psb200_lbfgs_handle h)
 {
-    delete h;
+    if (h)
+    {
+        psb::DeviceScope device_scope(h->l.device, h->l.ctx.stream != nullptr);
+        delete h;
+    }
     return PSB200_OK;
 }
 
