@@ -1288,6 +1288,173 @@ void AmgHierarchy::apply(const double *rhs, double *out, const int *done)
     PSB_CUDA(cudaMemcpyAsync(out, x, bytes, cudaMemcpyDeviceToDevice, ctx_.stream));
 }
 
+// ------------------------------------------------------------------------------------------ row-partitioned level 0
+struct AmgDistFine
+{
+    const CsrDev *A = nullptr; // rank-local rows of the fine matrix, halo columns
+    const double *dinv = nullptr;
+    long long row0 = 0, nl = 0, nl_pad = 0;
+    CsrDev P, R; // rows [row0, row0 + nl) of P_0 (nl x n_1) and their transpose (n_1 x nl)
+    DevBuf<double> u, ualt, t, cp, partial;
+    std::function<void(const double *, const int *)> push_halo;
+    std::function<void(const double *, double *, long long, const int *)> allreduce;
+};
+
+__global__ void slice_rowptr_kernel(int nl, const int *__restrict__ rp, int row0, int *__restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= nl)
+        out[i] = rp[row0 + i] - rp[row0];
+}
+
+void AmgHierarchy::setup_dist_fine(const CsrDev &A_local, const double *dinv_local, long long row0,
+                                   std::function<void(const double *, const int *)> push_halo,
+                                   std::function<void(const double *, double *, long long, const int *)> allreduce)
+{
+    if (levels_.empty())
+        throw std::runtime_error("psb200 amg: setup() before setup_dist_fine()");
+    if (std::max(1, prm_.block_size) > 1)
+        throw std::runtime_error("psb200 amg: the partitioned cycle is scalar (block problems use the rank-local hierarchy)");
+    cudaStream_t st = ctx_.stream;
+    auto D = std::make_shared<AmgDistFine>();
+    D->A = &A_local;
+    D->dinv = dinv_local;
+    D->row0 = row0;
+    D->nl = A_local.n;
+    D->nl_pad = (D->nl + 3) & ~3ll;
+    D->push_halo = std::move(push_halo);
+    D->allreduce = std::move(allreduce);
+    AmgLevel &L0 = *levels_[0];
+    if (row0 < 0 || row0 + D->nl > L0.n)
+        throw std::invalid_argument("psb200 amg: local row range outside the hierarchy's fine level");
+    const size_t np = (size_t)std::max<long long>(D->nl_pad, 4);
+    for (DevBuf<double> *b : {&D->u, &D->ualt, &D->t, &D->cp})
+        b->alloc(np, true);
+    if (levels_.size() > 1)
+    {
+        // P_local = rows of P_0, R_local = P_local^T (columns [row0, row0 + nl) of R_0 = P_0^T)
+        const CsrDev &P0 = L0.P;
+        const int nl = (int)D->nl;
+        int k0 = 0, k1 = 0;
+        PSB_CUDA(cudaMemcpyAsync(&k0, P0.rp.p + row0, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PSB_CUDA(cudaMemcpyAsync(&k1, P0.rp.p + row0 + nl, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PSB_CUDA(cudaStreamSynchronize(st));
+        CsrDev &P = D->P;
+        P.n = nl;
+        P.ncols = P0.ncols;
+        P.nnz = k1 - k0;
+        P.rp.alloc((size_t)nl + 1);
+        P.ci.alloc(std::max<long long>(1, P.nnz), false, 64);
+        P.va.alloc(std::max<long long>(1, P.nnz), false, 64);
+        slice_rowptr_kernel<<<nblk((long long)nl + 1), 256, 0, st>>>(nl, P0.rp.p, (int)row0, P.rp.p);
+        check_launch();
+        if (P.nnz)
+        {
+            PSB_CUDA(cudaMemcpyAsync(P.ci.p, P0.ci.p + k0, sizeof(int) * (size_t)P.nnz, cudaMemcpyDeviceToDevice, st));
+            PSB_CUDA(cudaMemcpyAsync(P.va.p, P0.va.p + k0, sizeof(double) * (size_t)P.nnz, cudaMemcpyDeviceToDevice, st));
+        }
+        Temp tmp;
+        transpose(ctx_, tmp, P, D->R);
+        PSB_CUDA(cudaStreamSynchronize(st));
+        P.plan("auto", st);
+        D->R.plan("auto", st);
+        D->partial.alloc((size_t)levels_[1]->n_pad + 4, true);
+    }
+    dist_ = D;
+}
+
+// AmgHierarchy::relax for the partitioned level 0: every vector that is multiplied next has its halo pushed first
+void AmgHierarchy::relax_dist(const double *rhs, double *&x, double *&x_alt, bool x_is_zero, const int *done)
+{
+    AmgDistFine &D = *dist_;
+    AmgLevel &L = *levels_[0];
+    if (prm_.relax_type == "chebyshev")
+    {
+        for (int k = 0; k < prm_.degree; ++k)
+        {
+            if (k == 0 && x_is_zero)
+                launch_vec(ctx_, "cheb_first", D.nl_pad, OpChebFirst{rhs, D.dinv, D.cp.p, x, L.alpha[0]}, FinNone{}, done);
+            else
+            {
+                launch_spmv(ctx_, "spmv_cheb_l0", *D.A, x, EpiCheb{rhs, D.dinv, x, D.cp.p, x_alt, L.alpha[k], L.beta[k]}, FinNone{}, done);
+                std::swap(x, x_alt);
+            }
+            D.push_halo(x, done);
+        }
+    }
+    else
+    {
+        // damped Jacobi: w = damping * D^-1 lives in the full-length level; the local slice starts at row0
+        // (EpiRelaxDiag / OpDiagFirst read it element-wise, so an odd row0 is fine for the SpMV epilogue only)
+        throw std::runtime_error("psb200 amg: the partitioned cycle provides the Chebyshev smoother (polysolve's default, AMGCL.cpp:36-47)");
+    }
+}
+
+// amgcl amg::cycle at the partitioned level 0; levels >= 1 run replicated through cycle(1, ...)
+void AmgHierarchy::cycle_dist(const double *rhs, double *&x, double *&x_alt, bool x_is_zero, const int *done)
+{
+    AmgDistFine &D = *dist_;
+    if (levels_.size() == 1)
+    {
+        bool zero = x_is_zero;
+        for (int i = 0; i < prm_.npre + prm_.npost; ++i)
+        {
+            relax_dist(rhs, x, x_alt, zero, done);
+            zero = false;
+        }
+        if (zero)
+            PSB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * D.nl_pad, ctx_.stream));
+        return;
+    }
+    AmgLevel &N = *levels_[1];
+    bool zero = x_is_zero;
+    for (int j = 0; j < prm_.ncycle; ++j)
+    {
+        for (int i = 0; i < prm_.npre; ++i)
+        {
+            relax_dist(rhs, x, x_alt, zero, done);
+            zero = false;
+        }
+        if (zero)
+        {
+            PSB_CUDA(cudaMemsetAsync(x, 0, sizeof(double) * D.nl_pad, ctx_.stream));
+            D.push_halo(x, done);
+            zero = false;
+        }
+        launch_spmv(ctx_, "spmv_residual", *D.A, x, EpiResidual{D.t.p, rhs}, FinNone{}, done);
+        // f_1 = R_0 t = sum over ranks of R_local t_local
+        launch_spmv(ctx_, "spmv_restrict", D.R, D.t.p, EpiStore{D.partial.p}, FinNone{}, done);
+        D.allreduce(D.partial.p, N.f.p, N.n, done);
+        double *nu = N.u.p, *nalt = N.ualt.p;
+        cycle(1, N.f.p, nu, nalt, true, done);
+        launch_spmv(ctx_, "spmv_prolong", D.P, nu, EpiAddTo{x}, FinNone{}, done);
+        D.push_halo(x, done);
+        for (int i = 0; i < prm_.npost; ++i)
+            relax_dist(rhs, x, x_alt, false, done);
+    }
+}
+
+void AmgHierarchy::apply_dist(const double *rhs, double *out, const int *done)
+{
+    if (!dist_)
+        throw std::runtime_error("psb200 amg: setup_dist_fine() has not been called");
+    AmgDistFine &D = *dist_;
+    const size_t bytes = sizeof(double) * (size_t)D.nl_pad;
+    if (prm_.pre_cycles <= 0)
+    {
+        PSB_CUDA(cudaMemcpyAsync(out, rhs, bytes, cudaMemcpyDeviceToDevice, ctx_.stream));
+        return;
+    }
+    double *x = D.u.p, *alt = D.ualt.p;
+    bool zero = true;
+    for (int i = 0; i < prm_.pre_cycles; ++i)
+    {
+        cycle_dist(rhs, x, alt, zero, done);
+        zero = false;
+    }
+    PSB_CUDA(cudaMemcpyAsync(out, x, bytes, cudaMemcpyDeviceToDevice, ctx_.stream));
+}
+
 std::string AmgHierarchy::info_json() const
 {
     std::ostringstream o;

@@ -2,9 +2,12 @@
 #pragma once
 #include "solver.hpp"
 
+#include <functional>
+
 namespace psb {
 
 struct AmgLevel;
+struct AmgDistFine;
 
 class AmgHierarchy
 {
@@ -22,6 +25,22 @@ public:
     // aggregate id per row of `level` (device pointer, rows(level) entries; -2 = removed); n_agg out
     const int *aggregates(int level, int *n_agg) const;
 
+    // Row-partitioned use (multi-GPU): the hierarchy was built from the WHOLE matrix on every rank, the cycle runs
+    // level 0 on the rank's own rows -- smoothing and residual with the partitioned matrix A_local (halo columns, one
+    // halo push per multiplied vector), restriction as a partial product summed across the ranks, prolongation of the
+    // rank's rows -- and the levels below replicated on every rank. Same hierarchy, same arithmetic as the single-GPU
+    // cycle up to summation order, so the iteration counts are those of the 1-GPU run.
+    //   row0           first global row of this rank; A_local.n rows
+    //   dinv_local     D^-1 of the local rows (padded, zero tail)
+    //   push_halo(v, done)                  pushes the boundary entries of the local vector v to the neighbours
+    //   allreduce(partial, out, len, done)  out = sum over ranks of partial
+    void setup_dist_fine(const CsrDev &A_local, const double *dinv_local, long long row0,
+                         std::function<void(const double *, const int *)> push_halo,
+                         std::function<void(const double *, double *, long long, const int *)> allreduce);
+    bool has_dist_fine() const { return (bool)dist_; }
+    // x_local = M^-1 rhs_local (collective: every rank calls it with its slice)
+    void apply_dist(const double *rhs_local, double *x_local, const int *done);
+
 private:
     void cycle(int l, const double *rhs, double *&x, double *&x_alt, bool x_is_zero, const int *done);
     void relax(int l, const double *rhs, double *&x, double *&x_alt, bool x_is_zero, const int *done);
@@ -29,6 +48,9 @@ private:
     AmgParams prm_;
     const CsrDev *A0_ = nullptr;
     std::vector<std::unique_ptr<AmgLevel>> levels_;
+    std::shared_ptr<AmgDistFine> dist_;
+    void relax_dist(const double *rhs, double *&x, double *&x_alt, bool x_is_zero, const int *done);
+    void cycle_dist(const double *rhs, double *&x, double *&x_alt, bool x_is_zero, const int *done);
 };
 
 } // namespace psb

@@ -165,7 +165,9 @@ private:
 // the peers' buffers (st.global on mapped peer pointers) and poll their own.
 //   [0, 4096)     reduction slots  RedSlot[2 parity][8 source ranks]   (flag-in-data words, no fences)
 //   [4096, 8192)  halo flags       unsigned long long[8 source ranks]  (monotonic count of landed push chunks)
+//                 bulk flags       the same for the bulk all-reduce, 1024 bytes further
 //   [8192, ...)   halo data        double[2 parity][8 source ranks][halo_cap]
+//                 bulk data        double[2 parity][8 source ranks][halo_cap]   (vector all-reduce, dist AMG restriction)
 constexpr int kMaxRanks = 8;
 // One fp64 travels as two 8-byte words {32 payload bits, 32-bit sequence tag}: an aligned 8-byte store is
 // single-copy atomic over NVLink, so a word whose tag matches carries valid payload -- the reader needs no
@@ -175,7 +177,7 @@ struct RedSlot
     uint4 w[kMaxRed]; // {lo, tag, hi, tag}
 };
 static_assert(sizeof(RedSlot) == 64, "RedSlot must be 64 bytes");
-constexpr size_t kCommFlagsOff = 4096, kCommHaloOff = 8192;
+constexpr size_t kCommFlagsOff = 4096, kCommBulkFlagsOff = 4096 + 1024, kCommHaloOff = 8192;
 constexpr int kPushChunk = 512; // halo entries per push chunk (one release-add on the consumer's flag per chunk)
 
 struct CommDev
@@ -186,6 +188,8 @@ struct CommDev
     int in_chunks[kMaxRanks];         // push chunks per epoch this rank receives from every source (0: none)
     unsigned long long *red_seq;      // local: number of all-reduces completed
     unsigned long long *push_epoch;   // local: number of halo pushes completed
+    unsigned long long *bulk_epoch;   // local: number of bulk all-reduce segments completed
+    unsigned long long *bulk_expect;  // local [8]: push chunks expected so far from every source (bulk all-reduce)
     int *error;                       // local: set to 1 on a spin-wait timeout
     __host__ __device__ RedSlot *slot(int owner, int parity, int src) const
     {
@@ -198,6 +202,14 @@ struct CommDev
     __host__ __device__ double *halo(int owner, int parity, int src) const
     {
         return reinterpret_cast<double *>(peer[owner] + kCommHaloOff) + ((long long)parity * kMaxRanks + src) * halo_cap;
+    }
+    __host__ __device__ unsigned long long *bulk_flag(int owner, int src) const
+    {
+        return reinterpret_cast<unsigned long long *>(peer[owner] + kCommBulkFlagsOff) + src;
+    }
+    __host__ __device__ double *bulk(int owner, int parity, int src) const
+    {
+        return reinterpret_cast<double *>(peer[owner] + kCommHaloOff) + ((long long)(2 + parity) * kMaxRanks + src) * halo_cap;
     }
 };
 

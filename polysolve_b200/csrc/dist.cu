@@ -228,10 +228,12 @@ __global__ void __launch_bounds__(THREADS) cg_dir_dist_kernel(long long n2, doub
 
 // push the boundary entries of an arbitrary local vector (initial guess x0)
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS) halo_push_kernel(const double *__restrict__ v, RedCtx rc, PushList pl)
+__global__ void __launch_bounds__(THREADS) halo_push_kernel(const double *__restrict__ v, RedCtx rc, PushList pl, const int *done)
 {
     griddep_launch_dependents();
     griddep_wait();
+    if (done && *done)
+        return;
     const unsigned long long push_no = *rc.comm.push_epoch + 1;
     push_section(pl, rc.comm, push_no, 0, (int)gridDim.x, [&](int row) { return v[row]; });
     double acc[1] = {0}, tot[1];
@@ -254,11 +256,11 @@ void Solver::dist_prepare(int rank, int world, long long halo_cap, char handle_o
     d.rank = rank;
     d.world = world;
     d.halo_cap = (halo_cap + 1) & ~1ll;
-    d.comm_bytes = kCommHaloOff + sizeof(double) * 2 * kMaxRanks * (size_t)d.halo_cap;
+    d.comm_bytes = kCommHaloOff + sizeof(double) * 4 * kMaxRanks * (size_t)d.halo_cap; // halo + bulk regions, 2 parities each
     PSB_CUDA(cudaMalloc(&d.comm_buf, d.comm_bytes));
     PSB_CUDA(cudaMemset(d.comm_buf, 0, d.comm_bytes));
-    PSB_CUDA(cudaMalloc(&d.counters, 64));
-    PSB_CUDA(cudaMemset(d.counters, 0, 64));
+    PSB_CUDA(cudaMalloc(&d.counters, 256));
+    PSB_CUDA(cudaMemset(d.counters, 0, 256));
     cudaIpcMemHandle_t hnd;
     PSB_CUDA(cudaIpcGetMemHandle(&hnd, d.comm_buf));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -295,6 +297,10 @@ void Solver::dist_connect(const char *handles)
     c.red_seq = d.counters;
     c.push_epoch = d.counters + 1;
     c.error = (int *)(d.counters + 2);
+    c.bulk_epoch = d.counters + 3;
+    c.bulk_expect = d.counters + 8;
+    for (int q = 0; q < kMaxRanks; ++q)
+        c.in_chunks[q] = 0;
     ctx.comm = c;
     d.connected = true;
 }
@@ -462,14 +468,90 @@ PushList make_push(DistState &d)
 // of a multi-rank run launches at least one so the epochs advance in lockstep.
 static int push_ctas(const DistState &d) { return d.world > 1 ? std::max(1, std::min(128, d.n_chunks)) : 0; }
 
-void Solver::push_halo_of(const double *d_v)
+void Solver::push_halo_of(const double *d_v, const int *done)
 {
     DistState &d = *dist;
     const int push_blocks = push_ctas(d);
     if (!push_blocks)
         return;
-    launch_chain(ctx, halo_push_kernel<kVecThreads>, push_blocks, kVecThreads, 0, d_v, ctx.red(), make_push(d));
+    launch_chain(ctx, halo_push_kernel<kVecThreads>, push_blocks, kVecThreads, 0, d_v, ctx.red(), make_push(d), done);
     check_launch();
+}
+
+// Sum of a vector across the ranks (the restriction of the distributed AMG cycle): every rank stores its partial
+// into region [parity][rank] of EVERY rank's bulk area (chunks of kPushChunk entries, one release-add per chunk on the
+// consumer's bulk flag), waits until all sources have delivered this segment and adds the `world` regions in rank order,
+// so every rank obtains the bit-identical sum. One kernel; a CTA first pushes its chunks, then waits, then sums them.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) bulk_allreduce_kernel(const double *__restrict__ partial, double *__restrict__ out, int len,
+                                                                 RedCtx rc, const int *done)
+{
+    if (done && *done)
+        return;
+    const CommDev &c = rc.comm;
+    const int nchunks = (len + kPushChunk - 1) / kPushChunk;
+    const unsigned long long epoch = *c.bulk_epoch + 1;
+    const int par = (int)(epoch & 1);
+    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x)
+    {
+        const int off = ch * kPushChunk, cnt = min(kPushChunk, len - off);
+        for (int e = threadIdx.x; e < cnt; e += THREADS)
+        {
+            const double v = partial[off + e];
+            for (int q = 0; q < c.world; ++q)
+                c.bulk(q, par, c.rank)[off + e] = v;
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < c.world)
+            red_release_sys_add(c.bulk_flag(threadIdx.x, c.rank), 1ull);
+    }
+    if ((int)threadIdx.x < c.world)
+    {
+        if (!spin_ge(c.bulk_flag(c.rank, threadIdx.x), c.bulk_expect[threadIdx.x] + (unsigned long long)nchunks))
+            *c.error = 1;
+        fence_acq_rel_sys();
+    }
+    __syncthreads();
+    for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x)
+    {
+        const int off = ch * kPushChunk, cnt = min(kPushChunk, len - off);
+        for (int e = threadIdx.x; e < cnt; e += THREADS)
+        {
+            double s = 0;
+            for (int q = 0; q < c.world; ++q)
+                s += __ldcg(c.bulk(c.rank, par, q) + off + e);
+            out[off + e] = s;
+        }
+    }
+    double acc[1] = {0}, tot[1];
+    if (grid_reduce<0, THREADS>(acc, rc, tot) && (int)threadIdx.x < c.world)
+    {
+        c.bulk_expect[threadIdx.x] += (unsigned long long)nchunks;
+        if (threadIdx.x == 0)
+            *c.bulk_epoch = epoch;
+    }
+}
+
+// out = sum over ranks of partial (length len, the same on every rank); segments of at most halo_cap entries
+void Solver::bulk_allreduce(const double *d_partial, double *d_out, long long len, const int *done)
+{
+    DistState &d = *dist;
+    if (d.world == 1)
+    {
+        if (d_out != d_partial)
+            PSB_CUDA(cudaMemcpyAsync(d_out, d_partial, sizeof(double) * len, cudaMemcpyDeviceToDevice, ctx.stream));
+        return;
+    }
+    for (long long off = 0; off < len; off += d.halo_cap)
+    {
+        const int seg = (int)std::min<long long>(d.halo_cap, len - off);
+        const int nchunks = (seg + kPushChunk - 1) / kPushChunk;
+        const int grid = std::max(1, std::min(nchunks, 2 * kSMs));
+        ctx.prof_begin("bulk_allreduce");
+        bulk_allreduce_kernel<kVecThreads><<<grid, kVecThreads, 0, ctx.stream>>>(d_partial + off, d_out + off, seg, ctx.red(), done);
+        check_launch();
+        ctx.prof_end();
+    }
 }
 
 // ---------------------------------------------------------------------------------- rank-local AMG
@@ -604,7 +686,7 @@ void Solver::run_cg_amgcl_dist(const double *d_b)
     PSB_CUDA(cudaMemsetAsync(vp.p, 0, sizeof(double) * n_pad, ctx.stream));
     if (push_blocks)
     {
-        launch_chain(ctx, halo_push_kernel<kVecThreads>, push_blocks, kVecThreads, 0, vx.p, rc, pl);
+        launch_chain(ctx, halo_push_kernel<kVecThreads>, push_blocks, kVecThreads, 0, vx.p, rc, pl, (const int *)nullptr);
         check_launch();
     }
     launch_spmv(ctx, "spmv_residual", A, vx.p, EpiResidualNorms{vr.p, d_b, dinv.p}, FinInitAmgcl{S});
@@ -612,6 +694,9 @@ void Solver::run_cg_amgcl_dist(const double *d_b)
         double *pc = vp.p, *pn = d.vp2.p;
         for (int i = 0; i < 2; ++i)
         {
+            if (amg->has_dist_fine())
+                amg->apply_dist(vr.p, vz.p, done); // level 0 partitioned (halo pushes, bulk all-reduce), coarse levels replicated
+            else
             {
                 LocalScope local(ctx);
                 amg->apply(vr.p, vz.p, done);
@@ -652,7 +737,7 @@ void Solver::run_cg_eigen_dist(const double *d_b)
     if (push_blocks)
     {
         ctx.prof_begin("halo_push");
-        launch_chain(ctx, halo_push_kernel<kVecThreads>, push_blocks, kVecThreads, 0, vx.p, rc, pl);
+        launch_chain(ctx, halo_push_kernel<kVecThreads>, push_blocks, kVecThreads, 0, vx.p, rc, pl, (const int *)nullptr);
         check_launch();
         ctx.prof_end();
     }

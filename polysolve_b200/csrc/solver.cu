@@ -342,6 +342,8 @@ Solver::Solver() {}
 
 Solver::~Solver()
 {
+    if (ctx.stream)
+        cudaStreamSynchronize(ctx.stream); // kernels in flight may still read the helper instance's matrix (full_)
     amg.reset();
     if (graph_exec)
         cudaGraphExecDestroy(graph_exec);
@@ -404,6 +406,12 @@ static void read_amg(const JValue &j, AmgParams &a)
         a.direct_coarse = j.at("direct_coarse").as_bool();
     if (j.contains("aggregation"))
         a.aggregation = j.at("aggregation").as_str();
+    if (j.contains("dist_mode"))
+    {
+        a.dist_mode = j.at("dist_mode").as_str();
+        if (a.dist_mode != "global" && a.dist_mode != "local")
+            throw std::runtime_error("psb200: amg dist_mode must be global or local");
+    }
     // AMGCL-shaped sub-objects (AMGCL.cpp:32-65): relax{type,degree,power_iters,higher,lower,scale}, coarsening{relax,estimate_spectral_radius,aggr{eps_strong}}
     if (j.contains("relax") && j.at("relax").is_obj())
     {
@@ -529,6 +537,20 @@ void Solver::analyze_pattern(long long n_, long long nnz_, const int *outer, con
     {
         // row-partitioned mode: build the local part on the host (dist.cu) and stop here
         analyze_pattern_dist(n_, nnz_, outer, inner);
+        if (amg_global())
+        {
+            if (!full_)
+                full_ = std::make_unique<Solver>();
+            full_->prm = prm;
+            full_->prm.precond = "jacobi";
+            full_->prm.krylov = "cg";
+            full_->prm.verify_pattern = false; // this instance has just hashed the same arrays
+            full_->prm.device = device;
+            AllocScope guard(full_->ctx.stream);
+            full_->analyze_pattern(n_, nnz_, outer, inner, precond_num_);
+        }
+        else
+            full_.reset();
         analyzed = true;
         t_analyze_ms = now_ms() - t0;
         return;
@@ -652,13 +674,38 @@ void Solver::factorize(long long n_, long long nnz_, const int *outer, const int
     const double t0 = now_ms();
     cudaStream_t st = ctx.stream;
     if (dist)
+    {
         factorize_values_dist(vals);
+        if (amg_global())
+            factorize_full_for_amg(vals, nullptr, 0.0);
+    }
     else if (nnz)
     {
         gather_vals_kernel<<<blocks_for(nnz, 256), 256, 0, st>>>(nnz, csc_vals.p, perm.p, A.va.p);
         check_launch();
     }
     factorize_tail(t0);
+}
+
+// Row partition + AMG in "global" mode (scalar problems): the hierarchy is that of the whole matrix.
+bool Solver::amg_global() const
+{
+    return dist && prm.precond == "amg" && prm.amg.dist_mode == "global" && std::max(1, prm.block_size) == 1;
+}
+
+// values of the whole matrix into the helper instance (pattern analysed in analyze_pattern)
+void Solver::factorize_full_for_amg(const double *h_vals, const double *d_vals, double diag_shift)
+{
+    if (!full_ || !full_->analyzed)
+        throw std::runtime_error("psb200 dist: the whole-matrix helper has no pattern (analyze_pattern with precond=amg first)");
+    // earlier solves on our stream may still read the previous values / hierarchy
+    PSB_CUDA(cudaStreamSynchronize(ctx.stream));
+    amg.reset();
+    AllocScope guard(full_->ctx.stream);
+    if (d_vals)
+        full_->factorize_device(n_global, nnz_global, d_vals, diag_shift);
+    else
+        full_->factorize(n_global, nnz_global, nullptr, nullptr, h_vals);
 }
 
 // Newton step with the Hessian values already on the device (reference call site Newton.cpp:173-214):
@@ -695,6 +742,8 @@ void Solver::factorize_device(long long n_, long long nnz_, const double *d_vals
         if (missing)
             throw std::runtime_error("psb200_factorize_csc_device: diag_shift needs a structurally present diagonal");
     }
+    if (amg_global())
+        factorize_full_for_amg(nullptr, d_vals, diag_shift);
     factorize_tail(t0);
 }
 
@@ -723,9 +772,22 @@ void Solver::factorize_tail(double t0)
         AmgParams ap = prm.amg;
         ap.block_size = pattern_block;
         amg = std::make_unique<AmgHierarchy>(ctx, ap);
-        if (dist)
+        if (dist && amg_global())
         {
-            // multi-GPU: every rank builds the hierarchy of its own diagonal block (no communication in the cycle)
+            // multi-GPU, scalar problems: the hierarchy of the WHOLE matrix on every rank (setup is redundant, reductions
+            // stay local), level 0 of the cycle partitioned, coarse levels replicated -- the iteration counts of 1 GPU
+            {
+                LocalScope local(ctx);
+                amg->setup(full_->A, imposed_aggregates);
+            }
+            amg->setup_dist_fine(
+                A, dinv.p, dist->plan.r0(), [this](const double *v, const int *done) { push_halo_of(v, done); },
+                [this](const double *partial, double *out, long long len, const int *done) { bulk_allreduce(partial, out, len, done); });
+        }
+        else if (dist)
+        {
+            // multi-GPU, block problems (or amg.dist_mode = local): every rank builds the hierarchy of its own diagonal
+            // block (block-Jacobi across ranks, no communication in the cycle)
             LocalScope local(ctx);
             build_diag_block_dist();
             amg->setup(dist->A_diag, imposed_aggregates);
@@ -1180,6 +1242,8 @@ void Solver::build_info()
     o << ",\"gpu_launches\":" << ctx.launches;
     if (amg)
         o << ",\"amg\":" << amg->info_json();
+    if (amg && dist)
+        o << ",\"amg_dist_mode\":" << jstr(amg->has_dist_fine() ? "global" : "local");
     if (!ctx.prof.empty())
     {
         o << ",\"profile\":{";

@@ -29,6 +29,9 @@ struct AmgParams
     double eps_strong = 0.0;
     int block_size = 1; // AMGCL_Block<B> (reference AMGCL.cpp:246-298): B x B value type
     std::string aggregation = "mis2"; // mis2 (parallel, deterministic) | imposed via debug hook
+    // row partitions: "global" = one hierarchy of the whole matrix, level 0 partitioned, coarse levels replicated (the
+    // iteration counts of the 1-GPU run); "local" = every rank its own hierarchy of its diagonal block (block-Jacobi)
+    std::string dist_mode = "global";
 };
 
 struct Params
@@ -108,6 +111,11 @@ struct Solver
     std::string graph_key;
     long long graph_launches_per_batch = 0;
 
+    // Row partition + AMG, "global" mode: a helper instance (not partitioned, same device) that holds the WHOLE matrix in
+    // CSR form; the hierarchy is built from it on every rank and only level 0 of the cycle is partitioned (amg.hpp).
+    std::unique_ptr<Solver> full_;
+    bool amg_global() const;
+    void factorize_full_for_amg(const double *h_vals, const double *d_vals, double diag_shift);
     std::unique_ptr<AmgHierarchy> amg;
     std::vector<std::vector<int>> imposed_aggregates;
 
@@ -126,7 +134,8 @@ struct Solver
     void factorize_device(long long n, long long nnz, const double *d_vals, double diag_shift);
     void factorize_tail(double t0);
     double residual_norm_device(const double *d_x, const double *d_b, long long n);
-    void push_halo_of(const double *d_v); // row partition: push the boundary entries of a local vector (dist.cu)
+    void push_halo_of(const double *d_v, const int *done = nullptr); // row partition: push the boundary entries of a local vector (dist.cu)
+    void bulk_allreduce(const double *d_partial, double *d_out, long long len, const int *done = nullptr); // sum of a vector across ranks
     // Dirichlet pre-processing (fem.cu; reference FEMSolver.cpp:97-372)
     DevBuf<unsigned char> dmask; // N: 1 for a Dirichlet dof
     void dirichlet_set_nodes(const int *nodes, long long count);

@@ -35,7 +35,7 @@ def _problem(P, n, block):
     return o, i, v, P.spmv_csr(o, i, v, P.splitmix64(42, N)), N
 
 
-def _worker(rank, world, port, n, tol, q, precond="jacobi", block=1):
+def _worker(rank, world, port, n, tol, q, precond="jacobi", block=1, amg_mode="global"):
     import torch
     import torch.distributed as dist
 
@@ -49,7 +49,7 @@ def _worker(rank, world, port, n, tol, q, precond="jacobi", block=1):
         o, i, v, b, N = _problem(P, n, block)
         s = psb.Solver.create("CUDA", "")
         s.set_parameters({"CUDA": {"tolerance": tol, "max_iter": 10000, "device": rank, "check_every": 8, "precond": precond,
-                                   "block_size": block}})
+                                   "block_size": block, "amg": {"dist_mode": amg_mode}}})
         s.dist_setup_torch(halo_cap=1 << 16)
         s.analyze_pattern_raw(N, o, i, N)
         s.factorize_raw(N, o, i, v)
@@ -67,12 +67,12 @@ def _worker(rank, world, port, n, tol, q, precond="jacobi", block=1):
         dist.destroy_process_group()
 
 
-def _run(world, n, tol, precond="jacobi", block=1):
+def _run(world, n, tol, precond="jacobi", block=1, amg_mode="global"):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     port = _free_port()
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, tol, q, precond, block)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, tol, q, precond, block, amg_mode)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
@@ -109,9 +109,41 @@ def test_dist_pcg_matches_oracle(orc, world):
 
 
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
-def test_dist_amg_pcg(orc, world):
-    """AMG-PCG on the row partition: rank-local SA-AMG (block-Jacobi across ranks) inside the global CG. The solution
-    must equal the single-GPU / oracle solution to the solver tolerance; the iteration count may grow with the rank count."""
+def test_dist_amg_pcg_global_hierarchy(psb, orc, world):
+    """AMG-PCG on the row partition, amg.dist_mode = global (default): the hierarchy of the WHOLE matrix, level 0 of the
+    cycle partitioned (halo push per smoothing step, restriction summed across ranks), coarse levels replicated. Same
+    hierarchy and arithmetic as the single-GPU solver up to summation order: same iteration count, same solution."""
+    if world > max(1, _ngpu()):
+        pytest.skip(f"needs {world} GPUs")
+    n, tol = 40, 1e-8
+    N = n ** 3
+    o, i, v = orc.poisson3d(n)
+    b = orc.spmv_csc(o, i, v, orc.splitmix64(42, N))
+    s1 = psb.Solver.create("CUDA", "")
+    s1.set_parameters({"CUDA": {"tolerance": tol, "max_iter": 1000, "precond": "amg"}})
+    s1.factorize_raw(N, o, i, v)
+    x1 = np.zeros(N)
+    s1.solve(b, x1)
+    it1 = s1.get_info()["solver_iter"]
+    levels1 = [lv["rows"] for lv in s1.get_info()["amg"]["levels"]]
+    del s1
+    res = _run(world, n, tol, "amg")
+    x = np.zeros(N)
+    for rank, a, e, xs, it, err, status, it2, dinfo in res:
+        x[a:e] = xs
+        assert status == "Converged"
+        assert it == res[0][4] == it1, (it, it1)     # the 1-GPU iteration count, on every rank
+        assert err < tol
+        assert it2 == 0
+    assert np.linalg.norm(x - x1) / np.linalg.norm(x1) < 1e-9   # same iterates up to summation order
+    assert np.linalg.norm(orc.spmv_csc(o, i, v, x) - b) / np.linalg.norm(b) < 2 * tol
+    assert len(levels1) >= 2
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_dist_amg_pcg_rank_local(orc, world):
+    """amg.dist_mode = local: rank-local SA-AMG of the diagonal block (block-Jacobi across ranks) inside the global CG.
+    The solution equals the oracle's to the solver tolerance; the iteration count grows with the rank count."""
     if world > max(1, _ngpu()):
         pytest.skip(f"needs {world} GPUs")
     n, tol = 40, 1e-8
@@ -119,7 +151,7 @@ def test_dist_amg_pcg(orc, world):
     o, i, v = orc.poisson3d(n)
     b = orc.spmv_csc(o, i, v, orc.splitmix64(42, N))
     x0, _, _, _ = orc.eigen_cg(o, i, v, b, tol=1e-12, max_iters=10000)
-    res = _run(world, n, tol, "amg")
+    res = _run(world, n, tol, "amg", 1, "local")
     x = np.zeros(N)
     for rank, a, e, xs, it, err, status, it2, dinfo in res:
         x[a:e] = xs
@@ -158,3 +190,28 @@ def test_dist_block3_amg_pcg_elasticity(psb, orc, world):
         assert it2 == 0
     assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) < 2 * tol
     assert np.linalg.norm(x - x0) / np.linalg.norm(x0) < 1e-5
+
+
+def test_two_devices_in_one_process(psb, orc):
+    """Solver instances on different GPUs driven from one host thread (every C-ABI call makes its device current)."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    o, i, v = orc.poisson3d(20)
+    N = 20 ** 3
+    b = orc.splitmix64(3, N)
+    ss = []
+    for dev in (0, 1):
+        s = psb.Solver.create("CUDA", "")
+        s.set_parameters({"CUDA": {"tolerance": 1e-10, "device": dev}})
+        ss.append(s)
+    for s in ss:              # interleaved: analyze both, then factorize both, then solve both
+        s.analyze_pattern_raw(N, o, i, N)
+    for s in ss:
+        s.factorize_raw(N, o, i, v)
+    xs = []
+    for s in reversed(ss):
+        x = np.zeros(N)
+        s.solve(b, x)
+        xs.append(x)
+    assert np.array_equal(xs[0], xs[1])
+    assert np.linalg.norm(orc.spmv_csc(o, i, v, xs[0]) - b) < 1e-8
