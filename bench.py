@@ -292,7 +292,7 @@ def run_ours(args):
 
     s = psb.Solver.create("CUDA", "")
     s.set_parameters({"CUDA": {"krylov": "cg", "precond": "jacobi", "tolerance": TOL, "max_iter": MAX_ITER,
-                               "check_every": args.check_every, "device": local, "cg_kernel": args.cg_kernel}})
+                               "check_every": args.check_every, "device": local, "cg_kernel": args.cg_kernel, "interior_first": args.interior_first}})
     if world > 1:
         s.dist_setup_torch(halo_cap=1 << 20)
     t0 = time.perf_counter()
@@ -473,6 +473,7 @@ def main():
     ap.add_argument("--check-every", type=int, default=16)
     ap.add_argument("--ref-iters", type=int, default=40, help="CG iterations per CPU sample step")
     ap.add_argument("--cg-kernel", default="auto", choices=["auto", "persistent", "split"])
+    ap.add_argument("--interior-first", action="store_true", help="row partitions: SpMV tiles without halo columns first, late halo wait")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-amg", action="store_true", help="skip the AMG-PCG (config 3) leg")
     ap.add_argument("--amg-cpu-n", type=int, default=0, help="grid side of the CPU AMG leg (0 = the full --n system)")

@@ -392,7 +392,8 @@ __global__ void __launch_bounds__(PCfg::threads, kPersistCtasPerSm) cg_persist_k
 // ------------------------------------------------------------------------------------------ host side
 int Solver::persist_grid()
 {
-    static int per_sm = 0;
+    static int per_sm_dev[16] = {0};
+    int &per_sm = per_sm_dev[device & 15];
     if (!per_sm)
     {
         PSB_CUDA(cudaFuncSetAttribute(cg_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCfg::bytes));

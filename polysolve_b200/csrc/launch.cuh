@@ -50,10 +50,11 @@ struct CsrDev
     unsigned halo_mask = 0;   // ranks that push halo values to this one
     DevBuf<int> tile_order;   // interior-first tile order of the stream schedule (row partitions only)
     int n_interior = 0, order_rows = 0; // order_rows: rows per tile the order was built for
+    bool use_order = false;   // Params::interior_first
     int stream_rows() const { return kSpmvThreads / std::max(1, lpr); }
     CsrView view() const
     {
-        const bool ord = kind == SPMV_STREAM && halo_mask != 0 && tile_order.p != nullptr && order_rows == stream_rows();
+        const bool ord = use_order && kind == SPMV_STREAM && halo_mask != 0 && tile_order.p != nullptr && order_rows == stream_rows();
         return CsrView{rp.p, ci.p, va.p, n, nl, halo_mask, ord ? tile_order.p : nullptr, ord ? n_interior : 0};
     }
     // Chooses the schedule. auto: the TMA stream schedule with the smallest lanes-per-row whose tiles fit the staging
@@ -308,7 +309,12 @@ template <class Epi, class Fin, class Cfg>
 void launch_spmv_stream(Ctx &c, const CsrDev &A, const double *x, Epi epi, Fin fin, const int *done, const int *only_if, int ctas_per_sm = 0)
 {
     auto kern = spmv_stream_kernel<Epi, Fin, Cfg>;
-    static int max_ctas = 0;
+    // the opt-in to > 48 KB of dynamic shared memory and the occupancy are per device (instances on several GPUs may
+    // live in one process)
+    static int max_ctas_dev[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int &max_ctas = max_ctas_dev[dev & 15];
     if (!max_ctas)
     {
         PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::bytes));

@@ -462,6 +462,8 @@ void Solver::set_parameters(const std::string &json)
         np.check_every = std::max(1, (int)j.at("check_every").as_num());
     if (j.contains("use_graph"))
         np.use_graph = j.at("use_graph").as_bool();
+    if (j.contains("interior_first"))
+        np.interior_first = j.at("interior_first").as_bool();
     if (j.contains("pdl"))
         np.pdl = j.at("pdl").as_bool();
     if (j.contains("spmv_kernel"))
@@ -498,6 +500,7 @@ void Solver::set_parameters(const std::string &json)
         A.plan(prm.spmv_kernel, ctx.stream);
     ctx.profile = prm.profile;
     ctx.pdl = prm.pdl;
+    A.use_order = prm.interior_first;
 }
 
 // ==================================================================================== analyze_pattern

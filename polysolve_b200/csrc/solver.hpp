@@ -42,6 +42,10 @@ struct Params
     int max_iter = 1000;
     int check_every = 16;
     bool use_graph = true;
+    // row partitions: the stream SpMV walks the tiles without halo columns first and waits for the halo before its first
+    // boundary tile. Off by default: A/B on 2 B200s (profiles/r01_interior_first.txt) 5780 vs 5515 it/s -- the extra
+    // dependent load of the tile order in the TMA issue path costs more than the hidden halo latency at that size
+    bool interior_first = false;
     // programmatic dependent launch between the kernels of the Krylov chain. Off by default: measured on B200
     // (profiles/r01_pdl.txt) it gains nothing at 1.26 M rows and loses 9 % at 10 M rows (dependents that become
     // resident while the predecessor drains land unevenly on the SMs, and the vector kernels are statically partitioned)
