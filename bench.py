@@ -262,7 +262,9 @@ def amg_dist_leg(args, psb, P, local, world, N, outer, inner, vals, b, barrier):
     rel = float(np.linalg.norm(P.spmv_csr(outer, inner, vals, xf) - b) / np.linalg.norm(b))
     return {"n": N, "n_gpus": world, "gpu_setup_s": float(t[0]), "gpu_solve_s": float(t[1]), "gpu_iters": info["num_iterations"],
             "rel_residual": rel, "levels_rank0": [lv["rows"] for lv in info["amg"]["levels"]],
-            "what": "rank-local SA-AMG of the diagonal block (block-Jacobi across ranks) inside the global PCG"}
+            "dist_mode": info.get("amg_dist_mode"),
+            "what": "SA-AMG-PCG on the row partition: hierarchy of the whole matrix, level 0 of the cycle partitioned (halo pushes, "
+                    "restriction summed over NVLink), coarse levels replicated"}
 
 
 def run_ours(args):
@@ -384,7 +386,12 @@ def run_ours(args):
         x = xt.cpu().numpy()
     amg_dist = None
     if world > 1 and not args.no_amg:
-        amg_dist = amg_dist_leg(args, psb, P, local, world, N, outer, inner, vals, b, barrier)
+        # a failure of this secondary leg must not cost the headline line; every rank catches on its own and keeps
+        # walking through the same barriers
+        try:
+            amg_dist = amg_dist_leg(args, psb, P, local, world, N, outer, inner, vals, b, barrier)
+        except Exception as e:  # noqa: BLE001
+            amg_dist = {"error": str(e)[:300]}
     if rank != 0:
         return
     rel_res = float(np.linalg.norm(P.spmv_csr(outer, inner, vals, x) - b) / np.linalg.norm(b))
