@@ -418,7 +418,7 @@ void Solver::launch_cg_persist(double *p_cur, double *p_other, int iters)
     PersistArgs a{};
     a.A = A.view();
     a.order = a.A.tile_order;
-    a.n_interior = a.A.tile_order ? a.A.n_interior : 0x7fffffff;
+    a.n_interior = a.A.tile_order ? a.A.n_interior : 0; // no order: every tile may touch halo columns, wait before the first
     a.push = PushList{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
     a.comm = ctx.comm;
     if (dist)
