@@ -254,9 +254,12 @@ __device__ __forceinline__ uint4 ld_ll(const uint4 *p)
     asm volatile("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
     return v;
 }
-// spin until *p >= want (system scope); false on timeout
-__device__ __forceinline__ bool spin_ge(const unsigned long long *p, unsigned long long want)
+// spin until *p >= want (system scope); false on timeout. Once a wait has timed out on this rank (*err set) every later
+// wait gives up at once: a lost peer costs one spin limit, not one per kernel of a captured graph.
+__device__ __forceinline__ bool spin_ge(const unsigned long long *p, unsigned long long want, const int *err = nullptr)
 {
+    if (err && *(const volatile int *)err)
+        return false;
     const long long t0 = clock64();
     while (ld_sys(p) < want)
     {
@@ -346,13 +349,14 @@ __device__ __forceinline__ void comm_allreduce_seq(const CommDev &c, double (&to
             st_ll(&dst->w[i], sh[i], tag);
         const RedSlot *src = c.slot(c.rank, par, threadIdx.x);
         const long long t0 = clock64();
+        const bool failed_before = *(const volatile int *)c.error != 0;
 #pragma unroll
         for (int i = 0; i < NV; ++i)
         {
             uint4 v = ld_ll(&src->w[i]);
             while (v.y != tag || v.w != tag)
             {
-                if (clock64() - t0 > kSpinLimit)
+                if (failed_before || clock64() - t0 > kSpinLimit)
                 {
                     *c.error = 1;
                     break;

@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(THREADS) bulk_allreduce_kernel(const double *_
     }
     if ((int)threadIdx.x < c.world)
     {
-        if (!spin_ge(c.bulk_flag(c.rank, threadIdx.x), c.bulk_expect[threadIdx.x] + (unsigned long long)nchunks))
+        if (!spin_ge(c.bulk_flag(c.rank, threadIdx.x), c.bulk_expect[threadIdx.x] + (unsigned long long)nchunks, c.error))
             *c.error = 1;
         fence_acq_rel_sys();
     }

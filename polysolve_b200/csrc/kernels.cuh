@@ -57,7 +57,7 @@ __device__ __forceinline__ const double *wait_halo_epoch(unsigned halo_mask, con
 {
     if ((int)threadIdx.x < c.world && ((halo_mask >> threadIdx.x) & 1u))
     {
-        if (!spin_ge(c.halo_flag(c.rank, threadIdx.x), epoch * (unsigned long long)c.in_chunks[threadIdx.x]))
+        if (!spin_ge(c.halo_flag(c.rank, threadIdx.x), epoch * (unsigned long long)c.in_chunks[threadIdx.x], c.error))
             *c.error = 1;
         fence_acq_rel_sys();
     }

@@ -4,7 +4,6 @@
     python scripts/amg_profile.py launches [n]     -> factorize (outside the profiler range) + ONE solve with graphs off
                                                       between cudaProfilerStart/Stop (run under ncu --profile-from-start off)
 """
-import ctypes
 import json
 import os
 import sys
@@ -44,7 +43,6 @@ if mode == "timers":
                           "solve_ms": info.get("solve_ms"), "amg": {kk: vv for kk, vv in info["amg"].items() if kk != "levels"}}), flush=True)
 else:
     s.factorize_raw(N, o, i, v)
-    rt = ctypes.CDLL("libcudart.so.12") if False else None
     import torch
     x = np.zeros(N)
     torch.cuda.cudart().cudaProfilerStart()

@@ -35,7 +35,7 @@ def _problem(P, n, block):
     return o, i, v, P.spmv_csr(o, i, v, P.splitmix64(42, N)), N
 
 
-def _worker(rank, world, port, n, tol, q, precond="jacobi", block=1, amg_mode="global"):
+def _worker(rank, world, port, n, tol, q, precond="jacobi", block=1, amg_mode="global", extra=None):
     import torch
     import torch.distributed as dist
 
@@ -48,8 +48,10 @@ def _worker(rank, world, port, n, tol, q, precond="jacobi", block=1, amg_mode="g
         P = psb.problems
         o, i, v, b, N = _problem(P, n, block)
         s = psb.Solver.create("CUDA", "")
-        s.set_parameters({"CUDA": {"tolerance": tol, "max_iter": 10000, "device": rank, "check_every": 8, "precond": precond,
-                                   "block_size": block, "amg": {"dist_mode": amg_mode}}})
+        prm = {"tolerance": tol, "max_iter": 10000, "device": rank, "check_every": 8, "precond": precond,
+               "block_size": block, "amg": {"dist_mode": amg_mode}}
+        prm.update(extra or {})
+        s.set_parameters({"CUDA": prm})
         s.dist_setup_torch(halo_cap=1 << 16)
         s.analyze_pattern_raw(N, o, i, N)
         s.factorize_raw(N, o, i, v)
@@ -67,12 +69,12 @@ def _worker(rank, world, port, n, tol, q, precond="jacobi", block=1, amg_mode="g
         dist.destroy_process_group()
 
 
-def _run(world, n, tol, precond="jacobi", block=1, amg_mode="global"):
+def _run(world, n, tol, precond="jacobi", block=1, amg_mode="global", extra=None):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     port = _free_port()
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, tol, q, precond, block, amg_mode)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, tol, q, precond, block, amg_mode, extra)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
@@ -106,6 +108,29 @@ def test_dist_pcg_matches_oracle(orc, world):
         assert dinfo["world"] == world
     assert np.linalg.norm(x - x0) / np.linalg.norm(x0) < 10 * tol
     assert np.linalg.norm(orc.spmv_csc(o, i, v, x) - b) / np.linalg.norm(b) < 2 * tol
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+@pytest.mark.parametrize("extra", [{"cg_kernel": "persistent"}, {"cg_kernel": "persistent", "interior_first": True},
+                                   {"interior_first": True}])
+def test_dist_pcg_kernel_variants(orc, world, extra):
+    """The persistent cooperative kernel and the interior-first tile order on the row partition: same result as the
+    default path (oracle iteration count within the summation-order band, solution to the solver tolerance)."""
+    if world > max(1, _ngpu()):
+        pytest.skip(f"needs {world} GPUs")
+    n, tol = 40, 1e-8
+    N = n ** 3
+    o, i, v = orc.poisson3d(n)
+    b = orc.spmv_csc(o, i, v, orc.splitmix64(42, N))
+    x0, it0, _, _ = orc.eigen_cg(o, i, v, b, tol=tol, max_iters=10000)
+    res = _run(world, n, tol, extra=extra)
+    x = np.zeros(N)
+    for rank, a, e, xs, it, err, status, it2, dinfo in res:
+        x[a:e] = xs
+        assert status == "Converged" and it == res[0][4]
+        assert abs(it - it0) <= max(1, 0.02 * it0)
+        assert err < tol and it2 == 0
+    assert np.linalg.norm(x - x0) / np.linalg.norm(x0) < 10 * tol
 
 
 @pytest.mark.parametrize("world", [1, 2, 4, 8])

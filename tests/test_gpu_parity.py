@@ -313,6 +313,26 @@ def test_pre_factor_protocol(psb, orc):
         np.testing.assert_allclose(x, x0, rtol=0, atol=1e-11)
 
 
+def test_release_cached_memory_keeps_the_solver_usable(psb, orc):
+    """Device buffers come from the stream-ordered pool; trimming it must not touch buffers in use."""
+    o, i, v = orc.poisson3d(24)
+    N = 24 ** 3
+    b = orc.splitmix64(6, N)
+    s = make(psb, tolerance=1e-9, precond="amg")
+    s.factorize_raw(N, o, i, v)
+    x = np.zeros(N)
+    s.solve(b, x)
+    it = s.get_info()["solver_iter"]
+    s.release_cached_memory()
+    x2 = np.zeros(N)
+    s.solve(b, x2)
+    assert s.get_info()["solver_iter"] == it and np.array_equal(x, x2)
+    s.factorize_raw(N, o, i, v)      # rebuilds the hierarchy from a trimmed pool
+    x3 = np.zeros(N)
+    s.solve(b, x3)
+    assert np.array_equal(x, x3)
+
+
 def test_solve_device_pointers(psb, orc):
     import torch
     o, i, v = orc.poisson3d(24)
