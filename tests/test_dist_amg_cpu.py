@@ -1,0 +1,151 @@
+"""CPU check of the multi-GPU AMG cycle in "global" mode (amg.cu cycle_dist): the hierarchy of
+the whole matrix, level 0 partitioned by rows, the levels below replicated. The cycle is restated in numpy from the
+oracle's hierarchy (matrices, Chebyshev interval), pinned against the oracle's own C++ cycle, and then run by two gloo
+ranks exactly as the GPUs do it -- halo values exchanged before every level-0 multiplication, the restriction as a sum of
+per-rank partial products, prolongation of the owned rows -- and compared with the single-process cycle."""
+import os
+import socket
+
+import numpy as np
+import scipy.sparse as sp
+
+
+def _levels(H):
+    out = []
+    for l in range(H.num_levels):
+        info = H.level_info(l)
+        A = sp.csr_matrix((H.matrix(l, "A")[2], H.matrix(l, "A")[1], H.matrix(l, "A")[0]), shape=(info["rows"], info["rows"]))
+        lv = {"A": A, "M": 1.0 / A.diagonal(), "d": info["d"], "c": info["c"]}
+        if l + 1 < H.num_levels:
+            nc = H.level_info(l + 1)["rows"]
+            p = H.matrix(l, "P")
+            r = H.matrix(l, "R")
+            lv["P"] = sp.csr_matrix((p[2], p[1], p[0]), shape=(info["rows"], nc))
+            lv["R"] = sp.csr_matrix((r[2], r[1], r[0]), shape=(nc, info["rows"]))
+        out.append(lv)
+    return out
+
+
+def _cheb(matvec, M, d, c, rhs, x, degree=16):
+    """amgcl relaxation::chebyshev::solve (oracle/amg_oracle.cpp chebyshev_apply)"""
+    p = np.zeros_like(x)
+    alpha = 0.0
+    for k in range(degree):
+        r = M * (rhs - matvec(x))
+        if k == 0:
+            alpha, beta = 1.0 / d, 0.0
+        elif k == 1:
+            alpha = 2 * d / (2 * d * d - c * c)
+            beta = alpha * d - 1
+        else:
+            alpha = 1.0 / (d - 0.25 * alpha * c * c)
+            beta = alpha * d - 1
+        p = alpha * r + beta * p
+        x = x + p
+    return x
+
+
+def _cycle(levels, l, rhs, x, ncycle=2):
+    """amgcl amg::cycle (oracle/amg_oracle.cpp cycle)"""
+    L = levels[l]
+    mv = lambda v: L["A"] @ v  # noqa: E731
+    if l + 1 == len(levels):
+        x = _cheb(mv, L["M"], L["d"], L["c"], rhs, x)
+        return _cheb(mv, L["M"], L["d"], L["c"], rhs, x)
+    for _ in range(ncycle):
+        x = _cheb(mv, L["M"], L["d"], L["c"], rhs, x)
+        f = L["R"] @ (rhs - mv(x))
+        u = _cycle(levels, l + 1, f, np.zeros(f.size), ncycle)
+        x = x + L["P"] @ u
+        x = _cheb(mv, L["M"], L["d"], L["c"], rhs, x)
+    return x
+
+
+def _hierarchy(orc, n=14):
+    o, i, v = orc.poisson3d(n)
+    H = orc.Amg(o, i, v, coarse_enough=200)
+    return H, n ** 3
+
+
+def test_numpy_cycle_equals_oracle_cycle(orc):
+    H, N = _hierarchy(orc)
+    assert H.num_levels >= 3
+    rhs = orc.splitmix64(5, N)
+    z = _cycle(_levels(H), 0, rhs, np.zeros(N))
+    z0 = H.apply(rhs)
+    assert np.linalg.norm(z - z0) <= 1e-12 * np.linalg.norm(z0)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    from oracle import oracle as orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        H, N = _hierarchy(orc)       # every rank builds the hierarchy of the WHOLE matrix (deterministic, so identical)
+        levels = _levels(H)
+        L0 = levels[0]
+        rp = L0["A"].indptr
+        off = orc.partition_rows(rp.astype(np.int32), world)
+        a, b = int(off[rank]), int(off[rank + 1])
+        A_loc = L0["A"][a:b]                     # owned rows, global columns (the halo columns are those outside [a, b))
+        P_loc = L0["P"][a:b]                     # rows of P_0
+        R_loc = sp.csr_matrix(P_loc.T)           # = columns [a, b) of R_0 (amg.cu setup_dist_fine)
+        M_loc = L0["M"][a:b]
+        rhs = orc.splitmix64(5, N)
+        rhs_loc = rhs[a:b]
+
+        def gather_full(x_loc):                  # the halo push: every multiplication sees the neighbours' current values
+            parts = [None] * world
+            dist.all_gather_object(parts, x_loc)
+            return np.concatenate(parts)
+
+        def mv(x_loc):
+            return A_loc @ gather_full(x_loc)
+
+        x = np.zeros(b - a)
+        f1_seen = []
+        for _ in range(2):                       # ncycle = 2 at level 0 too
+            x = _cheb(mv, M_loc, L0["d"], L0["c"], rhs_loc, x)
+            part = torch.from_numpy(R_loc @ (rhs_loc - mv(x)))
+            dist.all_reduce(part, op=dist.ReduceOp.SUM)   # the bulk all-reduce of the restriction
+            f1 = part.numpy()
+            f1_seen.append(f1.copy())
+            u = _cycle(levels, 1, f1, np.zeros(f1.size))  # replicated coarse levels
+            x = x + P_loc @ u
+            x = _cheb(mv, M_loc, L0["d"], L0["c"], rhs_loc, x)
+        z_full = _cycle(levels, 0, rhs, np.zeros(N))
+        err = float(np.linalg.norm(x - z_full[a:b]) / np.linalg.norm(z_full))
+        q.put((rank, a, b, err, [float(np.sum(f)) for f in f1_seen], [float(np.abs(f).max()) for f in f1_seen]))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_partitioned_cycle_equals_single_process_cycle():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    world, port = 2, _free_port()
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert res[0][2] == res[1][1]                       # contiguous, disjoint row ranges
+    for rank, a, b, err, sums, maxs in res:
+        assert err < 1e-12, (rank, err)                 # same arithmetic up to summation order
+    assert res[0][4] == res[1][4] and res[0][5] == res[1][5]   # both ranks hold the same coarse right-hand side
