@@ -113,7 +113,9 @@ int psb200_dirichlet_solve_prefactorized(psb200_handle h, const double *vals_or_
  *   3. every rank: psb200_dist_connect(all handles)
  * Afterwards analyze_pattern / factorize still receive the FULL CSC matrix on every rank (each rank
  * keeps its rows), psb200_solve receives full-length b / x (each rank reads and writes only its own
- * rows [row_begin, row_end)), psb200_solve_device receives the local slices. Jacobi-PCG only. */
+ * rows [row_begin, row_end)), psb200_solve_device receives the local slices. Every call is collective. krylov = cg with precond = jacobi | none |
+ * amg (scalar problems: one hierarchy of the whole matrix, fine level partitioned, "amg": {"dist_mode": "global"};
+ * block problems and "dist_mode": "local": a rank-local hierarchy per GPU). */
 int psb200_dist_prepare(psb200_handle h, int rank, int world, int64_t halo_cap_doubles, char handle_out[64]);
 int psb200_dist_connect(psb200_handle h, const char *handles /* world * 64 bytes */);
 int psb200_dist_local_range(psb200_handle h, int64_t *row_begin, int64_t *row_end);
