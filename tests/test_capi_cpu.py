@@ -97,3 +97,22 @@ def test_generators_match_oracle(psb, orc):
     assert np.array_equal(P.splitmix64(42, 257), orc.splitmix64(42, 257))
     assert P.spmv_bytes(10077696, 70263936) == 1044721156
     assert P.pcg_iter_bytes(10077696, 70263936) == 1931558404
+
+
+def test_headers_are_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: every header under include/ must compile as C99 (no C++ types in signatures)
+    and a C translation unit that references every declared function must link against libpsb200.so."""
+    import re
+    import subprocess
+    inc = os.path.join(ROOT, "include")
+    headers = sorted(h for h in os.listdir(inc) if h.endswith(".h"))
+    text = "".join(open(os.path.join(inc, h)).read() for h in headers)
+    names = sorted(set(re.findall(r"\b(psb200_[a-z0-9_]+)\s*\(", text)))
+    src = tmp_path / "abi.c"
+    src.write_text("".join(f'#include "{h}"\n' for h in headers)
+                   + "typedef void (*fn)(void);\nfn table[] = {\n" + "".join(f"    (fn){n},\n" for n in names) + "};\n"
+                   + "int main(void) { return table[0] == 0; }\n")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-Wno-pedantic", "-I", inc, "-c", str(src), "-o",
+                           str(tmp_path / "abi.o")])
+    lib = os.path.join(ROOT, "polysolve_b200", "csrc")
+    subprocess.check_call(["gcc", str(tmp_path / "abi.o"), "-L", lib, "-lpsb200", "-Wl,-rpath," + lib, "-o", str(tmp_path / "abi")])
