@@ -149,3 +149,82 @@ def test_gloo_world2_partitioned_cycle_equals_single_process_cycle():
     for rank, a, b, err, sums, maxs in res:
         assert err < 1e-12, (rank, err)                 # same arithmetic up to summation order
     assert res[0][4] == res[1][4] and res[0][5] == res[1][5]   # both ranks hold the same coarse right-hand side
+
+
+# ------------------------------------------------------------------------------------------ blueprint for the open item
+# levels 0 AND 1 partitioned by rows (halo exchange per multiplication, restriction as a sum of
+# partial products, the coarse iterate gathered before the prolongation), the small levels below replicated. Pure
+# numpy / gloo: the arithmetic the CUDA implementation of the next round has to reproduce.
+def _worker_two_levels(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+
+    from oracle import oracle as orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        H, N = _hierarchy(orc)
+        levels = _levels(H)
+        npart = 2                                             # partitioned levels: 0 and 1
+        rng_of = []
+        for l in range(npart):
+            off = orc.partition_rows(levels[l]["A"].indptr.astype(np.int32), world)
+            rng_of.append((int(off[rank]), int(off[rank + 1])))
+
+        def gather(l, x_loc):                                 # halo push / all-gather of a level-l vector
+            parts = [None] * world
+            dist.all_gather_object(parts, x_loc)
+            return np.concatenate(parts)
+
+        def allreduce(v):
+            t = torch.from_numpy(np.ascontiguousarray(v))
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return t.numpy()
+
+        def cycle(l, rhs_loc, x_loc):
+            if l == npart:                                    # replicated levels: rhs_loc / x_loc are full vectors here
+                return _cycle(levels, l, rhs_loc, x_loc)
+            L = levels[l]
+            a, b = rng_of[l]
+            A_loc, M_loc = L["A"][a:b], L["M"][a:b]
+            P_loc = L["P"][a:b]
+            R_loc = sp.csr_matrix(P_loc.T)
+            mv = lambda v: A_loc @ gather(l, v)  # noqa: E731
+            for _ in range(2):
+                x_loc = _cheb(mv, M_loc, L["d"], L["c"], rhs_loc, x_loc)
+                f_full = allreduce(R_loc @ (rhs_loc - mv(x_loc)))          # every rank holds the whole coarse rhs
+                if l + 1 < npart:
+                    a1, b1 = rng_of[l + 1]
+                    u_loc = cycle(l + 1, f_full[a1:b1], np.zeros(b1 - a1))
+                    u_full = gather(l + 1, u_loc)                           # coarse iterate gathered for the prolongation
+                else:
+                    u_full = cycle(l + 1, f_full, np.zeros(f_full.size))
+                x_loc = x_loc + P_loc @ u_full
+                x_loc = _cheb(mv, M_loc, L["d"], L["c"], rhs_loc, x_loc)
+            return x_loc
+
+        rhs = orc.splitmix64(5, N)
+        a, b = rng_of[0]
+        x = cycle(0, rhs[a:b], np.zeros(b - a))
+        z_full = _cycle(levels, 0, rhs, np.zeros(N))
+        q.put((rank, float(np.linalg.norm(x - z_full[a:b]) / np.linalg.norm(z_full))))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_two_partitioned_levels_blueprint():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    world, port = 2, _free_port()
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_two_levels, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, err in res:
+        assert err < 1e-12, (rank, err)
