@@ -160,7 +160,7 @@ def run_reference(args):
     faithful = it1 / (time.perf_counter() - t1)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"poisson3d_{n}^3 ({N} DoF, 7-pt), Jacobi-PCG tol {TOL}", "n": N, "nnz": int(outer[-1]),
                    "note": "reference deps Eigen 5.0.1 / AMGCL 1.4.3 not installable offline; CPU numbers are from an "
