@@ -136,6 +136,10 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1 for its workers; the reference arm is the CPU path on ALL host cores (libgomp reads
+    # the variable when the oracle library is loaded, which happens below)
+    if world > 1 and os.environ.get("OMP_NUM_THREADS") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     from oracle import oracle as O
     n = args.n
     N, outer, inner, vals, b, _ = build_problem(n)
