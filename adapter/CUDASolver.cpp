@@ -34,6 +34,15 @@ namespace polysolve::linear
             psb200_destroy(impl_->h);
     }
 
+    std::string CUDASolver::map_precond(const std::string &precond)
+    {
+        if (precond == "Eigen::IdentityPreconditioner" || precond == "none")
+            return "none";
+        if (precond == "amg" || precond == "AMGCL" || precond == "AMG")
+            return "amg";
+        return "jacobi"; // "Eigen::DiagonalPreconditioner", "", unknown names
+    }
+
     void CUDASolver::set_parameters(const json &params)
     {
         // polysolve namespaces parameters by solver name (params["CUDA"]...), cf. MASSolver.cu:605-614

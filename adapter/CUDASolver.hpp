@@ -42,6 +42,13 @@ namespace polysolve::linear
 
         std::string name() const override { return "CUDA"; } // Solver.hpp:131
 
+        // Second argument of Solver::create(name, precond) (Solver.cpp:307) -> value of params["CUDA"]["precond"].
+        // The reference's names select an Eigen preconditioner class (Solver.cpp:230-305 PrecondHelper*): Diagonal ->
+        // "jacobi", Identity -> "none"; "amg" / "AMGCL" select the SA-AMG V-cycle. Anything else (including the empty
+        // string and Eigen's incomplete factorizations, which have no counterpart here) falls back to the default, as
+        // PrecondHelper::create does.
+        static std::string map_precond(const std::string &precond);
+
     public:
         // ---- beyond the Solver virtuals (optional). The reference's FEMSolver free functions
         // (FEMSolver.cpp:97-372) call these instead of their host-side triplet rebuild when `solver` is a CUDASolver

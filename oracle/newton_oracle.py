@@ -39,8 +39,6 @@ class LineSearch:
     def __init__(self, p):
         ls = p.get("line_search", {})
         self.method = ls.get("method", "RobustArmijo")
-        if self.method == "RobustArmijo":
-            self.method = "Armijo"
         self.min_step = ls.get("min_step_size", 1e-10)
         self.max_iter = ls.get("max_step_size_iter", 30)
         self.min_step_final = ls.get("min_step_size_final", 1e-20)
@@ -49,6 +47,7 @@ class LineSearch:
         self.ratio = ls.get("step_ratio", 0.5)
         self.use_grad_norm_tol = ls.get("use_grad_norm_tol", 1e-6)
         self.c = ls.get("Armijo", {}).get("c", 1e-4)
+        self.delta_rel_tol = ls.get("RobustArmijo", {}).get("delta_relative_tolerance", 0.1)  # nonlinear-solver-spec.json:683-688
         self.final = False
         self.total = 0
 
@@ -96,8 +95,14 @@ class LineSearch:
             if f.is_step_valid(x, nx):
                 e = f.value(nx)
                 if math.isfinite(e):
-                    if self.method == "Armijo":
-                        ok = e <= e0 + step * arm
+                    if self.method in ("Armijo", "RobustArmijo"):
+                        ok = e <= e0 + step * arm  # Armijo.cpp:20-32; RobustArmijo.cpp:27 tries it first
+                        if not ok and self.method == "RobustArmijo" and abs(e - e0) <= self.delta_rel_tol * abs(e0):
+                            # RobustArmijo.cpp:30-44
+                            ng = np.asarray(f.gradient(nx), float)
+                            dE = step / 2 * float(dx @ (ng + g0))
+                            eps = step / 2 * abs(float(dx @ (ng - g0)))
+                            ok = dE + eps <= step * arm
                     elif use_gn:
                         ok = np.linalg.norm(f.gradient(nx)) < gn
                     else:

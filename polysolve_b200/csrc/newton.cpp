@@ -88,8 +88,7 @@ const char *status_message(Status s)
 bool is_converged_status(Status s)
 {
     return s == Status::XDeltaTolerance || s == Status::FDeltaTolerance || s == Status::GradNormTolerance ||
-           s == Status::RelGradNormTolerance || s == Status::RelXDeltaTolerance || s == Status::NewtonDecrementTolerance ||
-           s == Status::ObjectiveCustomStop;
+           s == Status::RelGradNormTolerance || s == Status::RelXDeltaTolerance || s == Status::NewtonDecrementTolerance;
 }
 
 struct Criteria
@@ -214,6 +213,7 @@ struct LineSearch
     double min_step_size = 1e-10, min_step_size_final = 1e-20, default_init_step_size = 1, step_ratio = 0.5;
     int max_step_size_iter = 30, max_step_size_iter_final = 100;
     double use_grad_norm_tol = 1e-6, armijo_c = 1e-4;
+    double delta_relative_tolerance = 0.1; // RobustArmijo (nonlinear-solver-spec.json:683-688)
     bool is_final_strategy = false;
     int cur_iter = 0;
     long total_iterations = 0;
@@ -248,7 +248,8 @@ struct LineSearch
     double descent_step(const std::vector<double> &x, const std::vector<double> &dx, const Problem &f, bool use_grad_norm,
                         double old_energy, const std::vector<double> &old_grad, double step)
     {
-        if (method == "Armijo")
+        const bool armijo = method == "Armijo" || method == "RobustArmijo";
+        if (armijo)
             armijo_criteria = armijo_c * dot(dx, old_grad); // Armijo.cpp:13-18
         std::vector<double> nx, ng;
         for (; step > cur_min_step() && cur_iter < cur_max_iter(); step *= step_ratio, ++cur_iter)
@@ -261,8 +262,25 @@ struct LineSearch
             if (!std::isfinite(e))
                 continue;
             bool ok;
-            if (method == "Armijo")
-                ok = e <= old_energy + step * armijo_criteria;
+            if (armijo)
+            {
+                ok = e <= old_energy + step * armijo_criteria; // Armijo.cpp:20-32 (RobustArmijo tries it first)
+                if (!ok && method == "RobustArmijo" && std::fabs(e - old_energy) <= delta_relative_tolerance * std::fabs(old_energy))
+                {
+                    // RobustArmijo.cpp:30-44 (Longva et al. 2023): when the energy difference drowns in rounding error,
+                    // estimate it from the gradients at both ends (trapezoid rule) plus a bound on the estimate's error
+                    f.gradient(nx, ng);
+                    double dsum = 0, ddif = 0;
+                    for (size_t i = 0; i < dx.size(); ++i)
+                    {
+                        dsum += dx[i] * (ng[i] + old_grad[i]);
+                        ddif += dx[i] * (ng[i] - old_grad[i]);
+                    }
+                    const double deltaE_approx = step / 2 * dsum;
+                    const double abs_eps_est = step / 2 * std::fabs(ddif);
+                    ok = deltaE_approx + abs_eps_est <= step * armijo_criteria;
+                }
+            }
             else if (use_grad_norm)
             {
                 f.gradient(nx, ng);
@@ -595,9 +613,7 @@ void build(psb200_nl_solver &S, const std::string &solver_json, const std::strin
 
     const JValue lsj = jsub(j, "line_search");
     S.ls.method = jgets(lsj, "method", "RobustArmijo");
-    if (S.ls.method == "RobustArmijo")
-        S.ls.method = "Armijo"; // RobustArmijo's rounding-error guard (RobustArmijo.cpp:16-46) is not restated; plain Armijo is used
-    if (S.ls.method != "Backtracking" && S.ls.method != "Armijo" && S.ls.method != "None")
+    if (S.ls.method != "Backtracking" && S.ls.method != "Armijo" && S.ls.method != "RobustArmijo" && S.ls.method != "None")
         throw std::runtime_error("Unknown line search " + S.ls.method);
     S.ls.use_grad_norm_tol = jget(lsj, "use_grad_norm_tol", 1e-6);
     S.ls.min_step_size = jget(lsj, "min_step_size", 1e-10);
@@ -607,6 +623,7 @@ void build(psb200_nl_solver &S, const std::string &solver_json, const std::strin
     S.ls.default_init_step_size = jget(lsj, "default_init_step_size", 1);
     S.ls.step_ratio = jget(lsj, "step_ratio", 0.5);
     S.ls.armijo_c = jget(jsub(lsj, "Armijo"), "c", 1e-4);
+    S.ls.delta_relative_tolerance = jget(jsub(lsj, "RobustArmijo"), "delta_relative_tolerance", 0.1);
 
     S.solver_name = jgets(j, "solver", "Newton");
     if (S.solver_name == "Newton" || S.solver_name == "SparseNewton" || S.solver_name == "sparse_newton")

@@ -409,9 +409,12 @@ static void read_amg(const JValue &j, AmgParams &a)
     if (j.contains("dist_mode"))
     {
         a.dist_mode = j.at("dist_mode").as_str();
-        if (a.dist_mode != "global" && a.dist_mode != "local")
-            throw std::runtime_error("psb200: amg dist_mode must be global or local");
+        if (a.dist_mode != "partitioned" && a.dist_mode != "global" && a.dist_mode != "local")
+            throw std::runtime_error("psb200: amg dist_mode must be partitioned, global or local");
     }
+    num(j, "replicate_below", a.replicate_below);
+    if (a.aggregation != "mis2")
+        throw std::runtime_error("psb200: unknown amg aggregation '" + a.aggregation + "' (mis2)");
     // AMGCL-shaped sub-objects (AMGCL.cpp:32-65): relax{type,degree,power_iters,higher,lower,scale}, coarsening{relax,estimate_spectral_radius,aggr{eps_strong}}
     if (j.contains("relax") && j.at("relax").is_obj())
     {
@@ -437,6 +440,24 @@ static void read_amg(const JValue &j, AmgParams &a)
     }
     if (a.relax_type != "chebyshev" && a.relax_type != "damped_jacobi")
         throw std::runtime_error("psb200: unsupported amg relax type '" + a.relax_type + "'");
+}
+
+// names CsrDev::plan understands (validated before a parameter document is committed)
+static bool spmv_kernel_name_ok(const std::string &k)
+{
+    if (k == "auto" || k == "scalar" || k == "stream" || k == "bsr")
+        return true;
+    for (const char *pre : {"stream", "vector"})
+        if (k.rfind(pre, 0) == 0)
+        {
+            const std::string num = k.substr(6);
+            if (num.empty() || num.size() > 2 || num.find_first_not_of("0123456789") != std::string::npos)
+                return false;
+            const int v = std::stoi(num);
+            const bool pow2 = v > 0 && (v & (v - 1)) == 0;
+            return pow2 && v <= (pre[0] == 's' ? 16 : 32);
+        }
+    return false;
 }
 
 void Solver::set_parameters(const std::string &json)
@@ -478,18 +499,33 @@ void Solver::set_parameters(const std::string &json)
         np.profile = j.at("profile").as_bool();
     if (j.contains("verify_pattern"))
         np.verify_pattern = j.at("verify_pattern").as_bool();
+    if (j.contains("comm_timeout_s"))
+        np.comm_timeout_s = j.at("comm_timeout_s").as_num();
     if (j.contains("amg") && j.at("amg").is_obj())
         read_amg(j.at("amg"), np.amg);
-    if (np.krylov != "cg" && np.krylov != "bicgstab")
-        throw std::runtime_error("psb200: unknown krylov '" + np.krylov + "' (cg | bicgstab)");
+    if (np.krylov != "cg" && np.krylov != "cg1r" && np.krylov != "bicgstab")
+        throw std::runtime_error("psb200: unknown krylov '" + np.krylov + "' (cg | cg1r | bicgstab)");
+    if (np.krylov == "cg1r" && np.precond == "amg")
+        throw std::runtime_error("psb200: cg1r is the single-reduction form of Jacobi-PCG (precond jacobi | none); AMG-PCG uses krylov=cg");
+    if (!(np.comm_timeout_s >= 0))
+        throw std::runtime_error("psb200: comm_timeout_s must be >= 0");
+    if (!spmv_kernel_name_ok(np.spmv_kernel))
+        throw std::runtime_error("psb200: unknown spmv_kernel '" + np.spmv_kernel + "' (auto | stream | stream<2|4|8|16> | vector<1|2|4|8|16|32> | scalar | bsr)");
     if (np.precond != "jacobi" && np.precond != "amg" && np.precond != "none")
         throw std::runtime_error("psb200: unknown precond '" + np.precond + "' (jacobi | amg | none)");
     if (np.cg_kernel != "auto" && np.cg_kernel != "persistent" && np.cg_kernel != "split")
         throw std::runtime_error("psb200: unknown cg_kernel '" + np.cg_kernel + "' (auto | persistent | split)");
     if (np.krylov == "bicgstab" && np.precond == "amg")
         throw std::runtime_error("psb200: bicgstab + amg is not available yet");
+    // everything is validated: commit. A change of the preconditioner (or of anything the hierarchy / D^-1 was built from)
+    // invalidates the factorization: solve() then asks for a new factorize() instead of silently using the old one.
+    const bool refactor = np.precond != prm.precond || np.block_size != prm.block_size || !np.amg.same_as(prm.amg);
     prm = np;
-    // a change of schedule/preconditioner invalidates captured graphs and the factorization
+    if (refactor && factorized)
+    {
+        factorized = false;
+        amg.reset();
+    }
     if (graph_exec)
     {
         cudaGraphExecDestroy(graph_exec);
@@ -512,6 +548,10 @@ void Solver::analyze_pattern(long long n_, long long nnz_, const int *outer, con
         throw std::invalid_argument("psb200_analyze_pattern_csc: int32 index range exceeded (reference limit, BSRMatrix.cu:439-442)");
     if (n_ > 0 && (outer[0] != 0 || outer[n_] != nnz_))
         throw std::invalid_argument("psb200_analyze_pattern_csc: matrix is not compressed (outer[0] != 0 or outer[n] != nnz); call makeCompressed() first (cf. BSRMatrix.cu:444-452)");
+    // O(n) host check before any kernel indexes `inner` with these values (an out-of-range read would poison the context)
+    for (long long c = 0; c < n_; ++c)
+        if (outer[c] > outer[c + 1] || outer[c] < 0)
+            throw std::invalid_argument("psb200_analyze_pattern_csc: outer index array is not non-decreasing");
     ensure_ctx(*this);
     const double t0 = now_ms();
     precond_num = precond_num_;
@@ -661,18 +701,26 @@ void Solver::factorize(long long n_, long long nnz_, const int *outer, const int
         if (nnz_)
             PSB_CUDA(cudaMemcpyAsync(csc_vals.p, vals, sizeof(double) * nnz_, cudaMemcpyHostToDevice, ctx.stream));
     }
-    if (!need && prm.verify_pattern && outer && inner)
+    try
     {
-        // guard against a silently changed pattern (Newton re-assembles every iteration, Newton.cpp:189-191)
-        unsigned long long h = hash_words(outer, sizeof(int) * (size_t)(n_ + 1), 0x5bd1e995ull + (unsigned long long)n_);
-        h = hash_words(inner, sizeof(int) * (size_t)nnz_, h);
-        need = h != pattern_hash;
+        if (!need && prm.verify_pattern && outer && inner)
+        {
+            // guard against a silently changed pattern (Newton re-assembles every iteration, Newton.cpp:189-191)
+            unsigned long long h = hash_words(outer, sizeof(int) * (size_t)(n_ + 1), 0x5bd1e995ull + (unsigned long long)n_);
+            h = hash_words(inner, sizeof(int) * (size_t)nnz_, h);
+            need = h != pattern_hash;
+        }
+        if (need)
+        {
+            if (!outer || (!inner && nnz_ > 0))
+                throw std::invalid_argument("psb200_factorize_csc: pattern unknown and no index arrays given");
+            analyze_pattern(n_, nnz_, outer, inner, precond_num > 0 ? precond_num : (int)n_);
+        }
     }
-    if (need)
+    catch (...)
     {
-        if (!outer || (!inner && nnz_ > 0))
-            throw std::invalid_argument("psb200_factorize_csc: pattern unknown and no index arrays given");
-        analyze_pattern(n_, nnz_, outer, inner, precond_num > 0 ? precond_num : (int)n_);
+        cudaStreamSynchronize(ctx.stream); // the value copy above may still be reading the caller's buffer
+        throw;
     }
     const double t0 = now_ms();
     cudaStream_t st = ctx.stream;

@@ -29,14 +29,26 @@ struct AmgParams
     double eps_strong = 0.0;
     int block_size = 1; // AMGCL_Block<B> (reference AMGCL.cpp:246-298): B x B value type
     std::string aggregation = "mis2"; // mis2 (parallel, deterministic) | imposed via debug hook
-    // row partitions: "global" = one hierarchy of the whole matrix, level 0 partitioned, coarse levels replicated (the
-    // iteration counts of the 1-GPU run); "local" = every rank its own hierarchy of its diagonal block (block-Jacobi)
-    std::string dist_mode = "global";
+    // row partitions: "partitioned" = every level is row-partitioned (decoupled aggregation, rank-local P / R, distributed
+    // Galerkin product, per-level halo exchange) down to the levels below replicate_below rows, which are replicated;
+    // "global" = one hierarchy of the whole matrix on every rank, only level 0 partitioned (the iteration counts of the
+    // 1-GPU run, no memory partitioning); "local" = every rank its own hierarchy of its diagonal block (block-Jacobi)
+    std::string dist_mode = "partitioned";
+    // partitioned mode: levels with fewer global rows than this are replicated on every rank (their cycle needs no exchange)
+    long long replicate_below = 400000;
+    bool same_as(const AmgParams &o) const
+    {
+        return max_levels == o.max_levels && coarse_enough == o.coarse_enough && direct_coarse == o.direct_coarse && ncycle == o.ncycle &&
+               npre == o.npre && npost == o.npost && pre_cycles == o.pre_cycles && relax_type == o.relax_type && degree == o.degree &&
+               power_iters == o.power_iters && higher == o.higher && lower == o.lower && scale == o.scale && damping == o.damping &&
+               sa_relax == o.sa_relax && estimate_spectral_radius == o.estimate_spectral_radius && eps_strong == o.eps_strong &&
+               aggregation == o.aggregation && dist_mode == o.dist_mode && replicate_below == o.replicate_below;
+    }
 };
 
 struct Params
 {
-    std::string krylov = "cg";      // cg | bicgstab
+    std::string krylov = "cg";      // cg | cg1r (single-reduction CG, row partitions) | bicgstab
     std::string precond = "jacobi"; // jacobi | amg | none
     double tolerance = 1e-12;       // relative to ||b|| (Eigen / AMGCL semantics); spec default of Eigen iterative solvers
     int max_iter = 1000;
@@ -56,6 +68,7 @@ struct Params
     int block_size = 1;
     bool profile = false;
     bool verify_pattern = true;
+    double comm_timeout_s = 3.0; // row partitions: a kernel that waits longer than this for a peer fails the solve
     AmgParams amg;
 };
 

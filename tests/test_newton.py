@@ -81,6 +81,53 @@ def test_newton_oracle_converges_on_reference_problems():
             assert min(np.linalg.norm(x - s) for s in prob.solutions()) < 1e-7 or info["grad_norm"] < 1e-7
 
 
+class HugeOffset(Base):
+    """f = C + 0.5 |x - 1|^2 with C = 1e17: the energy difference of a good step drowns in the rounding error of C, so plain
+    Armijo (Armijo.cpp:20-32) rejects every step size while RobustArmijo's gradient-based estimate (RobustArmijo.cpp:30-44)
+    accepts the full Newton step."""
+    def __init__(self, n=6): self.n = n
+    def value(self, x): return 1e17 + 0.5 * float((x - 1) @ (x - 1))
+    def gradient(self, x): return x - 1
+    def hessian(self, x, psd=False): return sp.identity(self.n, format="csc")
+    def solutions(self): return [np.ones(self.n)]
+
+
+def test_robust_armijo_oracle_accepts_steps_below_rounding_error():
+    from oracle import newton_oracle as NO
+    prob = HugeOffset()
+    x0 = np.full(prob.n, 1.0 + 1e-3)
+    ra = dict(PARAMS, line_search={"method": "RobustArmijo"})
+    x, info = NO.minimize(prob, x0, ra, direct)
+    assert info["status"] == "GradNormTolerance" and np.abs(x - 1).max() < 1e-7
+    # the default line search of the reference is RobustArmijo (nonlinear-solver-spec.json:603-604)
+    assert NO.LineSearch({}).method == "RobustArmijo"
+    # plain Armijo cannot see a decrease of 3e-6 next to 1e17 when the rounding goes the wrong way: perturb so that it does
+    ls = NO.LineSearch(ra)
+    class Noisy(HugeOffset):
+        def value(self, x): return 1e17 + (16.0 if np.abs(x - x0).max() > 0 else 0.0)  # every trial point "rises" by one ulp(1e17)
+    step = ls.line_search(x0, -(x0 - 1), Noisy())
+    # full step: dE_approx + eps = -|g|^2/2 + |g|^2/2 = 0 is not a sufficient decrease; half step: (-3/8 + 1/8)|g|^2 is
+    assert step == 0.5
+    ls_plain = NO.LineSearch(dict(PARAMS, line_search={"method": "Armijo"}))
+    assert np.isnan(ls_plain.line_search(x0, -(x0 - 1), Noisy()))
+
+
+@pytest.mark.gpu
+def test_robust_armijo_driver_matches_oracle(psb):
+    """The driver's RobustArmijo takes the same branch as the restatement on the rounding-error problem."""
+    from oracle import newton_oracle as NO
+    prob = HugeOffset()
+    x0 = np.full(prob.n, 1.0 + 1e-3)
+    ra = dict(PARAMS, line_search={"method": "RobustArmijo"})
+    xo, io = NO.minimize(prob, x0, ra, direct)
+    x = x0.copy()
+    s = psb.NonlinearSolver.create(ra, _lin())
+    s.minimize(prob, x)
+    info = s.get_info()
+    assert info["succeeded"] and info["iterations"] == io["iterations"] and info["line_search"] == "RobustArmijo"
+    assert np.abs(x - xo).max() < 1e-10
+
+
 def test_nl_create_rejects_unknown_solver(psb):
     with pytest.raises(RuntimeError, match="Unrecognized solver type"):
         psb.NonlinearSolver.create({"solver": "L-BFGS-B"}, {"solver": "CUDA"})
@@ -109,7 +156,7 @@ def _lin(tol=1e-12, precond="jacobi"):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("method", ["Backtracking", "Armijo"])
+@pytest.mark.parametrize("method", ["Backtracking", "Armijo", "RobustArmijo"])
 def test_reference_problems_on_gpu(psb, method):
     """tests/test_nonlinear_solver.cpp:422-426 for the Newton chain: every start converges; indefinite Rosenbrock Hessians
     exercise the Newton -> ProjectedNewton -> RegularizedNewton fallback (Newton.cpp:156-162, Solver.cpp:375-394)."""
