@@ -12,6 +12,11 @@ step   : one complete solve(b, x) from x0 = 0 to the relative residual 1e-8.
 `e2e`   : the same metric through the public C-ABI call path with HOST buffers: every step does
           factorize_csc(host values) + solve(host b, host x), so the H2D of the matrix values and
           of b/x and the D2H of x are inside the timed region.
+N > 1   : the same ONE system, row-partitioned; the Krylov method is the single-reduction CG (krylov = cg1r: the same
+          iterates as the Eigen ordering in exact arithmetic, one all-reduce per iteration), stated in config.krylov; the
+          Eigen-ordering number of the same run is reported beside it (eigen_ordering), and a `parity` block checks the
+          N-rank path against the oracle on a small system (partition / halo lists bit-exact, x, iteration counts).
+`--config c4`: BASELINE configs[3] (119^3-node P1 elasticity, block-3 SA-AMG-PCG) as a separate line.
 `--impl reference`: the reference's CPU path (Eigen::ConjugateGradient restatement from oracle/,
           see DESIGN.md: Eigen/AMGCL are not installable offline) on the box's host cores.
 """
@@ -178,6 +183,32 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def amg_roofline(info, t_solve, hbm_peak, world=1):
+    """Algorithmic HBM bytes of one AMG-PCG solve from the actual hierarchy: per preconditioner application
+    level l is entered ncycle^l times; every entry of a non-last level runs ncycle x (pre-smooth + residual + post-smooth)
+    = ncycle x (2 degree + 1) SpMVs (the first pre-smoothing step from a zero iterate is a vector kernel), one restriction
+    and one prolongation per inner cycle; the last level runs 2 degree - 1 SpMVs. Every SpMV counts 12 nnz + 20 n bytes plus
+    32 n for the fused Chebyshev epilogue; CG itself adds one fine SpMV and 11 vector passes per iteration."""
+    amg = info["amg"]
+    lv = amg["levels"]
+    nc, deg, its = amg["ncycle"], amg["degree"], max(1, info["num_iterations"])
+    per_apply = 0.0
+    for l, L in enumerate(lv):
+        entries = nc ** l
+        n, nnz = L["rows"], L["nnz"]
+        spmv = 12.0 * nnz + 20.0 * n
+        if l + 1 < len(lv):
+            k = entries * (nc * (2 * deg + 1) - 1)
+            per_apply += k * (spmv + 32.0 * n) + entries * nc * 2 * (12.0 * L["p_nnz"] + 20.0 * n)
+        else:
+            per_apply += entries * (2 * deg - 1) * (spmv + 32.0 * n)
+    n0, nnz0 = lv[0]["rows"], lv[0]["nnz"]
+    total = (its + 1) * per_apply + its * (12.0 * nnz0 + 20.0 * n0 + 88.0 * n0)
+    gbs = total / t_solve / 1e9
+    return {"bound": "hbm", "achieved": gbs, "peak": hbm_peak * world, "unit": "GB/s", "frac": gbs / (hbm_peak * world),
+            "algorithmic_bytes_per_solve": total, "what": "sum over levels of SpMV applications x (12 nnz + 20 n + 32 n epilogue) + transfer operators + CG"}
+
+
 def amg_leg(args, psb, P, local, hbm_peak):
     """Config 3 of BASELINE.json (SA-AMG-PCG, polysolve's AMGCL defaults) next to the CPU restatement
     (oracle/, OpenMP, all host cores) on the SAME full-size system: setup and solve timed separately.
@@ -209,7 +240,9 @@ def amg_leg(args, psb, P, local, hbm_peak):
         t_solve = min(solves)
         info = s.get_info()
         rel = float(np.linalg.norm(P.spmv_csr(outer, inner, vals, x) - b) / np.linalg.norm(b))
+        rf = amg_roofline(info, t_solve, hbm_peak)
         out[tag] = {"n": N, "gpu_setup_s": t_setup, "gpu_solve_s": t_solve, "gpu_setup_s_all": setups, "gpu_solve_s_all": solves, "gpu_iters": info["num_iterations"], "rel_residual": rel,
+                    "roofline": rf,
                     "levels": [lv["rows"] for lv in info["amg"]["levels"]], "operator_complexity": info["amg"]["operator_complexity"],
                     "gpu_setup_ms_by_level": [lv.get("setup_ms") for lv in info["amg"]["levels"]]}
         del s
@@ -228,13 +261,16 @@ def amg_leg(args, psb, P, local, hbm_peak):
     return out
 
 
-def amg_dist_leg(args, psb, P, local, world, N, outer, inner, vals, b, barrier):
-    """Config 3 on the row partition: rank-local SA-AMG (AMGCL defaults) inside the global CG, halo push + fused
-    all-reduce over NVLink. Wall clock between barriers, max over ranks (every rank times the same collective call)."""
+def amg_dist_leg(args, psb, P, local, world, N, outer, inner, vals, b, barrier, hbm_peak):
+    """Config 3 on the row partition: SA-AMG-PCG with the PARTITIONED hierarchy (decoupled aggregation, rank-local P / R,
+    distributed Galerkin product, per-level halo plans, small levels replicated). Wall clock between barriers, max over
+    ranks (every rank times the same collective call)."""
     import torch
     import torch.distributed as dist
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
     s = psb.Solver.create("CUDA", "")
-    s.set_parameters({"CUDA": {"precond": "amg", "tolerance": TOL, "max_iter": 1000, "device": local}})
+    s.set_parameters({"CUDA": {"precond": "amg", "tolerance": TOL, "max_iter": 1000, "device": local, "amg": {"dist_mode": args.amg_dist_mode}}})
     s.dist_setup_torch(halo_cap=1 << 20)
     s.analyze_pattern_raw(N, outer, inner, N)
     s.factorize_raw(N, outer, inner, vals)
@@ -256,19 +292,115 @@ def amg_dist_leg(args, psb, P, local, world, N, outer, inner, vals, b, barrier):
         barrier()
         solves.append(time.perf_counter() - t0)
     info = s.get_info()
+    torch.cuda.synchronize()
+    used = free0 - torch.cuda.mem_get_info()[0]
     r0, r1 = s.dist_local_range()
     xt = torch.zeros(N, dtype=torch.float64, device="cuda")
     xt[r0:r1] = torch.from_numpy(x[r0:r1]).cuda()
     dist.all_reduce(xt, op=dist.ReduceOp.SUM)
-    t = torch.tensor([min(setups), min(solves)], dtype=torch.float64, device="cuda")
+    t = torch.tensor([min(setups), min(solves), float(used)], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     xf = xt.cpu().numpy()
     rel = float(np.linalg.norm(P.spmv_csr(outer, inner, vals, xf) - b) / np.linalg.norm(b))
+    amg = info["amg"]
     return {"n": N, "n_gpus": world, "gpu_setup_s": float(t[0]), "gpu_solve_s": float(t[1]), "gpu_iters": info["num_iterations"],
-            "rel_residual": rel, "levels_rank0": [lv["rows"] for lv in info["amg"]["levels"]],
-            "dist_mode": info.get("amg_dist_mode"),
-            "what": "SA-AMG-PCG on the row partition: hierarchy of the whole matrix, level 0 of the cycle partitioned (halo pushes, "
-                    "restriction summed over NVLink), coarse levels replicated"}
+            "rel_residual": rel, "levels": [lv["rows"] for lv in amg["levels"]], "operator_complexity": amg["operator_complexity"],
+            "partitioned_levels": amg.get("partitioned_levels"), "replicated_levels": amg.get("replicated_levels"),
+            "dist_mode": info.get("amg_dist_mode"), "device_bytes_per_rank_max": int(t[2]),
+            "fine_matrix_bytes_total": 12 * int(outer[-1]) + 4 * N,
+            "roofline": amg_roofline(info, float(t[1]), hbm_peak, world),
+            "what": "SA-AMG-PCG on the row partition: every level above amg.replicate_below rows partitioned (decoupled aggregation, "
+                    "rank-local P/R, distributed Galerkin product, per-level halo pushes over NVLink), small levels replicated; "
+                    "device_bytes_per_rank_max = device memory this leg allocated on the fullest rank (comm buffer 268 MB included)"}
+
+
+def parity_block(psb, P, local, world, rank, barrier):
+    """N-rank path against the oracle (the checker) on a 40^3 Poisson system, printed with the bench line because the
+    driver's pytest box has one GPU: partition offsets / halo lists / value map bit-exact against the oracle's index
+    functions, x and the iteration count of the Eigen-ordering PCG, the single-reduction CG, and the AMG-PCG iteration
+    count of the partitioned hierarchy next to the 1-GPU hierarchy's."""
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as O
+    n, tol = 40, 1e-8
+    N = n ** 3
+    o, i, v = P.poisson3d(n)
+    b = P.spmv_csr(o, i, v, P.splitmix64(42, N))
+    out = {"n": N, "tol": tol}
+    rp, ci, perm = O.csc_to_csr(N, o, i)
+    off0 = O.partition_rows(rp, world)
+    plan = psb.Solver.dist_plan_host(N, o, i, rank, world, 1 << 16)
+    a, e = int(off0[rank]), int(off0[rank + 1])
+    lc0, halo0 = O.halo_for_rank(rp, ci, a, e)
+    ok = (np.array_equal(plan["offsets"], off0) and np.array_equal(plan["halo_cols"], halo0)
+          and np.array_equal(plan["perm"], perm[rp[a]:rp[e]]) and np.array_equal(plan["rp"], rp[a:e + 1] - rp[a]))
+    x0, it0, _, _ = O.eigen_cg(o, i, v, b, tol=tol, max_iters=10000)
+
+    def solve(prm):
+        s = psb.Solver.create("CUDA", "")
+        s.set_parameters({"CUDA": dict({"tolerance": tol, "max_iter": 10000, "device": local}, **prm)})
+        s.dist_setup_torch(halo_cap=1 << 16)
+        s.analyze_pattern_raw(N, o, i, N)
+        s.factorize_raw(N, o, i, v)
+        x = np.zeros(N)
+        s.solve(b, x)
+        info = s.get_info()
+        r0, r1 = s.dist_local_range()
+        xt = torch.zeros(N, dtype=torch.float64, device="cuda")
+        xt[r0:r1] = torch.from_numpy(x[r0:r1]).cuda()
+        dist.all_reduce(xt, op=dist.ReduceOp.SUM)
+        return xt.cpu().numpy(), info
+
+    x, info = solve({"krylov": "cg"})
+    out["pcg_iters"], out["oracle_iters"] = info["solver_iter"], it0
+    out["pcg_x_rel_diff_vs_oracle"] = float(np.linalg.norm(x - x0) / np.linalg.norm(x0))
+    x, info = solve({"krylov": "cg1r"})
+    out["cg1r_iters"] = info["solver_iter"]
+    out["cg1r_x_rel_diff_vs_oracle"] = float(np.linalg.norm(x - x0) / np.linalg.norm(x0))
+    x, info = solve({"precond": "amg", "max_iter": 200, "amg": {"replicate_below": 3000}})
+    out["amg_partitioned_iters"] = info["solver_iter"]
+    out["amg_partitioned_levels"] = [lv["rows"] for lv in info["amg"]["levels"]]
+    out["amg_rel_residual"] = float(np.linalg.norm(P.spmv_csr(o, i, v, x) - b) / np.linalg.norm(b))
+    s1 = psb.Solver.create("CUDA", "")
+    s1.set_parameters({"CUDA": {"tolerance": tol, "max_iter": 200, "device": local, "precond": "amg"}})
+    s1.factorize_raw(N, o, i, v)
+    x1 = np.zeros(N)
+    s1.solve(b, x1)
+    out["amg_one_gpu_iters"] = s1.get_info()["solver_iter"]
+    del s1
+    flag = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out["plan_bit_exact_all_ranks"] = bool(flag[0] == 1.0)
+    out["ok"] = bool(out["plan_bit_exact_all_ranks"] and abs(out["pcg_iters"] - it0) <= max(1, 0.02 * it0)
+                     and abs(out["cg1r_iters"] - it0) <= max(1, 0.02 * it0) and out["pcg_x_rel_diff_vs_oracle"] < 10 * tol
+                     and out["cg1r_x_rel_diff_vs_oracle"] < 10 * tol and out["amg_partitioned_iters"] <= out["amg_one_gpu_iters"] + 1
+                     and out["amg_rel_residual"] < 2 * tol)
+    return out
+
+
+def cusparse_leg(args, N, outer, inner, vals):
+    """the reference's own GPU building blocks on the same box -- cusparseSpMV (CSR, fp64, ALG_DEFAULT,
+    MASSolver.cu:245-290) and one unfused MAS-style PCG iteration (MASSolver.cu:469-595). Measurement only: the library
+    libpsb200_cmp.so is separate from the product."""
+    import ctypes as C
+    from polysolve_b200 import problems as P
+    path = os.path.join(ROOT, "polysolve_b200", "csrc", "libpsb200_cmp.so")
+    L = C.CDLL(path)
+    i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+    f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+    L.psb200_cmp_run.argtypes = [C.c_int64, C.c_int64, i32p, i32p, f64p, C.c_int, C.c_int, f64p]
+    L.psb200_cmp_last_error.restype = C.c_char_p
+    out = np.zeros(4)
+    nnz = int(outer[-1])
+    rc = L.psb200_cmp_run(N, nnz, outer, inner, vals, 50, 50, out)  # symmetric matrix: the CSC arrays are the CSR arrays
+    if rc:
+        return {"error": L.psb200_cmp_last_error().decode()}
+    b_spmv = P.spmv_bytes(N, nnz)
+    return {"cusparse_spmv_ms": out[0], "cusparse_spmv_gbs": b_spmv / (out[0] * 1e-3) / 1e9,
+            "unfused_iter_ms": out[1], "unfused_iter_per_s": 1e3 / out[1], "cusparse_workspace_bytes": int(out[2]),
+            "checksum_sum_A1": out[3],
+            "what": "cusparseSpMV CSR fp64 ALG_DEFAULT, 50 reps; MAS-style unfused PCG iteration (cusparseSpMV + 2 atomic dots + "
+                    "3 axpby + diagonal apply + 2 scalar kernels), 50 iterations, same matrix, same GPU"}
 
 
 def run_ours(args):
@@ -296,9 +428,10 @@ def run_ours(args):
     nnz = int(outer[-1])
     hbm_peak, peak_src = peaks()
 
+    krylov = args.krylov if args.krylov != "auto" else ("cg1r" if world > 1 else "cg")
     s = psb.Solver.create("CUDA", "")
-    s.set_parameters({"CUDA": {"krylov": "cg", "precond": "jacobi", "tolerance": TOL, "max_iter": MAX_ITER,
-                               "check_every": args.check_every, "device": local, "cg_kernel": args.cg_kernel, "interior_first": args.interior_first}})
+    s.set_parameters({"CUDA": {"krylov": krylov, "precond": "jacobi", "tolerance": TOL, "max_iter": MAX_ITER,
+                               "check_every": args.check_every, "device": local, "interior_first": args.interior_first}})
     if world > 1:
         s.dist_setup_torch(halo_cap=1 << 20)
     t0 = time.perf_counter()
@@ -366,6 +499,23 @@ def run_ours(args):
     barrier()
     e2e_dt = time.perf_counter() - t0
 
+    # ---- the other Krylov ordering in the same run (N > 1: Eigen ordering next to the single-reduction headline)
+    other = None
+    if world > 1:
+        other_k = "cg" if krylov == "cg1r" else "cg1r"
+        s.set_parameters({"CUDA": {"krylov": other_k}})
+        device_step()
+        barrier()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record(stream)
+        oit = 0
+        for _ in range(2):
+            oit += device_step()
+        o1.record(stream)
+        barrier()
+        other = (other_k, oit, o0.elapsed_time(o1))
+        s.set_parameters({"CUDA": {"krylov": krylov}})
+
     # ---- roofline of the dominant kernel (fused SpMV + p.Ap), measured live: one extra solve with CUDA
     #      events around every launch on the solver's stream (graphs off), after the timed region.
     s.set_parameters({"CUDA": {"profile": True}})
@@ -379,9 +529,10 @@ def run_ours(args):
     x[r0:r1] = xl
     if world > 1:
         import torch.distributed as dist
-        t = torch.tensor([ms, e2e_dt], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, e2e_dt, other[2]], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_dt = float(t[0]), float(t[1])
+        other = (other[0], other[1], float(t[2]))
         c = torch.tensor([launches], dtype=torch.float64, device="cuda")
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         launches = int(c[0])
@@ -389,15 +540,20 @@ def run_ours(args):
         dist.all_reduce(xt, op=dist.ReduceOp.SUM)
         x = xt.cpu().numpy()
     amg_dist = None
-    # The partitioned AMG cycle was validated on 2 and 4 GPUs this round (profiles/r01d_bench_n{2,4}.json); at 8 ranks it
-    # runs only on request, so that an unvalidated secondary leg can never cost the headline line of the scaling run.
-    if world > 1 and not args.no_amg and (world <= 4 or args.amg_dist):
-        # a failure of this secondary leg must not cost the headline line; every rank catches on its own and keeps
-        # walking through the same barriers
+    parity = None
+    if world > 1:
+        # secondary legs: a failure must not cost the headline line; every rank catches on its own and keeps walking
+        # through the same barriers
+        del s
         try:
-            amg_dist = amg_dist_leg(args, psb, P, local, world, N, outer, inner, vals, b, barrier)
+            parity = parity_block(psb, P, local, world, rank, barrier)
         except Exception as e:  # noqa: BLE001
-            amg_dist = {"error": str(e)[:300]}
+            parity = {"ok": False, "error": str(e)[:300]}
+        if not args.no_amg:
+            try:
+                amg_dist = amg_dist_leg(args, psb, P, local, world, N, outer, inner, vals, b, barrier, hbm_peak)
+            except Exception as e:  # noqa: BLE001
+                amg_dist = {"error": str(e)[:300]}
     if rank != 0:
         return
     rel_res = float(np.linalg.norm(P.spmv_csr(outer, inner, vals, x) - b) / np.linalg.norm(b))
@@ -405,7 +561,7 @@ def run_ours(args):
     e2e_value = e2e_iters / e2e_dt
 
     total_prof_ms = sum(v["ms"] for v in prof.values()) or 1.0
-    k = prof.get("spmv_dot", {"ms": 0.0, "launches": 1})
+    k = prof.get("spmv_cg1r" if krylov == "cg1r" else "spmv_dot", {"ms": 0.0, "launches": 1})
     spmv_ms = k["ms"] / max(1, k["launches"])
     # per-launch algorithmic bytes of THIS rank's kernel (rank 0's row range)
     lnnz = info.get("dist", {}).get("local_nnz", nnz)
@@ -437,6 +593,12 @@ def run_ours(args):
         cpu = {"value": cpu_val, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{args.ref_iters} CG iterations on the full {N}-DoF system, OpenMP row-parallel CSR (oracle/)",
                "eigen_faithful_1thread": faithful}
+    cusp = None
+    if world == 1 and not args.no_cusparse:
+        try:
+            cusp = cusparse_leg(args, N, outer, inner, vals)
+        except Exception as e:  # noqa: BLE001
+            cusp = {"error": str(e)[:300]}
     if world == 1 and not args.no_amg:
         del s
         amg = amg_leg(args, psb, P, local, hbm_peak)
@@ -451,14 +613,16 @@ def run_ours(args):
                    "l2_policy": "inputs_exceed_l2 (0.88 GB matrix + 0.4 GB vectors per iteration vs 126 MB L2)"
                    if world <= 2 else "per-GPU working set approaches L2 size at this rank count; no flush (strong scaling of the fixed system)",
                    "iters_per_solve": iters / args.steps, "rel_residual": rel_res,
-                   "spmv_kernel": info["spmv_kernel"], "cg_kernel": info.get("cg_kernel"), "check_every": args.check_every,
-                   "persist_phase_us_per_iter": [round(c / 1.965e3 / max(1, info["solver_iter"]), 2) for c in info.get("persist_cycles", [])],
+                   "krylov": krylov + (" (single-reduction CG: one all-reduce + two kernels per iteration; same iterates as the Eigen "
+                                       "ordering in exact arithmetic)" if krylov == "cg1r" else " (Eigen::ConjugateGradient ordering)"),
+                   "spmv_kernel": info["spmv_kernel"], "check_every": args.check_every,
                    "analyze_s": t_analyze, "factorize_s": t_factorize},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (8 * nnz + 16 * N) // world, "d2h_bytes_per_step": 8 * N // world,
                 "what": "factorize_csc(host values) + solve(host b, x) per step, pinned host buffers; bytes are per rank"},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "spmv_stream_kernel<EpiDot> (fused SpMV + p.Ap)", "achieved": achieved,
+        "roofline": {"bound": "hbm", "kernel": "spmv_stream_kernel<EpiCg1r> (fused SpMV + 3 dots + all-reduce)" if krylov == "cg1r"
+                     else "spmv_stream_kernel<EpiDot> (fused SpMV + p.Ap)", "achieved": achieved,
                      "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": b_spmv, "avg_launch_ms": spmv_ms,
                      "kernel_share_of_step": k["ms"] / total_prof_ms,
@@ -473,6 +637,100 @@ def run_ours(args):
         line["amg_pcg"] = amg
     if amg_dist:
         line["amg_pcg_dist"] = amg_dist
+    if parity:
+        line["parity"] = parity
+    if other:
+        line["other_krylov"] = {"krylov": other[0], "value": other[1] / (other[2] * 1e-3), "unit": UNIT, "iters_per_solve": other[1] / 2}
+    if cusp:
+        line["cusparse"] = cusp
+        if "cusparse_spmv_gbs" in cusp:
+            line["cusparse"]["ours_vs_cusparse_spmv"] = achieved / cusp["cusparse_spmv_gbs"] if cusp["cusparse_spmv_gbs"] else None
+            line["cusparse"]["ours_vs_unfused_iteration"] = value / cusp["unfused_iter_per_s"]
+    print(json.dumps(line), flush=True)
+
+
+def run_c4(args):
+    """BASELINE configs[3]: P1-tet linear elasticity on m^3 nodes (m = 119: 5,055,477 DoF, 224 M scalar non-zeros),
+    block-3 SA-AMG-PCG (AMGCL_Block<3> semantics, AMGCL.cpp:246-298), rows split over the ranks, tol 1e-8. One JSON line:
+    value = setup + solve wall clock (max over ranks), with the hierarchy, the iteration count and the residual
+    recomputed on the host."""
+    import torch
+    import polysolve_b200 as psb
+    from polysolve_b200 import problems as P
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hbm_peak, _ = peaks()
+    m = args.c4_nodes
+    t0 = time.perf_counter()
+    outer, inner, vals, b = P.elasticity3d(m)
+    t_build = time.perf_counter() - t0
+    N = 3 * m ** 3
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    s = psb.Solver.create("CUDA", "")
+    s.set_parameters({"CUDA": {"precond": "amg", "block_size": 3, "tolerance": TOL, "max_iter": 1000, "device": local,
+                               "amg": {"dist_mode": args.amg_dist_mode}}})
+    if world > 1:
+        s.dist_setup_torch(halo_cap=1 << 21)
+    t0 = time.perf_counter()
+    s.analyze_pattern_raw(N, outer, inner, N)
+    t_analyze = time.perf_counter() - t0
+    s.factorize_raw(N, outer, inner, vals)
+    setups, solves = [], []
+    for _ in range(max(1, args.steps // 3)):
+        barrier()
+        t0 = time.perf_counter()
+        s.factorize_raw(N, outer, inner, vals)
+        barrier()
+        setups.append(time.perf_counter() - t0)
+    hb, hx = pinned_copy(b), pinned_copy(np.zeros(N))
+    x = hx.numpy()
+    s.solve(hb.numpy(), x)
+    for _ in range(max(2, args.steps // 2)):
+        x[:] = 0
+        barrier()
+        t0 = time.perf_counter()
+        s.solve(hb.numpy(), x)
+        barrier()
+        solves.append(time.perf_counter() - t0)
+    info = s.get_info()
+    torch.cuda.synchronize()
+    used = free0 - torch.cuda.mem_get_info()[0]
+    r0, r1 = s.dist_local_range() if world > 1 else (0, N)
+    t = torch.tensor([min(setups), min(solves), float(used)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        xt = torch.zeros(N, dtype=torch.float64, device="cuda")
+        xt[r0:r1] = torch.from_numpy(x[r0:r1]).cuda()
+        dist.all_reduce(xt, op=dist.ReduceOp.SUM)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        x = xt.cpu().numpy()
+    if rank != 0:
+        return
+    rel = float(np.linalg.norm(P.spmv_csr(outer, inner, vals, x) - b) / np.linalg.norm(b))
+    amg = info["amg"]
+    nnz = int(outer[-1])
+    line = {"metric": "amg_pcg_setup_plus_solve_s", "value": float(t[0] + t[1]), "unit": "s", "n_gpus": world, "steps": len(solves), "warmup": 1,
+            "ms_per_step": 1e3 * float(t[1]), "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"elasticity3d_{m}^3 nodes ({N} DoF, P1 tets, E=1 nu=0.3, x=0 clamped), block-3 SA-AMG-PCG (AMGCL defaults) tol {TOL}",
+                       "n": N, "nnz": nnz, "nnz_blocks": nnz // 9, "dist_mode": info.get("amg_dist_mode"), "host_build_s": t_build, "analyze_s": t_analyze},
+            "setup_s": float(t[0]), "solve_s": float(t[1]), "setup_s_all": setups, "solve_s_all": solves,
+            "iters": info["num_iterations"], "rel_residual": rel, "levels": [lv["rows"] for lv in amg["levels"]],
+            "level_nnz": [lv["nnz"] for lv in amg["levels"]], "operator_complexity": amg["operator_complexity"],
+            "partitioned_levels": amg.get("partitioned_levels"), "replicated_levels": amg.get("replicated_levels"),
+            "device_bytes_per_rank_max": int(t[2]), "fine_matrix_csr_bytes_total": 12 * nnz + 4 * N,
+            "spmv_kernel": info["spmv_kernel"], "roofline": amg_roofline(info, float(t[1]), hbm_peak, world),
+            "gpu_launches": info["gpu_launches"]}
     print(json.dumps(line), flush=True)
 
 
@@ -485,15 +743,20 @@ def main():
     ap.add_argument("--n", type=int, default=216, help="grid points per side (216 -> 10,077,696 DoF)")
     ap.add_argument("--check-every", type=int, default=16)
     ap.add_argument("--ref-iters", type=int, default=40, help="CG iterations per CPU sample step")
-    ap.add_argument("--cg-kernel", default="auto", choices=["auto", "persistent", "split"])
+    ap.add_argument("--krylov", default="auto", choices=["auto", "cg", "cg1r"], help="auto: cg on one GPU (Eigen ordering), cg1r on a row partition")
+    ap.add_argument("--no-cusparse", action="store_true", help="skip the cuSPARSE / MAS-style comparator (N = 1)")
+    ap.add_argument("--amg-dist-mode", default="partitioned", choices=["partitioned", "global", "local"])
+    ap.add_argument("--config", default="c2", choices=["c2", "c4"], help="c2: the headline (10M-DoF Poisson Jacobi-PCG + the C3 AMG legs); c4: 119^3-node elasticity, block-3 AMG-PCG")
+    ap.add_argument("--c4-nodes", type=int, default=119)
     ap.add_argument("--interior-first", action="store_true", help="row partitions: SpMV tiles without halo columns first, late halo wait")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-amg", action="store_true", help="skip the AMG-PCG (config 3) leg")
-    ap.add_argument("--amg-dist", action="store_true", help="run the multi-GPU AMG-PCG leg at any rank count (default: up to 4 ranks)")
     ap.add_argument("--amg-cpu-n", type=int, default=0, help="grid side of the CPU AMG leg (0 = the full --n system)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "c4":
+        run_c4(args)
     else:
         run_ours(args)
 

@@ -113,11 +113,19 @@ int psb200_dirichlet_solve_prefactorized(psb200_handle h, const double *vals_or_
  *   3. every rank: psb200_dist_connect(all handles)
  * Afterwards analyze_pattern / factorize still receive the FULL CSC matrix on every rank (each rank
  * keeps its rows), psb200_solve receives full-length b / x (each rank reads and writes only its own
- * rows [row_begin, row_end)), psb200_solve_device receives the local slices. Every call is collective. krylov = cg with precond = jacobi | none |
- * amg (scalar problems: one hierarchy of the whole matrix, fine level partitioned, "amg": {"dist_mode": "global"};
- * block problems and "dist_mode": "local": a rank-local hierarchy per GPU). */
+ * rows [row_begin, row_end)), psb200_solve_device receives the local slices. Every call is collective.
+ * krylov = cg | cg1r (single-reduction CG: one all-reduce per iteration) with precond = jacobi | none, krylov = cg with
+ * precond = amg. "amg": {"dist_mode": ...}: "partitioned" (default) = every level above amg.replicate_below rows is
+ * row-partitioned like the fine matrix (decoupled aggregation, rank-local P / R, distributed Galerkin product, per-level
+ * halo exchange; scalar and block problems; device memory per rank ~ 1 / world), smaller levels are replicated;
+ * "global" = one hierarchy of the whole matrix on every rank, fine level partitioned (scalar problems); "local" = a
+ * rank-local hierarchy per GPU (block-Jacobi across ranks).
+ * A wait for a peer that exceeds "comm_timeout_s" fails the call with PSB200_ERR_COMM and leaves the handle unusable
+ * (every later call returns PSB200_ERR_COMM) until the application has synchronised the ranks on the host, every rank has
+ * called psb200_dist_reset, and the ranks have synchronised again. */
 int psb200_dist_prepare(psb200_handle h, int rank, int world, int64_t halo_cap_doubles, char handle_out[64]);
 int psb200_dist_connect(psb200_handle h, const char *handles /* world * 64 bytes */);
+int psb200_dist_reset(psb200_handle h);
 int psb200_dist_local_range(psb200_handle h, int64_t *row_begin, int64_t *row_end);
 /* Host-only plan of one rank (no GPU needed; used by the CPU tests to check partition offsets and halo
  * lists bit-exactly against the oracle). Caller-allocated arrays: offsets[world+1], counts[3] =

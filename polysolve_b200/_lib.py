@@ -21,7 +21,7 @@ SYMBOLS = [
     "psb200_create", "psb200_destroy", "psb200_set_parameters", "psb200_set_tolerance", "psb200_set_block_size",
     "psb200_analyze_pattern_csc", "psb200_factorize_csc", "psb200_solve", "psb200_solve_device", "psb200_get_info",
     "psb200_name", "psb200_last_error", "psb200_release_cached_memory", "psb200_factorize_csc_device", "psb200_residual_norm_device",
-    "psb200_dirichlet_solve", "psb200_dirichlet_prefactorize", "psb200_dirichlet_solve_prefactorized", "psb200_dist_prepare", "psb200_dist_connect", "psb200_dist_local_range",
+    "psb200_dirichlet_solve", "psb200_dirichlet_prefactorize", "psb200_dirichlet_solve_prefactorized", "psb200_dist_prepare", "psb200_dist_connect", "psb200_dist_reset", "psb200_dist_local_range",
     "psb200_dist_plan_host", "psb200_dist_plan_host_aligned", "psb200_debug_get_csr",
     "psb200_spmv", "psb200_bench_spmv", "psb200_get_stream", "psb200_debug_set_aggregates", "psb200_debug_get_level",
     "psb200_precond_apply", "psb200_debug_get_aggregates",
@@ -88,6 +88,7 @@ def lib():
     L.psb200_last_error.restype = C.c_char_p
     L.psb200_dist_prepare.argtypes = [H, C.c_int, C.c_int, C.c_int64, C.c_char_p]
     L.psb200_dist_connect.argtypes = [H, C.c_char_p]
+    L.psb200_dist_reset.argtypes = [H]
     L.psb200_dist_local_range.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
     L.psb200_dist_plan_host.argtypes = [C.c_int64, C.c_int64, i32p, i32p, C.c_int, C.c_int, C.c_int64, i64p, i64p,

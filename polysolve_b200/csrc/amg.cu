@@ -8,6 +8,7 @@
 // difference: AMGCL's aggregation is a sequential greedy sweep; here it is a deterministic parallel
 // MIS-2 (aggregates can also be imposed through psb200_debug_set_aggregates for parity tests).
 #include "amg.hpp"
+#include "amg_internal.hpp"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -70,12 +71,12 @@ __global__ void gershgorin_kernel(CsrView A, unsigned long long *out)
         atomicMax(out, (unsigned long long)__double_as_longlong(s));
 }
 // counter-based splitmix64 -> U(-1,1): element i of the stream seeded with `seed`
-__global__ void splitmix_kernel(long long n, unsigned long long seed, double *out)
+__global__ void splitmix_kernel(long long n, unsigned long long seed, long long offset, double *out)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
-    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(offset + i + 1);
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     z ^= z >> 31;
@@ -542,26 +543,6 @@ __global__ void spgemm_count_kernel(CsrView A, const int *__restrict__ b_rp, lon
     }
     cnt[i] = c;
 }
-// 8 lanes per row walk the row's products; every product gets a slot in generation order
-__global__ void spgemm_expand_kernel(CsrView A, CsrView B, const long long *__restrict__ off, unsigned long long *__restrict__ keys,
-                                     double *__restrict__ vals)
-{
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A.n)
-        return;
-    long long o = off[i];
-    for (int k = A.rp[i]; k < A.rp[i + 1]; ++k)
-    {
-        const int a = A.ci[k];
-        const double va = A.va[k];
-        for (int q = B.rp[a]; q < B.rp[a + 1]; ++q)
-        {
-            keys[o] = ((unsigned long long)(unsigned)i << 32) | (unsigned)B.ci[q];
-            vals[o] = va * B.va[q];
-            ++o;
-        }
-    }
-}
 __global__ void head_flags_kernel(long long n, const unsigned long long *__restrict__ keys, int *__restrict__ flag)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -632,15 +613,7 @@ struct OpDiagFirst
     }
 };
 
-struct Temp
-{
-    DevBuf<unsigned char> buf;
-    void *get(size_t bytes)
-    {
-        buf.alloc(bytes, false, 256);
-        return buf.p;
-    }
-};
+} // namespace
 
 void exclusive_scan_int(Ctx &c, Temp &tmp, const int *in, int *out, long long n)
 {
@@ -655,14 +628,6 @@ void exclusive_scan_ll(Ctx &c, Temp &tmp, const long long *in, long long *out, l
     PSB_CUDA(cub::DeviceScan::ExclusiveSum(tmp.get(bytes), bytes, in, out, n, c.stream));
 }
 
-template <typename T>
-T d2h(Ctx &c, const T *p)
-{
-    T v;
-    PSB_CUDA(cudaMemcpyAsync(&v, p, sizeof(T), cudaMemcpyDeviceToHost, c.stream));
-    PSB_CUDA(cudaStreamSynchronize(c.stream));
-    return v;
-}
 
 // T = M^T for a CSR matrix with ncols columns. Stable sort by column keeps the fine-row order inside
 // every row of the transpose (the same idiom as the CSC -> CSR ingest).
@@ -698,19 +663,58 @@ void transpose(Ctx &c, Temp &tmp, const CsrDev &M, CsrDev &T)
     PSB_CUDA(cudaStreamSynchronize(c.stream));
 }
 
-// C = A * B (B has ncolsB columns). Expand all products, stable radix sort by (row, col), sum runs.
+// first row r >= from whose product offset reaches `limit` (host-side chunking of the expansion)
+__global__ void chunk_end_kernel(int n, const long long *__restrict__ off, int from, long long limit, int *out)
+{
+    if (blockIdx.x || threadIdx.x)
+        return;
+    int lo = from + 1, hi = n; // the chunk always takes at least one row
+    while (lo < hi)
+    {
+        const int mid = (lo + hi + 1) >> 1;
+        if (off[mid] - off[from] <= limit)
+            lo = mid;
+        else
+            hi = mid - 1;
+    }
+    *out = lo;
+}
+__global__ void spgemm_expand_rows_kernel(CsrView A, CsrView B, const long long *__restrict__ off, int r0, int r1, unsigned long long *__restrict__ keys,
+                                          double *__restrict__ vals)
+{
+    const long long i = (long long)r0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r1)
+        return;
+    long long o = off[i] - off[r0];
+    for (int k = A.rp[i]; k < A.rp[i + 1]; ++k)
+    {
+        const int a = A.ci[k];
+        const double va = A.va[k];
+        for (int q = B.rp[a]; q < B.rp[a + 1]; ++q)
+        {
+            keys[o] = ((unsigned long long)(unsigned)i << 32) | (unsigned)B.ci[q];
+            vals[o] = va * B.va[q];
+            ++o;
+        }
+    }
+}
+
+// C = A * B (B has ncolsB columns). Expand all products, stable radix sort by (row, col), sum runs (deterministic: the
+// products of an entry are added in generation order). Rows are processed in chunks of at most 2^29 products, so the
+// temporaries stay bounded (C4: 5.4e9 products of A P on one GPU) whatever the size of the product.
 void spgemm(Ctx &c, Temp &tmp, const CsrDev &A, const CsrDev &B, int ncolsB, CsrDev &C)
 {
     cudaStream_t st = c.stream;
     C.n = A.n;
     C.ncols = ncolsB;
+    C.rp.alloc((size_t)C.n + 1);
     DevBuf<long long> cnt, off;
     cnt.alloc((size_t)A.n + 1, true);
     off.alloc((size_t)A.n + 1);
-    spgemm_count_kernel<<<nblk(A.n), 256, 0, st>>>(A.view(), B.rp.p, cnt.p);
+    if (A.n)
+        spgemm_count_kernel<<<nblk(A.n), 256, 0, st>>>(A.view(), B.rp.p, cnt.p);
     exclusive_scan_ll(c, tmp, cnt.p, off.p, (long long)A.n + 1);
     const long long T = d2h(c, off.p + A.n);
-    C.rp.alloc((size_t)C.n + 1);
     if (T == 0)
     {
         C.nnz = 0;
@@ -719,66 +723,97 @@ void spgemm(Ctx &c, Temp &tmp, const CsrDev &A, const CsrDev &B, int ncolsB, Csr
         PSB_CUDA(cudaMemsetAsync(C.rp.p, 0, sizeof(int) * ((size_t)C.n + 1), st));
         return;
     }
-    if (T > 0x7fffffffLL)
-        throw std::runtime_error("psb200 amg: Galerkin product exceeds 2^31 intermediate products on one GPU");
-    DevBuf<unsigned long long> keys, keys2;
-    DevBuf<double> vals, vals2;
-    keys.alloc(T);
-    keys2.alloc(T);
-    vals.alloc(T);
-    vals2.alloc(T);
-    spgemm_expand_kernel<<<nblk(A.n), 256, 0, st>>>(A.view(), B.view(), off.p, keys.p, vals.p);
-    check_launch();
-    int rbits = 1, cbits = 1;
+    constexpr long long kChunk = 1ll << 29;
+    int rbits = 1;
     while ((1ll << rbits) < A.n && rbits < 31)
         ++rbits;
-    while ((1ll << cbits) < ncolsB && cbits < 32)
-        ++cbits;
-    (void)cbits;
-    size_t bytes = 0;
-    PSB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys2.p, vals.p, vals2.p, (int)T, 0, 32 + rbits, st));
-    PSB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.get(bytes), bytes, keys.p, keys2.p, vals.p, vals2.p, (int)T, 0, 32 + rbits, st));
-    keys.release();
-    vals.release();
-    DevBuf<int> flag, pos, crow;
-    flag.alloc((size_t)T + 1, true);
-    pos.alloc((size_t)T + 1);
-    head_flags_kernel<<<nblk(T), 256, 0, st>>>(T, keys2.p, flag.p);
-    exclusive_scan_int(c, tmp, flag.p, pos.p, T + 1);
-    const int nnzC = d2h(c, pos.p + T);
-    C.nnz = nnzC;
-    C.ci.alloc(std::max(1, nnzC), false, 64);
-    C.va.alloc(std::max(1, nnzC), false, 64);
-    crow.alloc(std::max(1, nnzC));
-    compress_kernel<<<nblk(T), 256, 0, st>>>(T, keys2.p, vals2.p, flag.p, pos.p, C.ci.p, C.va.p, crow.p);
-    lower_bound_rows_kernel<<<nblk((long long)C.n + 1), 256, 0, st>>>(C.n, nnzC, crow.p, C.rp.p);
+    struct Piece
+    {
+        DevBuf<int> ci, row;
+        DevBuf<double> va;
+        int nnz = 0;
+    };
+    std::vector<Piece> pieces;
+    long long total = 0;
+    int *d_end = (int *)c.counter.p + 3;
+    for (int r0 = 0; r0 < A.n;)
+    {
+        chunk_end_kernel<<<1, 1, 0, st>>>(A.n, off.p, r0, kChunk, d_end);
+        const int r1 = d2h(c, d_end);
+        long long o01[2];
+        PSB_CUDA(cudaMemcpyAsync(&o01[0], off.p + r0, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        PSB_CUDA(cudaMemcpyAsync(&o01[1], off.p + r1, sizeof(long long), cudaMemcpyDeviceToHost, st));
+        PSB_CUDA(cudaStreamSynchronize(st));
+        const long long Tc = o01[1] - o01[0];
+        if (Tc > 0x7fffffffLL)
+            throw std::runtime_error("psb200 amg: one row of the Galerkin product has more than 2^31 intermediate products");
+        pieces.emplace_back();
+        Piece &pc = pieces.back();
+        if (Tc > 0)
+        {
+            DevBuf<unsigned long long> keys, keys2;
+            DevBuf<double> vals, vals2;
+            keys.alloc(Tc);
+            keys2.alloc(Tc);
+            vals.alloc(Tc);
+            vals2.alloc(Tc);
+            spgemm_expand_rows_kernel<<<nblk(r1 - r0), 256, 0, st>>>(A.view(), B.view(), off.p, r0, r1, keys.p, vals.p);
+            check_launch();
+            size_t bytes = 0;
+            PSB_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys2.p, vals.p, vals2.p, (int)Tc, 0, 32 + rbits, st));
+            PSB_CUDA(cub::DeviceRadixSort::SortPairs(tmp.get(bytes), bytes, keys.p, keys2.p, vals.p, vals2.p, (int)Tc, 0, 32 + rbits, st));
+            keys.release();
+            vals.release();
+            DevBuf<int> flag, pos;
+            flag.alloc((size_t)Tc + 1, true);
+            pos.alloc((size_t)Tc + 1);
+            head_flags_kernel<<<nblk(Tc), 256, 0, st>>>(Tc, keys2.p, flag.p);
+            exclusive_scan_int(c, tmp, flag.p, pos.p, Tc + 1);
+            pc.nnz = d2h(c, pos.p + Tc);
+            pc.ci.alloc(std::max(1, pc.nnz), false, 64);
+            pc.va.alloc(std::max(1, pc.nnz), false, 64);
+            pc.row.alloc(std::max(1, pc.nnz));
+            compress_kernel<<<nblk(Tc), 256, 0, st>>>(Tc, keys2.p, vals2.p, flag.p, pos.p, pc.ci.p, pc.va.p, pc.row.p);
+            check_launch();
+            PSB_CUDA(cudaStreamSynchronize(st));
+        }
+        total += pc.nnz;
+        r0 = r1;
+    }
+    if (total > 0x7fffffffLL - 1024)
+        throw std::runtime_error("psb200 amg: a coarse matrix exceeds the int32 index range on one GPU");
+    C.nnz = total;
+    if (pieces.size() == 1 && total > 0)
+    {
+        // the common case: one chunk, its buffers become the result
+        C.ci = std::move(pieces[0].ci);
+        C.va = std::move(pieces[0].va);
+        lower_bound_rows_kernel<<<nblk((long long)C.n + 1), 256, 0, st>>>(C.n, total, pieces[0].row.p, C.rp.p);
+        check_launch();
+        PSB_CUDA(cudaStreamSynchronize(st));
+        return;
+    }
+    C.ci.alloc(std::max<long long>(1, total), false, 64);
+    C.va.alloc(std::max<long long>(1, total), false, 64);
+    DevBuf<int> crow;
+    crow.alloc(std::max<long long>(1, total));
+    long long o = 0;
+    for (Piece &pc : pieces)
+    {
+        if (pc.nnz)
+        {
+            PSB_CUDA(cudaMemcpyAsync(C.ci.p + o, pc.ci.p, sizeof(int) * (size_t)pc.nnz, cudaMemcpyDeviceToDevice, st));
+            PSB_CUDA(cudaMemcpyAsync(C.va.p + o, pc.va.p, sizeof(double) * (size_t)pc.nnz, cudaMemcpyDeviceToDevice, st));
+            PSB_CUDA(cudaMemcpyAsync(crow.p + o, pc.row.p, sizeof(int) * (size_t)pc.nnz, cudaMemcpyDeviceToDevice, st));
+        }
+        o += pc.nnz;
+    }
+    lower_bound_rows_kernel<<<nblk((long long)C.n + 1), 256, 0, st>>>(C.n, total, crow.p, C.rp.p);
     check_launch();
     PSB_CUDA(cudaStreamSynchronize(st));
 }
 
-} // namespace
-
 // ====================================================================================== level
-struct AmgLevel
-{
-    CsrDev Aown;
-    const CsrDev *A = nullptr;
-    CsrDev P, R;
-    int n = 0;
-    long long n_pad = 0;
-    DevBuf<double> dinv, w, f, u, ualt, t, cp;
-    DevBuf<int> agg;
-    int n_agg = 0;
-    // block mode: Ahat = Dblk^-1 A is the smoother's operator (Asm), dinvb the inverted diagonal blocks, bh = Dblk^-1 rhs
-    CsrDev Ahat;
-    const CsrDev *Asm = nullptr;
-    DevBuf<double> dinvb, bh;
-    DevBuf<int> agg_node;
-    double rho = 0, cheb_d = 0, cheb_c = 0, omega = 0;
-    std::vector<double> alpha, beta;
-    int mis_rounds = 0;
-    double t_relax = 0, t_agg = 0, t_prolong = 0, t_transpose = 0, t_ap = 0, t_rap = 0; // setup phase wall-clock, ms
-};
 
 AmgHierarchy::AmgHierarchy(Ctx &ctx, const AmgParams &prm) : ctx_(ctx), prm_(prm) {}
 AmgHierarchy::~AmgHierarchy() {}
@@ -814,13 +849,68 @@ static double gershgorin(Ctx &c, const CsrDev &A)
     return bits_to_double(d2h(c, d_max));
 }
 
-static void setup_relaxation(Ctx &c, const AmgParams &prm, AmgLevel &L, int level_index)
+// node graph S of a block matrix: Frobenius norms of the B x B blocks (amgcl math::norm), all columns kept
+static void block_norm_graph(Ctx &c, int B, const CsrDev &A, CsrDev &S)
+{
+    cudaStream_t st = c.stream;
+    const long long nb = A.n / B;
+    S.n = (int)nb;
+    S.ncols = A.ncols / B;
+    S.nnz = A.nnz / (B * B);
+    S.rp.alloc((size_t)nb + 1);
+    S.ci.alloc(std::max<long long>(1, S.nnz), false, 64);
+    S.va.alloc(std::max<long long>(1, S.nnz), false, 64);
+    if (B == 2)
+        block_norm_matrix_kernel<2><<<nblk(nb + 1), 256, 0, st>>>(A.view(), S.rp.p, S.ci.p, S.va.p);
+    else
+        block_norm_matrix_kernel<3><<<nblk(nb + 1), 256, 0, st>>>(A.view(), S.rp.p, S.ci.p, S.va.p);
+    check_launch();
+}
+
+// dinvb = inverted diagonal blocks of A, Ahat = Dblk^-1 A (same pattern)
+static void block_scaled_matrix(Ctx &c, int B, const CsrDev &A, DevBuf<double> &dinvb, CsrDev &Ahat)
+{
+    cudaStream_t st = c.stream;
+    if (A.n % B)
+        throw std::runtime_error("psb200 amg: level size is not a multiple of the block size");
+    const long long nb = A.n / B;
+    dinvb.alloc((size_t)nb * B * B);
+    int *d_bad = (int *)c.counter.p + 3;
+    PSB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
+    if (B == 2)
+        block_diag_inv_kernel<2><<<nblk(nb), 256, 0, st>>>(A.view(), dinvb.p, d_bad);
+    else
+        block_diag_inv_kernel<3><<<nblk(nb), 256, 0, st>>>(A.view(), dinvb.p, d_bad);
+    check_launch();
+    if (d2h(c, d_bad))
+        throw std::runtime_error("psb200 amg: singular or missing diagonal block (block_size " + std::to_string(B) + ")");
+    Ahat.n = A.n;
+    Ahat.ncols = A.ncols;
+    Ahat.nnz = A.nnz;
+    Ahat.nl = A.nl;
+    Ahat.halo_mask = A.halo_mask;
+    Ahat.rp.alloc((size_t)A.n + 1);
+    Ahat.ci.alloc(std::max<long long>(1, A.nnz), false, 64);
+    Ahat.va.alloc(std::max<long long>(1, A.nnz), false, 64);
+    PSB_CUDA(cudaMemcpyAsync(Ahat.rp.p, A.rp.p, sizeof(int) * ((size_t)A.n + 1), cudaMemcpyDeviceToDevice, st));
+    if (A.nnz)
+        PSB_CUDA(cudaMemcpyAsync(Ahat.ci.p, A.ci.p, sizeof(int) * (size_t)A.nnz, cudaMemcpyDeviceToDevice, st));
+    if (B == 2)
+        block_scale_rows_kernel<2><<<nblk(A.n), 256, 0, st>>>(A.view(), dinvb.p, Ahat.va.p);
+    else
+        block_scale_rows_kernel<3><<<nblk(A.n), 256, 0, st>>>(A.view(), dinvb.p, Ahat.va.p);
+    check_launch();
+    Ahat.kind = A.kind;
+    Ahat.lpr = A.lpr;
+}
+
+void setup_relaxation(Ctx &c, const AmgParams &prm, AmgLevel &L, int seed_index, const SetupHooks *hooks)
 {
     cudaStream_t st = c.stream;
     const CsrDev &A = *L.A;
     L.n = A.n;
     L.n_pad = ((long long)A.n + 3) & ~3ll;
-    const size_t np = (size_t)L.n_pad;
+    const size_t np = (size_t)std::max<long long>(L.n_pad, 4);
     L.dinv.alloc(np, true);
     L.f.alloc(np, true);
     L.u.alloc(np, true);
@@ -834,40 +924,16 @@ static void setup_relaxation(Ctx &c, const AmgParams &prm, AmgLevel &L, int leve
     if (B > 1)
     {
         // Dblk^-1 once, Ahat = Dblk^-1 A; from here on the scalar code runs on Ahat with a unit diagonal scaling
-        if (A.n % B)
-            throw std::runtime_error("psb200 amg: level size is not a multiple of the block size");
-        const long long nb = A.n / B;
-        L.dinvb.alloc((size_t)nb * B * B);
+        block_scaled_matrix(c, B, A, L.dinvb, L.Ahat);
         L.bh.alloc(np, true);
-        int *d_bad = (int *)c.counter.p + 3;
-        PSB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
-        if (B == 2)
-            block_diag_inv_kernel<2><<<nblk(nb), 256, 0, st>>>(A.view(), L.dinvb.p, d_bad);
-        else
-            block_diag_inv_kernel<3><<<nblk(nb), 256, 0, st>>>(A.view(), L.dinvb.p, d_bad);
-        check_launch();
-        if (d2h(c, d_bad))
-            throw std::runtime_error("psb200 amg: singular or missing diagonal block (block_size " + std::to_string(B) + ")");
-        L.Ahat.n = A.n;
-        L.Ahat.ncols = A.ncols;
-        L.Ahat.nnz = A.nnz;
-        L.Ahat.rp.alloc((size_t)A.n + 1);
-        L.Ahat.ci.alloc(std::max<long long>(1, A.nnz), false, 64);
-        L.Ahat.va.alloc(std::max<long long>(1, A.nnz), false, 64);
-        PSB_CUDA(cudaMemcpyAsync(L.Ahat.rp.p, A.rp.p, sizeof(int) * ((size_t)A.n + 1), cudaMemcpyDeviceToDevice, st));
-        PSB_CUDA(cudaMemcpyAsync(L.Ahat.ci.p, A.ci.p, sizeof(int) * (size_t)A.nnz, cudaMemcpyDeviceToDevice, st));
-        if (B == 2)
-            block_scale_rows_kernel<2><<<nblk(A.n), 256, 0, st>>>(A.view(), L.dinvb.p, L.Ahat.va.p);
-        else
-            block_scale_rows_kernel<3><<<nblk(A.n), 256, 0, st>>>(A.view(), L.dinvb.p, L.Ahat.va.p);
-        check_launch();
-        L.Ahat.kind = A.kind;
-        L.Ahat.lpr = A.lpr;
         L.Asm = &L.Ahat;
-        fill_kernel<<<nblk(A.n), 256, 0, st>>>(A.n, L.dinv.p, 1.0);
-        fill_kernel<<<nblk(A.n), 256, 0, st>>>(A.n, diag.p, 1.0);
+        if (A.n)
+        {
+            fill_kernel<<<nblk(A.n), 256, 0, st>>>(A.n, L.dinv.p, 1.0);
+            fill_kernel<<<nblk(A.n), 256, 0, st>>>(A.n, diag.p, 1.0);
+        }
     }
-    else
+    else if (A.n)
     {
         diag_kernel<<<nblk(A.n), 256, 0, st>>>(A.view(), diag.p);
         inv_kernel<<<nblk(A.n), 256, 0, st>>>(A.n, diag.p, L.dinv.p, 1.0);
@@ -881,32 +947,41 @@ static void setup_relaxation(Ctx &c, const AmgParams &prm, AmgLevel &L, int leve
             throw std::runtime_error("psb200 amg: chebyshev with scale=false is not supported");
         double rho;
         if (prm.power_iters <= 0)
-            rho = gershgorin(c, As);
+        {
+            rho = A.n ? gershgorin(c, As) : 0.0;
+            if (hooks && hooks->allmax)
+                rho = hooks->allmax(rho);
+        }
         else
         {
-            // b0 = the same counter-based splitmix64 stream the CPU restatement starts from
+            // b0 = the same counter-based splitmix64 stream the CPU restatement starts from (indexed by the GLOBAL row)
             DevBuf<double> b0, b1, scal;
             b0.alloc(np, true);
             b1.alloc(np, true);
             scal.alloc(4, true);
-            splitmix_kernel<<<nblk(A.n), 256, 0, st>>>(A.n, 1000ull + (unsigned long long)(level_index + 1), b0.p);
+            const long long row0 = hooks ? hooks->row0 : 0;
+            if (A.n)
+                splitmix_kernel<<<nblk(A.n), 256, 0, st>>>(A.n, 1000ull + (unsigned long long)(seed_index + 1), row0, b0.p);
             check_launch();
-            launch_vec(c, "amg_setup", L.n_pad, OpDot{b0.p, b0.p}, FinStore{scal.p, 1});
-            launch_vec(c, "amg_setup", L.n_pad, OpScale{b0.p, b0.p, scal.p, 0.0}, FinNone{});
+            launch_vec(c, "amg_setup", np, OpDot{b0.p, b0.p}, FinStore{scal.p, 1});
+            launch_vec(c, "amg_setup", np, OpScale{b0.p, b0.p, scal.p, 0.0}, FinNone{});
             for (int it = 0; it < prm.power_iters; ++it)
             {
+                if (hooks && hooks->push)
+                    hooks->push(b0.p);
                 launch_spmv(c, "amg_setup", As, b0.p, EpiPower{b1.p, b0.p, L.dinv.p}, FinStore{scal.p, 2});
                 if (it + 1 < prm.power_iters)
-                    launch_vec(c, "amg_setup", L.n_pad, OpScale{b0.p, b1.p, scal.p, 0.0}, FinNone{});
+                    launch_vec(c, "amg_setup", np, OpScale{b0.p, b1.p, scal.p, 0.0}, FinNone{});
             }
             if (B > 1)
             {
                 // the block algorithm takes |.| of the per-node inner product, not of every scalar product
                 DevBuf<double> terms;
                 terms.alloc(np, true);
-                block_radius_terms_kernel<<<nblk(A.n / B), 256, 0, st>>>(B, A.n / B, b1.p, b0.p, terms.p);
+                if (A.n)
+                    block_radius_terms_kernel<<<nblk(A.n / B), 256, 0, st>>>(B, A.n / B, b1.p, b0.p, terms.p);
                 check_launch();
-                launch_vec(c, "amg_setup", L.n_pad, OpDot{terms.p, L.dinv.p}, FinStore{scal.p + 1, 1});
+                launch_vec(c, "amg_setup", np, OpDot{terms.p, L.dinv.p}, FinStore{scal.p + 1, 1});
             }
             double h[2];
             PSB_CUDA(cudaMemcpyAsync(h, scal.p, 16, cudaMemcpyDeviceToHost, st));
@@ -946,10 +1021,32 @@ static void setup_relaxation(Ctx &c, const AmgParams &prm, AmgLevel &L, int leve
     {
         // damped Jacobi: w = damping / a_ii
         L.w.alloc(np, true);
-        inv_kernel<<<nblk(A.n), 256, 0, st>>>(A.n, diag.p, L.w.p, prm.damping);
+        if (A.n)
+            inv_kernel<<<nblk(A.n), 256, 0, st>>>(A.n, diag.p, L.w.p, prm.damping);
         check_launch();
     }
     PSB_CUDA(cudaStreamSynchronize(st));
+}
+
+// amgcl spectral_radius<true> with power_iters = 0 (the bound omega of the prolongation smoothing is made from)
+double gershgorin_rho(Ctx &c, const AmgParams &prm, const AmgLevel &L)
+{
+    const int B = std::max(1, prm.block_size);
+    const CsrDev &A = *L.A;
+    if (A.n == 0)
+        return 0.0;
+    if (B == 1)
+        return gershgorin(c, A);
+    CsrDev S;
+    block_norm_graph(c, B, A, S);
+    unsigned long long *d_max = (unsigned long long *)c.partials.p;
+    PSB_CUDA(cudaMemsetAsync(d_max, 0, 8, c.stream));
+    if (B == 2)
+        block_gershgorin_kernel<2><<<nblk(S.n), 256, 0, c.stream>>>(S.view(), L.dinvb.p, d_max);
+    else
+        block_gershgorin_kernel<3><<<nblk(S.n), 256, 0, c.stream>>>(S.view(), L.dinvb.p, d_max);
+    check_launch();
+    return bits_to_double(d2h(c, d_max));
 }
 
 // Deterministic parallel MIS-2 aggregation. Returns the number of aggregates; agg[i] in [0, n_agg) or -2 (removed).
@@ -966,13 +1063,15 @@ static int aggregate_mis2(Ctx &c, Temp &tmp, const CsrDev &A, const double *diag
     root_id.alloc(n + 1);
     agg1.alloc(n);
     agg.alloc(n);
+    rounds = 0;
+    if (n == 0)
+        return 0;
     m0.alloc(n);
     m1.alloc(n);
     f0.alloc(n);
     f1.alloc(n);
     int *d_flags = (int *)c.counter.p + 2; // [changed, remaining]
     agg_init_kernel<<<nblk(n), 256, 0, st>>>(A.view(), diag, eps2, state.p);
-    rounds = 0;
     for (;;)
     {
         ++rounds;
@@ -1003,24 +1102,130 @@ static int aggregate_mis2(Ctx &c, Temp &tmp, const CsrDev &A, const double *diag
     return n_agg;
 }
 
-static double wall_ms(cudaStream_t st)
+double wall_ms(cudaStream_t st)
 {
     cudaStreamSynchronize(st);
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// amgcl plain_aggregates on the square matrix Asq (block mode: on the node graph with Frobenius block norms)
+void build_aggregates(Ctx &c, Temp &tmp, const AmgParams &prm, const CsrDev &Asq, double eps_strong, const std::vector<int> *imposed, AmgLevel &L)
+{
+    cudaStream_t st = c.stream;
+    const long long n = Asq.n;
+    const int B = std::max(1, prm.block_size);
+    if (B > 1 && eps_strong != 0.0)
+        throw std::runtime_error("psb200 amg: block_size > 1 supports eps_strong = 0 only (polysolve's default, AMGCL.cpp:52)");
+    if (imposed && !imposed->empty())
+    {
+        // imposed ids are per node in block mode, per row otherwise
+        if ((long long)imposed->size() != n / B)
+            throw std::invalid_argument("psb200 amg: imposed aggregate array has the wrong length");
+        DevBuf<int> &dst = B > 1 ? L.agg_node : L.agg;
+        dst.alloc(n / B);
+        PSB_CUDA(cudaMemcpyAsync(dst.p, imposed->data(), sizeof(int) * (n / B), cudaMemcpyHostToDevice, st));
+        PSB_CUDA(cudaStreamSynchronize(st));
+        int mx = -1;
+        for (int a : *imposed)
+            mx = std::max(mx, a);
+        L.n_agg = mx + 1;
+    }
+    else if (B > 1)
+    {
+        CsrDev S; // node graph with Frobenius block norms
+        DevBuf<double> sdiag;
+        block_norm_graph(c, B, Asq, S);
+        sdiag.alloc((size_t)std::max<long long>(1, S.n));
+        if (S.n)
+            diag_kernel<<<nblk(S.n), 256, 0, st>>>(S.view(), sdiag.p);
+        check_launch();
+        L.n_agg = aggregate_mis2(c, tmp, S, sdiag.p, eps_strong, L.agg_node, L.mis_rounds);
+    }
+    else
+    {
+        DevBuf<double> diag;
+        diag.alloc((size_t)std::max<long long>(1, n));
+        if (n)
+            diag_kernel<<<nblk(n), 256, 0, st>>>(Asq.view(), diag.p);
+        check_launch();
+        L.n_agg = aggregate_mis2(c, tmp, Asq, diag.p, eps_strong, L.agg, L.mis_rounds);
+    }
+    if (B > 1)
+    {
+        L.agg.alloc(n);
+        if (n)
+            block_expand_agg_kernel<<<nblk(n / B), 256, 0, st>>>(B, n / B, L.agg_node.p, L.agg.p);
+        check_launch();
+        L.n_agg *= B;
+    }
+    PSB_CUDA(cudaStreamSynchronize(st));
+}
+
+// amgcl smoothed_aggregation::transfer_operators: P = (I - omega D_f^-1 A_f) P_tent on the square matrix Asq
+void build_prolongation(Ctx &c, Temp &tmp, const AmgParams &prm, const CsrDev &Asq, const CsrDev *Ahat, double eps_strong, double omega, AmgLevel &L)
+{
+    cudaStream_t st = c.stream;
+    const long long n = Asq.n;
+    const int B = std::max(1, prm.block_size);
+    const double eps2 = eps_strong * eps_strong;
+    CsrDev Ahat_own;
+    DevBuf<double> dinvb_own;
+    const CsrDev *Asm = &Asq;
+    if (B > 1)
+    {
+        if (!Ahat)
+        {
+            block_scaled_matrix(c, B, Asq, dinvb_own, Ahat_own);
+            Ahat = &Ahat_own;
+        }
+        Asm = Ahat;
+    }
+    DevBuf<double> diag;
+    diag.alloc((size_t)std::max<long long>(1, n));
+    if (n)
+    {
+        if (B > 1)
+            fill_kernel<<<nblk(n), 256, 0, st>>>(n, diag.p, 1.0);
+        else
+            diag_kernel<<<nblk(n), 256, 0, st>>>(Asq.view(), diag.p);
+    }
+    check_launch();
+    DevBuf<int> scol, cnt;
+    DevBuf<double> sval;
+    scol.alloc(std::max<long long>(1, Asm->nnz));
+    sval.alloc(std::max<long long>(1, Asm->nnz));
+    cnt.alloc(n + 1, true);
+    if (n)
+        prolong_rows_kernel<<<nblk(n), 256, 0, st>>>(Asm->view(), diag.p, eps2, L.agg.p, omega, scol.p, sval.p, cnt.p, B > 1);
+    check_launch();
+    L.P.n = (int)n;
+    L.P.ncols = L.n_agg;
+    L.P.rp.alloc(n + 1);
+    exclusive_scan_int(c, tmp, cnt.p, L.P.rp.p, n + 1);
+    L.P.nnz = d2h(c, L.P.rp.p + n);
+    L.P.ci.alloc(std::max<long long>(1, L.P.nnz), false, 64);
+    L.P.va.alloc(std::max<long long>(1, L.P.nnz), false, 64);
+    if (n)
+        compact_rows_kernel<<<nblk(n), 256, 0, st>>>(n, Asm->rp.p, L.P.rp.p, scol.p, sval.p, L.P.ci.p, L.P.va.p);
+    check_launch();
+    PSB_CUDA(cudaStreamSynchronize(st));
+}
+
 // amgcl amg::do_init (SURVEY A.3 "Hierarchy build")
-void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &imposed)
+void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &imposed, int level_base)
 {
     if (prm_.direct_coarse)
         throw std::runtime_error("psb200 amg: direct_coarse=true is not available yet (polysolve's default is false, AMGCL.cpp:45)");
     cudaStream_t st = ctx_.stream;
     levels_.clear();
     A0_ = &A0;
+    level_base_ = level_base;
     Temp tmp;
     auto cur = std::make_unique<AmgLevel>();
     cur->A = &A0;
     double eps_strong = prm_.eps_strong;
+    for (int i = 0; i < level_base; ++i)
+        eps_strong *= 0.5; // amgcl halves eps_strong after every level
     while (cur && cur->A->n > prm_.coarse_enough)
     {
         levels_.push_back(std::move(cur));
@@ -1028,118 +1233,29 @@ void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &
         const CsrDev &A = *L.A;
         const int li = (int)levels_.size() - 1;
         double tp = wall_ms(st);
-        setup_relaxation(ctx_, prm_, L, li);
+        setup_relaxation(ctx_, prm_, L, level_base + li);
         L.t_relax = wall_ms(st) - tp;
-        if ((int)levels_.size() >= prm_.max_levels)
+        if (level_base + (int)levels_.size() >= prm_.max_levels)
             break; // last level is a plain smoothing-only level
-        const long long n = A.n;
-        const double eps2 = eps_strong * eps_strong;
-        const int B = std::max(1, prm_.block_size);
-        if (B > 1 && eps_strong != 0.0)
-            throw std::runtime_error("psb200 amg: block_size > 1 supports eps_strong = 0 only (polysolve's default, AMGCL.cpp:52)");
-        const CsrDev &Asm = *L.Asm; // Dblk^-1 A in block mode, A otherwise
-        DevBuf<double> diag;
-        diag.alloc(n);
-        if (B > 1)
-            fill_kernel<<<nblk(n), 256, 0, st>>>(n, diag.p, 1.0);
-        else
-            diag_kernel<<<nblk(n), 256, 0, st>>>(A.view(), diag.p);
-        check_launch();
-        const double *pdiag = diag.p;
         // ---- aggregates
         tp = wall_ms(st);
-        CsrDev S; // block mode: node graph with Frobenius block norms
-        DevBuf<double> sdiag;
-        if (B > 1)
-        {
-            const long long nb = n / B;
-            S.n = (int)nb;
-            S.ncols = (int)nb;
-            S.nnz = A.nnz / (B * B);
-            S.rp.alloc((size_t)nb + 1);
-            S.ci.alloc(std::max<long long>(1, S.nnz), false, 64);
-            S.va.alloc(std::max<long long>(1, S.nnz), false, 64);
-            if (B == 2)
-                block_norm_matrix_kernel<2><<<nblk(nb + 1), 256, 0, st>>>(A.view(), S.rp.p, S.ci.p, S.va.p);
-            else
-                block_norm_matrix_kernel<3><<<nblk(nb + 1), 256, 0, st>>>(A.view(), S.rp.p, S.ci.p, S.va.p);
-            sdiag.alloc((size_t)nb);
-            diag_kernel<<<nblk(nb), 256, 0, st>>>(S.view(), sdiag.p);
-            check_launch();
-        }
-        if (li < (int)imposed.size() && !imposed[li].empty())
-        {
-            // imposed ids are per node in block mode, per row otherwise
-            if ((long long)imposed[li].size() != n / B)
-                throw std::invalid_argument("psb200 amg: imposed aggregate array has the wrong length");
-            DevBuf<int> &dst = B > 1 ? L.agg_node : L.agg;
-            dst.alloc(n / B);
-            PSB_CUDA(cudaMemcpyAsync(dst.p, imposed[li].data(), sizeof(int) * (n / B), cudaMemcpyHostToDevice, st));
-            int mx = -1;
-            for (int a : imposed[li])
-                mx = std::max(mx, a);
-            L.n_agg = mx + 1;
-        }
-        else if (B > 1)
-            L.n_agg = aggregate_mis2(ctx_, tmp, S, sdiag.p, eps_strong, L.agg_node, L.mis_rounds);
-        else
-            L.n_agg = aggregate_mis2(ctx_, tmp, A, diag.p, eps_strong, L.agg, L.mis_rounds);
-        if (B > 1)
-        {
-            L.agg.alloc(n);
-            block_expand_agg_kernel<<<nblk(n / B), 256, 0, st>>>(B, n / B, L.agg_node.p, L.agg.p);
-            check_launch();
-            L.n_agg *= B;
-        }
+        const int gi = level_base + li;
+        build_aggregates(ctx_, tmp, prm_, A, eps_strong, gi < (int)imposed.size() ? &imposed[gi] : nullptr, L);
         L.t_agg = wall_ms(st) - tp;
-        eps_strong *= 0.5; // amgcl halves eps_strong after every level
         if (L.n_agg <= 0)
             break;
         // ---- omega = relax * (4/3) / rho_Gershgorin(D^-1 A)
         double omega = prm_.sa_relax;
         if (prm_.estimate_spectral_radius)
-        {
-            double rho_g;
-            if (B > 1)
-            {
-                unsigned long long *d_max = (unsigned long long *)ctx_.partials.p;
-                PSB_CUDA(cudaMemsetAsync(d_max, 0, 8, st));
-                if (B == 2)
-                    block_gershgorin_kernel<2><<<nblk(S.n), 256, 0, st>>>(S.view(), L.dinvb.p, d_max);
-                else
-                    block_gershgorin_kernel<3><<<nblk(S.n), 256, 0, st>>>(S.view(), L.dinvb.p, d_max);
-                check_launch();
-                rho_g = bits_to_double(d2h(ctx_, d_max));
-            }
-            else
-                rho_g = gershgorin(ctx_, A);
-            omega *= (4.0 / 3.0) / rho_g;
-        }
+            omega *= (4.0 / 3.0) / gershgorin_rho(ctx_, prm_, L);
         else
             omega *= 2.0 / 3.0;
         L.omega = omega;
         // ---- smoothed prolongation
         tp = wall_ms(st);
-        {
-            DevBuf<int> scol, cnt;
-            DevBuf<double> sval;
-            scol.alloc(std::max<long long>(1, A.nnz));
-            sval.alloc(std::max<long long>(1, A.nnz));
-            cnt.alloc(n + 1, true);
-            prolong_rows_kernel<<<nblk(n), 256, 0, st>>>(Asm.view(), pdiag, eps2, L.agg.p, omega, scol.p, sval.p, cnt.p, B > 1);
-            check_launch();
-            L.P.n = (int)n;
-            L.P.ncols = L.n_agg;
-            L.P.rp.alloc(n + 1);
-            exclusive_scan_int(ctx_, tmp, cnt.p, L.P.rp.p, n + 1);
-            L.P.nnz = d2h(ctx_, L.P.rp.p + n);
-            L.P.ci.alloc(std::max<long long>(1, L.P.nnz), false, 64);
-            L.P.va.alloc(std::max<long long>(1, L.P.nnz), false, 64);
-            compact_rows_kernel<<<nblk(n), 256, 0, st>>>(n, A.rp.p, L.P.rp.p, scol.p, sval.p, L.P.ci.p, L.P.va.p);
-            check_launch();
-            PSB_CUDA(cudaStreamSynchronize(st));
-        }
+        build_prolongation(ctx_, tmp, prm_, A, prm_.block_size > 1 ? &L.Ahat : nullptr, eps_strong, omega, L);
         L.t_prolong = wall_ms(st) - tp;
+        eps_strong *= 0.5;
         tp = wall_ms(st);
         transpose(ctx_, tmp, L.P, L.R);
         L.P.plan("auto", st);
@@ -1165,7 +1281,7 @@ void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &
         // coarsest level (rows <= coarse_enough): relaxation only (direct_coarse = false)
         levels_.push_back(std::move(cur));
         const double tp = wall_ms(st);
-        setup_relaxation(ctx_, prm_, *levels_.back(), (int)levels_.size() - 1);
+        setup_relaxation(ctx_, prm_, *levels_.back(), level_base + (int)levels_.size() - 1);
         levels_.back()->t_relax = wall_ms(st) - tp;
     }
     PSB_CUDA(cudaStreamSynchronize(st));
@@ -1174,49 +1290,58 @@ void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &
 // ====================================================================================== cycle
 // One smoother application (amgcl relaxation apply_pre == apply_post for chebyshev / damped jacobi).
 // x and x_alt ping-pong: the fused SpMV step reads x (gathered) and writes x_alt. On return `x` points
-// at the buffer that holds the result.
-void AmgHierarchy::relax(int l, const double *rhs, double *&x, double *&x_alt, bool x_is_zero, const int *done)
+// at the buffer that holds the result. after_step (row partitions): called with every new iterate, pushes its halo.
+void relax_level(Ctx &ctx, const AmgParams &prm, AmgLevel &L, bool fine, const double *rhs, double *&x, double *&x_alt, bool x_is_zero,
+                 const int *done, const std::function<void(const double *)> *after_step)
 {
-    AmgLevel &L = *levels_[l];
     const CsrDev &A = *L.Asm;
-    const int B = std::max(1, prm_.block_size);
+    const int B = std::max(1, prm.block_size);
     if (B > 1)
     {
         // M (b - A x) = Dblk^-1 b - Ahat x : scale the right-hand side once per application
         const long long nb = L.n / B;
-        ctx_.prof_begin("block_diag_apply");
+        ctx.prof_begin("block_diag_apply");
         if (B == 2)
-            block_diag_apply_kernel<2><<<nblk(nb), 256, 0, ctx_.stream>>>(nb, L.dinvb.p, rhs, L.bh.p, done);
+            block_diag_apply_kernel<2><<<nblk(nb), 256, 0, ctx.stream>>>(nb, L.dinvb.p, rhs, L.bh.p, done);
         else
-            block_diag_apply_kernel<3><<<nblk(nb), 256, 0, ctx_.stream>>>(nb, L.dinvb.p, rhs, L.bh.p, done);
+            block_diag_apply_kernel<3><<<nblk(nb), 256, 0, ctx.stream>>>(nb, L.dinvb.p, rhs, L.bh.p, done);
         check_launch();
-        ctx_.prof_end();
+        ctx.prof_end();
         rhs = L.bh.p;
     }
-    if (prm_.relax_type == "chebyshev")
+    if (prm.relax_type == "chebyshev")
     {
-        for (int k = 0; k < prm_.degree; ++k)
+        for (int k = 0; k < prm.degree; ++k)
         {
             if (k == 0 && x_is_zero)
+                launch_vec(ctx, "cheb_first", L.n_pad, OpChebFirst{rhs, L.dinv.p, L.cp.p, x, L.alpha[0]}, FinNone{}, done);
+            else
             {
-                launch_vec(ctx_, "cheb_first", L.n_pad, OpChebFirst{rhs, L.dinv.p, L.cp.p, x, L.alpha[0]}, FinNone{}, done);
-                continue;
+                launch_spmv(ctx, fine ? "spmv_cheb_l0" : "spmv_cheb_coarse", A, x, EpiCheb{rhs, L.dinv.p, x, L.cp.p, x_alt, L.alpha[k], L.beta[k]},
+                            FinNone{}, done);
+                std::swap(x, x_alt);
             }
-            launch_spmv(ctx_, l == 0 ? "spmv_cheb_l0" : "spmv_cheb_coarse", A, x,
-                        EpiCheb{rhs, L.dinv.p, x, L.cp.p, x_alt, L.alpha[k], L.beta[k]}, FinNone{}, done);
-            std::swap(x, x_alt);
+            if (after_step)
+                (*after_step)(x);
         }
     }
     else
     {
         if (x_is_zero)
-            launch_vec(ctx_, "jacobi_first", L.n_pad, OpDiagFirst{rhs, L.w.p, x}, FinNone{}, done);
+            launch_vec(ctx, "jacobi_first", L.n_pad, OpDiagFirst{rhs, L.w.p, x}, FinNone{}, done);
         else
         {
-            launch_spmv(ctx_, "spmv_jacobi", A, x, EpiRelaxDiag{rhs, L.w.p, x, x_alt}, FinNone{}, done);
+            launch_spmv(ctx, "spmv_jacobi", A, x, EpiRelaxDiag{rhs, L.w.p, x, x_alt}, FinNone{}, done);
             std::swap(x, x_alt);
         }
+        if (after_step)
+            (*after_step)(x);
     }
+}
+
+void AmgHierarchy::relax(int l, const double *rhs, double *&x, double *&x_alt, bool x_is_zero, const int *done)
+{
+    relax_level(ctx_, prm_, *levels_[l], l == 0 && level_base_ == 0, rhs, x, x_alt, x_is_zero, done, nullptr);
 }
 
 // amgcl amg::cycle (SURVEY A.3 "Cycle"). x/x_alt are this level's iterate buffers; returns with the
@@ -1455,15 +1580,20 @@ void AmgHierarchy::apply_dist(const double *rhs, double *out, const int *done)
     PSB_CUDA(cudaMemcpyAsync(out, x, bytes, cudaMemcpyDeviceToDevice, ctx_.stream));
 }
 
-std::string AmgHierarchy::info_json() const
+double AmgHierarchy::total_nnz() const
+{
+    double tot = 0;
+    for (auto &L : levels_)
+        tot += (double)L->A->nnz;
+    return tot;
+}
+
+std::string AmgHierarchy::levels_json() const
 {
     std::ostringstream o;
-    double fine_nnz = levels_.empty() ? 1 : (double)levels_[0]->A->nnz, tot = 0;
-    o << "{\"levels\":[";
     for (size_t l = 0; l < levels_.size(); ++l)
     {
         const AmgLevel &L = *levels_[l];
-        tot += (double)L.A->nnz;
         if (l)
             o << ",";
         o << "{\"rows\":" << L.A->n << ",\"nnz\":" << L.A->nnz << ",\"p_nnz\":" << L.P.nnz << ",\"aggregates\":" << L.n_agg
@@ -1472,9 +1602,27 @@ std::string AmgHierarchy::info_json() const
           << ",\"AP\":" << jnum(L.t_ap) << ",\"RAP\":" << jnum(L.t_rap) << "}"
           << ",\"spmv_kernel\":" << jstr(L.A->kernel_name()) << "}";
     }
-    o << "],\"block_size\":" << std::max(1, prm_.block_size) << ",\"operator_complexity\":" << jnum(tot / fine_nnz) << ",\"ncycle\":" << prm_.ncycle << ",\"degree\":" << prm_.degree
+    return o.str();
+}
+
+std::string AmgHierarchy::info_json() const
+{
+    std::ostringstream o;
+    const double fine_nnz = levels_.empty() ? 1 : (double)levels_[0]->A->nnz;
+    o << "{\"levels\":[" << levels_json();
+    o << "],\"block_size\":" << std::max(1, prm_.block_size) << ",\"operator_complexity\":" << jnum(total_nnz() / fine_nnz) << ",\"ncycle\":" << prm_.ncycle << ",\"degree\":" << prm_.degree
       << ",\"relax\":" << jstr(prm_.relax_type) << "}";
     return o.str();
+}
+
+double *AmgHierarchy::level0_f() { return levels_.at(0)->f.p; }
+
+double *AmgHierarchy::cycle0(const int *done)
+{
+    AmgLevel &L0 = *levels_.at(0);
+    double *x = L0.u.p, *alt = L0.ualt.p;
+    cycle(0, L0.f.p, x, alt, true, done);
+    return x;
 }
 
 } // namespace psb

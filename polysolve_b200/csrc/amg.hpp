@@ -14,12 +14,20 @@ class AmgHierarchy
 public:
     AmgHierarchy(Ctx &ctx, const AmgParams &prm);
     ~AmgHierarchy();
-    // Builds the hierarchy for the fine matrix A (borrowed: must outlive the hierarchy).
-    void setup(const CsrDev &A, const std::vector<std::vector<int>> &imposed_aggregates);
+    // Builds the hierarchy for the fine matrix A (borrowed: must outlive the hierarchy). level_base > 0: A is level
+    // `level_base` of a larger hierarchy whose upper levels are row-partitioned (amg_dist.cu); it counts against
+    // max_levels, selects the imposed aggregates and the power-iteration seeds, and halves eps_strong accordingly.
+    void setup(const CsrDev &A, const std::vector<std::vector<int>> &imposed_aggregates, int level_base = 0);
     // x = M^-1 rhs : pre_cycles cycles from a zero initial guess (amgcl amg::apply).
     void apply(const double *rhs, double *x, const int *done);
     int num_levels() const;
     std::string info_json() const;
+    std::string levels_json() const; // the comma-separated level objects of info_json
+    double total_nnz() const;
+    // one cycle from level 0 on caller-visible buffers (the replicated tail of a partitioned hierarchy):
+    // f / u / u_alt are the level-0 work vectors; after cycle0() the result is in the returned pointer
+    double *level0_f();
+    double *cycle0(const int *done);
     const CsrDev &matrix(int level, int which) const; // 0 A, 1 P, 2 R
     int matrix_cols(int level, int which) const;
     // aggregate id per row of `level` (device pointer, rows(level) entries; -2 = removed); n_agg out
@@ -47,6 +55,7 @@ private:
     Ctx &ctx_;
     AmgParams prm_;
     const CsrDev *A0_ = nullptr;
+    int level_base_ = 0;
     std::vector<std::unique_ptr<AmgLevel>> levels_;
     std::shared_ptr<AmgDistFine> dist_;
     void relax_dist(const double *rhs, double *&x, double *&x_alt, bool x_is_zero, const int *done);

@@ -21,8 +21,14 @@ int guarded(psb200_handle h, F &&f)
         h->s.err.clear();
         psb::DeviceScope device_scope(h->s.device, h->s.ctx.stream != nullptr);
         psb::AllocScope alloc_scope(h->s.ctx.stream); // buffers are allocated / freed in order on the solver's stream
+        h->s.check_not_poisoned();
         f(h->s);
         return PSB200_OK;
+    }
+    catch (const psb::CommError &e)
+    {
+        h->s.err = e.what();
+        return PSB200_ERR_COMM;
     }
     catch (const psb::CudaError &e)
     {

@@ -15,6 +15,12 @@ struct CudaError : std::runtime_error
     using std::runtime_error::runtime_error;
 };
 
+// a cross-GPU wait timed out (PSB200_ERR_COMM)
+struct CommError : std::runtime_error
+{
+    using std::runtime_error::runtime_error;
+};
+
 #define PSB_CUDA(expr)                                                                              \
     do                                                                                              \
     {                                                                                               \
@@ -163,11 +169,14 @@ private:
 // Multi-GPU communication over NVLink peer memory (one process per GPU; buffers exchanged as CUDA
 // IPC handles). Every rank owns one "comm buffer" with the same layout; kernels store straight into
 // the peers' buffers (st.global on mapped peer pointers) and poll their own.
-//   [0, 4096)     reduction slots  RedSlot[2 parity][8 source ranks]   (flag-in-data words, no fences)
+//   [0, 1024)     reduction slots  RedSlot[2 parity][8 source ranks]   (flag-in-data words, no fences)
+//   [1024, 3072)  wide slots       WideSlot[2 parity][8 source ranks]  (8 doubles per rank: host-level all-gather, setup only)
 //   [4096, 8192)  halo flags       unsigned long long[8 source ranks]  (monotonic count of landed push chunks)
-//                 bulk flags       the same for the bulk all-reduce, 1024 bytes further
+//                 bulk flags       the same for the bulk all-reduce / all-gather, 1024 bytes further
 //   [8192, ...)   halo data        double[2 parity][8 source ranks][halo_cap]
-//                 bulk data        double[2 parity][8 source ranks][halo_cap]   (vector all-reduce, dist AMG restriction)
+//                 bulk data        double[2 parity][8 source ranks][halo_cap]   (vector all-reduce / all-gather of the
+//                                  partitioned AMG cycle; during setup the same area is the staging arena of the
+//                                  host-level exchanges, one slot of 2 * halo_cap doubles per source rank)
 constexpr int kMaxRanks = 8;
 // One fp64 travels as two 8-byte words {32 payload bits, 32-bit sequence tag}: an aligned 8-byte store is
 // single-copy atomic over NVLink, so a word whose tag matches carries valid payload -- the reader needs no
@@ -177,23 +186,43 @@ struct RedSlot
     uint4 w[kMaxRed]; // {lo, tag, hi, tag}
 };
 static_assert(sizeof(RedSlot) == 64, "RedSlot must be 64 bytes");
-constexpr size_t kCommFlagsOff = 4096, kCommBulkFlagsOff = 4096 + 1024, kCommHaloOff = 8192;
+constexpr int kWide = 8;
+struct WideSlot
+{
+    uint4 w[kWide];
+};
+constexpr size_t kCommWideOff = 1024, kCommFlagsOff = 4096, kCommBulkFlagsOff = 4096 + 1024, kCommHaloOff = 8192;
 constexpr int kPushChunk = 512; // halo entries per push chunk (one release-add on the consumer's flag per chunk)
 
+// Flow control of the halo exchange. Every rank executes the same sequence of pushes (one per multiplied vector, at
+// every level of the AMG cycle); push number e writes the parity-(e & 1) halo regions of its consumers in chunks and
+// adds 1 to the consumer's flag per chunk. A consumer does not count epochs times a fixed chunk number (levels differ
+// in their halo sizes, and a new pattern changes them): its own push kernel of the same epoch adds the number of chunks
+// it is about to receive from every source to halo_expect[], and waiters compare the flag with that running total.
+// Neighbour relations are symmetric (nbr_mask: union over all levels of "sends to" and "receives from"), every push
+// delivers at least one (possibly empty) chunk to every neighbour, and a push first waits until the previous epoch has
+// landed completely -- so a rank can never overwrite a parity buffer a neighbour is still reading.
 struct CommDev
 {
     int world = 1, rank = 0;
+    unsigned nbr_mask = 0;            // ranks this one exchanges halo values with (symmetric)
     long long halo_cap = 0;           // doubles per (parity, source rank) region
+    long long spin_limit = 6000000000ll; // SM clocks a wait may take before the solve fails (Params::comm_timeout_s)
     unsigned char *peer[kMaxRanks];   // comm buffer base of every rank (peer[rank] is local)
-    int in_chunks[kMaxRanks];         // push chunks per epoch this rank receives from every source (0: none)
     unsigned long long *red_seq;      // local: number of all-reduces completed
     unsigned long long *push_epoch;   // local: number of halo pushes completed
+    unsigned long long *halo_expect;  // local [8]: push chunks expected so far from every source (all pushes up to push_epoch)
     unsigned long long *bulk_epoch;   // local: number of bulk all-reduce segments completed
-    unsigned long long *bulk_expect;  // local [8]: push chunks expected so far from every source (bulk all-reduce)
-    int *error;                       // local: set to 1 on a spin-wait timeout
+    unsigned long long *bulk_expect;  // local [8]: chunks expected so far from every source (bulk exchanges)
+    unsigned long long *wide_seq;     // local: number of wide all-gathers completed
+    int *error;                       // local: set to 1 on a spin-wait timeout; stays set until psb200_dist_reset
     __host__ __device__ RedSlot *slot(int owner, int parity, int src) const
     {
         return reinterpret_cast<RedSlot *>(peer[owner]) + parity * kMaxRanks + src;
+    }
+    __host__ __device__ WideSlot *wide(int owner, int parity, int src) const
+    {
+        return reinterpret_cast<WideSlot *>(peer[owner] + kCommWideOff) + parity * kMaxRanks + src;
     }
     __host__ __device__ unsigned long long *halo_flag(int owner, int src) const
     {
@@ -211,9 +240,14 @@ struct CommDev
     {
         return reinterpret_cast<double *>(peer[owner] + kCommHaloOff) + ((long long)(2 + parity) * kMaxRanks + src) * halo_cap;
     }
+    // setup-time staging arena: the bulk area seen as one slot of 2 * halo_cap doubles per source rank
+    __host__ __device__ unsigned char *arena(int owner, int src) const
+    {
+        return reinterpret_cast<unsigned char *>(reinterpret_cast<double *>(peer[owner] + kCommHaloOff) + (long long)(2 * kMaxRanks + 2 * src) * halo_cap);
+    }
+    __host__ __device__ size_t arena_slot_bytes() const { return (size_t)(2 * halo_cap) * sizeof(double); }
 };
 
-constexpr long long kSpinLimit = 6000000000ll; // ~3 s of SM clocks: a lost peer becomes an error, not a hang
 
 __device__ __forceinline__ unsigned long long ld_sys(const unsigned long long *p)
 {
@@ -256,14 +290,14 @@ __device__ __forceinline__ uint4 ld_ll(const uint4 *p)
 }
 // spin until *p >= want (system scope); false on timeout. Once a wait has timed out on this rank (*err set) every later
 // wait gives up at once: a lost peer costs one spin limit, not one per kernel of a captured graph.
-__device__ __forceinline__ bool spin_ge(const unsigned long long *p, unsigned long long want, const int *err = nullptr)
+__device__ __forceinline__ bool spin_ge(const unsigned long long *p, unsigned long long want, const int *err, long long limit)
 {
     if (err && *(const volatile int *)err)
         return false;
     const long long t0 = clock64();
     while (ld_sys(p) < want)
     {
-        if (clock64() - t0 > kSpinLimit)
+        if (clock64() - t0 > limit)
             return false;
         __nanosleep(20);
     }
@@ -356,7 +390,7 @@ __device__ __forceinline__ void comm_allreduce_seq(const CommDev &c, double (&to
             uint4 v = ld_ll(&src->w[i]);
             while (v.y != tag || v.w != tag)
             {
-                if (failed_before || clock64() - t0 > kSpinLimit)
+                if (failed_before || clock64() - t0 > c.spin_limit)
                 {
                     *c.error = 1;
                     break;

@@ -20,16 +20,36 @@ struct DistPlanHost
     std::vector<int> halo_cols;     // global ids of the halo columns, ascending (grouped by owner automatically)
     long long r0() const { return offsets[rank]; }
     long long r1() const { return offsets[rank + 1]; }
-    // align: row offsets are rounded up to a multiple of `align` (block problems keep the rows of a node together)
+    // align: row offsets are rounded up to a multiple of `align` (block problems keep the rows of a node together), and
+    // halo / send lists are completed to whole nodes (all `align` dofs of a node travel together), so that the local
+    // matrix can be expanded to full align x align blocks including its halo columns
     void build(long long n, long long nnz, const int *outer, const int *inner, int rank_, int world_, long long halo_cap_, int align = 1);
 };
 
-// Device view of the send side of the halo exchange (see push_section, dist.cu)
+// Device view of the send side of one halo exchange (see push_section, dist.cu)
 struct PushList
 {
-    const int *rows;                                          // local row ids, grouped by destination
+    const int *rows;                                             // local row ids, grouped by destination
     const int *chunk_peer, *chunk_start, *chunk_cnt, *chunk_off; // per chunk: destination, first entry in rows, entries, offset in the destination's region
     int nchunks;
+    int in_chunks[kMaxRanks]; // chunks this rank receives from every source in the same push (0: not a neighbour)
+};
+
+// Halo exchange plan of one row-partitioned matrix (the fine matrix, or one level of the partitioned AMG hierarchy):
+// host lists + the device push list. finalize() cuts the send lists into chunks for a given neighbour mask: every
+// neighbour gets at least one (possibly empty) chunk per push, see CommDev.
+struct HaloPlan
+{
+    std::vector<int> send_begin, send_rows, recv_count;
+    DevBuf<int> push_rows, chunk_tab;
+    int n_push = 0, n_chunks = 0, world = 1;
+    int in_chunks[kMaxRanks] = {};
+    unsigned mask() const; // ranks this plan sends to or receives from
+    void finalize(unsigned nbr_mask, cudaStream_t st);
+    PushList push() const;
+    // CTAs that push: one per chunk up to 128 (a CTA loops over chunks beyond that); at least one on a multi-rank run so
+    // that the epochs advance in lockstep
+    int push_ctas() const { return world > 1 ? std::max(1, std::min(128, n_chunks)) : 0; }
 };
 
 struct DistState
@@ -40,13 +60,12 @@ struct DistState
     size_t comm_bytes = 0;
     void *peer[kMaxRanks] = {};
     bool connected = false;
-    unsigned long long *counters = nullptr; // device: [0] red_seq, [1] push_epoch, [2] error (int)
+    bool poisoned = false; // a wait timed out: the ranks' counters may disagree; every call fails until psb200_dist_reset
+    unsigned long long *counters = nullptr; // device: see dist_connect
     DistPlanHost plan;
-    // device push list: send rows of all destinations concatenated + the chunk table [peer | start | count | offset]
-    DevBuf<int> push_rows, chunk_tab;
-    int n_push = 0, n_chunks = 0;
-    unsigned send_mask = 0, recv_mask = 0;
-    DevBuf<double> vp2; // second direction buffer (p ping-pongs so pushed values never race with the update)
+    HaloPlan fine;         // halo exchange of the fine matrix
+    unsigned nbr_mask = 0; // union of the neighbour masks of the fine matrix and of every partitioned AMG level
+    DevBuf<double> vp2;    // second direction buffer (p ping-pongs so pushed values never race with the update)
     // values ingest: the CSC window [val_lo, val_hi) that holds every local entry is uploaded as one
     // contiguous copy and gathered on the device (d_perm[k] = perm[k] - val_lo)
     long long val_lo = 0, val_hi = 0;
@@ -57,7 +76,5 @@ struct DistState
     DevBuf<int> diag_src; // A_diag.va[k] = A.va[diag_src[k]]
     ~DistState();
 };
-
-PushList make_push(DistState &d);
 
 } // namespace psb

@@ -15,7 +15,8 @@ struct KState
 {
     double rz, rz_new, pAp, rn2, bn2, thr, tol;
     double rho, rho_old, alpha, omega, r0v, tt, ts, r0n2;
-    int iter, done, status, max_iter, restart, restarts, pad0, pad1;
+    double c_beta; // cg1r: beta of the current trip
+    int iter, done, status, max_iter, restart, restarts, c_started, pad1;
 };
 enum : int
 {
@@ -36,7 +37,7 @@ struct CsrView
     // row-partitioned (multi-GPU) matrices: columns >= nl address the halo values the peers pushed
     // into this rank's comm buffer instead of the local x. Single GPU: nl = INT_MAX, halo_mask = 0.
     int nl;
-    unsigned halo_mask; // bit q set: rank q pushes halo values to this rank
+    unsigned halo_mask; // non-zero: the matrix has halo columns (the ranks to wait for are CommDev::nbr_mask)
     // stream schedule on a row partition: sequence position -> tile with the tiles that touch no halo column first
     // (positions < n_interior), so the multiplication starts while the neighbours' pushes are still on the wire
     const int *tile_order;
@@ -50,26 +51,26 @@ __device__ __forceinline__ double ldx(const double *__restrict__ x, const double
     return c < nl ? __ldg(x + c) : __ldcg(xh + (c - nl));
 }
 
-// Waits until every neighbour's push number `epoch` has landed completely: the consumer's flag of source q
-// counts landed push chunks, so push `epoch` is complete once it reaches epoch * in_chunks[q]. Called by all
-// threads of a CTA; returns the halo base pointer of that epoch.
-__device__ __forceinline__ const double *wait_halo_epoch(unsigned halo_mask, const CommDev &c, unsigned long long epoch)
+// Waits until everything the neighbours have pushed so far has landed completely: the flag of source q counts landed
+// push chunks and halo_expect[q] is the running total this rank's own push kernels have announced (common.cuh, CommDev).
+// Called by all threads of a CTA.
+__device__ __forceinline__ void wait_pushes_landed(const CommDev &c)
 {
-    if ((int)threadIdx.x < c.world && ((halo_mask >> threadIdx.x) & 1u))
+    if ((int)threadIdx.x < c.world && ((c.nbr_mask >> threadIdx.x) & 1u))
     {
-        if (!spin_ge(c.halo_flag(c.rank, threadIdx.x), epoch * (unsigned long long)c.in_chunks[threadIdx.x], c.error))
+        if (!spin_ge(c.halo_flag(c.rank, threadIdx.x), c.halo_expect[threadIdx.x], c.error, c.spin_limit))
             *c.error = 1;
         fence_acq_rel_sys();
     }
     __syncthreads();
-    return c.halo(c.rank, (int)(epoch & 1), 0);
 }
-// Kernel-start form: pushes completed locally == epoch of the vector being multiplied.
+// Kernel-start form for a multiplying kernel: returns the halo base pointer of the vector pushed last.
 __device__ __forceinline__ const double *wait_halo(const CsrView &A, const CommDev &c)
 {
     if (A.halo_mask == 0)
         return nullptr;
-    return wait_halo_epoch(A.halo_mask, c, *c.push_epoch);
+    wait_pushes_landed(c);
+    return c.halo(c.rank, (int)(*c.push_epoch & 1), 0);
 }
 
 // ---------------------------------------------------------------------------------- finalizers

@@ -4,6 +4,7 @@
 #include "solver.hpp"
 #include "amg.hpp"
 #include "dist.hpp"
+#include "amg_dist.hpp"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -298,6 +299,36 @@ inline int blocks_for(long long n, int threads) { return (int)std::max<long long
 
 } // namespace
 
+// Sorts every row of a CSR pattern by column (insertion sort, one thread per row; rows are short and nearly sorted: the
+// local rows of a row partition are three ascending runs after the [local | halo] column remap). perm moves along.
+__global__ void sort_rows_kernel(int n, const int *__restrict__ rp, int *__restrict__ ci, int *__restrict__ perm)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const int kb = rp[i], ke = rp[i + 1];
+    for (int k = kb + 1; k < ke; ++k)
+    {
+        const int c = ci[k], p = perm[k];
+        int q = k - 1;
+        while (q >= kb && ci[q] > c)
+        {
+            ci[q + 1] = ci[q];
+            perm[q + 1] = perm[q];
+            --q;
+        }
+        ci[q + 1] = c;
+        perm[q + 1] = p;
+    }
+}
+void sort_rows_by_column(Ctx &ctx, long long n, DevBuf<int> &rp, DevBuf<int> &ci, DevBuf<int> &perm)
+{
+    if (n <= 0)
+        return;
+    sort_rows_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx.stream>>>((int)n, rp.p, ci.p, perm.p);
+    check_launch();
+}
+
 // Full-block expansion of a sorted scalar CSR pattern (see the comment above merged_block_cols): rp / ci / perm are
 // replaced by the expanded arrays (perm = -1 marks fill-in); returns the new nnz. n must be a multiple of B.
 long long expand_block_pattern(Ctx &ctx, int B, long long n, DevBuf<int> &rp, DevBuf<int> &ci, DevBuf<int> &perm)
@@ -345,6 +376,7 @@ Solver::~Solver()
     if (ctx.stream)
         cudaStreamSynchronize(ctx.stream); // kernels in flight may still read the helper instance's matrix (full_)
     amg.reset();
+    amg_dist.reset();
     if (graph_exec)
         cudaGraphExecDestroy(graph_exec);
     for (auto &e : ev)
@@ -513,8 +545,8 @@ void Solver::set_parameters(const std::string &json)
         throw std::runtime_error("psb200: unknown spmv_kernel '" + np.spmv_kernel + "' (auto | stream | stream<2|4|8|16> | vector<1|2|4|8|16|32> | scalar | bsr)");
     if (np.precond != "jacobi" && np.precond != "amg" && np.precond != "none")
         throw std::runtime_error("psb200: unknown precond '" + np.precond + "' (jacobi | amg | none)");
-    if (np.cg_kernel != "auto" && np.cg_kernel != "persistent" && np.cg_kernel != "split")
-        throw std::runtime_error("psb200: unknown cg_kernel '" + np.cg_kernel + "' (auto | persistent | split)");
+    if (np.cg_kernel != "auto" && np.cg_kernel != "split")
+        throw std::runtime_error("psb200: unknown cg_kernel '" + np.cg_kernel + "' (auto | split)");
     if (np.krylov == "bicgstab" && np.precond == "amg")
         throw std::runtime_error("psb200: bicgstab + amg is not available yet");
     // everything is validated: commit. A change of the preconditioner (or of anything the hierarchy / D^-1 was built from)
@@ -525,7 +557,10 @@ void Solver::set_parameters(const std::string &json)
     {
         factorized = false;
         amg.reset();
+        amg_dist.reset();
     }
+    if (dist && dist->connected)
+        ctx.comm.spin_limit = (long long)std::max(1.0, prm.comm_timeout_s * 1.9e9);
     if (graph_exec)
     {
         cudaGraphExecDestroy(graph_exec);
@@ -537,6 +572,23 @@ void Solver::set_parameters(const std::string &json)
     ctx.profile = prm.profile;
     ctx.pdl = prm.pdl;
     A.use_order = prm.interior_first;
+}
+
+// Hash of the index arrays. On a row partition of W ranks every rank hashes only the W-th part of both arrays that
+// corresponds to its rank (the parts cover the arrays; the ranks combine their verdicts, see analyze_pattern), so the
+// per-factorize pattern check costs 1/W of a pass over the indices per rank instead of a full pass on every rank.
+unsigned long long Solver::pattern_hash_of(long long n_, long long nnz_, const int *outer, const int *inner) const
+{
+    const unsigned long long seed = 0x5bd1e995ull + (unsigned long long)n_;
+    if (dist && dist->connected && dist->world > 1)
+    {
+        const long long W = dist->world, r = dist->rank;
+        const long long o0 = (n_ + 1) * r / W, o1 = (n_ + 1) * (r + 1) / W, i0 = nnz_ * r / W, i1 = nnz_ * (r + 1) / W;
+        unsigned long long h = hash_words(outer + o0, sizeof(int) * (size_t)(o1 - o0), seed + (unsigned long long)nnz_);
+        return hash_words(inner + i0, sizeof(int) * (size_t)(i1 - i0), h);
+    }
+    unsigned long long h = hash_words(outer, sizeof(int) * (size_t)(n_ + 1), seed);
+    return hash_words(inner, sizeof(int) * (size_t)nnz_, h);
 }
 
 // ==================================================================================== analyze_pattern
@@ -555,9 +607,11 @@ void Solver::analyze_pattern(long long n_, long long nnz_, const int *outer, con
     ensure_ctx(*this);
     const double t0 = now_ms();
     precond_num = precond_num_;
-    unsigned long long h = hash_words(outer, sizeof(int) * (size_t)(n_ + 1), 0x5bd1e995ull + (unsigned long long)n_);
-    h = hash_words(inner, sizeof(int) * (size_t)nnz_, h);
-    if (analyzed && n_global == n_ && nnz_global == nnz_ && h == pattern_hash && pattern_block == std::max(1, prm.block_size))
+    const unsigned long long h = pattern_hash_of(n_, nnz_, outer, inner);
+    bool same = analyzed && n_global == n_ && nnz_global == nnz_ && h == pattern_hash && pattern_block == std::max(1, prm.block_size);
+    if (dist && dist->connected && dist->world > 1)
+        same = dist_max(same ? 0.0 : 1.0) == 0.0; // collective decision: a change seen by any rank re-analyses on all
+    if (same)
     {
         analyze_skipped = true; // Newton calls analyze_pattern every iteration with an unchanged pattern (Newton.cpp:189)
         t_analyze_ms = now_ms() - t0;
@@ -567,6 +621,7 @@ void Solver::analyze_pattern(long long n_, long long nnz_, const int *outer, con
     analyzed = false;
     factorized = false;
     amg.reset();
+    amg_dist.reset();
     if (graph_exec)
     {
         cudaGraphExecDestroy(graph_exec);
@@ -706,9 +761,9 @@ void Solver::factorize(long long n_, long long nnz_, const int *outer, const int
         if (!need && prm.verify_pattern && outer && inner)
         {
             // guard against a silently changed pattern (Newton re-assembles every iteration, Newton.cpp:189-191)
-            unsigned long long h = hash_words(outer, sizeof(int) * (size_t)(n_ + 1), 0x5bd1e995ull + (unsigned long long)n_);
-            h = hash_words(inner, sizeof(int) * (size_t)nnz_, h);
-            need = h != pattern_hash;
+            need = pattern_hash_of(n_, nnz_, outer, inner) != pattern_hash;
+            if (dist && dist->connected && dist->world > 1)
+                need = dist_max(need ? 1.0 : 0.0) != 0.0;
         }
         if (need)
         {
@@ -743,6 +798,8 @@ bool Solver::amg_global() const
 {
     return dist && prm.precond == "amg" && prm.amg.dist_mode == "global" && std::max(1, prm.block_size) == 1;
 }
+// Row partition + AMG with every large level partitioned (amg_dist.cu): scalar and block problems
+bool Solver::amg_partitioned() const { return dist && prm.precond == "amg" && prm.amg.dist_mode == "partitioned"; }
 
 // values of the whole matrix into the helper instance (pattern analysed in analyze_pattern)
 void Solver::factorize_full_for_amg(const double *h_vals, const double *d_vals, double diag_shift)
@@ -822,11 +879,20 @@ void Solver::factorize_tail(double t0)
         const double t1 = now_ms();
         AmgParams ap = prm.amg;
         ap.block_size = pattern_block;
-        amg = std::make_unique<AmgHierarchy>(ctx, ap);
-        if (dist && amg_global())
+        amg.reset();
+        amg_dist.reset();
+        if (amg_partitioned())
+        {
+            // multi-GPU: every level above amg.replicate_below rows is row-partitioned (decoupled aggregation, rank-local
+            // P / R, distributed Galerkin product), the small levels are replicated; memory per rank ~ 1 / world
+            amg_dist = std::make_unique<AmgDist>(*this, ap);
+            amg_dist->setup(imposed_aggregates);
+        }
+        else if (dist && amg_global())
         {
             // multi-GPU, scalar problems: the hierarchy of the WHOLE matrix on every rank (setup is redundant, reductions
             // stay local), level 0 of the cycle partitioned, coarse levels replicated -- the iteration counts of 1 GPU
+            amg = std::make_unique<AmgHierarchy>(ctx, ap);
             {
                 LocalScope local(ctx);
                 amg->setup(full_->A, imposed_aggregates);
@@ -837,14 +903,18 @@ void Solver::factorize_tail(double t0)
         }
         else if (dist)
         {
-            // multi-GPU, block problems (or amg.dist_mode = local): every rank builds the hierarchy of its own diagonal
-            // block (block-Jacobi across ranks, no communication in the cycle)
+            // multi-GPU, amg.dist_mode = local (and block problems in global mode): every rank builds the hierarchy of its
+            // own diagonal block (block-Jacobi across ranks, no communication in the cycle)
+            amg = std::make_unique<AmgHierarchy>(ctx, ap);
             LocalScope local(ctx);
             build_diag_block_dist();
             amg->setup(dist->A_diag, imposed_aggregates);
         }
         else
+        {
+            amg = std::make_unique<AmgHierarchy>(ctx, ap);
             amg->setup(A, imposed_aggregates);
+        }
         PSB_CUDA(cudaStreamSynchronize(st));
         t_setup_precond_ms = now_ms() - t1;
         if (graph_exec)
@@ -855,7 +925,10 @@ void Solver::factorize_tail(double t0)
         }
     }
     else
+    {
         amg.reset();
+        amg_dist.reset();
+    }
     factorized = true;
     last_iters = 0;
     last_error = 0;
@@ -874,7 +947,9 @@ void Solver::gather_values_to_csr(const double *d_csc_vals)
 
 void Solver::run_solver(const double *d_b)
 {
-    if (dist)
+    if (prm.krylov == "cg1r")
+        run_cg1r(d_b);
+    else if (dist)
         prm.precond == "amg" ? run_cg_amgcl_dist(d_b) : run_cg_eigen_dist(d_b);
     else if (prm.krylov == "bicgstab")
         run_bicgstab(d_b);
@@ -1040,8 +1115,6 @@ void Solver::finish_solve()
     if (prm.profile)
         ctx.prof_collect();
     const KState &s = h_state[2];
-    if (s.status == ST_COMM)
-        throw std::runtime_error("psb200_solve: a grid-wide or cross-GPU wait timed out inside the persistent CG kernel");
     last_iters = s.iter;
     last_status = s.done ? s.status : ST_MAXITER;
     if (s.status == ST_ZERO_RHS)
@@ -1072,15 +1145,6 @@ void init_state(Solver &s, double tol, int max_iter)
 // Jacobi-PCG in Eigen's ordering (reference path EigenSolver.tpp:108-114 -> Eigen
 // conjugate_gradient()). Per iteration: 1 fused SpMV+dot, 1 fused x/r update + ||r||^2 + r.z,
 // 1 direction update = B_spmv + 88 N bytes of compulsory traffic.
-// The persistent kernel implements the TMA stream schedule only; per-launch profiling needs the split kernels.
-// auto = split: measured on B200 (profiles/r01_persist_vs_split.txt) the kernel-per-phase path is faster at 1 and 2
-// GPUs (at 4 CTAs / SM the vector phases of the fused kernel lose ~15 % of the HBM bandwidth to load imbalance
-// between SMs); the persistent kernel stays selectable for latency-bound partitions (many ranks, small systems).
-bool Solver::use_persist() const
-{
-    return prm.cg_kernel == "persistent" && A.kind == SPMV_STREAM && A.lpr == 1 && !prm.profile && n > 0;
-}
-
 void Solver::run_cg_eigen(const double *d_b)
 {
     KState *S = d_state;
@@ -1088,19 +1152,6 @@ void Solver::run_cg_eigen(const double *d_b)
     init_state(*this, prm.tolerance, prm.max_iter);
     launch_spmv(ctx, "spmv_residual", A, vx.p, EpiResidualNorms{vr.p, d_b, dinv.p}, FinInitEigen{S});
     launch_vec(ctx, "cg_dir", n_pad, OpCgDirEigen<true>{vp.p, vr.p, dinv.p, S, 0.0}, FinNone{}, done);
-    if (use_persist())
-    {
-        const int batch_iters = std::max(2, prm.check_every & ~1);
-        vp2.alloc((size_t)n_pad, false);
-        persist_reset();
-        auto batch = [&]() { launch_cg_persist(vp.p, vp2.p, batch_iters); };
-        std::ostringstream key;
-        key << "cg_persist/" << n << "/" << (void *)vx.p << "/" << (void *)A.va.p << "/" << (void *)vp2.p << "/" << batch_iters;
-        drive(batch, batch_iters, key.str());
-        finish_solve();
-        persist_collect();
-        return;
-    }
     auto batch = [&]() {
         for (int i = 0; i < prm.check_every; ++i)
         {
@@ -1276,25 +1327,20 @@ void Solver::build_info()
     if (dist)
         o << ",\"dist\":{\"rank\":" << dist->rank << ",\"world\":" << dist->world << ",\"row_begin\":" << dist->plan.r0()
           << ",\"row_end\":" << dist->plan.r1() << ",\"local_nnz\":" << nnz << ",\"halo_in\":" << dist->plan.halo_cols.size()
-          << ",\"halo_out\":" << dist->n_push << "}";
+          << ",\"halo_out\":" << dist->fine.send_rows.size() << ",\"nbr_mask\":" << dist->nbr_mask << "}";
     o << ",\"symmetric_pattern\":" << (sym_pattern ? "true" : "false");
     o << ",\"analyze_skipped\":" << (analyze_skipped ? "true" : "false");
     o << ",\"spmv_kernel\":" << jstr(A.kernel_name());
-    o << ",\"cg_kernel\":" << jstr(use_persist() ? "persistent" : "split");
-    if (use_persist())
-    {
-        o << ",\"persist_cycles\":[";
-        for (int i = 0; i < 6; ++i)
-            o << (i ? "," : "") << jnum(persist_cycles[i]);
-        o << "]";
-    }
+    o << ",\"cg_kernel\":\"split\"";
     o << ",\"time_analyze_ms\":" << jnum(t_analyze_ms) << ",\"time_factorize_ms\":" << jnum(t_factorize_ms);
     o << ",\"time_precond_setup_ms\":" << jnum(t_setup_precond_ms) << ",\"time_solve_ms\":" << jnum(t_solve_ms);
     o << ",\"gpu_launches\":" << ctx.launches;
     if (amg)
         o << ",\"amg\":" << amg->info_json();
-    if (amg && dist)
-        o << ",\"amg_dist_mode\":" << jstr(amg->has_dist_fine() ? "global" : "local");
+    if (amg_dist)
+        o << ",\"amg\":" << amg_dist->info_json();
+    if ((amg || amg_dist) && dist)
+        o << ",\"amg_dist_mode\":" << jstr(amg_dist ? "partitioned" : amg->has_dist_fine() ? "global" : "local");
     if (!ctx.prof.empty())
     {
         o << ",\"profile\":{";

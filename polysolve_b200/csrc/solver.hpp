@@ -63,7 +63,7 @@ struct Params
     // resident while the predecessor drains land unevenly on the SMs, and the vector kernels are statically partitioned)
     bool pdl = false;
     std::string spmv_kernel = "auto";
-    std::string cg_kernel = "auto"; // Jacobi-PCG: persistent (one cooperative launch per batch) | split (one kernel per phase) | auto
+    std::string cg_kernel = "auto"; // Jacobi-PCG schedule: split (one kernel per phase) | auto (= split; the persistent cooperative kernel of round 1 measured slower and was removed)
     int device = -1; // -1: current device
     int block_size = 1;
     bool profile = false;
@@ -73,8 +73,10 @@ struct Params
 };
 
 class AmgHierarchy; // amg.cu
+class AmgDist;      // amg_dist.cu
 
 struct DistState; // dist.hpp / dist.cu
+struct HaloPlan;
 
 struct Solver
 {
@@ -94,8 +96,20 @@ struct Solver
     void factorize_values_dist(const double *vals);
     void run_cg_eigen_dist(const double *d_b);
     void run_cg_amgcl_dist(const double *d_b);
+    void run_cg1r(const double *d_b); // single-reduction PCG (any world size)
     void build_diag_block_dist();
     void check_comm_error();
+    void check_not_poisoned() const;
+    void dist_reset();
+    void dist_set_nbr_mask(unsigned mask);
+    // host-level collectives over the comm buffer (setup time; every rank calls them in the same order)
+    void dist_allgather8(const double in[8], double out[64]); // out[q * 8 + i] = in[i] of rank q; barrier semantics
+    void dist_barrier();
+    double dist_max(double v);
+    void dist_gather_ll(long long v, long long out[kMaxRanks]);
+    void dist_alltoallv(const void *const send[kMaxRanks], const size_t send_bytes[kMaxRanks], void *const recv[kMaxRanks], size_t recv_bytes[kMaxRanks]);
+    void push_halo(const HaloPlan &hp, const double *d_v, const int *done);
+    void bulk_allgather(const double *d_mine, double *d_out, const long long *offsets, const int *done);
 
     // pattern state (analyze_pattern)
     long long n = 0, nnz = 0;
@@ -113,14 +127,6 @@ struct Solver
 
     // work vectors (padded, zero tails)
     DevBuf<double> vb, vx, vr, vp, vq, vz, vy, vv, vt, vr0;
-    DevBuf<double> vp2;               // ping-pong partner of vp (persistent CG kernel)
-    DevBuf<unsigned long long> gbar;  // grid-sync state of the persistent CG kernel (cg_persist.cu)
-    bool use_persist() const;
-    int persist_grid();
-    void persist_reset();
-    void persist_collect();
-    double persist_cycles[6] = {0, 0, 0, 0, 0, 0}; // CTA 0: spmv, sync, update, sync, dir+push, sync (SM cycles, last solve)
-    void launch_cg_persist(double *p_cur, double *p_other, int iters);
     KState *d_state = nullptr;
     KState *h_state = nullptr; // pinned, 4 slots
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -132,6 +138,8 @@ struct Solver
     // CSR form; the hierarchy is built from it on every rank and only level 0 of the cycle is partitioned (amg.hpp).
     std::unique_ptr<Solver> full_;
     bool amg_global() const;
+    bool amg_partitioned() const;
+    std::unique_ptr<AmgDist> amg_dist; // row partition, amg.dist_mode = partitioned
     void factorize_full_for_amg(const double *h_vals, const double *d_vals, double diag_shift);
     std::unique_ptr<AmgHierarchy> amg;
     std::vector<std::vector<int>> imposed_aggregates;
@@ -146,6 +154,7 @@ struct Solver
     Solver();
     ~Solver();
     void set_parameters(const std::string &json);
+    unsigned long long pattern_hash_of(long long n, long long nnz, const int *outer, const int *inner) const;
     void analyze_pattern(long long n, long long nnz, const int *outer, const int *inner, int precond_num);
     void factorize(long long n, long long nnz, const int *outer, const int *inner, const double *vals);
     void factorize_device(long long n, long long nnz, const double *d_vals, double diag_shift);
@@ -183,6 +192,7 @@ struct Solver
 
 void ensure_ctx(Solver &s);
 long long expand_block_pattern(Ctx &ctx, int B, long long n, DevBuf<int> &rp, DevBuf<int> &ci, DevBuf<int> &perm);
+void sort_rows_by_column(Ctx &ctx, long long n, DevBuf<int> &rp, DevBuf<int> &ci, DevBuf<int> &perm);
 void init_state(Solver &s, double tol, int max_iter);
 
 } // namespace psb

@@ -193,6 +193,10 @@ class Solver:
         dist.barrier()
         return rank, world
 
+    def dist_reset(self):
+        """Collective recovery after a communication timeout (barrier on the host before and after)."""
+        self._check(self._L.psb200_dist_reset(self._h))
+
     def dist_local_range(self):
         a, b = C.c_int64(), C.c_int64()
         self._check(self._L.psb200_dist_local_range(self._h, C.byref(a), C.byref(b)))
