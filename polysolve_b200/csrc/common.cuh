@@ -208,14 +208,14 @@ struct CommDev
     unsigned nbr_mask = 0;            // ranks this one exchanges halo values with (symmetric)
     long long halo_cap = 0;           // doubles per (parity, source rank) region
     long long spin_limit = 6000000000ll; // SM clocks a wait may take before the solve fails (Params::comm_timeout_s)
-    unsigned char *peer[kMaxRanks];   // comm buffer base of every rank (peer[rank] is local)
-    unsigned long long *red_seq;      // local: number of all-reduces completed
-    unsigned long long *push_epoch;   // local: number of halo pushes completed
-    unsigned long long *halo_expect;  // local [8]: push chunks expected so far from every source (all pushes up to push_epoch)
-    unsigned long long *bulk_epoch;   // local: number of bulk all-reduce segments completed
-    unsigned long long *bulk_expect;  // local [8]: chunks expected so far from every source (bulk exchanges)
-    unsigned long long *wide_seq;     // local: number of wide all-gathers completed
-    int *error;                       // local: set to 1 on a spin-wait timeout; stays set until psb200_dist_reset
+    unsigned char *peer[kMaxRanks] = {}; // comm buffer base of every rank (peer[rank] is local)
+    unsigned long long *red_seq = nullptr;     // local: number of all-reduces completed
+    unsigned long long *push_epoch = nullptr;  // local: number of halo pushes completed
+    unsigned long long *halo_expect = nullptr; // local [8]: push chunks expected so far from every source (all pushes up to push_epoch)
+    unsigned long long *bulk_epoch = nullptr;  // local: number of bulk all-reduce segments completed
+    unsigned long long *bulk_expect = nullptr; // local [8]: chunks expected so far from every source (bulk exchanges)
+    unsigned long long *wide_seq = nullptr;    // local: number of wide all-gathers completed
+    int *error = nullptr;                      // local: set to 1 on a spin-wait timeout; stays set until psb200_dist_reset
     __host__ __device__ RedSlot *slot(int owner, int parity, int src) const
     {
         return reinterpret_cast<RedSlot *>(peer[owner]) + parity * kMaxRanks + src;

@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(THREADS) cg_dir_dist_kernel(long long n2, doub
         return;
     const double beta = FIRST ? 0.0 : st->rz_new / st->rz;
     const int push_blocks = (int)gridDim.x - vec_blocks;
-    const unsigned long long push_no = *rc.comm.push_epoch + 1;
+    const unsigned long long push_no = push_blocks > 0 ? *rc.comm.push_epoch + 1 : 0ull; // single GPU: no comm state
     if ((int)blockIdx.x >= push_blocks)
     {
         const long long stride = (long long)vec_blocks * THREADS;
@@ -1032,7 +1032,7 @@ __global__ void __launch_bounds__(THREADS) cg_dir_amgcl_dist_kernel(long long n2
         return;
     const double beta = st->iter ? st->rho / st->rho_old : 0.0;
     const int push_blocks = (int)gridDim.x - vec_blocks;
-    const unsigned long long push_no = *rc.comm.push_epoch + 1;
+    const unsigned long long push_no = push_blocks > 0 ? *rc.comm.push_epoch + 1 : 0ull; // single GPU: no comm state
     if ((int)blockIdx.x >= push_blocks)
     {
         const long long stride = (long long)vec_blocks * THREADS;
@@ -1216,7 +1216,7 @@ __global__ void __launch_bounds__(THREADS) cg1r_start_kernel(long long n2, doubl
     if (done && *done)
         return;
     const int push_blocks = (int)gridDim.x - vec_blocks;
-    const unsigned long long push_no = *rc.comm.push_epoch + 1;
+    const unsigned long long push_no = push_blocks > 0 ? *rc.comm.push_epoch + 1 : 0ull; // single GPU: no comm state
     if ((int)blockIdx.x >= push_blocks)
     {
         const long long stride = (long long)vec_blocks * THREADS;
@@ -1250,7 +1250,7 @@ __global__ void __launch_bounds__(THREADS) cg1r_update_kernel(long long n2, doub
         return;
     const double alpha = st->alpha, beta = st->c_beta;
     const int push_blocks = (int)gridDim.x - vec_blocks;
-    const unsigned long long push_no = *rc.comm.push_epoch + 1;
+    const unsigned long long push_no = push_blocks > 0 ? *rc.comm.push_epoch + 1 : 0ull; // single GPU: no comm state
     if ((int)blockIdx.x >= push_blocks)
     {
         const long long stride = (long long)vec_blocks * THREADS;
