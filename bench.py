@@ -310,7 +310,7 @@ def amg_dist_leg(args, psb, P, local, world, N, outer, inner, vals, b, barrier, 
             "dist_mode": info.get("amg_dist_mode"), "device_bytes_per_rank_max": int(t[2]),
             "fine_matrix_bytes_total": 12 * int(outer[-1]) + 4 * N,
             "roofline": amg_roofline(info, float(t[1]), hbm_peak, world),
-            "what": "SA-AMG-PCG on the row partition: every level above amg.replicate_below rows partitioned (decoupled aggregation, "
+            "what": "SA-AMG-PCG on the row partition: every level above amg.replicate_below non-zeros partitioned (decoupled aggregation, "
                     "rank-local P/R, distributed Galerkin product, per-level halo pushes over NVLink), small levels replicated; "
                     "device_bytes_per_rank_max = device memory this leg allocated on the fullest rank (comm buffer 268 MB included)"}
 
@@ -358,7 +358,7 @@ def parity_block(psb, P, local, world, rank, barrier):
     x, info = solve({"krylov": "cg1r"})
     out["cg1r_iters"] = info["solver_iter"]
     out["cg1r_x_rel_diff_vs_oracle"] = float(np.linalg.norm(x - x0) / np.linalg.norm(x0))
-    x, info = solve({"precond": "amg", "max_iter": 200, "amg": {"replicate_below": 3000}})
+    x, info = solve({"precond": "amg", "max_iter": 200, "amg": {"replicate_below": 50000}})
     out["amg_partitioned_iters"] = info["solver_iter"]
     out["amg_partitioned_levels"] = [lv["rows"] for lv in info["amg"]["levels"]]
     out["amg_rel_residual"] = float(np.linalg.norm(P.spmv_csr(o, i, v, x) - b) / np.linalg.norm(b))

@@ -115,7 +115,7 @@ int psb200_dirichlet_solve_prefactorized(psb200_handle h, const double *vals_or_
  * keeps its rows), psb200_solve receives full-length b / x (each rank reads and writes only its own
  * rows [row_begin, row_end)), psb200_solve_device receives the local slices. Every call is collective.
  * krylov = cg | cg1r (single-reduction CG: one all-reduce per iteration) with precond = jacobi | none, krylov = cg with
- * precond = amg. "amg": {"dist_mode": ...}: "partitioned" (default) = every level above amg.replicate_below rows is
+ * precond = amg. "amg": {"dist_mode": ...}: "partitioned" (default) = every level above amg.replicate_below non-zeros is
  * row-partitioned like the fine matrix (decoupled aggregation, rank-local P / R, distributed Galerkin product, per-level
  * halo exchange; scalar and block problems; device memory per rank ~ 1 / world), smaller levels are replicated;
  * "global" = one hierarchy of the whole matrix on every rank, fine level partitioned (scalar problems); "local" = a

@@ -704,6 +704,13 @@ __global__ void spgemm_expand_rows_kernel(CsrView A, CsrView B, const long long 
 // temporaries stay bounded (C4: 5.4e9 products of A P on one GPU) whatever the size of the product.
 void spgemm(Ctx &c, Temp &tmp, const CsrDev &A, const CsrDev &B, int ncolsB, CsrDev &C)
 {
+    if (spgemm_use_hash() && spgemm_hash(c, tmp, A, B, ncolsB, C))
+        return; // the hand-written shared-memory hash product (spgemm.cu); what follows is the fallback for huge rows
+    spgemm_sort(c, tmp, A, B, ncolsB, C);
+}
+
+void spgemm_sort(Ctx &c, Temp &tmp, const CsrDev &A, const CsrDev &B, int ncolsB, CsrDev &C)
+{
     cudaStream_t st = c.stream;
     C.n = A.n;
     C.ncols = ncolsB;
@@ -1100,6 +1107,12 @@ static int aggregate_mis2(Ctx &c, Temp &tmp, const CsrDev &A, const double *diag
     check_launch();
     PSB_CUDA(cudaStreamSynchronize(st));
     return n_agg;
+}
+
+bool &spgemm_use_hash()
+{
+    static bool on = std::getenv("PSB200_SPGEMM") == nullptr || std::string(std::getenv("PSB200_SPGEMM")) != "sort";
+    return on;
 }
 
 double wall_ms(cudaStream_t st)

@@ -12,7 +12,7 @@
 //    columns (row lengths, then global coarse column ids and values through the staging arena), then two local SpGEMMs;
 //  * every partitioned level has its own halo plan (send lists obtained from the consumers' requests), the smoother
 //    pushes the halo of every iterate exactly like the fine level does;
-//  * levels with fewer than amg.replicate_below rows are replicated: their matrix is all-gathered once at setup, the
+//  * levels with fewer than amg.replicate_below stored non-zeros (summed over the ranks) are replicated: their matrix is all-gathered once at setup, the
 //    cycle all-gathers the coarse right-hand side (one fused kernel over NVLink), runs the remaining levels redundantly on
 //    every rank -- no latency-bound exchanges on tiny levels -- and every rank prolongs from its own slice.
 //
@@ -417,7 +417,7 @@ void AmgDist::setup(const std::vector<std::vector<int>> &imposed)
         s_.dist_gather_ll(Acg.nnz, cnnz);
         const long long cnnz_global = std::accumulate(cnnz, cnnz + W, 0ll);
 
-        const bool replicate = ncg < prm_.replicate_below || li + 2 >= prm_.max_levels || ncg <= prm_.coarse_enough;
+        const bool replicate = cnnz_global < prm_.replicate_below || li + 2 >= prm_.max_levels || ncg <= prm_.coarse_enough;
         tp = wall_ms(st);
         if (replicate)
         {

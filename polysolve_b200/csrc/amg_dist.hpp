@@ -1,4 +1,4 @@
-// Row-partitioned smoothed-aggregation AMG: every level above `replicate_below` rows is partitioned across
+// Row-partitioned smoothed-aggregation AMG: every level above `replicate_below` non-zeros is partitioned across
 // the ranks like the fine matrix, the small levels below are replicated. See amg_dist.cu.
 #pragma once
 #include "amg.hpp"

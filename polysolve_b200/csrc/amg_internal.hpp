@@ -63,6 +63,11 @@ void exclusive_scan_ll(Ctx &c, Temp &tmp, const long long *in, long long *out, l
 void transpose(Ctx &c, Temp &tmp, const CsrDev &M, CsrDev &T);
 // C = A * B, columns of A index the rows of B; rows of C sorted by column
 void spgemm(Ctx &c, Temp &tmp, const CsrDev &A, const CsrDev &B, int ncolsB, CsrDev &C);
+// the two implementations behind spgemm(): shared-memory hashing (spgemm.cu; false = a row exceeds its largest bin) and
+// expand - radix sort - compress (amg.cu; any matrix). PSB200_SPGEMM=sort in the environment forces the second (A/B runs).
+bool spgemm_hash(Ctx &c, Temp &tmp, const CsrDev &A, const CsrDev &B, int ncolsB, CsrDev &C);
+void spgemm_sort(Ctx &c, Temp &tmp, const CsrDev &A, const CsrDev &B, int ncolsB, CsrDev &C);
+bool &spgemm_use_hash();
 // D^-1 (or the inverted diagonal blocks + Ahat), spectral radius, Chebyshev coefficients, work vectors of one level.
 // seed_index: level number in the whole hierarchy (start vector of the power iteration)
 void setup_relaxation(Ctx &c, const AmgParams &prm, AmgLevel &L, int seed_index, const SetupHooks *hooks = nullptr);

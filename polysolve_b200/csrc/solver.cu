@@ -883,7 +883,7 @@ void Solver::factorize_tail(double t0)
         amg_dist.reset();
         if (amg_partitioned())
         {
-            // multi-GPU: every level above amg.replicate_below rows is row-partitioned (decoupled aggregation, rank-local
+            // multi-GPU: every level above amg.replicate_below non-zeros is row-partitioned (decoupled aggregation, rank-local
             // P / R, distributed Galerkin product), the small levels are replicated; memory per rank ~ 1 / world
             amg_dist = std::make_unique<AmgDist>(*this, ap);
             amg_dist->setup(imposed_aggregates);

@@ -30,12 +30,14 @@ struct AmgParams
     int block_size = 1; // AMGCL_Block<B> (reference AMGCL.cpp:246-298): B x B value type
     std::string aggregation = "mis2"; // mis2 (parallel, deterministic) | imposed via debug hook
     // row partitions: "partitioned" = every level is row-partitioned (decoupled aggregation, rank-local P / R, distributed
-    // Galerkin product, per-level halo exchange) down to the levels below replicate_below rows, which are replicated;
+    // Galerkin product, per-level halo exchange) down to the levels below replicate_below non-zeros, which are replicated;
     // "global" = one hierarchy of the whole matrix on every rank, only level 0 partitioned (the iteration counts of the
     // 1-GPU run, no memory partitioning); "local" = every rank its own hierarchy of its diagonal block (block-Jacobi)
     std::string dist_mode = "partitioned";
-    // partitioned mode: levels with fewer global rows than this are replicated on every rank (their cycle needs no exchange)
-    long long replicate_below = 400000;
+    // partitioned mode: levels with fewer stored non-zeros (summed over the ranks) than this are replicated on every rank.
+    // One SpMV of a replicated level costs its whole matrix on every GPU, a partitioned one 1 / world of it plus a halo
+    // push and wait (~10 us): the two break even near 7 M non-zeros on B200 (12 B per non-zero at ~6.5 TB/s).
+    long long replicate_below = 8000000;
     bool same_as(const AmgParams &o) const
     {
         return max_levels == o.max_levels && coarse_enough == o.coarse_enough && direct_coarse == o.direct_coarse && ncycle == o.ncycle &&

@@ -3,6 +3,7 @@
     python scripts/amg_profile.py timers [n]       -> 4 x factorize with the per-level setup timers, 3 x solve
     python scripts/amg_profile.py launches [n]     -> factorize (outside the profiler range) + ONE solve with graphs off
                                                       between cudaProfilerStart/Stop (run under ncu --profile-from-start off)
+    python scripts/amg_profile.py setup [n]        -> one warm factorize, then ONE factorize inside the profiler range
 """
 import json
 import os
@@ -41,6 +42,13 @@ if mode == "timers":
         info = s.get_info()
         print(json.dumps({"solve": k, "wall_s": dt, "iters": info["num_iterations"], "launches": info["gpu_launches"],
                           "solve_ms": info.get("solve_ms"), "amg": {kk: vv for kk, vv in info["amg"].items() if kk != "levels"}}), flush=True)
+elif mode == "setup":
+    s.factorize_raw(N, o, i, v)
+    import torch
+    torch.cuda.cudart().cudaProfilerStart()
+    s.factorize_raw(N, o, i, v)
+    torch.cuda.cudart().cudaProfilerStop()
+    print(json.dumps({"levels": [lv["rows"] for lv in s.get_info()["amg"]["levels"]]}))
 else:
     s.factorize_raw(N, o, i, v)
     import torch

@@ -32,8 +32,8 @@ leaf("/CUDA/tolerance", 1e-12, "float", "Convergence tolerance relative to ||b||
 leaf("/CUDA/max_iter", 1000, "int", "Maximum number of iterations.")
 leaf("/CUDA/check_every", 16, "int", "Iterations per CUDA-graph batch between host polls of the device-side stop flag.", min=1)
 leaf("/CUDA/use_graph", True, "bool", "Replay each batch of iterations as one CUDA graph.")
-leaf("/CUDA/cg_kernel", "auto", "string", "Jacobi-PCG schedule: one kernel per phase, or one persistent cooperative kernel.",
-     options=["auto", "split", "persistent"])
+leaf("/CUDA/cg_kernel", "auto", "string", "Jacobi-PCG schedule: one kernel per phase (the persistent cooperative kernel of round 1 was removed).",
+     options=["auto", "split"])
 leaf("/CUDA/spmv_kernel", "auto", "string", "SpMV schedule: auto | stream | stream<2|4|8|16> | vector<1..32> | scalar | bsr.")
 leaf("/CUDA/block_size", 1, "int", "Block size of vector-valued problems (AMGCL_Block<B>, AMGCL.cpp:111-123).", options=[1, 2, 3])
 leaf("/CUDA/device", -1, "int", "CUDA device ordinal; -1 = the current device.")
@@ -56,7 +56,7 @@ leaf("/CUDA/amg/dist_mode", "partitioned", "string", "Row partitions: partitione
      "row-partitioned (decoupled aggregation, distributed Galerkin product); global = one hierarchy of the whole matrix on every "
      "rank with only level 0 partitioned; local = rank-local hierarchy of the diagonal block (block-Jacobi).",
      options=["partitioned", "global", "local"])
-leaf("/CUDA/amg/replicate_below", 400000, "int", "Row partitions: levels with fewer global rows are replicated on every rank.")
+leaf("/CUDA/amg/replicate_below", 8000000, "int", "Row partitions: levels with fewer stored non-zeros (all ranks together) are replicated on every rank.")
 obj("/CUDA/amg/relax", ["type", "degree", "power_iters", "higher", "lower", "scale", "damping"], "Smoother settings.")
 leaf("/CUDA/amg/relax/type", "chebyshev", "string", "Type of relaxation to use.", options=["chebyshev", "damped_jacobi"])
 leaf("/CUDA/amg/relax/degree", 16, "int", "Degree of the polynomial.")

@@ -208,11 +208,11 @@ def _one_gpu_amg(psb, N, o, i, v, b, tol, block=1):
 
 
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
-@pytest.mark.parametrize("replicate_below", [400000, 3000])
+@pytest.mark.parametrize("replicate_below", [10000000, 50000])
 def test_dist_amg_pcg_partitioned(psb, orc, world, replicate_below):
     """amg.dist_mode = partitioned (default): decoupled aggregation per rank, rank-local P / R, distributed Galerkin product
-    (one exchange of P rows), per-level halo plans, small levels replicated. replicate_below = 400000 keeps only level 0
-    partitioned at this size; 3000 also partitions level 1 (~8k rows), so the coarse-level halo exchange, the request
+    (one exchange of P rows), per-level halo plans, small levels replicated. replicate_below (non-zeros) = 1e7 keeps only
+    level 0 partitioned at this size; 5e4 also partitions level 1 (~6k rows, 1.7e5 non-zeros), so the coarse-level halo exchange, the request
     exchange of the level plans and the partitioned -> replicated transition below it are all exercised.
     Bar: iterations <= 1-GPU + 1 at every rank count, same solution to the solver tolerance."""
     if world > max(1, _ngpu()):
@@ -231,7 +231,7 @@ def test_dist_amg_pcg_partitioned(psb, orc, world, replicate_below):
         assert err < tol and it2 == 0
         assert dinfo["amg_dist_mode"] == "partitioned"
         amg = dinfo["amg"]
-        assert amg["partitioned_levels"] == (1 if replicate_below > N else 2), amg
+        assert amg["partitioned_levels"] == (1 if replicate_below > 1000000 else 2), amg
         assert amg["levels"][0]["rows"] == N and amg["levels"][0]["partitioned"]
         assert sum(1 for lv in amg["levels"]) >= 2
         if world == 1:
@@ -255,7 +255,7 @@ def test_dist_block3_amg_pcg_elasticity(psb, orc, world):
     A = sp.csc_matrix((v, i, o), shape=(N, N))
     x0 = spla.spsolve(A, b)
     _, it1, _ = _one_gpu_amg(psb, N, o, i, v, b, tol, block=3)
-    res = _run(world, m, tol, "amg", 3, "partitioned", {"amg": {"replicate_below": 1500}})
+    res = _run(world, m, tol, "amg", 3, "partitioned", {"amg": {"replicate_below": 20000}})
     rp, ci, _ = orc.csc_to_csr(N, o, i)
     off0 = orc.partition_rows(rp, world, align=3)
     x = np.zeros(N)
