@@ -73,6 +73,9 @@ int psb200_factorize_csc_device(psb200_handle h, int64_t n, int64_t nnz, const d
  * (objFunc.grad_norm(hessian * direction + grad), Newton.cpp:207, with b = -grad). Row partitions: local slices in,
  * the global norm out on every rank. */
 int psb200_residual_norm_device(psb200_handle h, const double *d_x, const double *d_b, int64_t n, double *norm_out);
+/* The same check with full-length HOST vectors; on a row partition every rank passes the full vectors and obtains the
+ * global norm. */
+int psb200_residual_norm(psb200_handle h, const double *x, const double *b, int64_t n, double *norm_out);
 
 /* Solver::get_info(json&) -- Solver.hpp:96. Writes a JSON object with both key conventions:
  * "solver_iter","solver_error" (EigenSolver.tpp:88-89) and "num_iterations","final_res_norm"
@@ -126,6 +129,10 @@ int psb200_dirichlet_solve_prefactorized(psb200_handle h, const double *vals_or_
 int psb200_dist_prepare(psb200_handle h, int rank, int world, int64_t halo_cap_doubles, char handle_out[64]);
 int psb200_dist_connect(psb200_handle h, const char *handles /* world * 64 bytes */);
 int psb200_dist_reset(psb200_handle h);
+/* Every rank contributes its own rows [row_begin, row_end) of x_full and receives everybody's (host vector of n values;
+ * one fused all-gather over NVLink). After psb200_solve this turns the rank-local result into the whole solution on every
+ * rank -- what a Newton driver that evaluates its Problem redundantly needs. No-op on a single GPU. */
+int psb200_dist_allgather(psb200_handle h, double *x_full_inout, int64_t n);
 int psb200_dist_local_range(psb200_handle h, int64_t *row_begin, int64_t *row_end);
 /* Host-only plan of one rank (no GPU needed; used by the CPU tests to check partition offsets and halo
  * lists bit-exactly against the oracle). Caller-allocated arrays: offsets[world+1], counts[3] =

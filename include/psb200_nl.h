@@ -51,6 +51,13 @@ typedef struct psb200_nl_problem
     void (*post_step)(void *user, int iteration, const double *x, const double *grad, int64_t n);
     /* Problem::stop(x) -- Problem.hpp:114; non-zero stops with status "ObjectiveCustomStop" */
     int (*stop)(void *user, const double *x, int64_t n);
+    /* Optional (may be NULL): Problem::hessian with the VALUES left in device memory -- the Hessian is assembled by the
+     * caller's own CUDA kernel straight into a fixed compressed-column pattern (outer / inner: host arrays, the same on
+     * every call) and goes to the linear solver through psb200_factorize_csc_device: nothing of the matrix crosses PCIe
+     * in a Newton step (Newton.cpp:173-214 device-resident; RegularizedNewton's shift is applied on the device and needs
+     * a structurally present diagonal). When set, it is used instead of `hessian`. */
+    int (*hessian_device)(void *user, const double *x, int64_t n, int project_to_psd, int64_t *nnz, const int32_t **outer,
+                          const int32_t **inner, const double **d_vals);
 } psb200_nl_problem;
 
 /* nonlinear::Solver::create. solver_params: the reference's nonlinear JSON (keys and defaults of
@@ -60,6 +67,12 @@ typedef struct psb200_nl_problem
  * Either may be NULL for the defaults. */
 int psb200_nl_create(psb200_nl_handle *out, const char *solver_params_json, const char *linear_params_json);
 int psb200_nl_destroy(psb200_nl_handle h);
+/* Calls hook(user, lin) once for every linear solver the driver owns (one per Newton strategy, Newton.cpp:32-52), in
+ * creation order, before they are first used: a multi-GPU application connects them there (psb200_dist_prepare, exchange
+ * of the IPC handles, psb200_dist_connect -- collectively, every rank in the same order). With connected solvers the
+ * driver all-gathers every Newton step (psb200_dist_allgather), so each rank keeps the whole iterate and evaluates the
+ * Problem redundantly; the Problem must then be deterministic across ranks. `lin` is the linear solver handle of psb200.h (a psb200_handle). */
+int psb200_nl_set_linear_solver_hook(psb200_nl_handle h, void (*hook)(void *user, void *lin), void *user);
 /* nonlinear::Solver::minimize(problem, x): x is in/out. Returns 0 when the loop ended with a converged status;
  * non-zero (message in psb200_nl_last_error) where the reference throws (NaN, iteration limit without
  * allow_out_of_iterations, failure on the last strategy). x always holds the last iterate. */

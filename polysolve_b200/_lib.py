@@ -21,7 +21,7 @@ SYMBOLS = [
     "psb200_create", "psb200_destroy", "psb200_set_parameters", "psb200_set_tolerance", "psb200_set_block_size",
     "psb200_analyze_pattern_csc", "psb200_factorize_csc", "psb200_solve", "psb200_solve_device", "psb200_get_info",
     "psb200_name", "psb200_last_error", "psb200_release_cached_memory", "psb200_factorize_csc_device", "psb200_residual_norm_device",
-    "psb200_dirichlet_solve", "psb200_dirichlet_prefactorize", "psb200_dirichlet_solve_prefactorized", "psb200_dist_prepare", "psb200_dist_connect", "psb200_dist_reset", "psb200_dist_local_range",
+    "psb200_dirichlet_solve", "psb200_dirichlet_prefactorize", "psb200_dirichlet_solve_prefactorized", "psb200_dist_prepare", "psb200_dist_connect", "psb200_dist_reset", "psb200_dist_allgather", "psb200_residual_norm", "psb200_dist_local_range",
     "psb200_dist_plan_host", "psb200_dist_plan_host_aligned", "psb200_debug_get_csr",
     "psb200_spmv", "psb200_bench_spmv", "psb200_get_stream", "psb200_debug_set_aggregates", "psb200_debug_get_level",
     "psb200_precond_apply", "psb200_debug_get_aggregates",
@@ -31,7 +31,10 @@ SYMBOLS = [
     # include/psb200_nl.h
     "psb200_nl_create", "psb200_nl_destroy", "psb200_nl_minimize", "psb200_nl_get_info", "psb200_nl_last_error",
     "psb200_lbfgs_create", "psb200_lbfgs_destroy", "psb200_lbfgs_reset", "psb200_lbfgs_direction", "psb200_lbfgs_direction_device",
-    "psb200_lbfgs_last_error",
+    "psb200_lbfgs_last_error", "psb200_nl_set_linear_solver_hook",
+    # include/psb200_problems.h
+    "psb200_nh_create", "psb200_nh_destroy", "psb200_nh_pattern", "psb200_nh_value", "psb200_nh_gradient", "psb200_nh_hessian_device",
+    "psb200_nh_hessian_host", "psb200_nh_last_error",
 ]
 
 
@@ -89,6 +92,8 @@ def lib():
     L.psb200_dist_prepare.argtypes = [H, C.c_int, C.c_int, C.c_int64, C.c_char_p]
     L.psb200_dist_connect.argtypes = [H, C.c_char_p]
     L.psb200_dist_reset.argtypes = [H]
+    L.psb200_dist_allgather.argtypes = [H, f64p, C.c_int64]
+    L.psb200_residual_norm.argtypes = [H, f64p, f64p, C.c_int64, C.POINTER(C.c_double)]
     L.psb200_dist_local_range.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
     L.psb200_dist_plan_host.argtypes = [C.c_int64, C.c_int64, i32p, i32p, C.c_int, C.c_int, C.c_int64, i64p, i64p,

@@ -135,6 +135,20 @@ int psb200_residual_norm_device(psb200_handle h, const double *d_x, const double
     });
 }
 
+int psb200_residual_norm(psb200_handle h, const double *x, const double *b, int64_t n, double *norm_out)
+{
+    return guarded(h, [&](psb::Solver &s) {
+        const double r = s.residual_norm_host(x, b, n);
+        if (norm_out)
+            *norm_out = r;
+    });
+}
+
+int psb200_dist_allgather(psb200_handle h, double *x_full_inout, int64_t n)
+{
+    return guarded(h, [&](psb::Solver &s) { s.dist_allgather_host(x_full_inout, n); });
+}
+
 int psb200_solve(psb200_handle h, const double *b, double *x, int64_t n)
 {
     return guarded(h, [&](psb::Solver &s) { s.solve_host(b, x, n); });

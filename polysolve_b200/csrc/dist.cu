@@ -852,7 +852,8 @@ void Solver::bulk_allreduce(const double *d_partial, double *d_out, long long le
 // bulk all-reduce: chunk-counted release flags per source, two parities.
 struct GatherOffsets
 {
-    int off[kMaxRanks + 1];
+    int off[kMaxRanks]; // where the segment of rank q starts in the output
+    int len[kMaxRanks]; // its length (<= halo_cap)
 };
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) bulk_allgather_kernel(const double *__restrict__ mine, double *__restrict__ out, GatherOffsets go,
@@ -861,7 +862,7 @@ __global__ void __launch_bounds__(THREADS) bulk_allgather_kernel(const double *_
     if (done && *done)
         return;
     const CommDev &c = rc.comm;
-    const int len = go.off[c.rank + 1] - go.off[c.rank];
+    const int len = go.len[c.rank];
     const int nchunks = (len + kPushChunk - 1) / kPushChunk;
     const unsigned long long epoch = *c.bulk_epoch + 1;
     const int par = (int)(epoch & 1);
@@ -884,7 +885,7 @@ __global__ void __launch_bounds__(THREADS) bulk_allgather_kernel(const double *_
     if ((int)threadIdx.x < c.world)
     {
         const int q = threadIdx.x;
-        const int inq = q == c.rank ? 0 : (go.off[q + 1] - go.off[q] + kPushChunk - 1) / kPushChunk;
+        const int inq = q == c.rank ? 0 : (go.len[q] + kPushChunk - 1) / kPushChunk;
         s_in[q] = inq;
         if (inq > 0)
         {
@@ -898,7 +899,7 @@ __global__ void __launch_bounds__(THREADS) bulk_allgather_kernel(const double *_
     {
         if (q == c.rank)
             continue;
-        const int lq = go.off[q + 1] - go.off[q];
+        const int lq = go.len[q];
         const double *src = c.bulk(c.rank, par, q);
         for (int e = blockIdx.x * THREADS + threadIdx.x; e < lq; e += gridDim.x * THREADS)
             out[go.off[q] + e] = __ldcg(src + e);
@@ -912,23 +913,45 @@ __global__ void __launch_bounds__(THREADS) bulk_allgather_kernel(const double *_
     }
 }
 
+// out[offsets[q] .. offsets[q+1]) = the slice of rank q, on every rank; slices longer than halo_cap travel in segments.
+// Every rank must have a non-empty slice (parity flow control: everybody hears from everybody in every exchange).
 void Solver::bulk_allgather(const double *d_mine, double *d_out, const long long *offsets, const int *done)
 {
     DistState &d = *dist;
-    GatherOffsets go{};
-    long long mx = 0;
-    for (int q = 0; q <= kMaxRanks; ++q)
-        go.off[q] = (int)offsets[std::min(q, d.world)];
+    long long mx = 0, mn = 1ll << 62;
     for (int q = 0; q < d.world; ++q)
+    {
         mx = std::max(mx, offsets[q + 1] - offsets[q]);
-    if (mx > d.halo_cap)
-        throw std::runtime_error("psb200 dist: a slice of a replicated AMG level exceeds halo_cap (raise halo_cap or lower amg.replicate_below)");
-    const int nchunks = (int)((mx + kPushChunk - 1) / kPushChunk);
-    const int grid = std::max(1, std::min(nchunks, 2 * kSMs));
-    ctx.prof_begin("bulk_allgather");
-    bulk_allgather_kernel<kVecThreads><<<grid, kVecThreads, 0, ctx.stream>>>(d_mine, d_out, go, ctx.red(), done);
-    check_launch();
-    ctx.prof_end();
+        mn = std::min(mn, offsets[q + 1] - offsets[q]);
+    }
+    if (mn <= 0)
+        throw std::runtime_error("psb200 dist: all-gather with an empty slice");
+    const long long cap = d.halo_cap;
+    const long long nseg = (mx + cap - 1) / cap;
+    for (long long sg = 0; sg < nseg; ++sg)
+    {
+        GatherOffsets go{};
+        long long smx = 0;
+        for (int q = 0; q < d.world; ++q)
+        {
+            const long long lenq = offsets[q + 1] - offsets[q];
+            // spread every slice evenly over the segments so that no rank has an empty one
+            const long long a = lenq * sg / nseg, b = lenq * (sg + 1) / nseg;
+            go.off[q] = (int)(offsets[q] + a);
+            go.len[q] = (int)(b - a);
+            smx = std::max(smx, b - a);
+            if (b - a <= 0)
+                throw std::runtime_error("psb200 dist: all-gather segment became empty (slices too unbalanced for halo_cap)");
+        }
+        const long long mylen = offsets[d.rank + 1] - offsets[d.rank];
+        const long long my_a = mylen * sg / nseg;
+        const int nchunks = (int)((smx + kPushChunk - 1) / kPushChunk);
+        const int grid = std::max(1, std::min(nchunks, 2 * kSMs));
+        ctx.prof_begin("bulk_allgather");
+        bulk_allgather_kernel<kVecThreads><<<grid, kVecThreads, 0, ctx.stream>>>(d_mine + my_a, d_out, go, ctx.red(), done);
+        check_launch();
+        ctx.prof_end();
+    }
 }
 
 // ---------------------------------------------------------------------------------- rank-local AMG

@@ -458,13 +458,25 @@ struct NewtonStrategy : Strategy
         int64_t nnz = 0;
         const int32_t *outer = nullptr, *inner = nullptr;
         const double *vals = nullptr;
+        const double *d_vals = nullptr; // device-resident values (Problem::hessian_device)
         {
             ScopedTimer t(assembly_time);
-            if (f.p->hessian(f.p->user, x.data(), n, project_to_psd ? 1 : 0, &nnz, &outer, &inner, &vals) != 0)
-                return false;
-            if (kind == 2 && reg_weight > 0)
-                regularize(n, outer, inner, vals, nnz);
+            if (f.p->hessian_device)
+            {
+                if (f.p->hessian_device(f.p->user, x.data(), n, project_to_psd ? 1 : 0, &nnz, &outer, &inner, &d_vals) != 0)
+                    return false;
+            }
+            else
+            {
+                if (f.p->hessian(f.p->user, x.data(), n, project_to_psd ? 1 : 0, &nnz, &outer, &inner, &vals) != 0)
+                    return false;
+                if (kind == 2 && reg_weight > 0)
+                    regularize(n, outer, inner, vals, nnz);
+            }
         }
+        std::vector<double> rhs(g.size());
+        for (size_t i = 0; i < g.size(); ++i)
+            rhs[i] = -g[i];
         {
             ScopedTimer t(inverting_time);
             // Newton.cpp:189: analyze_pattern every iteration (cached by hash on the solver side)
@@ -476,33 +488,29 @@ struct NewtonStrategy : Strategy
             if (rc != PSB200_OK)
                 return false;
             // Newton.cpp:191-202: a failing factorize is recoverable (NaN residual -> next strategy)
-            rc = psb200_factorize_csc(lin, n, nnz, outer, inner, vals);
+            if (d_vals) // RegularizedNewton: hessian += reg_weight I on the device (Newton.cpp:287-290)
+                rc = psb200_factorize_csc_device(lin, n, nnz, d_vals, kind == 2 ? reg_weight : 0.0);
+            else
+                rc = psb200_factorize_csc(lin, n, nnz, outer, inner, vals);
             if (rc == PSB200_ERR_CUDA || rc == PSB200_ERR_COMM || rc == PSB200_ERR_INVALID)
                 throw std::runtime_error(std::string("factorize: ") + psb200_last_error(lin));
             if (rc != PSB200_OK)
                 return false;
             // Newton.cpp:204: solve(-grad, direction); direction carries the previous step in as the initial guess
-            std::vector<double> rhs(g.size());
-            for (size_t i = 0; i < g.size(); ++i)
-                rhs[i] = -g[i];
             dx.resize(g.size());
             if (psb200_solve(lin, rhs.data(), dx.data(), n) != PSB200_OK)
             {
                 err = psb200_last_error(lin); // an exception from solve() propagates in the reference (Newton.cpp:204)
                 throw std::runtime_error(err);
             }
+            // row-partitioned solver: every rank needs the whole step (no-op on one GPU)
+            if (psb200_dist_allgather(lin, dx.data(), n) != PSB200_OK)
+                throw std::runtime_error(std::string("dist_allgather: ") + psb200_last_error(lin));
         }
-        // Newton.cpp:207: residual = ||H dx + g||, through the product SpMV kernel
-        hd.resize(g.size());
-        if (psb200_spmv(lin, dx.data(), hd.data(), n) != PSB200_OK)
+        // Newton.cpp:207: residual = ||H dx + g|| = ||H dx - rhs||, through the product SpMV kernel (global norm on a partition)
+        double residual = 0;
+        if (psb200_residual_norm(lin, dx.data(), rhs.data(), n, &residual) != PSB200_OK)
             throw std::runtime_error(psb200_last_error(lin));
-        double r2 = 0;
-        for (size_t i = 0; i < g.size(); ++i)
-        {
-            const double r = hd[i] + g[i];
-            r2 += r * r;
-        }
-        const double residual = std::sqrt(r2);
         // Newton.cpp:209-211
         std::vector<char> buf(1 << 15);
         size_t need = 0;
@@ -891,6 +899,16 @@ int psb200_nl_create(psb200_nl_handle *out, const char *solver_params_json, cons
 int psb200_nl_destroy(psb200_nl_handle h)
 {
     delete h;
+    return PSB200_OK;
+}
+
+int psb200_nl_set_linear_solver_hook(psb200_nl_handle h, void (*hook)(void *user, void *lin), void *user)
+{
+    if (!h || !hook)
+        return PSB200_ERR_INVALID;
+    for (auto &st : h->strategies)
+        if (auto *ns = dynamic_cast<NewtonStrategy *>(st.get()))
+            hook(user, ns->lin);
     return PSB200_OK;
 }
 

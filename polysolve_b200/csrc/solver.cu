@@ -1047,6 +1047,46 @@ double Solver::residual_norm_device(const double *d_x, const double *d_b, long l
     return std::sqrt(h[0]);
 }
 
+// ||A x - b||_2 with full-length host vectors (on a row partition every rank passes the full vectors and obtains the
+// global norm: the reduction all-reduces inside its kernel). The Newton residual check of Newton.cpp:207.
+double Solver::residual_norm_host(const double *x, const double *b, long long n_)
+{
+    if (!factorized)
+        throw std::runtime_error("psb200_residual_norm: factorize() has not been called");
+    if (n_ != n_global || !x || !b)
+        throw std::invalid_argument("psb200_residual_norm: size mismatch or null vector");
+    ensure_vectors();
+    const long long row0 = dist ? dist->plan.r0() : 0;
+    DevBuf<double> dx, db;
+    dx.alloc((size_t)n_pad, true);
+    db.alloc((size_t)n_pad, true);
+    PSB_CUDA(cudaMemcpyAsync(dx.p, x + row0, sizeof(double) * n, cudaMemcpyHostToDevice, ctx.stream));
+    PSB_CUDA(cudaMemcpyAsync(db.p, b + row0, sizeof(double) * n, cudaMemcpyHostToDevice, ctx.stream));
+    return residual_norm_device(dx.p, db.p, n);
+}
+
+// Row partition: every rank contributes its own rows of x_full and receives everybody's (the Newton driver needs the whole
+// step on every rank). One fused all-gather kernel over NVLink.
+void Solver::dist_allgather_host(double *x_full, long long n_)
+{
+    if (!dist)
+        return; // single GPU: x is complete already
+    if (!analyzed || n_ != n_global || !x_full)
+        throw std::invalid_argument("psb200_dist_allgather: analyze_pattern first / size mismatch");
+    DevBuf<double> mine, full;
+    mine.alloc((size_t)n_pad, true);
+    full.alloc((size_t)n_global + 4, true);
+    const long long row0 = dist->plan.r0();
+    PSB_CUDA(cudaMemcpyAsync(mine.p, x_full + row0, sizeof(double) * n, cudaMemcpyHostToDevice, ctx.stream));
+    if (dist->world > 1)
+        bulk_allgather(mine.p, full.p, dist->plan.offsets.data(), nullptr);
+    else
+        PSB_CUDA(cudaMemcpyAsync(full.p, mine.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, ctx.stream));
+    PSB_CUDA(cudaMemcpyAsync(x_full, full.p, sizeof(double) * n_global, cudaMemcpyDeviceToHost, ctx.stream));
+    PSB_CUDA(cudaStreamSynchronize(ctx.stream));
+    check_comm_error();
+}
+
 // Launches batches of iterations until the device-side `done` flag is seen. Two batches are kept in
 // flight so the GPU never waits for the host; kernels launched after convergence exit immediately
 // (they read st->done first), so x is exactly the iterate at the converged iteration.

@@ -162,6 +162,8 @@ struct Solver
     void factorize_device(long long n, long long nnz, const double *d_vals, double diag_shift);
     void factorize_tail(double t0);
     double residual_norm_device(const double *d_x, const double *d_b, long long n);
+    double residual_norm_host(const double *x, const double *b, long long n);
+    void dist_allgather_host(double *x_full, long long n);
     void push_halo_of(const double *d_v, const int *done = nullptr); // row partition: push the boundary entries of a local vector (dist.cu)
     void bulk_allreduce(const double *d_partial, double *d_out, long long len, const int *done = nullptr); // sum of a vector across ranks
     // Dirichlet pre-processing (fem.cu; reference FEMSolver.cpp:97-372)

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(THREADS) spgemm_numeric_kernel(CsrView A, CsrV
         for (int q = __ldg(B.rp + a) + lane; q < q1; q += G)
         {
             const int c = __ldg(B.ci + q);
-            const double v = va * __ldg(B.va + q);
+            const double v = __dmul_rn(va, __ldg(B.va + q)); // product rounded on its own (no FMA contraction): the sort-based path and the CPU oracle round it too
             unsigned s = slot_of(c, H);
             for (;;)
             {

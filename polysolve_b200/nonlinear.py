@@ -60,12 +60,14 @@ _LSBEG = C.CFUNCTYPE(None, C.c_void_p, _f64p, _f64p, C.c_int64)
 _LSEND = C.CFUNCTYPE(None, C.c_void_p)
 _POST = C.CFUNCTYPE(None, C.c_void_p, C.c_int, _f64p, _f64p, C.c_int64)
 _STOP = C.CFUNCTYPE(C.c_int, C.c_void_p, _f64p, C.c_int64)
+_HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
 
 
 class _CProblem(C.Structure):
     _fields_ = [("user", C.c_void_p), ("value", _VALUE), ("gradient", _GRAD), ("hessian", _HESS),
                 ("solution_changed", _VOIDX), ("is_step_valid", _STEPV), ("max_step_size", _MAXST),
-                ("line_search_begin", _LSBEG), ("line_search_end", _LSEND), ("post_step", _POST), ("stop", _STOP)]
+                ("line_search_begin", _LSBEG), ("line_search_end", _LSEND), ("post_step", _POST), ("stop", _STOP),
+                ("hessian_device", _HESS)]
 
 
 def _vec(p, n):
@@ -98,6 +100,25 @@ class NonlinearSolver:
         if h:
             self._L.psb200_nl_destroy(h)
             self._h = None
+
+    def set_linear_solver_hook(self, fn):
+        """fn(solver) is called once for every linear solver the driver owns (a borrowed polysolve_b200.Solver), in creation
+        order: a multi-GPU application connects them there (solver.dist_setup_torch())."""
+        from .solver import Solver
+        self._L.psb200_nl_set_linear_solver_hook.argtypes = [C.c_void_p, _HOOK, C.c_void_p]
+        errors = []
+
+        def hook(_, lin):
+            try:
+                fn(Solver(_borrowed=lin))
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+        cb = _HOOK(hook)
+        rc = self._L.psb200_nl_set_linear_solver_hook(self._h, cb, None)
+        if errors:
+            raise errors[0]
+        if rc:
+            raise RuntimeError("psb200_nl_set_linear_solver_hook failed")
 
     def minimize(self, problem, x):
         """x is in/out (float64, contiguous). Raises RuntimeError where the reference throws."""
@@ -143,6 +164,17 @@ class NonlinearSolver:
             vals[0] = v.ctypes.data_as(_f64p)
             return 0
 
+        @guard(1)
+        def hessian_device(_, xp, nn, psd, nnz, outer, inner, vals):
+            # the Problem assembles on the GPU: (outer, inner) host int32 arrays of the fixed pattern, device pointer of the values
+            o, i, dptr = problem.hessian_device(_vec(xp, nn), bool(psd))
+            keep["hd"] = (o, i)
+            nnz[0] = int(o[-1])
+            outer[0] = o.ctypes.data_as(_i32p)
+            inner[0] = i.ctypes.data_as(_i32p)
+            vals[0] = C.cast(dptr, _f64p)
+            return 0
+
         @guard(None)
         def solution_changed(_, xp, nn):
             problem.solution_changed(_vec(xp, nn))
@@ -172,7 +204,8 @@ class NonlinearSolver:
             return 1 if problem.stop(_vec(xp, nn)) else 0
 
         cp = _CProblem(None, _VALUE(value), _GRAD(gradient), _HESS(hessian), _VOIDX(solution_changed), _STEPV(is_step_valid),
-                       _MAXST(max_step_size), _LSBEG(ls_begin), _LSEND(ls_end), _POST(post_step), _STOP(stop))
+                       _MAXST(max_step_size), _LSBEG(ls_begin), _LSEND(ls_end), _POST(post_step), _STOP(stop),
+                       _HESS(hessian_device) if hasattr(problem, "hessian_device") else C.cast(None, _HESS))
         rc = self._L.psb200_nl_minimize(self._h, C.byref(cp), x, n)
         if errors:
             raise errors[0]

@@ -45,19 +45,23 @@ class Solver:
             s.set_parameters({"CUDA": {"precond": pmap[precond]}})
         return s
 
-    def __init__(self):
+    def __init__(self, _borrowed=None):
         self._L = _lib.lib()
-        self._h = C.c_void_p()
-        rc = self._L.psb200_create(C.byref(self._h), None)
-        if rc:
-            raise RuntimeError(self._L.psb200_last_error(None).decode())
+        self._owned = _borrowed is None
+        if _borrowed is not None:
+            self._h = C.c_void_p(_borrowed)  # a handle owned by somebody else (the Newton driver's linear solvers)
+        else:
+            self._h = C.c_void_p()
+            rc = self._L.psb200_create(C.byref(self._h), None)
+            if rc:
+                raise RuntimeError(self._L.psb200_last_error(None).decode())
         self._keep = None
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and getattr(self, "_owned", False):
             self._L.psb200_destroy(h)
-            self._h = None
+        self._h = None
 
     def _check(self, rc):
         if rc:
@@ -192,6 +196,16 @@ class Solver:
         self.dist_connect(b"".join(gathered))
         dist.barrier()
         return rank, world
+
+    def dist_allgather(self, x_full):
+        """Every rank contributes its rows of x_full (in place) and receives everybody's. No-op on one GPU."""
+        self._check(self._L.psb200_dist_allgather(self._h, x_full, x_full.shape[0]))
+
+    def residual_norm(self, x, b):
+        """||A x - b||_2 with full-length host vectors (global norm on a row partition)."""
+        r = C.c_double()
+        self._check(self._L.psb200_residual_norm(self._h, np.ascontiguousarray(x, np.float64), np.ascontiguousarray(b, np.float64), x.shape[0], C.byref(r)))
+        return r.value
 
     def dist_reset(self):
         """Collective recovery after a communication timeout (barrier on the host before and after)."""
