@@ -590,6 +590,82 @@ struct OpChebFirst
         }
     }
 };
+// A whole Chebyshev application (all `degree` steps) of a level that fits one SM, in ONE launch: the matrix is staged
+// in shared memory once, the iterate and the Chebyshev direction live there too, steps are separated by __syncthreads.
+// Same arithmetic as the step-per-launch path (EpiCheb / OpChebFirst) up to the summation order inside a row; it replaces 2 degree - 1 launches per visit of the coarsest level (the level is visited
+// 2^(levels - 1) times per cycle and each of its SpMVs is pure launch latency).
+constexpr int kSmallRows = 1024, kSmallNnz = 12288, kSmallDegree = 64;
+struct ChebCoef
+{
+    double alpha[kSmallDegree], beta[kSmallDegree];
+};
+__global__ void __launch_bounds__(1024) cheb_sweep_small_kernel(CsrView A, const double *__restrict__ rhs, const double *__restrict__ dinv,
+                                                                double *__restrict__ x, double *__restrict__ cp, ChebCoef cf, int degree,
+                                                                int x_is_zero, const int *done)
+{
+    if (done && *done)
+        return;
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    double *sva = reinterpret_cast<double *>(sm_raw);
+    double *sx = sva + kSmallNnz;
+    double *sxn = sx + kSmallRows;
+    int *sci = reinterpret_cast<int *>(sxn + kSmallRows);
+    const int n = A.n, nnz = A.rp[n];
+    for (int k = threadIdx.x; k < nnz; k += blockDim.x)
+    {
+        sva[k] = A.va[k];
+        sci[k] = A.ci[k];
+    }
+    // LPR lanes per row (a power of two <= 32 with n * LPR <= 1024): the lanes of a row sit in one warp
+    int lpr = 1;
+    while (lpr < 32 && n * (lpr * 2) <= (int)blockDim.x)
+        lpr *= 2;
+    const int row = threadIdx.x / lpr, lane = threadIdx.x % lpr;
+    const bool live = row < n;
+    int kb = 0, ke = 0;
+    double b = 0, d = 0, p = 0;
+    if (live)
+    {
+        kb = A.rp[row];
+        ke = A.rp[row + 1];
+        b = rhs[row];
+        d = dinv[row];
+        if (lane == 0)
+            sx[row] = x_is_zero ? 0.0 : x[row];
+    }
+    __syncthreads();
+    for (int k = 0; k < degree; ++k)
+    {
+        const bool first = k == 0 && x_is_zero;
+        double s = 0;
+        if (live && !first)
+            for (int q = kb + lane; q < ke; q += lpr)
+                s += sva[q] * sx[sci[q]];
+        for (int o = lpr >> 1; o > 0; o >>= 1)
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (live && lane == 0)
+        {
+            if (first)
+                p = cf.alpha[0] * d * b; // OpChebFirst
+            else
+            {
+                const double res = d * (b - s); // EpiCheb
+                p = cf.alpha[k] * res + (cf.beta[k] != 0.0 ? cf.beta[k] * p : 0.0);
+            }
+            sxn[row] = sx[row] + p;
+        }
+        __syncthreads();
+        double *t = sx;
+        sx = sxn;
+        sxn = t;
+    }
+    if (live && lane == 0)
+    {
+        x[row] = sx[row];
+        cp[row] = p;
+    }
+}
+
 // relaxation from a zero iterate with diagonal weights: x = w b
 struct OpDiagFirst
 {
@@ -909,6 +985,7 @@ static void block_scaled_matrix(Ctx &c, int B, const CsrDev &A, DevBuf<double> &
     check_launch();
     Ahat.kind = A.kind;
     Ahat.lpr = A.lpr;
+    Ahat.narrow = A.narrow;
 }
 
 void setup_relaxation(Ctx &c, const AmgParams &prm, AmgLevel &L, int seed_index, const SetupHooks *hooks)
@@ -1107,6 +1184,13 @@ static int aggregate_mis2(Ctx &c, Temp &tmp, const CsrDev &A, const double *diag
     check_launch();
     PSB_CUDA(cudaStreamSynchronize(st));
     return n_agg;
+}
+
+// PSB200_SMALL_SWEEP=off in the environment disables the one-launch Chebyshev sweep of tiny levels (A/B runs)
+static bool small_sweep_enabled()
+{
+    static bool on = std::getenv("PSB200_SMALL_SWEEP") == nullptr || std::string(std::getenv("PSB200_SMALL_SWEEP")) != "off";
+    return on;
 }
 
 bool &spgemm_use_hash()
@@ -1321,6 +1405,31 @@ void relax_level(Ctx &ctx, const AmgParams &prm, AmgLevel &L, bool fine, const d
         check_launch();
         ctx.prof_end();
         rhs = L.bh.p;
+    }
+    if (prm.relax_type == "chebyshev" && !after_step && A.halo_mask == 0 && A.n <= kSmallRows && A.nnz <= kSmallNnz && prm.degree <= kSmallDegree &&
+        small_sweep_enabled())
+    {
+        // the whole application in one launch (levels that fit one SM; never on a row partition)
+        static bool attr_set[16] = {false};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        constexpr size_t smem = sizeof(double) * (kSmallNnz + 2 * kSmallRows) + sizeof(int) * kSmallNnz;
+        if (!attr_set[dev & 15])
+        {
+            PSB_CUDA(cudaFuncSetAttribute(cheb_sweep_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set[dev & 15] = true;
+        }
+        ChebCoef cf;
+        for (int k = 0; k < prm.degree; ++k)
+        {
+            cf.alpha[k] = L.alpha[k];
+            cf.beta[k] = L.beta[k];
+        }
+        ctx.prof_begin("cheb_sweep_small");
+        cheb_sweep_small_kernel<<<1, 1024, smem, ctx.stream>>>(A.view(), rhs, L.dinv.p, x, L.cp.p, cf, prm.degree, x_is_zero ? 1 : 0, done);
+        check_launch();
+        ctx.prof_end();
+        return;
     }
     if (prm.relax_type == "chebyshev")
     {

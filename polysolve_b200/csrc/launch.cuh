@@ -17,6 +17,10 @@ using StreamProd = StreamCfg<256, 2048, 2>;
 // long rows (30-80 nnz: Galerkin coarse levels, 3-dof elasticity): LPR lanes per row, 256 / LPR rows per tile
 template <int LPR>
 using StreamWide = StreamCfg<256, 3072, 2, LPR>;
+// the same with smaller stages for more resident CTAs (the gathers of scattered rows are latency bound: ncu shows 37 %
+// active warps at 3 CTAs / SM on the level-1 Galerkin matrix): LPR 4 -> 2048 entries (4 CTAs / SM), LPR 8 -> 1536 (6)
+template <int LPR>
+using StreamNarrow = StreamCfg<256, LPR == 4 ? 2048 : 1536, 2, LPR>;
 
 // number of tiles of `rows` rows whose staged nnz range would not fit `cap` entries
 template <int DUMMY>
@@ -46,6 +50,7 @@ struct CsrDev
     DevBuf<double> va;
     int kind = SPMV_VECTOR;
     int lpr = 1; // lanes per row for the vector schedule
+    bool narrow = false; // stream schedule with LPR 4 / 8: the StreamNarrow tile shape
     int nl = 0x7fffffff;      // local columns (multi-GPU: columns >= nl are halo columns)
     unsigned halo_mask = 0;   // ranks that push halo values to this one
     DevBuf<int> tile_order;   // interior-first tile order of the stream schedule (row partitions only)
@@ -78,10 +83,12 @@ struct CsrDev
     {
         const double avg = n > 0 ? (double)nnz / n : 0;
         const bool want_stream = forced.rfind("stream", 0) == 0;
+        narrow = false;
         if (want_stream && forced.size() > 6 && forced[6] != ':')
         {
             kind = SPMV_STREAM;
-            lpr = std::stoi(forced.substr(6));
+            lpr = std::stoi(forced.substr(6)); // "stream8n": stoi stops at the suffix
+            narrow = forced.back() == 'n' && (lpr == 4 || lpr == 8);
             return;
         }
         if (want_stream || (forced == "auto" && n >= 4 * StreamProd::threads))
@@ -122,7 +129,10 @@ struct CsrDev
         if (forced.rfind("vector", 0) == 0 && forced.size() > 6)
             lpr = std::stoi(forced.substr(6));
     }
-    std::string kernel_name() const { return kind == SPMV_STREAM ? (lpr == 1 ? "stream" : "stream" + std::to_string(lpr)) : "vector" + std::to_string(lpr); }
+    std::string kernel_name() const
+    {
+        return kind == SPMV_STREAM ? (lpr == 1 ? "stream" : "stream" + std::to_string(lpr) + (narrow ? "n" : "")) : "vector" + std::to_string(lpr);
+    }
 };
 
 struct ProfEntry
@@ -339,8 +349,18 @@ void launch_spmv(Ctx &c, const char *name, const CsrDev &A, const double *x, Epi
         switch (A.lpr)
         {
         case 2: launch_spmv_stream<Epi, Fin, StreamWide<2>>(c, A, x, epi, fin, done, only_if); break;
-        case 4: launch_spmv_stream<Epi, Fin, StreamWide<4>>(c, A, x, epi, fin, done, only_if); break;
-        case 8: launch_spmv_stream<Epi, Fin, StreamWide<8>>(c, A, x, epi, fin, done, only_if); break;
+        case 4:
+            if (A.narrow)
+                launch_spmv_stream<Epi, Fin, StreamNarrow<4>>(c, A, x, epi, fin, done, only_if);
+            else
+                launch_spmv_stream<Epi, Fin, StreamWide<4>>(c, A, x, epi, fin, done, only_if);
+            break;
+        case 8:
+            if (A.narrow)
+                launch_spmv_stream<Epi, Fin, StreamNarrow<8>>(c, A, x, epi, fin, done, only_if);
+            else
+                launch_spmv_stream<Epi, Fin, StreamWide<8>>(c, A, x, epi, fin, done, only_if);
+            break;
         case 16: launch_spmv_stream<Epi, Fin, StreamWide<16>>(c, A, x, epi, fin, done, only_if); break;
         default: launch_spmv_stream<Epi, Fin, StreamProd>(c, A, x, epi, fin, done, only_if); break;
         }

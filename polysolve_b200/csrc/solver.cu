@@ -482,7 +482,9 @@ static bool spmv_kernel_name_ok(const std::string &k)
     for (const char *pre : {"stream", "vector"})
         if (k.rfind(pre, 0) == 0)
         {
-            const std::string num = k.substr(6);
+            std::string num = k.substr(6);
+            if (pre[0] == 's' && (num == "4n" || num == "8n"))
+                return true; // narrow tile shapes of the stream schedule
             if (num.empty() || num.size() > 2 || num.find_first_not_of("0123456789") != std::string::npos)
                 return false;
             const int v = std::stoi(num);
@@ -542,7 +544,7 @@ void Solver::set_parameters(const std::string &json)
     if (!(np.comm_timeout_s >= 0))
         throw std::runtime_error("psb200: comm_timeout_s must be >= 0");
     if (!spmv_kernel_name_ok(np.spmv_kernel))
-        throw std::runtime_error("psb200: unknown spmv_kernel '" + np.spmv_kernel + "' (auto | stream | stream<2|4|8|16> | vector<1|2|4|8|16|32> | scalar | bsr)");
+        throw std::runtime_error("psb200: unknown spmv_kernel '" + np.spmv_kernel + "' (auto | stream | stream<2|4|8|16> | stream4n | stream8n | vector<1|2|4|8|16|32> | scalar | bsr)");
     if (np.precond != "jacobi" && np.precond != "amg" && np.precond != "none")
         throw std::runtime_error("psb200: unknown precond '" + np.precond + "' (jacobi | amg | none)");
     if (np.cg_kernel != "auto" && np.cg_kernel != "split")
@@ -1278,6 +1280,7 @@ double Solver::bench_spmv(const std::string &kernel, int reps)
     ensure_vectors();
     cudaStream_t st = ctx.stream;
     const int kind0 = A.kind, lpr0 = A.lpr;
+    const bool narrow0 = A.narrow;
     // tile-shape exploration of the stream schedule: "stream:<threads>:<cap>:<stages>[:<ctas_per_sm>]"
     std::function<void()> one = [&]() { launch_spmv(ctx, "spmv", A, vp.p, EpiStore{vq.p}, FinNone{}); };
     if (kernel.rfind("stream:", 0) == 0)
@@ -1327,6 +1330,7 @@ double Solver::bench_spmv(const std::string &kernel, int reps)
     cudaEventDestroy(b);
     A.kind = kind0;
     A.lpr = lpr0;
+    A.narrow = narrow0;
     return (double)ms / std::max(1, reps);
 }
 

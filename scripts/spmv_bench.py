@@ -44,7 +44,7 @@ A = sp.csr_matrix((v, i, o), shape=(pn ** 3, pn ** 3))
 A2 = (A @ A).tocsr()
 A2.sort_indices()
 run(f"poisson3d_{pn}_squared", A2.indptr.astype(np.int32), A2.indices.astype(np.int32), A2.data.astype(np.float64),
-    ["stream2", "stream4", "stream8", "stream16", "vector8", "vector16", "vector32"])
+    ["stream4", "stream4n", "stream8", "stream8n", "vector8"])
 del A, A2
 o, i, v, _ = P.elasticity3d(em)
-run(f"elasticity3d_{em}", o, i, v, ["stream4", "stream8", "stream16", "vector16", "vector32"])
+run(f"elasticity3d_{em}", o, i, v, ["stream4", "stream8", "stream8n", "vector16"])
