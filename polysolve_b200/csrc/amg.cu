@@ -986,6 +986,9 @@ static void block_scaled_matrix(Ctx &c, int B, const CsrDev &A, DevBuf<double> &
     Ahat.kind = A.kind;
     Ahat.lpr = A.lpr;
     Ahat.narrow = A.narrow;
+    Ahat.block = A.block;
+    Ahat.use_bsr = A.use_bsr;
+    Ahat.refresh_bsr(st);
 }
 
 void setup_relaxation(Ctx &c, const AmgParams &prm, AmgLevel &L, int seed_index, const SetupHooks *hooks)
@@ -1369,7 +1372,9 @@ void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &
             spgemm(ctx_, tmp, L.R, AP, L.n_agg, next->Aown);
             L.t_rap = wall_ms(st) - tp;
         }
+        next->Aown.block = std::max(1, prm_.block_size); // P, R and the Galerkin product keep the full-block pattern
         next->Aown.plan("auto", st);
+        next->Aown.refresh_bsr(st);
         next->A = &next->Aown;
         cur = std::move(next);
     }

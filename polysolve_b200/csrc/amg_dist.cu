@@ -462,7 +462,9 @@ void AmgDist::setup(const std::vector<std::vector<int>> &imposed)
             gatherv(Acg.ci.p, sizeof(int) * (size_t)Acg.nnz, (unsigned char *)T.ci.p, nnz_off, sizeof(int));
             gatherv(Acg.va.p, sizeof(double) * (size_t)Acg.nnz, (unsigned char *)T.va.p, nnz_off, sizeof(double));
             PSB_CUDA(cudaStreamSynchronize(st));
+            T.block = B;
             T.plan("auto", st);
+            T.refresh_bsr(st);
             tail_offsets_ = coff;
             for (int q = 0; q < W; ++q)
                 if (coff[q + 1] - coff[q] > D.halo_cap)
@@ -589,7 +591,9 @@ void AmgDist::setup(const std::vector<std::vector<int>> &imposed)
             check_launch();
             PSB_CUDA(cudaStreamSynchronize(st));
         }
+        An.block = B;
         An.plan("auto", st);
+        An.refresh_bsr(st);
         next->L.A = &next->L.Aown;
         next->plan = &next->plan_own;
         lv.t_plan = wall_ms(st) - tp;

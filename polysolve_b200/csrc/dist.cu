@@ -677,6 +677,7 @@ void Solver::analyze_pattern_dist(long long n_, long long nnz_, const int *outer
     A.nnz = nnz;
     A.va.alloc(std::max<long long>(nnz, 1), false, 64);
     A.halo_mask = P.halo_cols.empty() ? 0u : 1u;
+    A.block = (B > 1 && amg_partitioned()) ? B : 1; // full-block pattern only where the rows were expanded
     d.fine.world = d.world;
     d.fine.send_begin = P.send_begin;
     d.fine.send_rows = P.send_rows;
@@ -1032,6 +1033,7 @@ void Solver::build_diag_block_dist()
             // the invariant the block AMG kernels rely on (same expansion as the single-GPU analyze_pattern)
             D.nnz = expand_block_pattern(ctx, pattern_block, n, D.rp, D.ci, d.diag_src);
             D.va.alloc(std::max<long long>(1, D.nnz), false, 64);
+            D.block = pattern_block;
         }
         PSB_CUDA(cudaStreamSynchronize(st));
         D.plan("auto", st);
@@ -1039,6 +1041,7 @@ void Solver::build_diag_block_dist()
     if (D.nnz)
         diag_vals_kernel<<<(unsigned)((D.nnz + 255) / 256), 256, 0, st>>>(D.nnz, A.va.p, d.diag_src.p, D.va.p);
     check_launch();
+    D.refresh_bsr(st);
     PSB_CUDA(cudaStreamSynchronize(st));
 }
 

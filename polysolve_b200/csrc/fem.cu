@@ -195,6 +195,8 @@ void Solver::dirichlet_solve_prefactorized(const double *vals, double *f, double
         tmp_va.alloc(std::max<long long>(nnz, 1), false, 64);
         PSB_CUDA(cudaMemcpyAsync(csc_vals.p, vals, sizeof(double) * nnz_global, cudaMemcpyHostToDevice, st));
         std::swap(tmp_va.p, A.va.p);
+        const bool bsr_was_ready = A.bsr_ready;
+        A.bsr_ready = false; // the scratch values exist in scalar CSR form only: the lifting product takes the CSR schedule
         try
         {
             gather_values_to_csr(csc_vals.p);
@@ -204,9 +206,11 @@ void Solver::dirichlet_solve_prefactorized(const double *vals, double *f, double
         catch (...)
         {
             std::swap(tmp_va.p, A.va.p);
+            A.bsr_ready = bsr_was_ready;
             throw;
         }
         std::swap(tmp_va.p, A.va.p);
+        A.bsr_ready = bsr_was_ready;
     }
     else
         dirichlet_lift(vz.p, vb.p); // the resident masked matrix: the lifting term vanishes, g = f

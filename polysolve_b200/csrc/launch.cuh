@@ -41,6 +41,37 @@ enum SpmvKind : int
     SPMV_VECTOR = 0,
     SPMV_STREAM = 1
 };
+// BSR-3 tile shape: 32 block rows (96 scalar rows) per tile, 8 lanes per block row, 544 staged blocks (41 KB) per stage
+using BsrProd = BsrCfg<256, 544, 2, 8>;
+
+// block row pointer / block columns of a scalar CSR whose rows 3 i .. 3 i + 2 share one list of full 3 x 3 blocks
+template <int DUMMY>
+__global__ void bsr3_pattern_kernel(int nb, const int *__restrict__ rp, const int *__restrict__ ci, int *__restrict__ brp, int *__restrict__ bci)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nb)
+        return;
+    const int k0 = rp[3 * i];
+    brp[i] = k0 / 9;
+    if (i == nb)
+        return;
+    const int len = (rp[3 * i + 1] - k0) / 3;
+    for (int q = 0; q < len; ++q)
+        bci[k0 / 9 + q] = ci[k0 + 3 * q] / 3;
+}
+// bva[9 (brp[i] + q) + 3 r + c] = va[rp[3 i + r] + 3 q + c]; one thread per scalar row
+template <int DUMMY>
+__global__ void bsr3_values_kernel(int n, const int *__restrict__ rp, const double *__restrict__ va, double *__restrict__ bva)
+{
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n)
+        return;
+    const int i = row / 3, r = row % 3;
+    const int kb = rp[row], len = rp[row + 1] - kb;
+    const size_t base = (size_t)rp[3 * i] + 3 * r; // = 9 brp[i] + 3 r
+    for (int e = 0; e < len; ++e)
+        bva[base + 9 * (size_t)(e / 3) + e % 3] = va[kb + e];
+}
 
 struct CsrDev
 {
@@ -51,6 +82,27 @@ struct CsrDev
     int kind = SPMV_VECTOR;
     int lpr = 1; // lanes per row for the vector schedule
     bool narrow = false; // stream schedule with LPR 4 / 8: the StreamNarrow tile shape
+    // BSR-3 form of a block-3 matrix (76 B per block instead of 108): kept BESIDE the scalar CSR, which stays the fallback
+    // (and what the setup kernels read). block: 3 when rows 3 i .. 3 i + 2 share one list of full 3 x 3 blocks.
+    int block = 1;
+    bool use_bsr = false, bsr_ready = false;
+    DevBuf<int> brp, bci;
+    DevBuf<double> bva;
+    BsrView bview() const { return BsrView{brp.p, bci.p, bva.p, n / 3, nl, halo_mask}; }
+    // (re)builds the BSR arrays from the scalar CSR: call whenever the values have changed
+    void refresh_bsr(cudaStream_t st)
+    {
+        bsr_ready = false;
+        if (!use_bsr || block != 3 || n <= 0 || n % 3)
+            return;
+        const int nb = n / 3;
+        brp.alloc((size_t)nb + 1, false, 64);
+        bci.alloc(std::max<long long>(1, nnz / 9), false, 64);
+        bva.alloc(std::max<long long>(1, nnz), false, 64);
+        bsr3_pattern_kernel<0><<<(nb + 256) / 256, 256, 0, st>>>(nb, rp.p, ci.p, brp.p, bci.p);
+        bsr3_values_kernel<0><<<(n + 255) / 256, 256, 0, st>>>(n, rp.p, va.p, bva.p);
+        bsr_ready = cudaGetLastError() == cudaSuccess;
+    }
     int nl = 0x7fffffff;      // local columns (multi-GPU: columns >= nl are halo columns)
     unsigned halo_mask = 0;   // ranks that push halo values to this one
     DevBuf<int> tile_order;   // interior-first tile order of the stream schedule (row partitions only)
@@ -81,6 +133,30 @@ struct CsrDev
     }
     void plan(const std::string &forced = "auto", cudaStream_t st = nullptr)
     {
+        plan_csr(forced == "bsr" ? "auto" : forced, st);
+        // BSR-3 on top when the matrix is a block-3 matrix large enough to stream and (almost) all its tiles fit the stage
+        use_bsr = false;
+        bsr_ready = false;
+        if ((forced == "bsr" || forced == "auto") && block == 3 && n % 3 == 0 && n >= 3 * 1024 && rp.p != nullptr)
+        {
+            // the block row pointer is rp[3 i] / 9: check the tiles on a temporary copy of it
+            const int nb = n / 3;
+            DevBuf<int> tb, tc;
+            tb.alloc((size_t)nb + 1, false, 64);
+            tc.alloc(std::max<long long>(1, nnz / 9), false, 64);
+            bsr3_pattern_kernel<0><<<(nb + 256) / 256, 256, 0, st>>>(nb, rp.p, ci.p, tb.p, tc.p);
+            plan_scratch.alloc(4, false);
+            PSB_CUDA(cudaMemsetAsync(plan_scratch.p, 0, sizeof(int), st));
+            const int ntiles = (nb + BsrProd::rows - 1) / BsrProd::rows;
+            tile_overflow_kernel<0><<<(ntiles + 255) / 256, 256, 0, st>>>(nb, tb.p, BsrProd::rows, BsrProd::capb, plan_scratch.p);
+            int h = 0;
+            PSB_CUDA(cudaMemcpyAsync(&h, plan_scratch.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            PSB_CUDA(cudaStreamSynchronize(st));
+            use_bsr = forced == "bsr" || (double)h / ntiles <= 0.02;
+        }
+    }
+    void plan_csr(const std::string &forced, cudaStream_t st)
+    {
         const double avg = n > 0 ? (double)nnz / n : 0;
         const bool want_stream = forced.rfind("stream", 0) == 0;
         narrow = false;
@@ -93,15 +169,27 @@ struct CsrDev
         }
         if (want_stream || (forced == "auto" && n >= 4 * StreamProd::threads))
         {
-            for (int L : {1, 2, 4, 8, 16})
+            // candidates in order of preference (measured on B200, profiles/r02_spmv_schedules.txt): the narrow tile shapes
+            // (more resident CTAs) beat the 3072-entry stage whenever their tiles fit -- 24.7 nnz/row: stream4n 0.76 of the
+            // HBM peak vs stream4 0.67; 43 nnz/row (P1 elasticity): stream8n 0.95 vs stream4 0.89
+            struct Cand
             {
-                const int rows = StreamProd::threads / L, cap = L == 1 ? StreamProd::cap : StreamWide<2>::cap;
-                if (avg * rows + 16 > cap)
+                int L, cap;
+                bool narrow;
+            };
+            const Cand cands[] = {{1, StreamProd::cap, false}, {2, StreamWide<2>::cap, false}, {4, StreamNarrow<4>::cap, true},
+                                  {8, StreamNarrow<8>::cap, true}, {4, StreamWide<4>::cap, false}, {8, StreamWide<8>::cap, false},
+                                  {16, StreamWide<16>::cap, false}};
+            for (const Cand &cd : cands)
+            {
+                const int rows = StreamProd::threads / cd.L;
+                if (avg * rows + 16 > cd.cap)
                     continue;
-                if (overflow_frac(rows, cap, st) > 0.02)
+                if (overflow_frac(rows, cd.cap, st) > 0.02)
                     continue;
                 kind = SPMV_STREAM;
-                lpr = L;
+                lpr = cd.L;
+                narrow = cd.narrow;
                 return;
             }
             if (want_stream)
@@ -131,6 +219,8 @@ struct CsrDev
     }
     std::string kernel_name() const
     {
+        if (use_bsr)
+            return "bsr3";
         return kind == SPMV_STREAM ? (lpr == 1 ? "stream" : "stream" + std::to_string(lpr) + (narrow ? "n" : "")) : "vector" + std::to_string(lpr);
     }
 };
@@ -338,13 +428,36 @@ void launch_spmv_stream(Ctx &c, const CsrDev &A, const double *x, Epi epi, Fin f
 }
 
 template <class Epi, class Fin>
+void launch_spmv_bsr3(Ctx &c, const CsrDev &A, const double *x, Epi epi, Fin fin, const int *done, const int *only_if)
+{
+    using Cfg = BsrProd;
+    auto kern = spmv_bsr3_kernel<Epi, Fin, Cfg>;
+    static int max_ctas_dev[16] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int &max_ctas = max_ctas_dev[dev & 15];
+    if (!max_ctas)
+    {
+        PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::bytes));
+        PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas, kern, Cfg::threads, Cfg::bytes));
+        max_ctas = std::max(1, max_ctas);
+    }
+    const int nb = A.n / 3;
+    const int ntiles = (nb + Cfg::rows - 1) / Cfg::rows;
+    const int grid = std::min(ntiles, kSMs * max_ctas);
+    launch_chain(c, kern, grid, Cfg::threads, Cfg::bytes, A.bview(), x, epi, c.red(), fin, done, only_if);
+}
+
+template <class Epi, class Fin>
 void launch_spmv(Ctx &c, const char *name, const CsrDev &A, const double *x, Epi epi, Fin fin, const int *done = nullptr,
                  const int *only_if = nullptr)
 {
     if (A.n == 0)
         return;
     c.prof_begin(name);
-    if (A.kind == SPMV_STREAM)
+    if (A.use_bsr && A.bsr_ready)
+        launch_spmv_bsr3<Epi, Fin>(c, A, x, epi, fin, done, only_if);
+    else if (A.kind == SPMV_STREAM)
     {
         switch (A.lpr)
         {

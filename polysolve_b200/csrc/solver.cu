@@ -570,7 +570,11 @@ void Solver::set_parameters(const std::string &json)
         graph_key.clear();
     }
     if (analyzed)
+    {
         A.plan(prm.spmv_kernel, ctx.stream);
+        if (factorized)
+            A.refresh_bsr(ctx.stream);
+    }
     ctx.profile = prm.profile;
     ctx.pdl = prm.pdl;
     A.use_order = prm.interior_first;
@@ -735,6 +739,7 @@ void Solver::analyze_pattern(long long n_, long long nnz_, const int *outer, con
         pattern_block = B;
         sym_pattern = false; // CSR arrays no longer alias the CSC arrays
     }
+    A.block = pattern_block;
     A.plan(prm.spmv_kernel, st);
     PSB_CUDA(cudaStreamSynchronize(st));
     analyzed = true;
@@ -861,6 +866,7 @@ void Solver::factorize_device(long long n_, long long nnz_, const double *d_vals
 void Solver::factorize_tail(double t0)
 {
     cudaStream_t st = ctx.stream;
+    A.refresh_bsr(st); // block-3 matrices: the BSR form follows every change of the values
     dinv.alloc(n_pad, true);
     int *d_bad = (int *)ctx.counter.p + 3;
     PSB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), st));
@@ -1280,7 +1286,7 @@ double Solver::bench_spmv(const std::string &kernel, int reps)
     ensure_vectors();
     cudaStream_t st = ctx.stream;
     const int kind0 = A.kind, lpr0 = A.lpr;
-    const bool narrow0 = A.narrow;
+    const bool narrow0 = A.narrow, bsr0 = A.use_bsr;
     // tile-shape exploration of the stream schedule: "stream:<threads>:<cap>:<stages>[:<ctas_per_sm>]"
     std::function<void()> one = [&]() { launch_spmv(ctx, "spmv", A, vp.p, EpiStore{vq.p}, FinNone{}); };
     if (kernel.rfind("stream:", 0) == 0)
@@ -1310,7 +1316,10 @@ double Solver::bench_spmv(const std::string &kernel, int reps)
             throw std::invalid_argument("psb200_bench_spmv: stream variant not compiled: " + kernel);
     }
     else if (!kernel.empty())
+    {
         A.plan(kernel, st);
+        A.refresh_bsr(st);
+    }
     // a non-trivial resident x
     launch_vec(ctx, "copy", n_pad, OpCopy{vp.p, dinv.p}, FinNone{});
     for (int i = 0; i < 3; ++i)
@@ -1331,6 +1340,11 @@ double Solver::bench_spmv(const std::string &kernel, int reps)
     A.kind = kind0;
     A.lpr = lpr0;
     A.narrow = narrow0;
+    if (A.use_bsr != bsr0)
+    {
+        A.use_bsr = bsr0;
+        A.refresh_bsr(st);
+    }
     return (double)ms / std::max(1, reps);
 }
 

@@ -498,4 +498,220 @@ __global__ void __launch_bounds__(Cfg::threads) spmv_stream_kernel(CsrView A, co
         fin(tot);
 }
 
+// ---------------------------------------------------------------------------------- BSR-3 stream schedule
+// Block problems (3 dofs per node: elasticity, AMGCL_Block<3>, reference AMGCL.cpp:246-298; the reference's own GPU path
+// stores BSR too, mas_utils/BSRMatrix.cu:195-474, CuSparseWrapper.hpp:123-156). One 3 x 3 block = 72 B of values + ONE
+// 4-byte block column: 76 B per block instead of 9 x 12 = 108 B of scalar CSR, and the three x values of a block column
+// are gathered once and reused by the three rows (a third of the gather instructions of the scalar schedule).
+// Same TMA pipeline as spmv_stream_kernel: a tile is ROWS block rows; the slice of the block row pointer, the value range
+// (72 B per block) and the block-column range are staged by three bulk copies per tile, two tiles ahead. LPB lanes share
+// a block row: lane l takes blocks kb + l, kb + l + LPB, ...; three row sums are reduced with shuffles and the lane that
+// holds them applies the (scalar-row) epilogue three times.
+struct BsrView
+{
+    const int *brp;    // block row pointer, nb + 1
+    const int *bci;    // block column (= scalar column / 3)
+    const double *bva; // 9 values per block, row-major
+    int nb;            // block rows
+    int nl;            // local SCALAR columns (row partitions: scalar columns >= nl are halo columns)
+    unsigned halo_mask;
+};
+
+template <int THREADS, int CAPB, int STAGES, int LPB>
+struct BsrCfg
+{
+    static constexpr int threads = THREADS, capb = CAPB, stages = STAGES, lpb = LPB, rows = THREADS / LPB;
+    static constexpr int rp_ints = rows + 4;
+    static constexpr size_t val_bytes = (size_t)STAGES * CAPB * 9 * sizeof(double);
+    static constexpr size_t col_bytes = (size_t)STAGES * CAPB * sizeof(int);
+    static constexpr size_t rp_bytes = (size_t)STAGES * rp_ints * sizeof(int);
+    static constexpr size_t bytes = val_bytes + col_bytes + rp_bytes + 128;
+};
+
+template <class Epi, class Fin, class Cfg>
+__global__ void __launch_bounds__(Cfg::threads) spmv_bsr3_kernel(BsrView A, const double *__restrict__ x, Epi epi, RedCtx rc, Fin fin,
+                                                                 const int *done, const int *only_if)
+{
+    constexpr int THREADS = Cfg::threads, CAPB = Cfg::capb, STAGES = Cfg::stages, LPB = Cfg::lpb, ROWS = Cfg::rows;
+    griddep_launch_dependents();
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *sval = reinterpret_cast<double *>(smem_raw);
+    int *scol = reinterpret_cast<int *>(smem_raw + Cfg::val_bytes);
+    int *srp = reinterpret_cast<int *>(smem_raw + Cfg::val_bytes + Cfg::col_bytes);
+    __shared__ __align__(8) unsigned long long bar[STAGES];
+
+    constexpr int NVA = Epi::NV > 0 ? Epi::NV : 1;
+    double acc[NVA];
+#pragma unroll
+    for (int i = 0; i < NVA; ++i)
+        acc[i] = 0;
+    const int ntiles = (A.nb + ROWS - 1) / ROWS;
+    unsigned long long policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+            mbar_init(&bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int tile, int s) {
+        const int r0 = tile * ROWS;
+        const int r1 = min(A.nb, r0 + ROWS);
+        const int k0 = __ldg(A.brp + r0), k1 = __ldg(A.brp + r1);
+        const int ka = k0 & ~3;                    // 4 blocks = 288 B of values / 16 B of columns: both 16-byte aligned
+        const int cnt4 = (k1 - ka + 3) & ~3;
+        const unsigned rp_b = (unsigned)(((r1 - r0 + 1) + 3) & ~3) * 4u;
+        unsigned bytes = rp_b;
+        const bool staged = cnt4 > 0 && cnt4 <= CAPB;
+        if (staged)
+            bytes += (unsigned)cnt4 * 76u;
+        mbar_expect_tx(&bar[s], bytes);
+        tma_bulk_g2s(srp + (size_t)s * Cfg::rp_ints, A.brp + r0, rp_b, &bar[s], policy);
+        if (staged)
+        {
+            tma_bulk_g2s(sval + (size_t)s * CAPB * 9, A.bva + (size_t)ka * 9, (unsigned)cnt4 * 72u, &bar[s], policy);
+            tma_bulk_g2s(scol + (size_t)s * CAPB, A.bci + ka, (unsigned)cnt4 * 4u, &bar[s], policy);
+        }
+    };
+    if (threadIdx.x == 0)
+    {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+        {
+            const int pos = blockIdx.x + s * gridDim.x;
+            if (pos < ntiles)
+                issue(pos, s);
+        }
+    }
+    griddep_wait();
+    if ((done && *done) || (only_if && !*only_if))
+    {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s)
+            if ((int)blockIdx.x + s * (int)gridDim.x < ntiles)
+                mbar_wait(&bar[s], 0);
+        return;
+    }
+    const double *xh = nullptr;
+    if (A.halo_mask != 0)
+    {
+        wait_pushes_landed(rc.comm);
+        xh = rc.comm.halo(rc.comm.rank, (int)(*rc.comm.push_epoch & 1), 0);
+    }
+    const int nl = A.nl;
+    int it = 0;
+    for (int pos = blockIdx.x; pos < ntiles; pos += gridDim.x, ++it)
+    {
+        const int s = it % STAGES;
+        const unsigned parity = (it / STAGES) & 1;
+        const int r0 = pos * ROWS;
+        const int nrow = min(A.nb - r0, ROWS);
+        const int trow = threadIdx.x / LPB, lane = threadIdx.x % LPB;
+        const int brow = r0 + trow;
+        const bool live = trow < nrow;
+        typename Epi::Pre pre0{}, pre1{}, pre2{};
+        if (live && lane == 0)
+        {
+            pre0 = epi.pre(3 * brow);
+            pre1 = epi.pre(3 * brow + 1);
+            pre2 = epi.pre(3 * brow + 2);
+        }
+        mbar_wait(&bar[s], parity);
+        const int *rps = srp + (size_t)s * Cfg::rp_ints;
+        const int k0 = rps[0], k1 = rps[nrow];
+        const int ka = k0 & ~3;
+        const bool staged = ((k1 - ka + 3) & ~3) <= CAPB;
+        int kb = 0, ke = 0;
+        if (live)
+        {
+            kb = rps[trow];
+            ke = rps[trow + 1];
+        }
+        double s0 = 0, s1 = 0, s2 = 0;
+        auto gather3 = [&](int bc, double &x0, double &x1, double &x2) {
+            const int c = 3 * bc;
+            const double *src = (c < nl) ? (x + c) : (xh + (c - nl));
+            if (c < nl)
+            {
+                x0 = __ldg(src);
+                x1 = __ldg(src + 1);
+                x2 = __ldg(src + 2);
+            }
+            else
+            {
+                x0 = __ldcg(src);
+                x1 = __ldcg(src + 1);
+                x2 = __ldcg(src + 2);
+            }
+        };
+        if (staged)
+        {
+            const double *sv = sval + (size_t)s * CAPB * 9 - (size_t)ka * 9;
+            const int *sc = scol + (size_t)s * CAPB - ka;
+            int k = kb + lane;
+            for (; k + LPB < ke; k += 2 * LPB)
+            {
+                // two blocks in flight per lane
+                const int c0 = sc[k], c1 = sc[k + LPB];
+                double a0, a1, a2, b0, b1, b2;
+                gather3(c0, a0, a1, a2);
+                gather3(c1, b0, b1, b2);
+                const double *v = sv + (size_t)k * 9, *w = sv + (size_t)(k + LPB) * 9;
+                s0 += v[0] * a0 + v[1] * a1 + v[2] * a2;
+                s1 += v[3] * a0 + v[4] * a1 + v[5] * a2;
+                s2 += v[6] * a0 + v[7] * a1 + v[8] * a2;
+                s0 += w[0] * b0 + w[1] * b1 + w[2] * b2;
+                s1 += w[3] * b0 + w[4] * b1 + w[5] * b2;
+                s2 += w[6] * b0 + w[7] * b1 + w[8] * b2;
+            }
+            if (k < ke)
+            {
+                double a0, a1, a2;
+                gather3(sc[k], a0, a1, a2);
+                const double *v = sv + (size_t)k * 9;
+                s0 += v[0] * a0 + v[1] * a1 + v[2] * a2;
+                s1 += v[3] * a0 + v[4] * a1 + v[5] * a2;
+                s2 += v[6] * a0 + v[7] * a1 + v[8] * a2;
+            }
+        }
+        else
+        {
+            for (int k = kb + lane; k < ke; k += LPB)
+            {
+                double a0, a1, a2;
+                gather3(__ldg(A.bci + k), a0, a1, a2);
+                const double *v = A.bva + (size_t)k * 9;
+                s0 += __ldg(v) * a0 + __ldg(v + 1) * a1 + __ldg(v + 2) * a2;
+                s1 += __ldg(v + 3) * a0 + __ldg(v + 4) * a1 + __ldg(v + 5) * a2;
+                s2 += __ldg(v + 6) * a0 + __ldg(v + 7) * a1 + __ldg(v + 8) * a2;
+            }
+        }
+#pragma unroll
+        for (int o = LPB / 2; o > 0; o >>= 1)
+        {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (live && lane == 0)
+        {
+            epi(3 * brow, s0, pre0, acc);
+            epi(3 * brow + 1, s1, pre1, acc);
+            epi(3 * brow + 2, s2, pre2, acc);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            const int next = pos + STAGES * gridDim.x;
+            if (next < ntiles)
+                issue(next, s);
+        }
+    }
+    double tot[NVA];
+    if (grid_reduce<Epi::NV, THREADS>(acc, rc, tot) && threadIdx.x == 0)
+        fin(tot);
+}
+
 } // namespace psb

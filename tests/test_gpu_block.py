@@ -164,3 +164,37 @@ def test_block3_amg_c4_shape(psb):
         assert np.linalg.norm(A @ x - b) / np.linalg.norm(b) < 1e-7
         its[B] = info["num_iterations"]
     assert its[3] <= its[1]
+
+
+@pytest.mark.parametrize("m", [11, 24])
+def test_bsr3_schedule_matches_scalar_csr_and_oracle(psb, orc, m):
+    """BSR-3 storage (76 B per 3 x 3 block; the reference's GPU path stores BSR too, mas_utils/BSRMatrix.cu:195-474): the
+    block-3 solver picks it automatically, its SpMV equals the oracle's CSC product to 1e-13 and the scalar-CSR schedules of
+    the same matrix, with unsymmetric values and an uneven block count per row; PCG on it takes the oracle's iterations."""
+    P = psb.problems
+    o, i, v, b = P.elasticity3d(m)
+    n = len(b)
+    v = v * (1.0 + 0.1 * orc.splitmix64(17, len(v)))   # unsymmetric values: exercises the row-major block layout
+    x = orc.splitmix64(3, n)
+    y0 = orc.spmv_csc(o, i, v, x)                       # CSC product = A x
+    # the oracle multiplies the CSC arrays as A; the solver reads the same arrays as CSC and transposes them to CSR
+    s = psb.Solver.create("CUDA", "")
+    s.set_parameters({"CUDA": {"tolerance": 1e-9, "max_iter": 5000}})
+    s.set_block_size(3)
+    s.factorize_raw(n, o, i, v)
+    info = s.get_info()
+    assert info["spmv_kernel"] == ("bsr3" if n >= 3072 else info["spmv_kernel"])
+    y = s.spmv(x)
+    assert np.abs(y - y0).max() <= 1e-13 * np.abs(y0).max()
+    for k in ("stream8n", "vector16", "bsr"):
+        s.set_parameters({"CUDA": {"spmv_kernel": k}})
+        assert np.abs(s.spmv(x) - y0).max() <= 1e-13 * np.abs(y0).max(), k
+    assert s.get_info()["spmv_kernel"] == "bsr3"
+    # symmetric values again: Jacobi-PCG on the BSR schedule == the oracle
+    o, i, v, b = P.elasticity3d(m)
+    s.factorize_raw(n, o, i, v)
+    xs = np.zeros(n)
+    s.solve(b, xs)
+    x0, it0, _, _ = orc.eigen_cg(o, i, v, b, tol=1e-9, max_iters=5000)
+    assert abs(s.get_info()["solver_iter"] - it0) <= max(2, 0.02 * it0)
+    assert np.linalg.norm(xs - x0) / np.linalg.norm(x0) < 1e-7
