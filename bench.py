@@ -244,6 +244,7 @@ def amg_leg(args, psb, P, local, hbm_peak):
         out[tag] = {"n": N, "gpu_setup_s": t_setup, "gpu_solve_s": t_solve, "gpu_setup_s_all": setups, "gpu_solve_s_all": solves, "gpu_iters": info["num_iterations"], "rel_residual": rel,
                     "roofline": rf,
                     "levels": [lv["rows"] for lv in info["amg"]["levels"]], "operator_complexity": info["amg"]["operator_complexity"],
+                    "level_spmv_kernels": [lv.get("spmv_kernel") for lv in info["amg"]["levels"]],
                     "gpu_setup_ms_by_level": [lv.get("setup_ms") for lv in info["amg"]["levels"]]}
         del s
         if n == cpu_n and not args.no_cpu:
@@ -759,7 +760,7 @@ def run_c5(args):
     lin = {"solver": "CUDA", "CUDA": {"precond": "amg", "block_size": 3, "tolerance": 1e-8, "max_iter": 1000, "device": local,
                                       "amg": {"dist_mode": args.amg_dist_mode}}}
     runs = []
-    for rep in range(max(1, args.steps // 2)):
+    for rep in range(1 + max(1, args.steps // 2)):  # the first run warms up (module load, pool growth, graph capture)
         s = psb.NonlinearSolver.create(nl, lin)
         if world > 1:
             s.set_linear_solver_hook(lambda solver: solver.dist_setup_torch(halo_cap=1 << 20))
@@ -774,6 +775,7 @@ def run_c5(args):
         info = s.get_info()
         runs.append((dt, info, x))
         del s
+    runs = runs[1:]
     dt, info, x = min(runs, key=lambda r: r[0])
     tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
     chk = torch.tensor([float(np.abs(x).sum())], dtype=torch.float64, device="cuda")

@@ -85,7 +85,7 @@ def _run(world, n, tol, precond="jacobi", block=1, amg_mode="partitioned", extra
     procs = [ctx.Process(target=_worker, args=(r, world, port, n, tol, q, precond, block, amg_mode, extra, second_n)) for r in range(world)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=300) for _ in range(world)]
+    res = [q.get(timeout=150) for _ in range(world)]
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
