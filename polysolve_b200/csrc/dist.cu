@@ -237,13 +237,22 @@ PushList HaloPlan::push() const
 // The push part shared by the kernels below: value(row) -> halo region of the consumer. The send list is cut
 // into chunks of kPushChunk entries per destination; a CTA stores a chunk and then adds 1 to the consumer's
 // flag with release semantics (no grid-level ticket, no second fence). push_no = number of this push (1-based).
-// Before the first store the CTA waits until the PREVIOUS push of every neighbour has landed here: a neighbour issues
-// that push only after it has finished reading the parity buffer this push is about to overwrite.
-template <class ValueFn>
+// A neighbour issues push e only after it has finished reading the parity buffer that push e + 1 overwrites, so a rank may
+// store as soon as the neighbours' push e has landed here. Kernels whose previous epoch was consumed by an SpMV of this
+// rank (the Krylov loops: the SpMV waited for exactly that) pass WAIT_PREV = false; the generic push (AMG smoother
+// iterates, where two pushes can follow each other without a consumer in between) waits itself -- with relaxed loads only:
+// nothing is read from the peers here, the wait merely orders this CTA's stores after the observation.
+template <bool WAIT_PREV, class ValueFn>
 __device__ __forceinline__ void push_section(const PushList &pl, const CommDev &c, unsigned long long push_no, int first_block, int nblocks,
                                              ValueFn value)
 {
-    wait_pushes_landed(c);
+    if (WAIT_PREV)
+    {
+        if ((int)threadIdx.x < c.world && ((c.nbr_mask >> threadIdx.x) & 1u))
+            if (!spin_ge(c.halo_flag(c.rank, threadIdx.x), c.halo_expect[threadIdx.x], c.error, c.spin_limit))
+                *c.error = 1;
+        __syncthreads();
+    }
     const int par = (int)(push_no & 1);
     for (int ch = (int)blockIdx.x - first_block; ch < pl.nchunks; ch += nblocks)
     {
@@ -301,7 +310,7 @@ __global__ void __launch_bounds__(THREADS) cg_dir_dist_kernel(long long n2, doub
         }
     }
     else
-        push_section(pl, rc.comm, push_no, 0, push_blocks, [&](int row) { return FIRST ? dinv[row] * r[row] : dinv[row] * r[row] + beta * p_old[row]; });
+        push_section<false>(pl, rc.comm, push_no, 0, push_blocks, [&](int row) { return FIRST ? dinv[row] * r[row] : dinv[row] * r[row] + beta * p_old[row]; });
     double acc[1] = {0}, tot[1];
     if (grid_reduce<0, THREADS>(acc, rc, tot))
     {
@@ -330,7 +339,7 @@ __global__ void __launch_bounds__(THREADS) halo_push_kernel(const double *__rest
     if (done && *done)
         return;
     const unsigned long long push_no = *rc.comm.push_epoch + 1;
-    push_section(pl, rc.comm, push_no, 0, (int)gridDim.x, [&](int row) { return v[row]; });
+    push_section<true>(pl, rc.comm, push_no, 0, (int)gridDim.x, [&](int row) { return v[row]; });
     double acc[1] = {0}, tot[1];
     if (grid_reduce<0, THREADS>(acc, rc, tot))
         push_complete(pl, rc.comm, push_no);
@@ -1072,7 +1081,7 @@ __global__ void __launch_bounds__(THREADS) cg_dir_amgcl_dist_kernel(long long n2
         }
     }
     else
-        push_section(pl, rc.comm, push_no, 0, push_blocks, [&](int row) { return s[row] + (beta != 0.0 ? beta * p_old[row] : 0.0); });
+        push_section<true>(pl, rc.comm, push_no, 0, push_blocks, [&](int row) { return s[row] + (beta != 0.0 ? beta * p_old[row] : 0.0); });
     double acc[1] = {0}, tot[1];
     if (grid_reduce<0, THREADS>(acc, rc, tot) && push_blocks > 0)
         push_complete(pl, rc.comm, push_no);
@@ -1256,7 +1265,7 @@ __global__ void __launch_bounds__(THREADS) cg1r_start_kernel(long long n2, doubl
         }
     }
     else
-        push_section(pl, rc.comm, push_no, 0, push_blocks, [&](int row) { return dinv[row] * r[row]; });
+        push_section<true>(pl, rc.comm, push_no, 0, push_blocks, [&](int row) { return dinv[row] * r[row]; });
     double acc[1] = {0}, tot[1];
     if (grid_reduce<0, THREADS>(acc, rc, tot) && push_blocks > 0)
         push_complete(pl, rc.comm, push_no);
@@ -1303,7 +1312,7 @@ __global__ void __launch_bounds__(THREADS) cg1r_update_kernel(long long n2, doub
         }
     }
     else
-        push_section(pl, rc.comm, push_no, 0, push_blocks,
+        push_section<false>(pl, rc.comm, push_no, 0, push_blocks,
                      [&](int row) { return dinv[row] * (r[row] - alpha * (w[row] + beta * s[row])); });
     double acc[1] = {0}, tot[1];
     if (grid_reduce<0, THREADS>(acc, rc, tot) && push_blocks > 0)
