@@ -12,9 +12,9 @@ step   : one complete solve(b, x) from x0 = 0 to the relative residual 1e-8.
 `e2e`   : the same metric through the public C-ABI call path with HOST buffers: every step does
           factorize_csc(host values) + solve(host b, host x), so the H2D of the matrix values and
           of b/x and the D2H of x are inside the timed region.
-N > 1   : the same ONE system, row-partitioned; the Krylov method is the single-reduction CG (krylov = cg1r: the same
-          iterates as the Eigen ordering in exact arithmetic, one all-reduce per iteration), stated in config.krylov; the
-          Eigen-ordering number of the same run is reported beside it (eigen_ordering), and a `parity` block checks the
+N > 1   : the same ONE system, row-partitioned; from 4 ranks on the Krylov method is the single-reduction CG (krylov = cg1r:
+          the same iterates as the Eigen ordering in exact arithmetic, one all-reduce per iteration), stated in
+          config.krylov; the other ordering is timed in the same run (other_krylov), and a `parity` block checks the
           N-rank path against the oracle on a small system (partition / halo lists bit-exact, x, iteration counts).
 `--config c4`: BASELINE configs[3] (119^3-node P1 elasticity, block-3 SA-AMG-PCG) as a separate line.
 `--impl reference`: the reference's CPU path (Eigen::ConjugateGradient restatement from oracle/,
@@ -430,7 +430,9 @@ def run_ours(args):
     nnz = int(outer[-1])
     hbm_peak, peak_src = peaks()
 
-    krylov = args.krylov if args.krylov != "auto" else ("cg1r" if world > 1 else "cg")
+    # measured on an 8 x B200 box (profiles/r02_bench_n*.json): the single-reduction form wins from 4 ranks on (+2 % at 4,
+    # +8 % at 8) and loses at 2 (-5 %: 12 % more bytes, and synchronisation is not yet the bottleneck there)
+    krylov = args.krylov if args.krylov != "auto" else ("cg1r" if world >= 4 else "cg")
     s = psb.Solver.create("CUDA", "")
     s.set_parameters({"CUDA": {"krylov": krylov, "precond": "jacobi", "tolerance": TOL, "max_iter": MAX_ITER,
                                "check_every": args.check_every, "device": local, "interior_first": args.interior_first}})
@@ -815,7 +817,7 @@ def main():
     ap.add_argument("--n", type=int, default=216, help="grid points per side (216 -> 10,077,696 DoF)")
     ap.add_argument("--check-every", type=int, default=16)
     ap.add_argument("--ref-iters", type=int, default=40, help="CG iterations per CPU sample step")
-    ap.add_argument("--krylov", default="auto", choices=["auto", "cg", "cg1r"], help="auto: cg on one GPU (Eigen ordering), cg1r on a row partition")
+    ap.add_argument("--krylov", default="auto", choices=["auto", "cg", "cg1r"], help="auto: cg (Eigen ordering) on 1-2 GPUs, cg1r (single reduction) from 4 ranks")
     ap.add_argument("--no-cusparse", action="store_true", help="skip the cuSPARSE / MAS-style comparator (N = 1)")
     ap.add_argument("--amg-dist-mode", default="partitioned", choices=["partitioned", "global", "local"])
     ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"], help="c2: the headline (10M-DoF Poisson Jacobi-PCG + the C3 AMG legs); c4: 119^3-node elasticity, block-3 AMG-PCG; c5: Newton on 70^3-node Neo-Hookean")

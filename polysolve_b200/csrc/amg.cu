@@ -1314,8 +1314,6 @@ void build_prolongation(Ctx &c, Temp &tmp, const AmgParams &prm, const CsrDev &A
 // amgcl amg::do_init (SURVEY A.3 "Hierarchy build")
 void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &imposed, int level_base)
 {
-    if (prm_.direct_coarse)
-        throw std::runtime_error("psb200 amg: direct_coarse=true is not available yet (polysolve's default is false, AMGCL.cpp:45)");
     cudaStream_t st = ctx_.stream;
     levels_.clear();
     A0_ = &A0;
@@ -1380,11 +1378,17 @@ void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &
     }
     if (cur)
     {
-        // coarsest level (rows <= coarse_enough): relaxation only (direct_coarse = false)
+        // coarsest level (rows <= coarse_enough): relaxation only, or the dense direct solve (direct_coarse = true)
         levels_.push_back(std::move(cur));
         const double tp = wall_ms(st);
-        setup_relaxation(ctx_, prm_, *levels_.back(), level_base + (int)levels_.size() - 1);
-        levels_.back()->t_relax = wall_ms(st) - tp;
+        AmgLevel &Lc = *levels_.back();
+        setup_relaxation(ctx_, prm_, Lc, level_base + (int)levels_.size() - 1);
+        if (prm_.direct_coarse)
+        {
+            dense_inverse_build(ctx_, *Lc.A, Lc.Zinv, Lc.z_np);
+            Lc.direct = true;
+        }
+        Lc.t_relax = wall_ms(st) - tp;
     }
     PSB_CUDA(cudaStreamSynchronize(st));
 }
@@ -1476,6 +1480,11 @@ void AmgHierarchy::relax(int l, const double *rhs, double *&x, double *&x_alt, b
 void AmgHierarchy::cycle(int l, const double *rhs, double *&x, double *&x_alt, bool x_is_zero, const int *done)
 {
     AmgLevel &L = *levels_[l];
+    if (l + 1 == (int)levels_.size() && L.direct)
+    {
+        dense_inverse_apply(ctx_, L.n, L.z_np, L.Zinv.p, rhs, x, done); // amgcl: (*lvl->solve)(rhs, x)
+        return;
+    }
     if (l + 1 == (int)levels_.size())
     {
         bool zero = x_is_zero;

@@ -196,8 +196,7 @@ void AmgDist::refinalize_plans()
 // ====================================================================================== setup
 void AmgDist::setup(const std::vector<std::vector<int>> &imposed)
 {
-    if (prm_.direct_coarse)
-        throw std::runtime_error("psb200 amg: direct_coarse=true is not available on a row partition");
+    // direct_coarse applies to the coarsest level, which always lives in the replicated tail
     if (prm_.relax_type != "chebyshev")
         throw std::runtime_error("psb200 amg: the partitioned cycle provides the Chebyshev smoother (polysolve's default, AMGCL.cpp:36-47)");
     Ctx &ctx = s_.ctx;

@@ -44,6 +44,10 @@ struct AmgLevel
     double rho = 0, cheb_d = 0, cheb_c = 0, omega = 0;
     std::vector<double> alpha, beta;
     int mis_rounds = 0;
+    // direct coarse solve (amg direct_coarse = true): Z = A^-1 dense, (z_np x z_np)
+    DevBuf<double> Zinv;
+    int z_np = 0;
+    bool direct = false;
     double t_relax = 0, t_agg = 0, t_prolong = 0, t_transpose = 0, t_ap = 0, t_rap = 0; // setup phase wall-clock, ms
 };
 
@@ -79,6 +83,9 @@ void build_aggregates(Ctx &c, Temp &tmp, const AmgParams &prm, const CsrDev &Asq
 // P = (I - omega D_f^-1 A_f) P_tent from the square matrix Asq and L.agg. Block mode smooths with Dblk^-1 Asq: pass the
 // level's Ahat when Asq is the level matrix itself, nullptr to have it computed from Asq.
 void build_prolongation(Ctx &c, Temp &tmp, const AmgParams &prm, const CsrDev &Asq, const CsrDev *Ahat, double eps_strong, double omega, AmgLevel &L);
+// dense.cu: Z = A^-1 of an SPD level matrix by blocked Cholesky on fp64 tensor cores; x = Z f
+void dense_inverse_build(Ctx &c, const CsrDev &A, DevBuf<double> &Z, int &np_out);
+void dense_inverse_apply(Ctx &c, int n, int np, const double *Z, const double *f, double *x, const int *done);
 double wall_ms(cudaStream_t st);
 // one smoother application on a level (see amg.cu); after_step pushes the halo of every new iterate on a row partition
 void relax_level(Ctx &ctx, const AmgParams &prm, AmgLevel &L, bool fine, const double *rhs, double *&x, double *&x_alt, bool x_is_zero,

@@ -121,6 +121,40 @@ def test_amg_mis2_matches_oracle_with_same_aggregates(psb, orc, n, kw):
     assert np.linalg.norm(orc.spmv_csc(o, i, v, x) - b) / np.linalg.norm(b) < 1e-9
 
 
+@pytest.mark.parametrize("n,coarse_enough", [(24, 3000), (36, 3000), (20, 300)])
+def test_amg_direct_coarse_matches_oracle(psb, orc, n, coarse_enough):
+    """direct_coarse = true (linear-solver-spec.json:363, AMGCL.cpp:45): the coarsest level is solved exactly -- AMGCL by a
+    skyline LU, the oracle by a dense LU, the GPU by Z = A_c^-1 from a blocked Cholesky on fp64 tensor cores (dense.cu) and
+    one dense GEMV per visit. Same hierarchy (GPU aggregates imposed on the oracle), same CG iteration count, same
+    solution; the preconditioner application agrees to 1e-9."""
+    N = n ** 3
+    o, i, v = orc.poisson3d(n)
+    b = orc.spmv_csc(o, i, v, orc.splitmix64(42, N))
+    s = make(psb, amg={"direct_coarse": True, "coarse_enough": coarse_enough})
+    s.factorize_raw(N, o, i, v)
+    amg = s.get_info()["amg"]
+    nlev = len(amg["levels"])
+    assert nlev >= 2 and amg["levels"][-1]["rows"] <= coarse_enough
+    aggs = [s.debug_get_aggregates(l, amg["levels"][l]["rows"])[0] for l in range(nlev - 1)]
+    H = orc.Amg(o, i, v, imposed=aggs, direct_coarse=1, coarse_enough=coarse_enough)
+    assert H.num_levels == nlev
+    r = orc.splitmix64(5, N)
+    z, z0 = s.precond_apply(r), H.apply(r)
+    assert np.linalg.norm(z - z0) / np.linalg.norm(z0) < 1e-9
+    x = np.zeros(N)
+    s.solve(b, x)
+    info = s.get_info()
+    x0, it0, _ = H.cg(b, tol=1e-10)
+    assert info["num_iterations"] == it0 and info["solver_status"] == "Converged"
+    assert np.linalg.norm(x - x0) / np.linalg.norm(x0) < 1e-9
+    # fewer (or equal) iterations than the smoothing-only coarsest level polysolve uses by default
+    s2 = make(psb, amg={"coarse_enough": coarse_enough})
+    s2.factorize_raw(N, o, i, v)
+    x2 = np.zeros(N)
+    s2.solve(b, x2)
+    assert info["num_iterations"] <= s2.get_info()["num_iterations"]
+
+
 def test_amg_mis2_aggregate_shape(psb, orc):
     """Aggregates are connected sets of radius <= 2 around a root; roots are >= 3 edges apart."""
     n = 20
