@@ -81,6 +81,23 @@ def test_protocol_errors(psb):
         s.analyze_pattern_raw(4, outer, inner, 4)
 
 
+def test_malformed_outer_array_is_rejected_before_any_kernel(psb):
+    """Round-1 advisor finding: a non-monotone outer array must come back as PSB200_ERR_INVALID from the host-side check,
+    not index device memory out of bounds (which would poison the CUDA context)."""
+    s = psb.Solver.create("CUDA", "")
+    outer = np.array([0, 3, 2, 4, 4], np.int32)   # outer[0] = 0 and outer[n] = nnz hold, but it decreases in between
+    inner = np.zeros(4, np.int32)
+    with pytest.raises(RuntimeError, match="non-decreasing"):
+        s.analyze_pattern_raw(4, outer, inner, 4)
+    with pytest.raises(RuntimeError, match="spmv_kernel"):
+        s.set_parameters({"CUDA": {"spmv_kernel": "vectorY"}})   # validated before the parameters are committed
+    with pytest.raises(RuntimeError, match="comm_timeout_s"):
+        s.set_parameters({"CUDA": {"comm_timeout_s": -1}})
+    with pytest.raises(RuntimeError, match="cg1r"):
+        s.set_parameters({"CUDA": {"krylov": "cg1r", "precond": "amg"}})
+    s.set_parameters({"CUDA": {"krylov": "cg1r", "comm_timeout_s": 10.0, "amg": {"dist_mode": "partitioned", "replicate_below": 1000}}})
+
+
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
 def test_compute_fails_loudly_without_gpu(psb):
     s = psb.Solver.create("CUDA", "")
