@@ -9,6 +9,7 @@
 // MIS-2 (aggregates can also be imposed through psb200_debug_set_aggregates for parity tests).
 #include "amg.hpp"
 #include "amg_internal.hpp"
+#include "push_epi.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -1398,7 +1399,7 @@ void AmgHierarchy::setup(const CsrDev &A0, const std::vector<std::vector<int>> &
 // x and x_alt ping-pong: the fused SpMV step reads x (gathered) and writes x_alt. On return `x` points
 // at the buffer that holds the result. after_step (row partitions): called with every new iterate, pushes its halo.
 void relax_level(Ctx &ctx, const AmgParams &prm, AmgLevel &L, bool fine, const double *rhs, double *&x, double *&x_alt, bool x_is_zero,
-                 const int *done, const std::function<void(const double *)> *after_step)
+                 const int *done, const std::function<void(const double *)> *after_step, const FusedPush *fused)
 {
     const CsrDev &A = *L.Asm;
     const int B = std::max(1, prm.block_size);
@@ -1446,6 +1447,14 @@ void relax_level(Ctx &ctx, const AmgParams &prm, AmgLevel &L, bool fine, const d
         {
             if (k == 0 && x_is_zero)
                 launch_vec(ctx, "cheb_first", L.n_pad, OpChebFirst{rhs, L.dinv.p, L.cp.p, x, L.alpha[0]}, FinNone{}, done);
+            else if (fused)
+            {
+                // row partition: the step pushes its own boundary rows (no separate push launch for this iterate)
+                launch_spmv(ctx, fine ? "spmv_cheb_l0" : "spmv_cheb_coarse", A, x,
+                            EpiChebPush{rhs, L.dinv.p, x, L.cp.p, x_alt, L.alpha[k], L.beta[k], fused->c, fused->pm}, FinPushDone{fused->c, fused->pm}, done);
+                std::swap(x, x_alt);
+                continue;
+            }
             else
             {
                 launch_spmv(ctx, fine ? "spmv_cheb_l0" : "spmv_cheb_coarse", A, x, EpiCheb{rhs, L.dinv.p, x, L.cp.p, x_alt, L.alpha[k], L.beta[k]},
@@ -1472,7 +1481,7 @@ void relax_level(Ctx &ctx, const AmgParams &prm, AmgLevel &L, bool fine, const d
 
 void AmgHierarchy::relax(int l, const double *rhs, double *&x, double *&x_alt, bool x_is_zero, const int *done)
 {
-    relax_level(ctx_, prm_, *levels_[l], l == 0 && level_base_ == 0, rhs, x, x_alt, x_is_zero, done, nullptr);
+    relax_level(ctx_, prm_, *levels_[l], l == 0 && level_base_ == 0, rhs, x, x_alt, x_is_zero, done, nullptr, nullptr);
 }
 
 // amgcl amg::cycle (SURVEY A.3 "Cycle"). x/x_alt are this level's iterate buffers; returns with the

@@ -19,6 +19,7 @@
 // Same Chebyshev smoother, cycle shape (ncycle, npre, npost) and parameters as the single-GPU hierarchy.
 #include "amg_dist.hpp"
 #include "amg_internal.hpp"
+#include "push_epi.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -157,6 +158,23 @@ __global__ void row_diff_kernel(int n, const int *__restrict__ rp, int *__restri
     else if (i == n)
         lens[i] = 0;
 }
+// flag[t] = 1 when tile t (rows_per_tile consecutive rows) holds a row that reads a halo column or is sent to a neighbour
+__global__ void boundary_tiles_kernel(CsrView A, const unsigned *__restrict__ send_bits, int rows_per_tile, int ntiles, int *__restrict__ flag)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles)
+        return;
+    const int r0 = t * rows_per_tile, r1 = min(A.n, r0 + rows_per_tile);
+    int f = 0;
+    for (int r = r0; r < r1 && !f; ++r)
+    {
+        if ((send_bits[r >> 5] >> (r & 31)) & 1u)
+            f = 1;
+        for (int k = A.rp[r]; k < A.rp[r + 1] && !f; ++k)
+            f = A.ci[k] >= A.nl;
+    }
+    flag[t] = f;
+}
 __global__ void rp_from_lengths_kernel(int n, const int *__restrict__ scan, int base, int *__restrict__ rp)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -165,6 +183,52 @@ __global__ void rp_from_lengths_kernel(int n, const int *__restrict__ scan, int 
 }
 
 } // namespace
+
+// Boundary-first tile order of a partitioned level matrix: the tiles whose rows are read by or sent to a neighbour come
+// first, so their new values are pushed (EpiChebPush) while the kernel still works on the interior tiles, and the
+// neighbours' next kernel finds its halo complete. One order for the stream schedule of the scalar CSR, one for BSR-3.
+static void build_boundary_first(Ctx &ctx, CsrDev &M, const HaloPlan &hp)
+{
+    cudaStream_t st = ctx.stream;
+    auto make = [&](int rows_per_tile, DevBuf<int> &out) {
+        const int ntiles = (M.n + rows_per_tile - 1) / rows_per_tile;
+        DevBuf<int> flag;
+        flag.alloc(std::max(1, ntiles));
+        boundary_tiles_kernel<<<nblk(ntiles), 256, 0, st>>>(M.view(), hp.send_bits.p, rows_per_tile, ntiles, flag.p);
+        check_launch();
+        std::vector<int> h(ntiles), order;
+        if (ntiles)
+            PSB_CUDA(cudaMemcpyAsync(h.data(), flag.p, sizeof(int) * ntiles, cudaMemcpyDeviceToHost, st));
+        PSB_CUDA(cudaStreamSynchronize(st));
+        order.reserve(ntiles);
+        for (int t = 0; t < ntiles; ++t)
+            if (h[t])
+                order.push_back(t);
+        for (int t = 0; t < ntiles; ++t)
+            if (!h[t])
+                order.push_back(t);
+        out.alloc(std::max(1, ntiles));
+        if (ntiles)
+            PSB_CUDA(cudaMemcpyAsync(out.p, order.data(), sizeof(int) * ntiles, cudaMemcpyHostToDevice, st));
+        PSB_CUDA(cudaStreamSynchronize(st));
+    };
+    M.use_order = false;
+    M.use_bsr_order = false;
+    if (M.n == 0 || M.halo_mask == 0)
+        return;
+    if (M.kind == SPMV_STREAM)
+    {
+        make(M.stream_rows(), M.tile_order);
+        M.n_interior = 0; // the halo is needed from the first tile on
+        M.order_rows = M.stream_rows();
+        M.use_order = true;
+    }
+    if (M.use_bsr && M.block == 3)
+    {
+        make(3 * BsrProd::rows, M.bsr_tile_order);
+        M.use_bsr_order = true;
+    }
+}
 
 // ====================================================================================== level
 struct DistAmgLevel
@@ -177,6 +241,13 @@ struct DistAmgLevel
     DevBuf<double> fc;              // restricted residual of the rank's coarse unknowns (input of the next level / the tail)
     double t_total = 0, t_exchange = 0, t_plan = 0;
 };
+
+// PSB200_FUSED_PUSH=off in the environment: every smoother step pushes with its own kernel (A/B runs)
+static bool fused_push_enabled()
+{
+    static bool on = std::getenv("PSB200_FUSED_PUSH") == nullptr || std::string(std::getenv("PSB200_FUSED_PUSH")) != "off";
+    return on;
+}
 
 AmgDist::AmgDist(Solver &s, const AmgParams &prm) : s_(s), prm_(prm) {}
 AmgDist::~AmgDist() {}
@@ -237,6 +308,12 @@ void AmgDist::setup(const std::vector<std::vector<int>> &imposed)
         double tp = wall_ms(st);
         setup_relaxation(ctx, prm_, L, li, &hooks); // the power iteration multiplies with the partitioned matrix, dots all-reduce
         L.t_relax = wall_ms(st) - tp;
+        if (fused_push_enabled() && W > 1)
+        {
+            build_boundary_first(ctx, li == 0 ? s_.A : L.Aown, *lv.plan);
+            if (B > 1)
+                build_boundary_first(ctx, L.Ahat, *lv.plan);
+        }
         if (li + 1 >= prm_.max_levels || lv.n_global <= prm_.coarse_enough)
             break; // relaxation-only last level (only when the whole hierarchy is a single level or max_levels is tiny)
 
@@ -516,6 +593,7 @@ void AmgDist::setup(const std::vector<std::vector<int>> &imposed)
         PSB_CUDA(cudaStreamSynchronize(st));
         HaloPlan &np = next->plan_own;
         np.world = W;
+        np.n_local = coff[me + 1] - coff[me];
         np.recv_count.assign(W, 0);
         {
             int q = 0;
@@ -609,7 +687,13 @@ void AmgDist::relax(int l, const double *rhs, double *&x, double *&x_alt, bool x
 {
     DistAmgLevel &lv = *levels_[l];
     std::function<void(const double *)> push = [this, &lv, done](const double *v) { s_.push_halo(*lv.plan, v, done); };
-    relax_level(s_.ctx, prm_, lv.L, l == 0, rhs, x, x_alt, x_is_zero, done, &push);
+    if (fused_push_enabled() && s_.dist->world > 1)
+    {
+        const FusedPush fp{s_.ctx.comm, lv.plan->push_map()};
+        relax_level(s_.ctx, prm_, lv.L, l == 0, rhs, x, x_alt, x_is_zero, done, &push, &fp);
+    }
+    else
+        relax_level(s_.ctx, prm_, lv.L, l == 0, rhs, x, x_alt, x_is_zero, done, &push);
 }
 
 // amgcl amg::cycle on the partitioned levels; below them the replicated tail runs one cycle from its level 0

@@ -88,8 +88,9 @@ void dense_inverse_build(Ctx &c, const CsrDev &A, DevBuf<double> &Z, int &np_out
 void dense_inverse_apply(Ctx &c, int n, int np, const double *Z, const double *f, double *x, const int *done);
 double wall_ms(cudaStream_t st);
 // one smoother application on a level (see amg.cu); after_step pushes the halo of every new iterate on a row partition
+struct FusedPush; // push_epi.cuh: with it the Chebyshev steps push their boundary rows from the SpMV epilogue
 void relax_level(Ctx &ctx, const AmgParams &prm, AmgLevel &L, bool fine, const double *rhs, double *&x, double *&x_alt, bool x_is_zero,
-                 const int *done, const std::function<void(const double *)> *after_step);
+                 const int *done, const std::function<void(const double *)> *after_step, const FusedPush *fused = nullptr);
 // D = M[local rows, local columns] of a row-partitioned matrix (columns >= M.nl dropped); src[k] = position in M (dist.cu)
 void extract_diag_block(Ctx &ctx, const CsrDev &M, CsrDev &D, DevBuf<int> &src);
 

@@ -173,7 +173,7 @@ private:
 //   [1024, 3072)  wide slots       WideSlot[2 parity][8 source ranks]  (8 doubles per rank: host-level all-gather, setup only)
 //   [4096, 8192)  halo flags       unsigned long long[8 source ranks]  (monotonic count of landed push chunks)
 //                 bulk flags       the same for the bulk all-reduce / all-gather, 1024 bytes further
-//   [8192, ...)   halo data        double[2 parity][8 source ranks][halo_cap]
+//   [8192, ...)   halo data        double[3 buffers][8 source ranks][halo_cap]  (buffer = push number mod 3)
 //                 bulk data        double[2 parity][8 source ranks][halo_cap]   (vector all-reduce / all-gather of the
 //                                  partitioned AMG cycle; during setup the same area is the staging arena of the
 //                                  host-level exchanges, one slot of 2 * halo_cap doubles per source rank)
@@ -193,6 +193,12 @@ struct WideSlot
 };
 constexpr size_t kCommWideOff = 1024, kCommFlagsOff = 4096, kCommBulkFlagsOff = 4096 + 1024, kCommHaloOff = 8192;
 constexpr int kPushChunk = 512; // halo entries per push chunk (one release-add on the consumer's flag per chunk)
+// Halo buffers per source. Two would do when every push is its own kernel (a rank pushes epoch e + 2 only after its
+// consumer of e + 1 has waited for the neighbours' e + 1, which they issued after reading e). The smoother of the
+// partitioned AMG levels pushes from INSIDE the multiplying kernel (EpiChebPush, amg_dist.cu): a neighbour may then
+// start pushing epoch e + 2 while this rank's kernel that reads epoch e is still running -- with three buffers the
+// writer of e + 3 is the first to reuse the buffer of e, and it cannot start before this rank's kernel e + 2 has pushed.
+constexpr int kHaloBufs = 3;
 
 // Flow control of the halo exchange. Every rank executes the same sequence of pushes (one per multiplied vector, at
 // every level of the AMG cycle); push number e writes the parity-(e & 1) halo regions of its consumers in chunks and
@@ -228,9 +234,9 @@ struct CommDev
     {
         return reinterpret_cast<unsigned long long *>(peer[owner] + kCommFlagsOff) + src;
     }
-    __host__ __device__ double *halo(int owner, int parity, int src) const
+    __host__ __device__ double *halo(int owner, int buf, int src) const
     {
-        return reinterpret_cast<double *>(peer[owner] + kCommHaloOff) + ((long long)parity * kMaxRanks + src) * halo_cap;
+        return reinterpret_cast<double *>(peer[owner] + kCommHaloOff) + ((long long)buf * kMaxRanks + src) * halo_cap;
     }
     __host__ __device__ unsigned long long *bulk_flag(int owner, int src) const
     {
@@ -238,12 +244,12 @@ struct CommDev
     }
     __host__ __device__ double *bulk(int owner, int parity, int src) const
     {
-        return reinterpret_cast<double *>(peer[owner] + kCommHaloOff) + ((long long)(2 + parity) * kMaxRanks + src) * halo_cap;
+        return reinterpret_cast<double *>(peer[owner] + kCommHaloOff) + ((long long)(kHaloBufs + parity) * kMaxRanks + src) * halo_cap;
     }
     // setup-time staging arena: the bulk area seen as one slot of 2 * halo_cap doubles per source rank
     __host__ __device__ unsigned char *arena(int owner, int src) const
     {
-        return reinterpret_cast<unsigned char *>(reinterpret_cast<double *>(peer[owner] + kCommHaloOff) + (long long)(2 * kMaxRanks + 2 * src) * halo_cap);
+        return reinterpret_cast<unsigned char *>(reinterpret_cast<double *>(peer[owner] + kCommHaloOff) + (long long)(kHaloBufs * kMaxRanks + 2 * src) * halo_cap);
     }
     __host__ __device__ size_t arena_slot_bytes() const { return (size_t)(2 * halo_cap) * sizeof(double); }
 };

@@ -23,7 +23,9 @@
 
 #include <algorithm>
 #include <cstring>
+#include <functional>
 #include <sstream>
+#include <thread>
 
 namespace psb {
 
@@ -39,14 +41,70 @@ void DistPlanHost::build(long long n, long long nnz, const int *outer, const int
     n_global = n;
     nnz_global = nnz;
     halo_cap = halo_cap_;
-    // CSR row pointer of the whole matrix (counting pass over the CSC row indices)
+    // Host threads for the two passes over all nnz entries (the plan of a 70 M-nnz matrix took 0.3-0.6 s on one thread,
+    // more than the GPU needs for everything else in analyze_pattern). Column ranges are dealt in order, so the result
+    // does not depend on the thread count.
+    const unsigned T = (unsigned)std::max<long long>(1, std::min<long long>({(long long)std::thread::hardware_concurrency(), 16ll, nnz / (1 << 20) + 1}));
+    auto col_range = [&](unsigned t, long long &c0, long long &c1) {
+        // split the columns so that every thread gets about the same number of entries
+        const long long k0 = nnz * t / T, k1 = nnz * (t + 1) / T;
+        c0 = std::upper_bound(outer, outer + n + 1, (int)k0) - outer - 1;
+        c1 = t + 1 == T ? n : std::upper_bound(outer, outer + n + 1, (int)k1) - outer - 1;
+        c0 = std::max<long long>(0, std::min(c0, n));
+        c1 = std::max(c0, std::min(c1, n));
+        if (t == 0)
+            c0 = 0;
+    };
+    auto run_threads = [&](const std::function<void(unsigned)> &fn) {
+        std::vector<std::thread> th;
+        std::vector<std::exception_ptr> errs(T);
+        for (unsigned t = 1; t < T; ++t)
+            th.emplace_back([&, t]() {
+                try
+                {
+                    fn(t);
+                }
+                catch (...)
+                {
+                    errs[t] = std::current_exception();
+                }
+            });
+        try
+        {
+            fn(0);
+        }
+        catch (...)
+        {
+            errs[0] = std::current_exception();
+        }
+        for (auto &x : th)
+            x.join();
+        for (auto &e : errs)
+            if (e)
+                std::rethrow_exception(e);
+    };
+    // CSR row pointer of the whole matrix (counting pass over the CSC row indices): per-thread histograms, summed
     std::vector<int> row_ptr(n + 1, 0);
-    for (long long k = 0; k < nnz; ++k)
     {
-        const int i = inner[k];
-        if (i < 0 || i >= n)
-            throw std::invalid_argument("psb200 dist: inner index out of range");
-        row_ptr[i + 1]++;
+        std::vector<std::vector<int>> hist(T);
+        run_threads([&](unsigned t) {
+            long long c0, c1;
+            col_range(t, c0, c1);
+            std::vector<int> &h = hist[t];
+            if (t > 0)
+                h.assign(n + 1, 0);
+            int *dst = t == 0 ? row_ptr.data() : h.data();
+            for (long long k = outer[c0]; k < outer[c1]; ++k)
+            {
+                const int i = inner[k];
+                if (i < 0 || i >= n)
+                    throw std::invalid_argument("psb200 dist: inner index out of range");
+                dst[i + 1]++;
+            }
+        });
+        for (unsigned t = 1; t < T; ++t)
+            for (long long i = 0; i <= n; ++i)
+                row_ptr[i] += hist[t][i];
     }
     for (long long i = 0; i < n; ++i)
         row_ptr[i + 1] += row_ptr[i];
@@ -70,7 +128,8 @@ void DistPlanHost::build(long long n, long long nnz, const int *outer, const int
             ++q;
         return q;
     };
-    // local rows by a counting transpose restricted to [a, b): columns come out ascending
+    // local rows by a counting transpose restricted to [a, b): columns come out ascending. Every thread first counts the
+    // entries of its column range per local row, then writes them behind the entries of the lower ranges.
     rp.assign(nl + 1, 0);
     for (int i = 0; i <= nl; ++i)
         rp[i] = row_ptr[a + i] - row_ptr[a];
@@ -78,18 +137,46 @@ void DistPlanHost::build(long long n, long long nnz, const int *outer, const int
     std::vector<int> gcol(lnnz);
     perm.assign(lnnz, 0);
     {
-        std::vector<int> cur(rp.begin(), rp.end() - 1);
-        for (long long c = 0; c < n; ++c)
-            for (int k = outer[c]; k < outer[c + 1]; ++k)
+        std::vector<std::vector<int>> cnt(T);
+        run_threads([&](unsigned t) {
+            long long c0, c1;
+            col_range(t, c0, c1);
+            std::vector<int> &h = cnt[t];
+            h.assign(nl, 0);
+            for (long long k = outer[c0]; k < outer[c1]; ++k)
             {
                 const int i = inner[k];
                 if (i >= a && i < b)
-                {
-                    const int pos = cur[i - a]++;
-                    gcol[pos] = (int)c;
-                    perm[pos] = k;
-                }
+                    h[i - a]++;
             }
+        });
+        // cnt[t][i] -> first position of thread t in local row i
+        for (int i = 0; i < nl; ++i)
+        {
+            int pos = rp[i];
+            for (unsigned t = 0; t < T; ++t)
+            {
+                const int c = cnt[t][i];
+                cnt[t][i] = pos;
+                pos += c;
+            }
+        }
+        run_threads([&](unsigned t) {
+            long long c0, c1;
+            col_range(t, c0, c1);
+            std::vector<int> &cur = cnt[t];
+            for (long long c = c0; c < c1; ++c)
+                for (int k = outer[c]; k < outer[c + 1]; ++k)
+                {
+                    const int i = inner[k];
+                    if (i >= a && i < b)
+                    {
+                        const int pos = cur[i - a]++;
+                        gcol[pos] = (int)c;
+                        perm[pos] = k;
+                    }
+                }
+        });
     }
     // halo columns: distinct off-range columns, ascending (=> grouped by owner); block problems: whole nodes
     halo_cols.clear();
@@ -220,7 +307,73 @@ void HaloPlan::finalize(unsigned nbr_mask, cudaStream_t st)
         PSB_CUDA(cudaMemcpyAsync(push_rows.p, send_rows.data(), sizeof(int) * n_push, cudaMemcpyHostToDevice, st));
     if (!tab.empty())
         PSB_CUDA(cudaMemcpyAsync(chunk_tab.p, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, st));
+    // ---- maps for the fused push: row -> (destination, position, chunk)
+    std::vector<int> first_chunk(world + 1, 0);
+    {
+        int ch = 0;
+        for (int q = 0; q < world; ++q)
+        {
+            first_chunk[q] = ch;
+            while (ch < n_chunks && cpeer[ch] == q)
+                ++ch;
+        }
+        first_chunk[world] = ch;
+    }
+    struct Slot
+    {
+        int row, peer, off, chunk;
+    };
+    std::vector<Slot> slots;
+    slots.reserve(n_push);
+    for (int q = 0; q < world; ++q)
+        for (int e = send_begin[q]; e < send_begin[q + 1]; ++e)
+        {
+            const int off = e - send_begin[q];
+            slots.push_back(Slot{send_rows[e], q, off, first_chunk[q] + off / kPushChunk});
+        }
+    std::stable_sort(slots.begin(), slots.end(), [](const Slot &a, const Slot &b) { return a.row < b.row; });
+    std::vector<int> h_brow, h_bptr, h_slot(3 * slots.size());
+    std::vector<unsigned> h_bits((size_t)(n_local + 31) / 32 + 1, 0u);
+    for (size_t k = 0; k < slots.size(); ++k)
+    {
+        if (k == 0 || slots[k].row != slots[k - 1].row)
+        {
+            h_brow.push_back(slots[k].row);
+            h_bptr.push_back((int)k);
+            if (slots[k].row < 0 || slots[k].row >= n_local)
+                throw std::logic_error("psb200 dist: send row outside the local range");
+            h_bits[slots[k].row >> 5] |= 1u << (slots[k].row & 31);
+        }
+        h_slot[k] = slots[k].peer;
+        h_slot[slots.size() + k] = slots[k].off;
+        h_slot[2 * slots.size() + k] = slots[k].chunk;
+    }
+    h_bptr.push_back((int)slots.size());
+    n_brow = (int)h_brow.size();
+    n_slots = (int)slots.size();
+    send_bits.alloc(h_bits.size());
+    brow.alloc(std::max(1, n_brow));
+    bptr.alloc((size_t)n_brow + 1);
+    slot_tab.alloc(std::max<size_t>(1, h_slot.size()));
+    chunk_done.alloc((size_t)n_chunks + 1, true); // counters restart with every finalize (a collective point of the setup)
+    PSB_CUDA(cudaMemcpyAsync(send_bits.p, h_bits.data(), sizeof(unsigned) * h_bits.size(), cudaMemcpyHostToDevice, st));
+    if (n_brow)
+        PSB_CUDA(cudaMemcpyAsync(brow.p, h_brow.data(), sizeof(int) * n_brow, cudaMemcpyHostToDevice, st));
+    PSB_CUDA(cudaMemcpyAsync(bptr.p, h_bptr.data(), sizeof(int) * h_bptr.size(), cudaMemcpyHostToDevice, st));
+    if (!h_slot.empty())
+        PSB_CUDA(cudaMemcpyAsync(slot_tab.p, h_slot.data(), sizeof(int) * h_slot.size(), cudaMemcpyHostToDevice, st));
     PSB_CUDA(cudaStreamSynchronize(st)); // staging vectors are stack-scoped
+}
+
+PushMap HaloPlan::push_map() const
+{
+    const int *t = chunk_tab.p;
+    const int nc = n_chunks;
+    PushMap pm{send_bits.p, brow.p, bptr.p, slot_tab.p, slot_tab.p + n_slots, slot_tab.p + 2 * n_slots, t + 2 * nc, t, chunk_done.p, chunk_done.p + nc,
+               n_brow, nc, {}};
+    for (int q = 0; q < kMaxRanks; ++q)
+        pm.in_chunks[q] = in_chunks[q];
+    return pm;
 }
 
 PushList HaloPlan::push() const
@@ -253,7 +406,7 @@ __device__ __forceinline__ void push_section(const PushList &pl, const CommDev &
                 *c.error = 1;
         __syncthreads();
     }
-    const int par = (int)(push_no & 1);
+    const int par = (int)(push_no % kHaloBufs);
     for (int ch = (int)blockIdx.x - first_block; ch < pl.nchunks; ch += nblocks)
     {
         const int peer = pl.chunk_peer[ch], start = pl.chunk_start[ch], cnt = pl.chunk_cnt[ch];
@@ -526,7 +679,7 @@ void Solver::dist_prepare(int rank, int world, long long halo_cap, char handle_o
     d.rank = rank;
     d.world = world;
     d.halo_cap = (halo_cap + 5) / 6 * 6; // a multiple of 2 and 3: halo column ids keep their dof index modulo the block size
-    d.comm_bytes = kCommHaloOff + sizeof(double) * 4 * kMaxRanks * (size_t)d.halo_cap; // halo + bulk regions, 2 parities each
+    d.comm_bytes = kCommHaloOff + sizeof(double) * (kHaloBufs + 2) * kMaxRanks * (size_t)d.halo_cap; // 3 halo buffers + 2 bulk parities per source
     PSB_CUDA(cudaMalloc(&d.comm_buf, d.comm_bytes));
     PSB_CUDA(cudaMemset(d.comm_buf, 0, d.comm_bytes));
     PSB_CUDA(cudaMalloc(&d.counters, 512));
@@ -688,6 +841,7 @@ void Solver::analyze_pattern_dist(long long n_, long long nnz_, const int *outer
     A.halo_mask = P.halo_cols.empty() ? 0u : 1u;
     A.block = (B > 1 && amg_partitioned()) ? B : 1; // full-block pattern only where the rows were expanded
     d.fine.world = d.world;
+    d.fine.n_local = n;
     d.fine.send_begin = P.send_begin;
     d.fine.send_rows = P.send_rows;
     d.fine.recv_count = P.recv_count;

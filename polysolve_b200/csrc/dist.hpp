@@ -35,6 +35,21 @@ struct PushList
     int in_chunks[kMaxRanks]; // chunks this rank receives from every source in the same push (0: not a neighbour)
 };
 
+// Device view of the send side for pushes issued from the EPILOGUE of the multiplying kernel (fused push): which local
+// rows travel where. bits: one bit per local row; brow: the sent rows, ascending; bptr: CSR over brow into the slot
+// arrays (destination rank, position in that rank's halo region, chunk id). chunk_done counts the entries stored per
+// chunk, monotonically over the launches (fused_seq = launches completed): the thread whose increment completes a chunk
+// releases the consumer's flag.
+struct PushMap
+{
+    const unsigned *bits;
+    const int *brow, *bptr, *slot_peer, *slot_off, *slot_chunk;
+    const int *chunk_cnt, *chunk_peer;
+    unsigned long long *chunk_done, *fused_seq;
+    int n_brow, nchunks;
+    int in_chunks[kMaxRanks];
+};
+
 // Halo exchange plan of one row-partitioned matrix (the fine matrix, or one level of the partitioned AMG hierarchy):
 // host lists + the device push list. finalize() cuts the send lists into chunks for a given neighbour mask: every
 // neighbour gets at least one (possibly empty) chunk per push, see CommDev.
@@ -47,6 +62,13 @@ struct HaloPlan
     unsigned mask() const; // ranks this plan sends to or receives from
     void finalize(unsigned nbr_mask, cudaStream_t st);
     PushList push() const;
+    // fused push (see PushMap); built by finalize()
+    DevBuf<unsigned> send_bits;
+    DevBuf<int> brow, bptr, slot_tab; // slot_tab = [peer | off | chunk]
+    DevBuf<unsigned long long> chunk_done; // [n_chunks] + fused_seq at the end
+    int n_brow = 0, n_slots = 0;
+    long long n_local = 0; // local rows of the matrix this plan belongs to (bitmap length)
+    PushMap push_map() const;
     // CTAs that push: one per chunk up to 128 (a CTA loops over chunks beyond that); at least one on a multi-rank run so
     // that the epochs advance in lockstep
     int push_ctas() const { return world > 1 ? std::max(1, std::min(128, n_chunks)) : 0; }

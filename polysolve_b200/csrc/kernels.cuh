@@ -70,7 +70,7 @@ __device__ __forceinline__ const double *wait_halo(const CsrView &A, const CommD
     if (A.halo_mask == 0)
         return nullptr;
     wait_pushes_landed(c);
-    return c.halo(c.rank, (int)(*c.push_epoch & 1), 0);
+    return c.halo(c.rank, (int)(*c.push_epoch % kHaloBufs), 0);
 }
 
 // ---------------------------------------------------------------------------------- finalizers

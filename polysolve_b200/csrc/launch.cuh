@@ -21,6 +21,9 @@ using StreamWide = StreamCfg<256, 3072, 2, LPR>;
 // active warps at 3 CTAs / SM on the level-1 Galerkin matrix): LPR 4 -> 2048 entries (4 CTAs / SM), LPR 8 -> 1536 (6)
 template <int LPR>
 using StreamNarrow = StreamCfg<256, LPR == 4 ? 2048 : 1536, 2, LPR>;
+// in between for 4 lanes per row: 2304 entries (55 KB) still gives 4 CTAs / SM and fits rows of up to ~35 nnz
+// (the level-1 Galerkin matrix of the 7-point Laplacian has 33)
+using StreamMid4 = StreamCfg<256, 2304, 2, 4>;
 
 // number of tiles of `rows` rows whose staged nnz range would not fit `cap` entries
 template <int DUMMY>
@@ -81,14 +84,16 @@ struct CsrDev
     DevBuf<double> va;
     int kind = SPMV_VECTOR;
     int lpr = 1; // lanes per row for the vector schedule
-    bool narrow = false; // stream schedule with LPR 4 / 8: the StreamNarrow tile shape
+    int narrow = 0; // stream schedule with LPR 4 / 8: 0 = 3072-entry stage, 1 = StreamNarrow, 2 = StreamMid4 (LPR 4 only)
     // BSR-3 form of a block-3 matrix (76 B per block instead of 108): kept BESIDE the scalar CSR, which stays the fallback
     // (and what the setup kernels read). block: 3 when rows 3 i .. 3 i + 2 share one list of full 3 x 3 blocks.
     int block = 1;
     bool use_bsr = false, bsr_ready = false;
     DevBuf<int> brp, bci;
     DevBuf<double> bva;
-    BsrView bview() const { return BsrView{brp.p, bci.p, bva.p, n / 3, nl, halo_mask}; }
+    DevBuf<int> bsr_tile_order; // row partitions: boundary tiles first (tiles of BsrProd::rows block rows)
+    bool use_bsr_order = false;
+    BsrView bview() const { return BsrView{brp.p, bci.p, bva.p, n / 3, nl, halo_mask, use_bsr_order && bsr_tile_order.p ? bsr_tile_order.p : nullptr}; }
     // (re)builds the BSR arrays from the scalar CSR: call whenever the values have changed
     void refresh_bsr(cudaStream_t st)
     {
@@ -159,12 +164,12 @@ struct CsrDev
     {
         const double avg = n > 0 ? (double)nnz / n : 0;
         const bool want_stream = forced.rfind("stream", 0) == 0;
-        narrow = false;
+        narrow = 0;
         if (want_stream && forced.size() > 6 && forced[6] != ':')
         {
             kind = SPMV_STREAM;
             lpr = std::stoi(forced.substr(6)); // "stream8n": stoi stops at the suffix
-            narrow = forced.back() == 'n' && (lpr == 4 || lpr == 8);
+            narrow = (forced.back() == 'n' && (lpr == 4 || lpr == 8)) ? 1 : (forced.back() == 'm' && lpr == 4) ? 2 : 0;
             return;
         }
         if (want_stream || (forced == "auto" && n >= 4 * StreamProd::threads))
@@ -175,11 +180,11 @@ struct CsrDev
             struct Cand
             {
                 int L, cap;
-                bool narrow;
+                int narrow;
             };
-            const Cand cands[] = {{1, StreamProd::cap, false}, {2, StreamWide<2>::cap, false}, {4, StreamNarrow<4>::cap, true},
-                                  {8, StreamNarrow<8>::cap, true}, {4, StreamWide<4>::cap, false}, {8, StreamWide<8>::cap, false},
-                                  {16, StreamWide<16>::cap, false}};
+            const Cand cands[] = {{1, StreamProd::cap, 0}, {2, StreamWide<2>::cap, 0}, {4, StreamNarrow<4>::cap, 1}, {4, StreamMid4::cap, 2},
+                                  {8, StreamNarrow<8>::cap, 1}, {4, StreamWide<4>::cap, 0}, {8, StreamWide<8>::cap, 0},
+                                  {16, StreamWide<16>::cap, 0}};
             for (const Cand &cd : cands)
             {
                 const int rows = StreamProd::threads / cd.L;
@@ -221,7 +226,7 @@ struct CsrDev
     {
         if (use_bsr)
             return "bsr3";
-        return kind == SPMV_STREAM ? (lpr == 1 ? "stream" : "stream" + std::to_string(lpr) + (narrow ? "n" : "")) : "vector" + std::to_string(lpr);
+        return kind == SPMV_STREAM ? (lpr == 1 ? "stream" : "stream" + std::to_string(lpr) + (narrow == 1 ? "n" : narrow == 2 ? "m" : "")) : "vector" + std::to_string(lpr);
     }
 };
 
@@ -427,10 +432,9 @@ void launch_spmv_stream(Ctx &c, const CsrDev &A, const double *x, Epi epi, Fin f
     launch_chain(c, kern, grid, Cfg::threads, Cfg::bytes, A.view(), x, epi, c.red(), fin, done, only_if);
 }
 
-template <class Epi, class Fin>
+template <class Epi, class Fin, class Cfg = BsrProd>
 void launch_spmv_bsr3(Ctx &c, const CsrDev &A, const double *x, Epi epi, Fin fin, const int *done, const int *only_if)
 {
-    using Cfg = BsrProd;
     auto kern = spmv_bsr3_kernel<Epi, Fin, Cfg>;
     static int max_ctas_dev[16] = {0};
     int dev = 0;
@@ -463,8 +467,10 @@ void launch_spmv(Ctx &c, const char *name, const CsrDev &A, const double *x, Epi
         {
         case 2: launch_spmv_stream<Epi, Fin, StreamWide<2>>(c, A, x, epi, fin, done, only_if); break;
         case 4:
-            if (A.narrow)
+            if (A.narrow == 1)
                 launch_spmv_stream<Epi, Fin, StreamNarrow<4>>(c, A, x, epi, fin, done, only_if);
+            else if (A.narrow == 2)
+                launch_spmv_stream<Epi, Fin, StreamMid4>(c, A, x, epi, fin, done, only_if);
             else
                 launch_spmv_stream<Epi, Fin, StreamWide<4>>(c, A, x, epi, fin, done, only_if);
             break;

@@ -1,0 +1,89 @@
+// Fused halo push: the Chebyshev step of a row-partitioned AMG level stores the boundary entries of the new iterate
+// into the consumers' halo buffers from the EPILOGUE of the multiplying kernel (no separate push launch), and with the
+// boundary-first tile order the values are on the wire while the kernel is still working on its interior rows.
+// See CommDev (common.cuh) for the flow control and kHaloBufs for why three halo buffers make this safe.
+#pragma once
+#include "dist.hpp"
+
+namespace psb {
+
+struct FusedPush
+{
+    CommDev c;
+    PushMap pm;
+};
+
+// One Chebyshev step (EpiCheb, spmv.cuh) + push of the rows other ranks read
+struct EpiChebPush
+{
+    static constexpr int NV = 0;
+    using Pre = Pre4;
+    const double *b, *dinv, *xin;
+    double *p, *xout;
+    double alpha, beta;
+    CommDev c;
+    PushMap pm;
+    __device__ __forceinline__ Pre pre(int row) const
+    {
+        return {__ldg(b + row), __ldg(dinv + row), __ldg(xin + row), beta != 0.0 ? p[row] : 0.0};
+    }
+    __device__ __forceinline__ void operator()(int row, double s, Pre q, double (&)[1]) const
+    {
+        const double res = q.b * (q.a - s);
+        const double pn = alpha * res + beta * q.d;
+        p[row] = pn;
+        const double xn = q.c + pn;
+        xout[row] = xn;
+        if ((__ldg(pm.bits + (row >> 5)) >> (row & 31)) & 1u)
+            push_row(row, xn);
+    }
+    __device__ __noinline__ void push_row(int row, double v) const
+    {
+        // the epoch and the launch counter are updated by the last CTA of this kernel, after every epilogue has run
+        const unsigned long long epoch = __ldcg(c.push_epoch), seq = __ldcg(pm.fused_seq);
+        const int buf = (int)((epoch + 1) % kHaloBufs);
+        int lo = 0, hi = pm.n_brow;
+        while (lo < hi)
+        {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(pm.brow + mid) < row)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        for (int s = __ldg(pm.bptr + lo); s < __ldg(pm.bptr + lo + 1); ++s)
+        {
+            const int peer = __ldg(pm.slot_peer + s), off = __ldg(pm.slot_off + s), ch = __ldg(pm.slot_chunk + s);
+            c.halo(peer, buf, c.rank)[off] = v;
+            __threadfence(); // the value is ordered before the count
+            const unsigned long long old = atomicAdd(pm.chunk_done + ch, 1ull);
+            if (old + 1 == (unsigned long long)__ldg(pm.chunk_cnt + ch) * (seq + 1))
+            {
+                // this store completed the chunk: everything counted before (by any thread of this GPU) is released to the
+                // consumer with the flag
+                fence_acq_rel_sys();
+                red_release_sys_add(c.halo_flag(peer, c.rank), 1ull);
+            }
+        }
+    }
+};
+
+// Run by thread 0 of the last CTA: the bookkeeping of a completed push (running totals of expected chunks, epoch), the
+// release of the empty chunks (neighbours that receive nothing from this level still get their one chunk per push)
+struct FinPushDone
+{
+    CommDev c;
+    PushMap pm;
+    __device__ __forceinline__ void operator()(const double *) const
+    {
+        for (int q = 0; q < c.world; ++q)
+            c.halo_expect[q] += (unsigned long long)pm.in_chunks[q];
+        for (int ch = 0; ch < pm.nchunks; ++ch)
+            if (pm.chunk_cnt[ch] == 0)
+                red_release_sys_add(c.halo_flag(pm.chunk_peer[ch], c.rank), 1ull);
+        *pm.fused_seq += 1;
+        *c.push_epoch += 1;
+    }
+};
+
+} // namespace psb

@@ -483,7 +483,7 @@ static bool spmv_kernel_name_ok(const std::string &k)
         if (k.rfind(pre, 0) == 0)
         {
             std::string num = k.substr(6);
-            if (pre[0] == 's' && (num == "4n" || num == "8n"))
+            if (pre[0] == 's' && (num == "4n" || num == "8n" || num == "4m"))
                 return true; // narrow tile shapes of the stream schedule
             if (num.empty() || num.size() > 2 || num.find_first_not_of("0123456789") != std::string::npos)
                 return false;
@@ -544,7 +544,7 @@ void Solver::set_parameters(const std::string &json)
     if (!(np.comm_timeout_s >= 0))
         throw std::runtime_error("psb200: comm_timeout_s must be >= 0");
     if (!spmv_kernel_name_ok(np.spmv_kernel))
-        throw std::runtime_error("psb200: unknown spmv_kernel '" + np.spmv_kernel + "' (auto | stream | stream<2|4|8|16> | stream4n | stream8n | vector<1|2|4|8|16|32> | scalar | bsr)");
+        throw std::runtime_error("psb200: unknown spmv_kernel '" + np.spmv_kernel + "' (auto | stream | stream<2|4|8|16> | stream4n | stream4m | stream8n | vector<1|2|4|8|16|32> | scalar | bsr)");
     if (np.precond != "jacobi" && np.precond != "amg" && np.precond != "none")
         throw std::runtime_error("psb200: unknown precond '" + np.precond + "' (jacobi | amg | none)");
     if (np.cg_kernel != "auto" && np.cg_kernel != "split")
@@ -1286,7 +1286,8 @@ double Solver::bench_spmv(const std::string &kernel, int reps)
     ensure_vectors();
     cudaStream_t st = ctx.stream;
     const int kind0 = A.kind, lpr0 = A.lpr;
-    const bool narrow0 = A.narrow, bsr0 = A.use_bsr;
+    const int narrow0 = A.narrow;
+    const bool bsr0 = A.use_bsr;
     // tile-shape exploration of the stream schedule: "stream:<threads>:<cap>:<stages>[:<ctas_per_sm>]"
     std::function<void()> one = [&]() { launch_spmv(ctx, "spmv", A, vp.p, EpiStore{vq.p}, FinNone{}); };
     if (kernel.rfind("stream:", 0) == 0)
@@ -1314,6 +1315,31 @@ double Solver::bench_spmv(const std::string &kernel, int reps)
 #undef PSB_STREAM_VARIANT
         if (!found)
             throw std::invalid_argument("psb200_bench_spmv: stream variant not compiled: " + kernel);
+    }
+    else if (kernel.rfind("bsr:", 0) == 0)
+    {
+        // tile-shape exploration of the BSR-3 schedule: "bsr:<threads>:<capb>:<stages>"
+        int t = 0, cap = 0, stg = 0;
+        if (std::sscanf(kernel.c_str(), "bsr:%d:%d:%d", &t, &cap, &stg) < 3)
+            throw std::invalid_argument("psb200_bench_spmv: expected bsr:<threads>:<capb>:<stages>");
+        if (!(A.use_bsr && A.bsr_ready))
+            throw std::invalid_argument("psb200_bench_spmv: the matrix has no BSR-3 form");
+        bool found = false;
+#define PSB_BSR_VARIANT(T, C, S)                                                                                              \
+    if (t == T && cap == C && stg == S)                                                                                       \
+    {                                                                                                                         \
+        found = true;                                                                                                         \
+        one = [&]() { launch_spmv_bsr3<EpiStore, FinNone, BsrCfg<T, C, S, 8>>(ctx, A, vp.p, EpiStore{vq.p}, FinNone{}, nullptr, nullptr); }; \
+    }
+        PSB_BSR_VARIANT(256, 544, 2)
+        PSB_BSR_VARIANT(256, 544, 1)
+        PSB_BSR_VARIANT(128, 272, 2)
+        PSB_BSR_VARIANT(128, 272, 3)
+        PSB_BSR_VARIANT(128, 288, 4)
+        PSB_BSR_VARIANT(512, 1088, 1)
+#undef PSB_BSR_VARIANT
+        if (!found)
+            throw std::invalid_argument("psb200_bench_spmv: BSR variant not compiled: " + kernel);
     }
     else if (!kernel.empty())
     {

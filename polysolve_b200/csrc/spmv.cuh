@@ -515,6 +515,7 @@ struct BsrView
     int nb;            // block rows
     int nl;            // local SCALAR columns (row partitions: scalar columns >= nl are halo columns)
     unsigned halo_mask;
+    const int *tile_order; // optional: sequence position -> tile (row partitions: boundary tiles first)
 };
 
 template <int THREADS, int CAPB, int STAGES, int LPB>
@@ -575,6 +576,7 @@ __global__ void __launch_bounds__(Cfg::threads) spmv_bsr3_kernel(BsrView A, cons
             tma_bulk_g2s(scol + (size_t)s * CAPB, A.bci + ka, (unsigned)cnt4 * 4u, &bar[s], policy);
         }
     };
+    auto tile_at = [&](int pos) { return A.tile_order ? __ldg(A.tile_order + pos) : pos; };
     if (threadIdx.x == 0)
     {
 #pragma unroll
@@ -582,7 +584,7 @@ __global__ void __launch_bounds__(Cfg::threads) spmv_bsr3_kernel(BsrView A, cons
         {
             const int pos = blockIdx.x + s * gridDim.x;
             if (pos < ntiles)
-                issue(pos, s);
+                issue(tile_at(pos), s);
         }
     }
     griddep_wait();
@@ -598,7 +600,7 @@ __global__ void __launch_bounds__(Cfg::threads) spmv_bsr3_kernel(BsrView A, cons
     if (A.halo_mask != 0)
     {
         wait_pushes_landed(rc.comm);
-        xh = rc.comm.halo(rc.comm.rank, (int)(*rc.comm.push_epoch & 1), 0);
+        xh = rc.comm.halo(rc.comm.rank, (int)(*rc.comm.push_epoch % kHaloBufs), 0);
     }
     const int nl = A.nl;
     int it = 0;
@@ -606,7 +608,7 @@ __global__ void __launch_bounds__(Cfg::threads) spmv_bsr3_kernel(BsrView A, cons
     {
         const int s = it % STAGES;
         const unsigned parity = (it / STAGES) & 1;
-        const int r0 = pos * ROWS;
+        const int r0 = tile_at(pos) * ROWS;
         const int nrow = min(A.nb - r0, ROWS);
         const int trow = threadIdx.x / LPB, lane = threadIdx.x % LPB;
         const int brow = r0 + trow;
@@ -706,7 +708,7 @@ __global__ void __launch_bounds__(Cfg::threads) spmv_bsr3_kernel(BsrView A, cons
         {
             const int next = pos + STAGES * gridDim.x;
             if (next < ntiles)
-                issue(next, s);
+                issue(tile_at(next), s);
         }
     }
     double tot[NVA];

@@ -12,3 +12,6 @@ s = psb.Solver.create("CUDA", "")
 s.set_parameters({"CUDA": {"block_size": 3}})
 s.factorize_raw(n, o, i, v)
 print(s.get_info()["spmv_kernel"], s.bench_spmv(reps=5))
+for k in ("bsr:256:544:2", "bsr:256:544:1", "bsr:128:272:2", "bsr:128:272:3", "bsr:128:288:4", "bsr:512:1088:1"):
+    if "--sweep" in sys.argv:
+        print(k, round(s.bench_spmv(reps=30, kernel=k), 5), flush=True)

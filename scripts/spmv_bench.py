@@ -44,7 +44,23 @@ A = sp.csr_matrix((v, i, o), shape=(pn ** 3, pn ** 3))
 A2 = (A @ A).tocsr()
 A2.sort_indices()
 run(f"poisson3d_{pn}_squared", A2.indptr.astype(np.int32), A2.indices.astype(np.int32), A2.data.astype(np.float64),
-    ["stream4", "stream4n", "stream8", "stream8n", "vector8"])
+    ["stream4", "stream4n", "stream4m", "stream8n", "vector8"])
+# 33 nnz/row with scattered columns: the level-1 Galerkin matrix of the 216^3 Laplacian has this density; here A^2 of the
+# 7-point stencil plus the 8 body-diagonal neighbours
+import itertools  # noqa: E402
+n3 = 96
+idx = np.arange(n3 ** 3).reshape(n3, n3, n3)
+rows, cols = [], []
+offs = [d for d in itertools.product((-2, -1, 0, 1, 2), repeat=3) if sum(abs(t) for t in d) <= 2] + list(itertools.product((-1, 1), repeat=3))
+for d in offs:
+    src = idx[max(0, -d[0]):n3 - max(0, d[0]), max(0, -d[1]):n3 - max(0, d[1]), max(0, -d[2]):n3 - max(0, d[2])]
+    dst = idx[max(0, d[0]):n3 - max(0, -d[0]), max(0, d[1]):n3 - max(0, -d[1]), max(0, d[2]):n3 - max(0, -d[2])]
+    rows.append(src.reshape(-1))
+    cols.append(dst.reshape(-1))
+M = sp.csr_matrix((np.ones(sum(len(r) for r in rows)), (np.concatenate(rows), np.concatenate(cols))), shape=(n3 ** 3, n3 ** 3))
+M.sort_indices()
+run(f"stencil33_{n3}", M.indptr.astype(np.int32), M.indices.astype(np.int32), M.data.astype(np.float64), ["stream4", "stream4m", "stream8n", "vector16"])
+del M
 del A, A2
 o, i, v, _ = P.elasticity3d(em)
 run(f"elasticity3d_{em}", o, i, v, ["stream4", "stream8n", "vector16"])
