@@ -1451,7 +1451,8 @@ void relax_level(Ctx &ctx, const AmgParams &prm, AmgLevel &L, bool fine, const d
             {
                 // row partition: the step pushes its own boundary rows (no separate push launch for this iterate)
                 launch_spmv(ctx, fine ? "spmv_cheb_l0" : "spmv_cheb_coarse", A, x,
-                            EpiChebPush{rhs, L.dinv.p, x, L.cp.p, x_alt, L.alpha[k], L.beta[k], fused->c, fused->pm}, FinPushDone{fused->c, fused->pm}, done);
+                            EpiChebPush{rhs, L.dinv.p, x, L.cp.p, x_alt, L.alpha[k], L.beta[k], fused->push_epoch, fused->pm},
+                            FinPushDone{fused->push_epoch, fused->halo_expect, fused->world, fused->pm}, done);
                 std::swap(x, x_alt);
                 continue;
             }

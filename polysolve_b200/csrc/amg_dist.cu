@@ -261,7 +261,7 @@ void AmgDist::refinalize_plans()
     s_.dist_set_nbr_mask(mask); // re-cuts the fine plan
     for (auto &lv : levels_)
         if (lv->plan != &s_.dist->fine)
-            lv->plan->finalize(s_.dist->nbr_mask, s_.ctx.stream);
+            lv->plan->finalize(s_.dist->nbr_mask, s_.ctx.comm, s_.ctx.stream);
 }
 
 // ====================================================================================== setup
@@ -689,7 +689,7 @@ void AmgDist::relax(int l, const double *rhs, double *&x, double *&x_alt, bool x
     std::function<void(const double *)> push = [this, &lv, done](const double *v) { s_.push_halo(*lv.plan, v, done); };
     if (fused_push_enabled() && s_.dist->world > 1)
     {
-        const FusedPush fp{s_.ctx.comm, lv.plan->push_map()};
+        const FusedPush fp{s_.ctx.comm.push_epoch, s_.ctx.comm.halo_expect, s_.ctx.comm.world, lv.plan->push_map()};
         relax_level(s_.ctx, prm_, lv.L, l == 0, rhs, x, x_alt, x_is_zero, done, &push, &fp);
     }
     else

@@ -270,7 +270,7 @@ unsigned HaloPlan::mask() const
     return m;
 }
 
-void HaloPlan::finalize(unsigned nbr_mask, cudaStream_t st)
+void HaloPlan::finalize(unsigned nbr_mask, const CommDev &comm, cudaStream_t st)
 {
     n_push = (int)send_rows.size();
     std::vector<int> cpeer, cstart, ccnt, coff;
@@ -332,7 +332,8 @@ void HaloPlan::finalize(unsigned nbr_mask, cudaStream_t st)
             slots.push_back(Slot{send_rows[e], q, off, first_chunk[q] + off / kPushChunk});
         }
     std::stable_sort(slots.begin(), slots.end(), [](const Slot &a, const Slot &b) { return a.row < b.row; });
-    std::vector<int> h_brow, h_bptr, h_slot(3 * slots.size());
+    std::vector<int> h_brow, h_bptr, h_chunk(slots.size());
+    std::vector<unsigned long long> h_dst(slots.size()), h_flag(std::max(1, n_chunks));
     std::vector<unsigned> h_bits((size_t)(n_local + 31) / 32 + 1, 0u);
     for (size_t k = 0; k < slots.size(); ++k)
     {
@@ -344,36 +345,53 @@ void HaloPlan::finalize(unsigned nbr_mask, cudaStream_t st)
                 throw std::logic_error("psb200 dist: send row outside the local range");
             h_bits[slots[k].row >> 5] |= 1u << (slots[k].row & 31);
         }
-        h_slot[k] = slots[k].peer;
-        h_slot[slots.size() + k] = slots[k].off;
-        h_slot[2 * slots.size() + k] = slots[k].chunk;
+        h_dst[k] = (unsigned long long)(uintptr_t)(comm.halo(slots[k].peer, 0, comm.rank) + slots[k].off);
+        h_chunk[k] = slots[k].chunk;
     }
+    for (int ch = 0; ch < n_chunks; ++ch)
+        h_flag[ch] = (unsigned long long)(uintptr_t)comm.halo_flag(cpeer[ch], comm.rank);
     h_bptr.push_back((int)slots.size());
     n_brow = (int)h_brow.size();
     n_slots = (int)slots.size();
+    buf_stride = (long long)kMaxRanks * comm.halo_cap;
     send_bits.alloc(h_bits.size());
     brow.alloc(std::max(1, n_brow));
     bptr.alloc((size_t)n_brow + 1);
-    slot_tab.alloc(std::max<size_t>(1, h_slot.size()));
+    slot_chunk.alloc(std::max<size_t>(1, h_chunk.size()));
+    slot_dst.alloc(std::max<size_t>(1, h_dst.size()));
+    chunk_flag.alloc(h_flag.size());
+    in_chunks_dev.alloc(kMaxRanks);
     chunk_done.alloc((size_t)n_chunks + 1, true); // counters restart with every finalize (a collective point of the setup)
     PSB_CUDA(cudaMemcpyAsync(send_bits.p, h_bits.data(), sizeof(unsigned) * h_bits.size(), cudaMemcpyHostToDevice, st));
     if (n_brow)
         PSB_CUDA(cudaMemcpyAsync(brow.p, h_brow.data(), sizeof(int) * n_brow, cudaMemcpyHostToDevice, st));
     PSB_CUDA(cudaMemcpyAsync(bptr.p, h_bptr.data(), sizeof(int) * h_bptr.size(), cudaMemcpyHostToDevice, st));
-    if (!h_slot.empty())
-        PSB_CUDA(cudaMemcpyAsync(slot_tab.p, h_slot.data(), sizeof(int) * h_slot.size(), cudaMemcpyHostToDevice, st));
+    if (!h_chunk.empty())
+    {
+        PSB_CUDA(cudaMemcpyAsync(slot_chunk.p, h_chunk.data(), sizeof(int) * h_chunk.size(), cudaMemcpyHostToDevice, st));
+        PSB_CUDA(cudaMemcpyAsync(slot_dst.p, h_dst.data(), sizeof(unsigned long long) * h_dst.size(), cudaMemcpyHostToDevice, st));
+    }
+    PSB_CUDA(cudaMemcpyAsync(chunk_flag.p, h_flag.data(), sizeof(unsigned long long) * h_flag.size(), cudaMemcpyHostToDevice, st));
+    PSB_CUDA(cudaMemcpyAsync(in_chunks_dev.p, in_chunks, sizeof(int) * kMaxRanks, cudaMemcpyHostToDevice, st));
     PSB_CUDA(cudaStreamSynchronize(st)); // staging vectors are stack-scoped
 }
 
 PushMap HaloPlan::push_map() const
 {
-    const int *t = chunk_tab.p;
     const int nc = n_chunks;
-    PushMap pm{send_bits.p, brow.p, bptr.p, slot_tab.p, slot_tab.p + n_slots, slot_tab.p + 2 * n_slots, t + 2 * nc, t, chunk_done.p, chunk_done.p + nc,
-               n_brow, nc, {}};
-    for (int q = 0; q < kMaxRanks; ++q)
-        pm.in_chunks[q] = in_chunks[q];
-    return pm;
+    return PushMap{send_bits.p,
+                   brow.p,
+                   bptr.p,
+                   slot_chunk.p,
+                   reinterpret_cast<double *const *>(slot_dst.p),
+                   chunk_tab.p + 2 * nc,
+                   reinterpret_cast<unsigned long long *const *>(chunk_flag.p),
+                   chunk_done.p,
+                   chunk_done.p + nc,
+                   in_chunks_dev.p,
+                   buf_stride,
+                   n_brow,
+                   nc};
 }
 
 PushList HaloPlan::push() const
@@ -761,7 +779,7 @@ void Solver::dist_set_nbr_mask(unsigned mask)
     mask &= ~(1u << d.rank);
     d.nbr_mask = mask;
     ctx.comm.nbr_mask = mask;
-    d.fine.finalize(mask, ctx.stream);
+    d.fine.finalize(mask, ctx.comm, ctx.stream);
 }
 
 __global__ void mark_halo_rows_kernel(int n, int nl, const int *__restrict__ rp, const int *__restrict__ ci, int *flag)

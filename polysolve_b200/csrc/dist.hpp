@@ -37,17 +37,22 @@ struct PushList
 
 // Device view of the send side for pushes issued from the EPILOGUE of the multiplying kernel (fused push): which local
 // rows travel where. bits: one bit per local row; brow: the sent rows, ascending; bptr: CSR over brow into the slot
-// arrays (destination rank, position in that rank's halo region, chunk id). chunk_done counts the entries stored per
-// chunk, monotonically over the launches (fused_seq = launches completed): the thread whose increment completes a chunk
-// releases the consumer's flag.
+// arrays: slot_dst = address of the entry in the destination's halo buffer 0 (the other buffers follow at buf_stride
+// doubles), slot_chunk = chunk id. chunk_done counts the entries stored per chunk, monotonically over the launches
+// (fused_seq = launches completed): the thread whose increment completes a chunk releases the consumer's flag
+// (chunk_flag). Everything is reached through pointers with constant offsets: a kernel parameter struct that is indexed
+// dynamically (or whose address escapes) is copied to local memory by every thread.
 struct PushMap
 {
     const unsigned *bits;
-    const int *brow, *bptr, *slot_peer, *slot_off, *slot_chunk;
-    const int *chunk_cnt, *chunk_peer;
+    const int *brow, *bptr, *slot_chunk;
+    double *const *slot_dst;
+    const int *chunk_cnt;
+    unsigned long long *const *chunk_flag;
     unsigned long long *chunk_done, *fused_seq;
+    const int *in_chunks; // device copy of HaloPlan::in_chunks
+    long long buf_stride;
     int n_brow, nchunks;
-    int in_chunks[kMaxRanks];
 };
 
 // Halo exchange plan of one row-partitioned matrix (the fine matrix, or one level of the partitioned AMG hierarchy):
@@ -60,12 +65,14 @@ struct HaloPlan
     int n_push = 0, n_chunks = 0, world = 1;
     int in_chunks[kMaxRanks] = {};
     unsigned mask() const; // ranks this plan sends to or receives from
-    void finalize(unsigned nbr_mask, cudaStream_t st);
+    void finalize(unsigned nbr_mask, const CommDev &comm, cudaStream_t st);
     PushList push() const;
     // fused push (see PushMap); built by finalize()
     DevBuf<unsigned> send_bits;
-    DevBuf<int> brow, bptr, slot_tab; // slot_tab = [peer | off | chunk]
+    DevBuf<int> brow, bptr, slot_chunk, in_chunks_dev;
+    DevBuf<unsigned long long> slot_dst, chunk_flag; // device addresses stored as 64-bit integers
     DevBuf<unsigned long long> chunk_done; // [n_chunks] + fused_seq at the end
+    long long buf_stride = 0;
     int n_brow = 0, n_slots = 0;
     long long n_local = 0; // local rows of the matrix this plan belongs to (bitmap length)
     PushMap push_map() const;

@@ -44,8 +44,10 @@ enum SpmvKind : int
     SPMV_VECTOR = 0,
     SPMV_STREAM = 1
 };
-// BSR-3 tile shape: 32 block rows (96 scalar rows) per tile, 8 lanes per block row, 544 staged blocks (41 KB) per stage
-using BsrProd = BsrCfg<256, 544, 2, 8>;
+// BSR-3 tile shape: 16 block rows (48 scalar rows) per tile of 128 threads, 8 lanes per block row, 272 staged blocks
+// (20.7 KB) per stage -> 5 CTAs / SM. Sweep on B200 (profiles/r02_bsr_sweep.txt, 72^3-node elasticity): 128:272:2 0.0792 ms,
+// 256:544:1 0.0806, 256:544:2 0.0870, 512:1088:1 0.0893, 128:272:3 0.0988, 128:288:4 0.1244
+using BsrProd = BsrCfg<128, 272, 2, 8>;
 
 // block row pointer / block columns of a scalar CSR whose rows 3 i .. 3 i + 2 share one list of full 3 x 3 blocks
 template <int DUMMY>

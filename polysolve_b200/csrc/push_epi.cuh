@@ -9,7 +9,8 @@ namespace psb {
 
 struct FusedPush
 {
-    CommDev c;
+    unsigned long long *push_epoch, *halo_expect;
+    int world;
     PushMap pm;
 };
 
@@ -21,7 +22,7 @@ struct EpiChebPush
     const double *b, *dinv, *xin;
     double *p, *xout;
     double alpha, beta;
-    CommDev c;
+    const unsigned long long *push_epoch;
     PushMap pm;
     __device__ __forceinline__ Pre pre(int row) const
     {
@@ -35,34 +36,34 @@ struct EpiChebPush
         const double xn = q.c + pn;
         xout[row] = xn;
         if ((__ldg(pm.bits + (row >> 5)) >> (row & 31)) & 1u)
-            push_row(row, xn);
-    }
-    __device__ __noinline__ void push_row(int row, double v) const
-    {
-        // the epoch and the launch counter are updated by the last CTA of this kernel, after every epilogue has run
-        const unsigned long long epoch = __ldcg(c.push_epoch), seq = __ldcg(pm.fused_seq);
-        const int buf = (int)((epoch + 1) % kHaloBufs);
-        int lo = 0, hi = pm.n_brow;
-        while (lo < hi)
         {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(pm.brow + mid) < row)
-                lo = mid + 1;
-            else
-                hi = mid;
-        }
-        for (int s = __ldg(pm.bptr + lo); s < __ldg(pm.bptr + lo + 1); ++s)
-        {
-            const int peer = __ldg(pm.slot_peer + s), off = __ldg(pm.slot_off + s), ch = __ldg(pm.slot_chunk + s);
-            c.halo(peer, buf, c.rank)[off] = v;
-            __threadfence(); // the value is ordered before the count
-            const unsigned long long old = atomicAdd(pm.chunk_done + ch, 1ull);
-            if (old + 1 == (unsigned long long)__ldg(pm.chunk_cnt + ch) * (seq + 1))
+            // the epoch and the launch counter are updated by the last CTA of this kernel, after every epilogue has run
+            const unsigned long long epoch = __ldcg(push_epoch), seq = __ldcg(pm.fused_seq);
+            const long long shift = (long long)((epoch + 1) % kHaloBufs) * pm.buf_stride;
+            int lo = 0, hi = pm.n_brow;
+            while (lo < hi)
             {
-                // this store completed the chunk: everything counted before (by any thread of this GPU) is released to the
-                // consumer with the flag
-                fence_acq_rel_sys();
-                red_release_sys_add(c.halo_flag(peer, c.rank), 1ull);
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(pm.brow + mid) < row)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            const int s1 = __ldg(pm.bptr + lo + 1);
+            for (int sl = __ldg(pm.bptr + lo); sl < s1; ++sl)
+            {
+                const int ch = __ldg(pm.slot_chunk + sl);
+                double *dst = pm.slot_dst[sl] + shift;
+                *dst = xn;
+                __threadfence(); // the value is ordered before the count
+                const unsigned long long old = atomicAdd(pm.chunk_done + ch, 1ull);
+                if (old + 1 == (unsigned long long)__ldg(pm.chunk_cnt + ch) * (seq + 1))
+                {
+                    // this store completed the chunk: everything counted before (by any thread of this GPU) is released
+                    // to the consumer with the flag
+                    fence_acq_rel_sys();
+                    red_release_sys_add(pm.chunk_flag[ch], 1ull);
+                }
             }
         }
     }
@@ -72,17 +73,18 @@ struct EpiChebPush
 // release of the empty chunks (neighbours that receive nothing from this level still get their one chunk per push)
 struct FinPushDone
 {
-    CommDev c;
+    unsigned long long *push_epoch, *halo_expect;
+    int world;
     PushMap pm;
     __device__ __forceinline__ void operator()(const double *) const
     {
-        for (int q = 0; q < c.world; ++q)
-            c.halo_expect[q] += (unsigned long long)pm.in_chunks[q];
+        for (int q = 0; q < world; ++q)
+            halo_expect[q] += (unsigned long long)pm.in_chunks[q];
         for (int ch = 0; ch < pm.nchunks; ++ch)
             if (pm.chunk_cnt[ch] == 0)
-                red_release_sys_add(c.halo_flag(pm.chunk_peer[ch], c.rank), 1ull);
+                red_release_sys_add(pm.chunk_flag[ch], 1ull);
         *pm.fused_seq += 1;
-        *c.push_epoch += 1;
+        *push_epoch += 1;
     }
 };
 
