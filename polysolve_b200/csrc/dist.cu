@@ -348,8 +348,22 @@ void HaloPlan::finalize(unsigned nbr_mask, const CommDev &comm, cudaStream_t st)
         h_dst[k] = (unsigned long long)(uintptr_t)(comm.halo(slots[k].peer, 0, comm.rank) + slots[k].off);
         h_chunk[k] = slots[k].chunk;
     }
+    std::vector<unsigned long long> h_empty;
     for (int ch = 0; ch < n_chunks; ++ch)
+    {
         h_flag[ch] = (unsigned long long)(uintptr_t)comm.halo_flag(cpeer[ch], comm.rank);
+        if (ccnt[ch] == 0)
+            h_empty.push_back(h_flag[ch]);
+    }
+    std::vector<int> h_prefix(h_bits.size(), 0);
+    for (size_t w = 1; w < h_bits.size(); ++w)
+        h_prefix[w] = h_prefix[w - 1] + __builtin_popcount(h_bits[w - 1]);
+    bits_prefix.alloc(h_prefix.size());
+    PSB_CUDA(cudaMemcpyAsync(bits_prefix.p, h_prefix.data(), sizeof(int) * h_prefix.size(), cudaMemcpyHostToDevice, st));
+    n_empty = (int)h_empty.size();
+    empty_flag.alloc(std::max(1, n_empty));
+    if (n_empty)
+        PSB_CUDA(cudaMemcpyAsync(empty_flag.p, h_empty.data(), sizeof(unsigned long long) * n_empty, cudaMemcpyHostToDevice, st));
     h_bptr.push_back((int)slots.size());
     n_brow = (int)h_brow.size();
     n_slots = (int)slots.size();
@@ -380,18 +394,21 @@ PushMap HaloPlan::push_map() const
 {
     const int nc = n_chunks;
     return PushMap{send_bits.p,
+                   bits_prefix.p,
                    brow.p,
                    bptr.p,
                    slot_chunk.p,
                    reinterpret_cast<double *const *>(slot_dst.p),
                    chunk_tab.p + 2 * nc,
                    reinterpret_cast<unsigned long long *const *>(chunk_flag.p),
+                   reinterpret_cast<unsigned long long *const *>(empty_flag.p),
                    chunk_done.p,
                    chunk_done.p + nc,
                    in_chunks_dev.p,
                    buf_stride,
                    n_brow,
-                   nc};
+                   nc,
+                   n_empty};
 }
 
 PushList HaloPlan::push() const

@@ -45,14 +45,16 @@ struct PushList
 struct PushMap
 {
     const unsigned *bits;
+    const int *bits_prefix; // number of set bits in the words before this one
     const int *brow, *bptr, *slot_chunk;
     double *const *slot_dst;
     const int *chunk_cnt;
     unsigned long long *const *chunk_flag;
+    unsigned long long *const *empty_flag; // flags of the chunks without entries (released by the finalizer), n_empty of them
     unsigned long long *chunk_done, *fused_seq;
     const int *in_chunks; // device copy of HaloPlan::in_chunks
     long long buf_stride;
-    int n_brow, nchunks;
+    int n_brow, nchunks, n_empty;
 };
 
 // Halo exchange plan of one row-partitioned matrix (the fine matrix, or one level of the partitioned AMG hierarchy):
@@ -69,8 +71,9 @@ struct HaloPlan
     PushList push() const;
     // fused push (see PushMap); built by finalize()
     DevBuf<unsigned> send_bits;
-    DevBuf<int> brow, bptr, slot_chunk, in_chunks_dev;
-    DevBuf<unsigned long long> slot_dst, chunk_flag; // device addresses stored as 64-bit integers
+    DevBuf<int> brow, bptr, slot_chunk, in_chunks_dev, bits_prefix;
+    DevBuf<unsigned long long> slot_dst, chunk_flag, empty_flag; // device addresses stored as 64-bit integers
+    int n_empty = 0;
     DevBuf<unsigned long long> chunk_done; // [n_chunks] + fused_seq at the end
     long long buf_stride = 0;
     int n_brow = 0, n_slots = 0;

@@ -40,15 +40,9 @@ struct EpiChebPush
             // the epoch and the launch counter are updated by the last CTA of this kernel, after every epilogue has run
             const unsigned long long epoch = __ldcg(push_epoch), seq = __ldcg(pm.fused_seq);
             const long long shift = (long long)((epoch + 1) % kHaloBufs) * pm.buf_stride;
-            int lo = 0, hi = pm.n_brow;
-            while (lo < hi)
-            {
-                const int mid = (lo + hi) >> 1;
-                if (__ldg(pm.brow + mid) < row)
-                    lo = mid + 1;
-                else
-                    hi = mid;
-            }
+            // index of this row among the sent rows: rank of its bit (prefix count of the word + bits below it)
+            const unsigned word = __ldg(pm.bits + (row >> 5));
+            const int lo = __ldg(pm.bits_prefix + (row >> 5)) + __popc(word & ((1u << (row & 31)) - 1u));
             const int s1 = __ldg(pm.bptr + lo + 1);
             for (int sl = __ldg(pm.bptr + lo); sl < s1; ++sl)
             {
@@ -78,11 +72,16 @@ struct FinPushDone
     PushMap pm;
     __device__ __forceinline__ void operator()(const double *) const
     {
-        for (int q = 0; q < world; ++q)
-            halo_expect[q] += (unsigned long long)pm.in_chunks[q];
-        for (int ch = 0; ch < pm.nchunks; ++ch)
-            if (pm.chunk_cnt[ch] == 0)
-                red_release_sys_add(pm.chunk_flag[ch], 1ull);
+        int inc[kMaxRanks];
+#pragma unroll
+        for (int q = 0; q < kMaxRanks; ++q)
+            inc[q] = pm.in_chunks[q]; // independent loads, issued together
+#pragma unroll
+        for (int q = 0; q < kMaxRanks; ++q)
+            if (inc[q])
+                halo_expect[q] += (unsigned long long)inc[q];
+        for (int e = 0; e < pm.n_empty; ++e) // usually none: a neighbour of another level that receives nothing from this one
+            red_release_sys_add(pm.empty_flag[e], 1ull);
         *pm.fused_seq += 1;
         *push_epoch += 1;
     }
