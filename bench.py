@@ -271,7 +271,8 @@ def amg_dist_leg(args, psb, P, local, world, N, outer, inner, vals, b, barrier, 
     torch.cuda.synchronize()
     free0 = torch.cuda.mem_get_info()[0]
     s = psb.Solver.create("CUDA", "")
-    s.set_parameters({"CUDA": {"precond": "amg", "tolerance": TOL, "max_iter": 1000, "device": local, "amg": {"dist_mode": args.amg_dist_mode}}})
+    s.set_parameters({"CUDA": {"precond": "amg", "tolerance": TOL, "max_iter": 1000, "device": local,
+                               "amg": {"dist_mode": args.amg_dist_mode, "fused_push": bool(args.fused_push)}}})
     s.dist_setup_torch(halo_cap=1 << 20)
     s.analyze_pattern_raw(N, outer, inner, N)
     s.factorize_raw(N, outer, inner, vals)
@@ -683,7 +684,7 @@ def run_c4(args):
     free0 = torch.cuda.mem_get_info()[0]
     s = psb.Solver.create("CUDA", "")
     s.set_parameters({"CUDA": {"precond": "amg", "block_size": 3, "tolerance": TOL, "max_iter": 1000, "device": local,
-                               "amg": {"dist_mode": args.amg_dist_mode}}})
+                               "amg": {"dist_mode": args.amg_dist_mode, "fused_push": bool(args.fused_push)}}})
     if world > 1:
         s.dist_setup_torch(halo_cap=1 << 21)
     t0 = time.perf_counter()
@@ -737,6 +738,27 @@ def run_c4(args):
             "spmv_kernel": info["spmv_kernel"], "roofline": amg_roofline(info, float(t[1]), hbm_peak, world),
             "gpu_launches": info["gpu_launches"]}
     print(json.dumps(line), flush=True)
+
+
+def run_amg_dist_only(args):
+    """N > 1: only the partitioned SA-AMG-PCG leg of config 3 (A/B runs of amg.* switches without the Jacobi legs)."""
+    import torch
+    import torch.distributed as dist
+    import polysolve_b200 as psb
+    from polysolve_b200 import problems as P
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    N, outer, inner, vals, b, _ = build_problem(args.n)
+    hbm_peak, _ = peaks()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+    out = amg_dist_leg(args, psb, P, local, world, N, outer, inner, vals, b, barrier, hbm_peak)
+    if rank == 0:
+        out["fused_push"] = bool(args.fused_push)
+        print(json.dumps({"amg_pcg_dist": out, "n_gpus": world}), flush=True)
 
 
 def run_c5(args):
@@ -823,6 +845,8 @@ def main():
     ap.add_argument("--config", default="c2", choices=["c2", "c4", "c5"], help="c2: the headline (10M-DoF Poisson Jacobi-PCG + the C3 AMG legs); c4: 119^3-node elasticity, block-3 AMG-PCG; c5: Newton on 70^3-node Neo-Hookean")
     ap.add_argument("--c4-nodes", type=int, default=119)
     ap.add_argument("--c5-nodes", type=int, default=70)
+    ap.add_argument("--fused-push", action="store_true", help="multi-GPU AMG legs: amg.fused_push = true (halo pushed from the SpMV epilogue)")
+    ap.add_argument("--amg-dist-only", action="store_true", help="N > 1: run only the partitioned SA-AMG-PCG leg (config 3) and print its JSON")
     ap.add_argument("--interior-first", action="store_true", help="row partitions: SpMV tiles without halo columns first, late halo wait")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-amg", action="store_true", help="skip the AMG-PCG (config 3) leg")
@@ -830,6 +854,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.amg_dist_only:
+        run_amg_dist_only(args)
     elif args.config == "c4":
         run_c4(args)
     elif args.config == "c5":

@@ -242,10 +242,10 @@ struct DistAmgLevel
     double t_total = 0, t_exchange = 0, t_plan = 0;
 };
 
-// PSB200_FUSED_PUSH=off in the environment: every smoother step pushes with its own kernel (A/B runs)
-static bool fused_push_enabled()
+// amg.fused_push (or PSB200_FUSED_PUSH=on in the environment, for A/B runs of an unchanged caller)
+static bool env_fused_push()
 {
-    static bool on = std::getenv("PSB200_FUSED_PUSH") == nullptr || std::string(std::getenv("PSB200_FUSED_PUSH")) != "off";
+    static bool on = std::getenv("PSB200_FUSED_PUSH") != nullptr && std::string(std::getenv("PSB200_FUSED_PUSH")) == "on";
     return on;
 }
 
@@ -308,7 +308,7 @@ void AmgDist::setup(const std::vector<std::vector<int>> &imposed)
         double tp = wall_ms(st);
         setup_relaxation(ctx, prm_, L, li, &hooks); // the power iteration multiplies with the partitioned matrix, dots all-reduce
         L.t_relax = wall_ms(st) - tp;
-        if (fused_push_enabled() && W > 1)
+        if ((prm_.fused_push || env_fused_push()) && W > 1)
         {
             build_boundary_first(ctx, li == 0 ? s_.A : L.Aown, *lv.plan);
             if (B > 1)
@@ -687,7 +687,7 @@ void AmgDist::relax(int l, const double *rhs, double *&x, double *&x_alt, bool x
 {
     DistAmgLevel &lv = *levels_[l];
     std::function<void(const double *)> push = [this, &lv, done](const double *v) { s_.push_halo(*lv.plan, v, done); };
-    if (fused_push_enabled() && s_.dist->world > 1)
+    if ((prm_.fused_push || env_fused_push()) && s_.dist->world > 1)
     {
         const FusedPush fp{s_.ctx.comm.push_epoch, s_.ctx.comm.halo_expect, s_.ctx.comm.world, lv.plan->push_map()};
         relax_level(s_.ctx, prm_, lv.L, l == 0, rhs, x, x_alt, x_is_zero, done, &push, &fp);

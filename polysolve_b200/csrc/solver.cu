@@ -445,6 +445,8 @@ static void read_amg(const JValue &j, AmgParams &a)
             throw std::runtime_error("psb200: amg dist_mode must be partitioned, global or local");
     }
     num(j, "replicate_below", a.replicate_below);
+    if (j.contains("fused_push"))
+        a.fused_push = j.at("fused_push").as_bool();
     if (a.aggregation != "mis2")
         throw std::runtime_error("psb200: unknown amg aggregation '" + a.aggregation + "' (mis2)");
     // AMGCL-shaped sub-objects (AMGCL.cpp:32-65): relax{type,degree,power_iters,higher,lower,scale}, coarsening{relax,estimate_spectral_radius,aggr{eps_strong}}

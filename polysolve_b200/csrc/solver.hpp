@@ -38,13 +38,18 @@ struct AmgParams
     // One SpMV of a replicated level costs its whole matrix on every GPU, a partitioned one 1 / world of it plus a halo
     // push and wait (~10 us): the two break even near 7 M non-zeros on B200 (12 B per non-zero at ~6.5 TB/s).
     long long replicate_below = 8000000;
+    // partitioned mode: the Chebyshev steps push their boundary rows from the SpMV epilogue (boundary tiles first, three
+    // halo buffers) instead of a separate push kernel. Off by default: measured on 2 B200s it LOSES (C3 solve 0.0958 s vs
+    // 0.0882 s, C4 1.04 s vs 0.95 s: the per-row device fence + atomic + NVLink store sit on the critical path of the
+    // boundary tiles, ~12 us per launch, more than the 4 us push kernel they replace)
+    bool fused_push = false;
     bool same_as(const AmgParams &o) const
     {
         return max_levels == o.max_levels && coarse_enough == o.coarse_enough && direct_coarse == o.direct_coarse && ncycle == o.ncycle &&
                npre == o.npre && npost == o.npost && pre_cycles == o.pre_cycles && relax_type == o.relax_type && degree == o.degree &&
                power_iters == o.power_iters && higher == o.higher && lower == o.lower && scale == o.scale && damping == o.damping &&
                sa_relax == o.sa_relax && estimate_spectral_radius == o.estimate_spectral_radius && eps_strong == o.eps_strong &&
-               aggregation == o.aggregation && dist_mode == o.dist_mode && replicate_below == o.replicate_below;
+               aggregation == o.aggregation && dist_mode == o.dist_mode && replicate_below == o.replicate_below && fused_push == o.fused_push;
     }
 };
 

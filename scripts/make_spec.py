@@ -43,7 +43,7 @@ leaf("/CUDA/profile", False, "bool", "Time every kernel with CUDA events and rep
 leaf("/CUDA/verify_pattern", True, "bool", "factorize() re-hashes the index arrays to detect a silently changed pattern.")
 leaf("/CUDA/comm_timeout_s", 3.0, "float", "Row partitions: seconds a kernel waits for a peer GPU before the solve fails.", min=0)
 obj("/CUDA/amg", ["max_levels", "coarse_enough", "direct_coarse", "ncycle", "npre", "npost", "pre_cycles", "aggregation", "dist_mode",
-                  "replicate_below", "relax", "coarsening"], "SA-AMG preconditioner settings; mirrors /AMGCL/precond.")
+                  "replicate_below", "fused_push", "relax", "coarsening"], "SA-AMG preconditioner settings; mirrors /AMGCL/precond.")
 leaf("/CUDA/amg/max_levels", 6, "int", "Maximum number of levels.")
 leaf("/CUDA/amg/coarse_enough", 3000, "int", "Stop coarsening below this many rows (AMGCL default 3000 / block size).")
 leaf("/CUDA/amg/direct_coarse", False, "bool", "Use a direct solver for the coarsest level.")
@@ -57,6 +57,7 @@ leaf("/CUDA/amg/dist_mode", "partitioned", "string", "Row partitions: partitione
      "rank with only level 0 partitioned; local = rank-local hierarchy of the diagonal block (block-Jacobi).",
      options=["partitioned", "global", "local"])
 leaf("/CUDA/amg/replicate_below", 8000000, "int", "Row partitions: levels with fewer stored non-zeros (all ranks together) are replicated on every rank.")
+leaf("/CUDA/amg/fused_push", False, "bool", "Row partitions: push the halo of the smoother iterates from the SpMV epilogue (boundary tiles first).")
 obj("/CUDA/amg/relax", ["type", "degree", "power_iters", "higher", "lower", "scale", "damping"], "Smoother settings.")
 leaf("/CUDA/amg/relax/type", "chebyshev", "string", "Type of relaxation to use.", options=["chebyshev", "damped_jacobi"])
 leaf("/CUDA/amg/relax/degree", 16, "int", "Degree of the polynomial.")

@@ -240,6 +240,30 @@ def test_dist_amg_pcg_partitioned(psb, orc, world, replicate_below):
     assert np.linalg.norm(x - x1) / np.linalg.norm(x1) < 1e-6
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("block", [1, 3])
+def test_dist_amg_fused_push(psb, orc, world, block):
+    """amg.fused_push = true: the Chebyshev steps of the partitioned levels push their boundary rows from the SpMV
+    epilogue (boundary tiles first, three halo buffers, per-chunk completion counters) instead of a separate push kernel.
+    Same iteration count and the same solution as the default path."""
+    if world > max(1, _ngpu()):
+        pytest.skip(f"needs {world} GPUs")
+    tol = 1e-8
+    n = 40 if block == 1 else 16
+    rb = 50000 if block == 1 else 20000
+    out = {}
+    for fused in (False, True):
+        res = _run(world, n, tol, "amg", block, "partitioned", {"amg": {"replicate_below": rb, "fused_push": fused}})
+        N = n ** 3 * (3 if block == 3 else 1)
+        x = np.zeros(N)
+        for rank, a, e, xs, it, err, status, it2, dinfo in res:
+            x[a:e] = xs
+            assert status == "Converged" and err < tol and it2 == 0 and it == res[0][4]
+        out[fused] = (x, res[0][4])
+    assert out[True][1] == out[False][1]
+    assert np.linalg.norm(out[True][0] - out[False][0]) / np.linalg.norm(out[False][0]) < 1e-9
+
+
 @pytest.mark.parametrize("world", [1, 2, 4, 8])
 def test_dist_block3_amg_pcg_elasticity(psb, orc, world):
     """C4-shaped (BASELINE config 4): P1 linear elasticity, block-3 SA-AMG-PCG on the row partition with the partitioned
