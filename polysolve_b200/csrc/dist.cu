@@ -799,19 +799,6 @@ void Solver::dist_set_nbr_mask(unsigned mask)
     d.fine.finalize(mask, ctx.comm, ctx.stream);
 }
 
-__global__ void mark_halo_rows_kernel(int n, int nl, const int *__restrict__ rp, const int *__restrict__ ci, int *flag)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n)
-        return;
-    for (int k = rp[i]; k < rp[i + 1]; ++k)
-        if (ci[k] >= nl)
-        {
-            flag[0] = 1;
-            return;
-        }
-}
-
 void Solver::analyze_pattern_dist(long long n_, long long nnz_, const int *outer, const int *inner)
 {
     DistState &d = *dist;

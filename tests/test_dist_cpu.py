@@ -83,6 +83,39 @@ def test_plan_block_aligned_offsets(psb, orc, world):
         psb.Solver.dist_plan_host(n, o, i, 0, world, HALO_CAP, align=7)  # 648 is not a multiple of 7
 
 
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_plan_block_halos_are_whole_nodes(psb, orc, world):
+    """Block problems exchange whole nodes: with a pattern whose 3 x 3 blocks are incomplete (entries dropped at random, so
+    a rank may read only one dof of a remote node) the halo list of every rank is the node-completion of the oracle's halo
+    list, the send lists are whole nodes too, and what g sends to q is exactly what q expects -- the invariant the
+    partitioned block AMG needs to expand its rows to full blocks including the halo columns."""
+    rng = np.random.default_rng(7)
+    o, i, v, _ = psb.problems.elasticity3d(5)
+    n = len(o) - 1
+    A = sp.csc_matrix((v, i, o), shape=(n, n)).tocoo()
+    keep = (rng.random(A.nnz) < 0.6) | (A.row == A.col)
+    A = sp.csc_matrix((A.data[keep], (A.row[keep], A.col[keep])), shape=(n, n))
+    A.sort_indices()
+    o, i = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    rp, ci, perm = orc.csc_to_csr(n, o, i)
+    off0 = orc.partition_rows(rp, world, align=3)
+    plans = [psb.Solver.dist_plan_host(n, o, i, r, world, HALO_CAP, align=3) for r in range(world)]
+    for r, P in enumerate(plans):
+        a, b = int(off0[r]), int(off0[r + 1])
+        _, halo0 = orc.halo_for_rank(rp, ci, a, b)
+        want = np.unique((halo0[:, None] // 3 * 3 + np.arange(3)[None, :]).reshape(-1)) if len(halo0) else halo0
+        assert np.array_equal(P["halo_cols"], want)
+        assert len(P["halo_cols"]) % 3 == 0 and np.all(P["halo_cols"].reshape(-1, 3) % 3 == np.arange(3))
+        assert np.array_equal(P["perm"], perm[rp[a]:rp[b]])           # the matrix entries themselves are untouched
+    for g, Pg in enumerate(plans):
+        for q, Pq in enumerate(plans):
+            sent = Pg["send_rows"][Pg["send_begin"][q]:Pg["send_begin"][q + 1]].astype(np.int64) + off0[g]
+            want = Pq["halo_cols"][(Pq["halo_cols"] >= off0[g]) & (Pq["halo_cols"] < off0[g + 1])]
+            # the sender cannot know which of its columns the reader's ROWS touch beyond the pattern it sees: it sends the
+            # whole nodes of every column with an entry in a row of q -- exactly the reader's completed list
+            assert np.array_equal(sent, want), (g, q)
+
+
 def test_plan_halo_capacity_error(psb, orc):
     o, i, v = orc.poisson3d(12)
     with pytest.raises(RuntimeError):
