@@ -394,13 +394,15 @@ void AmgDist::setup(const std::vector<std::vector<int>> &imposed)
             const void *snd[kMaxRanks] = {};
             void *rcv[kMaxRanks] = {};
             size_t sb[kMaxRanks] = {}, rb[kMaxRanks] = {};
+            size_t ex[kMaxRanks] = {};
             for (int q = 0; q < W; ++q)
             {
                 snd[q] = lens.p + hp.send_begin[q];
                 sb[q] = sizeof(int) * (size_t)(hp.send_begin[q + 1] - hp.send_begin[q]);
                 rcv[q] = hl.p + seg_start[q];
+                ex[q] = sizeof(int) * (size_t)hp.recv_count[q];
             }
-            s_.dist_alltoallv(snd, sb, rcv, rb);
+            s_.dist_alltoallv(snd, sb, rcv, rb, ex);
             for (int q = 0; q < W; ++q)
                 if (rb[q] != sizeof(int) * (size_t)hp.recv_count[q])
                     throw std::logic_error("psb200 amg: halo plan mismatch between ranks (row lengths)");
@@ -439,13 +441,15 @@ void AmgDist::setup(const std::vector<std::vector<int>> &imposed)
             const void *snd[kMaxRanks] = {};
             void *rcv[kMaxRanks] = {};
             size_t sb[kMaxRanks] = {}, rb[kMaxRanks] = {};
+            size_t ex[kMaxRanks] = {};
             for (int q = 0; q < W; ++q)
             {
                 snd[q] = pc.p + h_lscan[hp.send_begin[q]];
                 sb[q] = sizeof(int) * (size_t)(h_lscan[hp.send_begin[q + 1]] - h_lscan[hp.send_begin[q]]);
                 rcv[q] = Pext.ci.p + L.P.nnz + h_hscan[seg_start[q]];
+                ex[q] = sizeof(int) * (size_t)(h_hscan[seg_start[q + 1]] - h_hscan[seg_start[q]]);
             }
-            s_.dist_alltoallv(snd, sb, rcv, rb);
+            s_.dist_alltoallv(snd, sb, rcv, rb, ex);
             for (int q = 0; q < W; ++q)
             {
                 if (rb[q] != sizeof(int) * (size_t)(h_hscan[seg_start[q + 1]] - h_hscan[seg_start[q]]))
@@ -453,8 +457,9 @@ void AmgDist::setup(const std::vector<std::vector<int>> &imposed)
                 snd[q] = pv.p + h_lscan[hp.send_begin[q]];
                 sb[q] *= 2;
                 rcv[q] = Pext.va.p + L.P.nnz + h_hscan[seg_start[q]];
+                ex[q] *= 2;
             }
-            s_.dist_alltoallv(snd, sb, rcv, rb);
+            s_.dist_alltoallv(snd, sb, rcv, rb, ex);
         }
         lv.t_exchange = wall_ms(st) - tp;
 
@@ -520,14 +525,15 @@ void AmgDist::setup(const std::vector<std::vector<int>> &imposed)
             auto gatherv = [&](const void *mine, size_t my_bytes, unsigned char *full, const long long *elem_off, size_t elem) {
                 const void *snd[kMaxRanks] = {};
                 void *rcv[kMaxRanks] = {};
-                size_t sb[kMaxRanks] = {}, rb[kMaxRanks] = {};
+                size_t sb[kMaxRanks] = {}, rb[kMaxRanks] = {}, ex[kMaxRanks] = {};
                 for (int q = 0; q < W; ++q)
                 {
                     snd[q] = mine;
                     sb[q] = my_bytes;
                     rcv[q] = full + (size_t)elem_off[q] * elem;
+                    ex[q] = (size_t)(elem_off[q + 1] - elem_off[q]) * elem;
                 }
-                s_.dist_alltoallv(snd, sb, rcv, rb);
+                s_.dist_alltoallv(snd, sb, rcv, rb, ex);
                 for (int q = 0; q < W; ++q)
                     if (rb[q] != (size_t)(elem_off[q + 1] - elem_off[q]) * elem)
                         throw std::logic_error("psb200 amg: all-gather size mismatch between ranks");
@@ -626,13 +632,15 @@ void AmgDist::setup(const std::vector<std::vector<int>> &imposed)
             const void *snd[kMaxRanks] = {};
             void *rcv[kMaxRanks] = {};
             size_t sb[kMaxRanks] = {}, rb[kMaxRanks] = {};
+            size_t ex[kMaxRanks] = {};
             for (int q = 0; q < W; ++q)
             {
                 snd[q] = halo_ids.p + seg2[q];
                 sb[q] = sizeof(int) * (size_t)np.recv_count[q];
                 rcv[q] = req.p + np.send_begin[q];
+                ex[q] = sizeof(int) * (size_t)(np.send_begin[q + 1] - np.send_begin[q]);
             }
-            s_.dist_alltoallv(snd, sb, rcv, rb);
+            s_.dist_alltoallv(snd, sb, rcv, rb, ex);
             np.send_rows.assign(nreq, 0);
             if (nreq)
                 PSB_CUDA(cudaMemcpyAsync(np.send_rows.data(), req.p, sizeof(int) * nreq, cudaMemcpyDeviceToHost, st));

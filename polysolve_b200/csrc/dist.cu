@@ -645,9 +645,11 @@ void Solver::dist_gather_ll(long long v, long long out[kMaxRanks])
         out[q] = q < dist->world ? (long long)o[q * 8] : 0;
 }
 
-// Every rank sends send_bytes[q] bytes (device memory, multiples of 4) to every rank q and receives recv_bytes[q] from it.
-// recv_bytes may be null on entry to have it filled from the senders' sizes. Chunked through the staging arena.
-void Solver::dist_alltoallv(const void *const send[kMaxRanks], const size_t send_bytes[kMaxRanks], void *const recv[kMaxRanks], size_t recv_bytes[kMaxRanks])
+// Every rank sends send_bytes[q] bytes (device memory, multiples of 4) to every rank q and receives recv_bytes[q] from it
+// (filled from the senders' sizes). expect_recv (optional): the sizes the receive buffers were allocated for -- a
+// disagreement is reported BEFORE anything is copied. Chunked through the staging arena.
+void Solver::dist_alltoallv(const void *const send[kMaxRanks], const size_t send_bytes[kMaxRanks], void *const recv[kMaxRanks], size_t recv_bytes[kMaxRanks],
+                            const size_t *expect_recv)
 {
     DistState &d = *dist;
     const int W = d.world;
@@ -665,6 +667,13 @@ void Solver::dist_alltoallv(const void *const send[kMaxRanks], const size_t send
             mx = std::max(mx, (size_t)all[s * 8 + q]);
     for (int q = 0; q < W; ++q)
         recv_bytes[q] = (size_t)all[q * 8 + d.rank];
+    if (expect_recv)
+    {
+        for (int q = 0; q < W; ++q)
+            if (recv_bytes[q] != expect_recv[q])
+                throw std::logic_error("psb200 dist: exchange size mismatch between ranks (rank " + std::to_string(q) + " sends " +
+                                       std::to_string(recv_bytes[q]) + " bytes, " + std::to_string(expect_recv[q]) + " expected)");
+    }
     const size_t slot = ctx.comm.arena_slot_bytes();
     for (size_t off = 0; off < mx; off += slot)
     {

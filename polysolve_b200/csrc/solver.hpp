@@ -114,7 +114,8 @@ struct Solver
     void dist_barrier();
     double dist_max(double v);
     void dist_gather_ll(long long v, long long out[kMaxRanks]);
-    void dist_alltoallv(const void *const send[kMaxRanks], const size_t send_bytes[kMaxRanks], void *const recv[kMaxRanks], size_t recv_bytes[kMaxRanks]);
+    void dist_alltoallv(const void *const send[kMaxRanks], const size_t send_bytes[kMaxRanks], void *const recv[kMaxRanks], size_t recv_bytes[kMaxRanks],
+                        const size_t *expect_recv = nullptr);
     void push_halo(const HaloPlan &hp, const double *d_v, const int *done);
     void bulk_allgather(const double *d_mine, double *d_out, const long long *offsets, const int *done);
 
