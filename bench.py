@@ -314,7 +314,7 @@ def amg_dist_leg(args, psb, P, local, world, N, outer, inner, vals, b, barrier, 
             "roofline": amg_roofline(info, float(t[1]), hbm_peak, world),
             "what": "SA-AMG-PCG on the row partition: every level above amg.replicate_below non-zeros partitioned (decoupled aggregation, "
                     "rank-local P/R, distributed Galerkin product, per-level halo pushes over NVLink), small levels replicated; "
-                    "device_bytes_per_rank_max = device memory this leg allocated on the fullest rank (comm buffer 268 MB included)"}
+                    "device_bytes_per_rank_max = device memory this leg allocated on the fullest rank (comm buffer 336 MB included)"}
 
 
 def parity_block(psb, P, local, world, rank, barrier):
