@@ -239,6 +239,24 @@ def test_single_reduction_cg_matches_eigen_ordering(psb, orc, n, check_every):
     assert np.linalg.norm(csc(o, i, v) @ out["cg1r"][0] - b) / np.linalg.norm(b) < 2e-9
 
 
+def test_single_reduction_cg_matches_its_restatement(psb, orc):
+    """krylov = cg1r on C1 against oracle/cg1r_oracle.py (the same recurrence in numpy, itself checked against the
+    Eigen-ordering oracle in test_oracle.py): iterations within 2, x to 1e-9, reported error below the tolerance."""
+    from oracle import cg1r_oracle
+
+    o, i, v = orc.poisson2d(32)
+    b = orc.splitmix64(42, 1024)
+    A = csc(o, i, v).tocsr()
+    xo, ito, erro, _ = cg1r_oracle.cg1r(A, b, dinv=1.0 / A.diagonal(), tol=1e-10, max_iters=1000)
+    s = make(psb, tolerance=1e-10, max_iter=1000, krylov="cg1r")
+    s.factorize_raw(1024, o, i, v)
+    x = np.zeros(1024)
+    s.solve(b, x)
+    info = s.get_info()
+    assert info["solver_status"] == "Converged" and abs(info["solver_iter"] - ito) <= 2
+    assert info["solver_error"] < 1e-10 and np.linalg.norm(x - xo) / np.linalg.norm(xo) < 1e-9
+
+
 def test_single_reduction_cg_max_iter_zero_rhs_and_no_precond(psb, orc):
     o, i, v = orc.poisson3d(16)
     N = 16 ** 3

@@ -211,3 +211,38 @@ def test_elasticity_generator_matches_element_assembly():
     H = BO.BlockAmg(o, i, v, 3)
     x, it, rel = H.cg(b, tol=1e-8)
     assert len(H.levels) == 2 and 0 < it < 30 and rel < 1e-8
+
+
+def test_single_reduction_cg_restatement_equals_eigen_ordering(orc):
+    """oracle/cg1r_oracle.py (what `krylov = cg1r` runs on the GPU) against the Eigen-ordering oracle: same iterates in
+    exact arithmetic => iteration counts within +-2 %, same x, same counting rule (C1: 115), same start-up rules."""
+    from oracle import cg1r_oracle
+
+    o, i, v = orc.poisson2d(32)
+    b = orc.splitmix64(42, 1024)
+    A = csc(o, i, v).tocsr()
+    dinv = 1.0 / A.diagonal()
+    x0, it0, err0, _ = orc.eigen_cg(o, i, v, b, tol=1e-10, max_iters=1000)
+    x, it, err, status = cg1r_oracle.cg1r(A, b, dinv=dinv, tol=1e-10, max_iters=1000)
+    assert status == "Converged" and abs(it - it0) <= 2 and it0 == 115
+    assert err < 1e-10 and np.linalg.norm(x - x0) / np.linalg.norm(x0) < 1e-9
+    # warm start => 0 iterations, x untouched; zero rhs => x = 0
+    x2, it2, _, _ = cg1r_oracle.cg1r(A, b, x0=x, dinv=dinv, tol=1e-10)
+    assert it2 == 0 and np.array_equal(x2, x)
+    x3, it3, err3, _ = cg1r_oracle.cg1r(A, np.zeros(1024), x0=b, dinv=dinv)
+    assert it3 == 0 and err3 == 0.0 and not x3.any()
+    # max_iter: the counter equals the number of trips (Eigen: `while (i < maxIters)`)
+    for mi in (1, 2, 7):
+        _, itm, _, st = cg1r_oracle.cg1r(A, b, dinv=dinv, tol=1e-14, max_iters=mi)
+        _, ite, _, _ = orc.eigen_cg(o, i, v, b, tol=1e-14, max_iters=mi)
+        assert itm == mi == ite and st == "Reach max iterations"
+    # a perturbed 3-D operator (non-constant diagonal)
+    o, i, v = orc.poisson3d(14)
+    N = 14 ** 3
+    v = v * (1.0 + 0.05 * orc.splitmix64(13, len(v)))
+    v = 0.5 * (v + v[orc.csc_to_csr(N, o, i)[2]])
+    b = orc.splitmix64(7, N)
+    A = csc(o, i, v).tocsr()
+    x0, it0, _, _ = orc.eigen_cg(o, i, v, b, tol=1e-9, max_iters=5000)
+    x, it, err, _ = cg1r_oracle.cg1r(A, b, dinv=1.0 / A.diagonal(), tol=1e-9, max_iters=5000)
+    assert abs(it - it0) <= max(1, 0.02 * it0) and np.linalg.norm(x - x0) / np.linalg.norm(x0) < 1e-7
