@@ -116,6 +116,37 @@ def test_plan_block_halos_are_whole_nodes(psb, orc, world):
             assert np.array_equal(sent, want), (g, q)
 
 
+def test_plan_edge_cases(psb, orc):
+    """More ranks than rows (empty ranks), no coupling at all (no halo anywhere), one dense row and column (every rank
+    needs row 0, rank 0 needs everybody): offsets, halo lists and send lists still equal the oracle's."""
+    B = sp.lil_matrix((50, 50))
+    B.setdiag(1.0)
+    B[0, :] = 1.0
+    B[:, 0] = 1.0
+    cases = [("diag5", sp.identity(5, format="csc"), 8), ("one", sp.identity(1, format="csc"), 2),
+             ("tri3", sp.diags([[-1.0] * 2, [2.0] * 3, [-1.0] * 2], [-1, 0, 1], format="csc"), 4), ("arrow", B.tocsc(), 4)]
+    for name, A, world in cases:
+        A = sp.csc_matrix(A)
+        A.sort_indices()
+        n = A.shape[0]
+        o, i = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+        rp, ci, perm = orc.csc_to_csr(n, o, i)
+        off0 = orc.partition_rows(rp, world)
+        plans = [psb.Solver.dist_plan_host(n, o, i, r, world, HALO_CAP) for r in range(world)]
+        for r, P in enumerate(plans):
+            a, b = int(off0[r]), int(off0[r + 1])
+            lc0, halo0 = orc.halo_for_rank(rp, ci, a, b)
+            assert np.array_equal(P["offsets"], off0) and P["n_local"] == b - a, name
+            assert np.array_equal(P["halo_cols"], halo0) and np.array_equal(compact_cols(P, world), lc0), name
+        for g, Pg in enumerate(plans):
+            for q, Pq in enumerate(plans):
+                sent = Pg["send_rows"][Pg["send_begin"][q]:Pg["send_begin"][q + 1]].astype(np.int64) + off0[g]
+                want = Pq["halo_cols"][(Pq["halo_cols"] >= off0[g]) & (Pq["halo_cols"] < off0[g + 1])]
+                assert np.array_equal(sent, want), (name, g, q)
+    assert sum(P["n_local"] == 0 for P in [psb.Solver.dist_plan_host(5, *[sp.identity(5, format="csc").indptr.astype(np.int32),
+               sp.identity(5, format="csc").indices.astype(np.int32)], r, 8, HALO_CAP) for r in range(8)]) == 3
+
+
 def test_plan_halo_capacity_error(psb, orc):
     o, i, v = orc.poisson3d(12)
     with pytest.raises(RuntimeError):
