@@ -37,6 +37,9 @@ METRIC = "cg_iters_per_sec"
 UNIT = "iter/s"
 TOL = 1e-8
 MAX_ITER = 10000
+# row partitions: how long a kernel may wait for a peer before the solve fails (library default 3 s). The bench starts on
+# a cold box with up to 8 ranks sharing the host cores for set-up, so it allows more skew; a lost rank still surfaces.
+COMM_TIMEOUT_S = 20.0
 
 
 def peaks():
@@ -271,7 +274,7 @@ def amg_dist_leg(args, psb, P, local, world, N, outer, inner, vals, b, barrier, 
     torch.cuda.synchronize()
     free0 = torch.cuda.mem_get_info()[0]
     s = psb.Solver.create("CUDA", "")
-    s.set_parameters({"CUDA": {"precond": "amg", "tolerance": TOL, "max_iter": 1000, "device": local,
+    s.set_parameters({"CUDA": {"precond": "amg", "tolerance": TOL, "max_iter": 1000, "device": local, "comm_timeout_s": COMM_TIMEOUT_S,
                                "amg": {"dist_mode": args.amg_dist_mode, "fused_push": bool(args.fused_push)}}})
     s.dist_setup_torch(halo_cap=1 << 20)
     s.analyze_pattern_raw(N, outer, inner, N)
@@ -341,7 +344,7 @@ def parity_block(psb, P, local, world, rank, barrier):
 
     def solve(prm):
         s = psb.Solver.create("CUDA", "")
-        s.set_parameters({"CUDA": dict({"tolerance": tol, "max_iter": 10000, "device": local}, **prm)})
+        s.set_parameters({"CUDA": dict({"tolerance": tol, "max_iter": 10000, "device": local, "comm_timeout_s": COMM_TIMEOUT_S}, **prm)})
         s.dist_setup_torch(halo_cap=1 << 16)
         s.analyze_pattern_raw(N, o, i, N)
         s.factorize_raw(N, o, i, v)
@@ -436,7 +439,8 @@ def run_ours(args):
     krylov = args.krylov if args.krylov != "auto" else ("cg1r" if world >= 4 else "cg")
     s = psb.Solver.create("CUDA", "")
     s.set_parameters({"CUDA": {"krylov": krylov, "precond": "jacobi", "tolerance": TOL, "max_iter": MAX_ITER,
-                               "check_every": args.check_every, "device": local, "interior_first": args.interior_first}})
+                               "check_every": args.check_every, "device": local, "interior_first": args.interior_first,
+                               "comm_timeout_s": COMM_TIMEOUT_S}})
     if world > 1:
         s.dist_setup_torch(halo_cap=1 << 20)
     t0 = time.perf_counter()
@@ -684,6 +688,7 @@ def run_c4(args):
     free0 = torch.cuda.mem_get_info()[0]
     s = psb.Solver.create("CUDA", "")
     s.set_parameters({"CUDA": {"precond": "amg", "block_size": 3, "tolerance": TOL, "max_iter": 1000, "device": local,
+                               "comm_timeout_s": COMM_TIMEOUT_S,
                                "amg": {"dist_mode": args.amg_dist_mode, "fused_push": bool(args.fused_push)}}})
     if world > 1:
         s.dist_setup_torch(halo_cap=1 << 21)
@@ -782,6 +787,7 @@ def run_c5(args):
     nl = {"solver": "Newton", "line_search": {"method": "Backtracking"}, "grad_norm_tol": 1e-8, "rel_grad_norm_tol": 0,
           "max_iterations": 100, "Newton": {"residual_tolerance": 1e-5}}
     lin = {"solver": "CUDA", "CUDA": {"precond": "amg", "block_size": 3, "tolerance": 1e-8, "max_iter": 1000, "device": local,
+                                      "comm_timeout_s": COMM_TIMEOUT_S,
                                       "amg": {"dist_mode": args.amg_dist_mode}}}
     runs = []
     for rep in range(1 + max(1, args.steps // 2)):  # the first run warms up (module load, pool growth, graph capture)
