@@ -215,3 +215,122 @@ def test_gloo_world2_distributed_spmv(psb, orc):
     for rank, err, derr in res:
         assert err < 1e-13, (rank, err)
         assert derr < 1e-10
+
+
+def _gloo_cg1r_worker(rank, world, port, q):
+    """Row-partitioned single-reduction PCG as `krylov = cg1r` runs it (dist.cu: cg1r_update_kernel pushes the halo of the
+    new u, the SpMV epilogue reduces gamma, delta, |r|^2 in ONE all-reduce), restated over gloo on the product's host
+    plan: per trip ONE halo exchange and ONE all-reduce of three doubles."""
+    import torch
+    import torch.distributed as dist
+
+    import polysolve_b200 as psb
+    from oracle import oracle as orc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        o, i, v = orc.poisson3d(10)
+        n = 1000
+        v = v * (1.0 + 0.05 * orc.splitmix64(13, len(v)))
+        v = 0.5 * (v + v[orc.csc_to_csr(n, o, i)[2]])
+        b = orc.splitmix64(42, n)
+        tol, max_iters = 1e-10, 1000
+        P = psb.Solver.dist_plan_host(n, o, i, rank, world, HALO_CAP)
+        a, e = int(P["offsets"][rank]), int(P["offsets"][rank + 1])
+        nl = e - a
+        vloc = v[P["perm"]]
+        rp = P["rp"][:-1].astype(np.int64)
+        diag = sp.csc_matrix((v, i, o), shape=(n, n)).diagonal()[a:e]
+        dinv = 1.0 / diag
+        n_exchanges = n_reductions = 0
+
+        def spmv(u_loc):
+            nonlocal n_exchanges
+            outbox = {dst: u_loc[P["send_rows"][P["send_begin"][dst]:P["send_begin"][dst + 1]]] for dst in range(world)}
+            boxes = [None] * world
+            dist.all_gather_object(boxes, outbox)
+            n_exchanges += 1
+            ext = np.zeros(nl + world * HALO_CAP)
+            ext[:nl] = u_loc
+            for src in range(world):
+                vals = boxes[src][rank]
+                ext[nl + src * HALO_CAP: nl + src * HALO_CAP + len(vals)] = vals
+            return np.add.reduceat(vloc * ext[P["ci"]], rp)
+
+        def allreduce(*vals):
+            nonlocal n_reductions
+            t = torch.tensor(vals, dtype=torch.float64)
+            dist.all_reduce(t)
+            n_reductions += 1
+            return [float(z) for z in t]
+
+        bl = b[a:e]
+        x = np.zeros(nl)
+        r = bl - spmv(x)
+        rn2, bn2 = allreduce(float(r @ r), float(bl @ bl))
+        thr = tol * tol * bn2
+        p = np.zeros(nl)
+        s = np.zeros(nl)
+        u = dinv * r
+        it = 0
+        gamma_old = alpha_old = None
+        ex0, red0 = n_exchanges, n_reductions
+        trips = 0
+        while True:
+            w = spmv(u)
+            gamma, delta, rn2 = allreduce(float(r @ u), float(w @ u), float(r @ r))
+            trips += 1
+            if gamma_old is not None and rn2 < thr:
+                break
+            if gamma_old is None:
+                beta, alpha = 0.0, gamma / delta
+            else:
+                beta = gamma / gamma_old
+                alpha = gamma / (delta - beta * gamma / alpha_old)
+                it += 1
+                if it >= max_iters:
+                    break
+            gamma_old, alpha_old = gamma, alpha
+            p = u + beta * p
+            s = w + beta * s
+            x = x + alpha * p
+            r = r - alpha * s
+            u = dinv * r
+        q.put((rank, a, e, x, it, float(np.sqrt(rn2 / bn2)), n_exchanges - ex0, n_reductions - red0, trips))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_world2_single_reduction_cg(psb, orc):
+    """The partitioned cg1r equals the single-process restatement (oracle/cg1r_oracle.py) and the Eigen-ordering oracle:
+    same iteration count (+-1 for the different summation order), same x; one halo exchange and one all-reduce per trip."""
+    import torch.multiprocessing as mp
+    from oracle import cg1r_oracle
+    ctx = mp.get_context("spawn")
+    world = 2
+    port = _free_port()
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_cg1r_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    o, i, v = orc.poisson3d(10)
+    n = 1000
+    v = v * (1.0 + 0.05 * orc.splitmix64(13, len(v)))
+    v = 0.5 * (v + v[orc.csc_to_csr(n, o, i)[2]])
+    b = orc.splitmix64(42, n)
+    A = sp.csc_matrix((v, i, o), shape=(n, n)).tocsr()
+    x1, it1, err1, _ = cg1r_oracle.cg1r(A, b, dinv=1.0 / A.diagonal(), tol=1e-10, max_iters=1000)
+    x0, it0, _, _ = orc.eigen_cg(o, i, v, b, tol=1e-10, max_iters=1000)
+    x = np.zeros(n)
+    for rank, a, e, xl, it, err, nex, nred, trips in res:
+        x[a:e] = xl
+        assert abs(it - it1) <= 1 and abs(it - it0) <= 1 and err < 1e-10
+        assert nex == trips and nred == trips            # ONE exchange and ONE reduction per trip
+    assert len({r[4] for r in res}) == 1                 # every rank took the same decisions
+    assert np.linalg.norm(x - x1) / np.linalg.norm(x1) < 1e-9
+    assert np.linalg.norm(x - x0) / np.linalg.norm(x0) < 1e-9
