@@ -493,15 +493,17 @@ def run_ours(args):
     # ---- e2e: host buffers through the C ABI (factorize values + solve), pinned host memory
     hv, hb = pinned_copy(vals), pinned_copy(b)
     hx = pinned_copy(np.zeros(N))
+    # x0 = 0: on a row partition a rank reads and writes only its own rows of the full-length x (solve_host), so that is
+    # the part it resets
     for _ in range(min(args.warmup, 2)):
-        hx.zero_()
+        hx[r0:r1].zero_()
         s.factorize_raw(N, outer, inner, hv.numpy())
         s.solve(hb.numpy(), hx.numpy())
     barrier()
     t0 = time.perf_counter()
     e2e_iters = 0
     for _ in range(args.steps):
-        hx.zero_()
+        hx[r0:r1].zero_()
         s.factorize_raw(N, outer, inner, hv.numpy())
         s.solve(hb.numpy(), hx.numpy())
         e2e_iters += s.get_info()["solver_iter"]
@@ -627,7 +629,7 @@ def run_ours(args):
                    "spmv_kernel": info["spmv_kernel"], "check_every": args.check_every,
                    "analyze_s": t_analyze, "factorize_s": t_factorize},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": (8 * nnz + 16 * N) // world, "d2h_bytes_per_step": 8 * N // world,
-                "what": "factorize_csc(host values) + solve(host b, x) per step, pinned host buffers; bytes are per rank"},
+                "what": "x0 = 0 + factorize_csc(host values) + solve(host b, x) per step, pinned host buffers; bytes are per rank"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "spmv_stream_kernel<EpiCg1r> (fused SpMV + 3 dots + all-reduce)" if krylov == "cg1r"
