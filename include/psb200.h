@@ -137,7 +137,8 @@ int psb200_dist_local_range(psb200_handle h, int64_t *row_begin, int64_t *row_en
 /* Host-only plan of one rank (no GPU needed; used by the CPU tests to check partition offsets and halo
  * lists bit-exactly against the oracle). Caller-allocated arrays: offsets[world+1], counts[3] =
  * {local rows, local nnz, halo columns}, local_rp[n+1], local_ci[nnz], local_perm[nnz],
- * send_begin[world+1], send_rows[n], recv_count[world], halo_cols[n]. */
+ * send_begin[world+1], send_rows[(world-1)*n] (a row can be sent to every other rank; send_begin[world] entries are
+ * written), recv_count[world], halo_cols[n]. */
 int psb200_dist_plan_host(int64_t n, int64_t nnz, const int32_t *outer, const int32_t *inner, int rank, int world,
                           int64_t halo_cap, int64_t *offsets, int64_t *counts, int32_t *local_rp, int32_t *local_ci,
                           int32_t *local_perm, int32_t *send_begin, int32_t *send_rows, int32_t *recv_count,

@@ -54,6 +54,8 @@ struct JValue
 class JParser
 {
     const char *p, *e;
+    int depth = 0; // nesting of the value being parsed: bounded, a malformed document must not overflow the stack
+    static constexpr int kMaxDepth = 128;
     void ws() { while (p < e && std::isspace((unsigned char)*p)) ++p; }
     [[noreturn]] void fail(const char *m) { throw std::runtime_error(std::string("json parse error: ") + m); }
     std::string str()
@@ -87,6 +89,15 @@ class JParser
         ++p;
         return s;
     }
+    struct Nest
+    {
+        JParser &P;
+        explicit Nest(JParser &P_) : P(P_)
+        {
+            if (++P.depth > kMaxDepth) P.fail("nesting too deep");
+        }
+        ~Nest() { --P.depth; }
+    };
     JValue val()
     {
         ws();
@@ -94,6 +105,7 @@ class JParser
         JValue v;
         if (*p == '{')
         {
+            Nest nest(*this);
             v.kind = JValue::Obj;
             ++p; ws();
             if (*p == '}') { ++p; return v; }
@@ -113,6 +125,7 @@ class JParser
         }
         else if (*p == '[')
         {
+            Nest nest(*this);
             v.kind = JValue::Arr;
             ++p; ws();
             if (*p == ']') { ++p; return v; }
@@ -171,6 +184,12 @@ inline std::string jstr(const std::string &s)
     {
         if (c == '"' || c == '\\') { o += '\\'; o += c; }
         else if (c == '\n') o += "\\n";
+        else if ((unsigned char)c < 0x20)
+        {
+            char buf[8];
+            std::snprintf(buf, sizeof buf, "\\u%04x", (unsigned)(unsigned char)c);
+            o += buf;
+        }
         else o += c;
     }
     return o + "\"";

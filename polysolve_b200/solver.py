@@ -227,7 +227,9 @@ class Solver:
         ci = np.zeros(max(nnz, 1), np.int32)
         perm = np.zeros(max(nnz, 1), np.int32)
         send_begin = np.zeros(world + 1, np.int32)
-        send_rows = np.zeros(max(n, 1), np.int32)
+        # a row is sent to every rank that has an entry in its column: at most (world - 1) * n and at most one per
+        # matrix entry (align per entry when nodes travel whole)
+        send_rows = np.zeros(max(min((world - 1) * n, align * nnz), 1), np.int32)
         recv_count = np.zeros(world, np.int32)
         halo_cols = np.zeros(max(n, 1), np.int32)
         rc = L.psb200_dist_plan_host_aligned(n, nnz, outer, inner, rank, world, halo_cap, align, offsets, counts, rp, ci, perm,

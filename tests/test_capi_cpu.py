@@ -98,6 +98,40 @@ def test_malformed_outer_array_is_rejected_before_any_kernel(psb):
     s.set_parameters({"CUDA": {"krylov": "cg1r", "comm_timeout_s": 10.0, "amg": {"dist_mode": "partitioned", "replicate_below": 1000}}})
 
 
+def test_parameter_text_is_parsed_defensively(psb):
+    """The parameter document crosses the C ABI as text (nlohmann dump()): malformed or hostile text must come back as an
+    error code, never crash -- truncated / mutated documents, and nesting deep enough to overflow a recursive parser."""
+    import json
+    import random
+    s = psb.Solver.create("CUDA", "")
+
+    def send(txt):
+        return s._L.psb200_set_parameters(s._h, txt.encode())
+
+    for depth in (129, 10 ** 4, 10 ** 6):
+        assert send("[" * depth) != 0 and "nesting too deep" in s._L.psb200_last_error(s._h).decode()
+        assert send('{"a":' * depth) != 0
+    assert send(json.dumps({"CUDA": {"amg": {"relax": {"degree": 8}}}})) == 0
+    rnd = random.Random(1)
+
+    def doc(d=0):
+        k = rnd.random()
+        if d > 4 or k < 0.3:
+            return rnd.choice([1, 2.5, -3e10, True, False, None, "a\"b\\c\n\t\u00e9", "", 1e308, -0.0])
+        if k < 0.65:
+            return {rnd.choice(["CUDA", "amg", "relax", "precond", "tolerance", "max_iter", "krylov", "x y"]): doc(d + 1)
+                    for _ in range(rnd.randint(0, 4))}
+        return [doc(d + 1) for _ in range(rnd.randint(0, 4))]
+
+    for _ in range(400):
+        txt = json.dumps(doc())
+        if rnd.random() < 0.4 and len(txt) > 2:
+            i = rnd.randrange(len(txt))
+            txt = txt[:i] + rnd.choice(["", "{", "}", '"', ",", ":", "\\", "[", "]", "tru", "nul", "1e", "-"]) + txt[i + rnd.randint(0, 2):]
+        assert send(txt) in (0, 1, 2, 3, 4, 5, 6)      # a status code, and the process is still here
+    s.set_parameters({"CUDA": {"tolerance": 1e-9}})    # the handle still works
+
+
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU failure mode")
 def test_compute_fails_loudly_without_gpu(psb):
     s = psb.Solver.create("CUDA", "")

@@ -147,6 +147,41 @@ def test_plan_edge_cases(psb, orc):
                sp.identity(5, format="csc").indices.astype(np.int32)], r, 8, HALO_CAP) for r in range(8)]) == 3
 
 
+def test_plan_randomised_matrices_and_rank_counts(psb, orc):
+    """120 random square patterns (empty to half dense, with and without a diagonal) on 1-8 ranks: every index array equals
+    the oracle's, send lists equal the readers' halo lists. Dense couplings send a row to several ranks, so the send list
+    of a rank can be longer than n (this once overflowed the wrapper's n-entry buffer)."""
+    import random
+    rnd = random.Random(5)
+    rng = np.random.default_rng(5)
+    longest = 0
+    for t in range(120):
+        n = rnd.randint(1, 60)
+        world = rnd.randint(1, 8)
+        A = sp.random(n, n, density=rnd.choice([0, 0.02, 0.1, 0.5]), random_state=rng, format="csc")
+        if rnd.random() < 0.7:
+            A = A + sp.identity(n, format="csc")
+        A = sp.csc_matrix(A)
+        A.sort_indices()
+        o, i = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+        rp, ci, perm = orc.csc_to_csr(n, o, i)
+        off0 = orc.partition_rows(rp, world)
+        plans = [psb.Solver.dist_plan_host(n, o, i, r, world, HALO_CAP) for r in range(world)]
+        for r, P in enumerate(plans):
+            a, b = int(off0[r]), int(off0[r + 1])
+            lc0, halo0 = orc.halo_for_rank(rp, ci, a, b)
+            assert np.array_equal(P["offsets"], off0) and np.array_equal(P["rp"], rp[a:b + 1] - rp[a]), t
+            assert np.array_equal(P["halo_cols"], halo0) and np.array_equal(compact_cols(P, world), lc0), t
+            assert np.array_equal(P["perm"], perm[rp[a]:rp[b]]), t
+            longest = max(longest, len(P["send_rows"]) / n)
+        for g, Pg in enumerate(plans):
+            for q, Pq in enumerate(plans):
+                sent = Pg["send_rows"][Pg["send_begin"][q]:Pg["send_begin"][q + 1]].astype(np.int64) + off0[g]
+                want = Pq["halo_cols"][(Pq["halo_cols"] >= off0[g]) & (Pq["halo_cols"] < off0[g + 1])]
+                assert np.array_equal(sent, want), (t, g, q)
+    assert longest > 1.0   # the case the n-entry buffer could not hold is exercised
+
+
 def test_plan_halo_capacity_error(psb, orc):
     o, i, v = orc.poisson3d(12)
     with pytest.raises(RuntimeError):

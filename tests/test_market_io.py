@@ -117,3 +117,56 @@ def test_replay_fixture_through_the_solver(psb, orc, tmp_path):
     s.solve(b, x)
     assert s.get_info()["solver_iter"] == 115      # the C1 known answer
     assert np.linalg.norm(B @ x - b) < 1e-8
+
+
+def test_randomised_files_match_scipy(psb, tmp_path):
+    """150 generated coordinate files -- real / integer / pattern, general / symmetric, shuffled entries, tabs and runs of
+    blanks as separators, LF and CRLF line ends, comments and blank lines before the size line, empty matrices, missing
+    final newline -- read with header-following symmetry (-1) == scipy.io.mmread; mode 0 == the stored entries;
+    mode 1 mirrors whatever the header says."""
+    import random
+    rnd = random.Random(3)
+    rng = np.random.default_rng(3)
+    for t in range(150):
+        rows = rnd.randint(1, 12)
+        cols = rows if rnd.random() < 0.6 else rnd.randint(1, 12)
+        A = sp.random(rows, cols, density=rnd.choice([0, 0.05, 0.3, 1.0]), random_state=rng, format="coo")
+        field = rnd.choice(["real", "integer", "pattern"])
+        sym = rows == cols and rnd.random() < 0.4
+        if sym:
+            A = sp.tril(A + A.T).tocoo()
+        if field == "integer":
+            A.data = np.round(A.data * 100) + 1
+        if field == "pattern":
+            A.data = np.ones_like(A.data)
+        lines = [f"%%MatrixMarket matrix coordinate {field} {'symmetric' if sym else 'general'}"]
+        if rnd.random() < 0.5:
+            lines.append("% a comment")
+        if rnd.random() < 0.3:
+            lines.append("")
+        lines.append(f"{rows} {cols} {A.nnz}")
+        ent = list(zip(A.row.tolist(), A.col.tolist(), A.data.tolist()))
+        rnd.shuffle(ent)
+        for i, j, v in ent:
+            s = rnd.choice([" ", "  ", "\t"])
+            if field == "pattern":
+                lines.append(f"{i + 1}{s}{j + 1}")
+            elif field == "integer":
+                lines.append(f"{i + 1}{s}{j + 1}{s}{int(v)}")
+            else:
+                lines.append(f"{i + 1}{s}{j + 1}{s}{v!r}" if rnd.random() < 0.7 else f"{i + 1}{s}{j + 1}{s}{v:.17E}")
+        eol = rnd.choice(["\n", "\r\n"])
+        path = tmp_path / f"f{t}.mtx"
+        with open(path, "w", newline="") as f:
+            f.write(eol.join(lines) + (eol if rnd.random() < 0.8 else ""))
+        ref = sp.csc_matrix(scipy.io.mmread(str(path)))
+        got = psb.io.load_market(path, symmetric=-1)
+        assert got.shape == ref.shape and (got.nnz + ref.nnz == 0 or abs(got - ref).max() == 0), t
+        stored = sp.csc_matrix((A.data, (A.row, A.col)), shape=(rows, cols))
+        got0 = psb.io.load_market(path, symmetric=0)
+        assert got0.shape == stored.shape and (got0.nnz + stored.nnz == 0 or abs(got0 - stored).max() == 0), t
+        if rows == cols:
+            strict = sp.tril(stored, -1)
+            got1 = psb.io.load_market(path, symmetric=1)
+            want1 = stored + strict.T if sym else stored + sp.csc_matrix((A.data, (A.col, A.row)), shape=(rows, cols)) - sp.diags(stored.diagonal())
+            assert got1.nnz + want1.nnz == 0 or abs(got1 - want1).max() <= 1e-15 * max(1.0, abs(want1).max()), t
