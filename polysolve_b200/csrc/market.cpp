@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <memory>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -123,7 +125,7 @@ extern "C" {
 
 const char *psb200_market_last_error(void) { return g_err.c_str(); }
 
-int psb200_market_load(const char *path, int symmetric_mode, psb200_market_handle *out, int64_t *rows, int64_t *cols, int64_t *nnz)
+static int market_load_impl(const char *path, int symmetric_mode, psb200_market_handle *out, int64_t *rows, int64_t *cols, int64_t *nnz)
 {
     if (!path || !out)
         return fail("psb200_market_load: null argument");
@@ -157,6 +159,10 @@ int psb200_market_load(const char *path, int symmetric_mode, psb200_market_handl
     if (q > le || M < 0 || N < 0 || L < 0 || M > 0x7ffffffeLL || N > 0x7ffffffeLL)
         return fail("psb200_market_load: bad size line");
     p = le < end ? le + 1 : end;
+    // an entry line needs at least 4 bytes ("1 1\n"): a size line that announces more than the file can hold is wrong,
+    // and must not be trusted with a reservation
+    if (L > (long long)(buf.size() / 4) + 1)
+        return fail("psb200_market_load: the size line announces " + std::to_string(L) + " entries, the file is too short for that");
     std::vector<Entry> entries;
     entries.reserve((size_t)(mirror ? 2 * L : L));
     long long count = 0;
@@ -195,16 +201,31 @@ int psb200_market_load(const char *path, int symmetric_mode, psb200_market_handl
         return fail("psb200_market_load: the size line announces " + std::to_string(L) + " entries, the file holds " + std::to_string(count));
     if (entries.size() > 0x7ffffffeull)
         return fail("psb200_market_load: more than 2^31 entries (int32 index range, reference Types.hpp:11-15)");
-    psb200_market *m = new psb200_market();
+    std::unique_ptr<psb200_market> m(new psb200_market());
     compress(M, N, entries, *m);
-    *out = m;
+    const int64_t stored = (int64_t)m->inner.size();
+    *out = m.release();
     if (rows)
         *rows = M;
     if (cols)
         *cols = N;
     if (nnz)
-        *nnz = (int64_t)m->inner.size();
+        *nnz = stored;
     return PSB200_OK;
+}
+
+int psb200_market_load(const char *path, int symmetric_mode, psb200_market_handle *out, int64_t *rows, int64_t *cols, int64_t *nnz)
+{
+    try
+    {
+        return market_load_impl(path, symmetric_mode, out, rows, cols, nnz);
+    }
+    catch (const std::exception &e) // e.g. bad_alloc for a size line that announces 2^31 columns
+    {
+        if (out)
+            *out = nullptr;
+        return fail(std::string("psb200_market_load: ") + e.what());
+    }
 }
 
 int psb200_market_get_csc(psb200_market_handle m, int32_t *outer, int32_t *inner, double *vals)
@@ -262,6 +283,8 @@ int psb200_market_load_vector(const char *path, double *out, int64_t cap, int64_
     const long long C = std::strtoll(q, &q, 10);
     if (M < 0 || C != 1)
         return fail("psb200_market_load_vector: expected an n x 1 array");
+    if (M > (long long)(buf.size() / 2) + 1) // a value needs at least 2 bytes ("1\n"): do not let the caller allocate for a lie
+        return fail("psb200_market_load_vector: the size line announces " + std::to_string(M) + " values, the file is too short for that");
     if (n)
         *n = M;
     if (!out)

@@ -170,3 +170,51 @@ def test_randomised_files_match_scipy(psb, tmp_path):
             got1 = psb.io.load_market(path, symmetric=1)
             want1 = stored + strict.T if sym else stored + sp.csc_matrix((A.data, (A.col, A.row)), shape=(rows, cols)) - sp.diags(stored.diagonal())
             assert got1.nnz + want1.nnz == 0 or abs(got1 - want1).max() <= 1e-15 * max(1.0, abs(want1).max()), t
+
+
+def test_mutated_files_never_crash_the_reader(psb, tmp_path):
+    """600 mutations of a valid file (deleted / inserted / corrupted lines, hostile size lines): every call returns a
+    matrix or raises RuntimeError with the reader's message -- no exception crosses the C ABI, no reservation trusts the
+    size line (a size line announcing 10^14 entries once ended the process in std::length_error)."""
+    import random
+    rnd = random.Random(11)
+    base = ["%%MatrixMarket matrix coordinate real general", "% c", "4 4 5", "1 1 1.5", "2 2 -2e3", "3 1 4", "4 4 1", "2 3 .5"]
+    junk = ["", "%", "0 0 0", "-1 2 3", "5 5 1", "1 1", "1", "a b c", "99999999999 1 1", "1 1 1e999", "2 2 nan",
+            "4 4 99999999999999999999", "1 1 1 1 1", "\x00\x01", "3 3 3", "2147483646 2147483646 1", "4 4 99999999999999"]
+    path = tmp_path / "m.mtx"
+    ok = err = 0
+    for _ in range(600):
+        lines = list(base)
+        for _ in range(rnd.randint(1, 3)):
+            k = rnd.randrange(len(lines))
+            op = rnd.random()
+            if op < 0.2:
+                del lines[k]
+            elif op < 0.4:
+                lines.insert(k, rnd.choice(junk))
+            elif lines[k]:
+                chars = list(lines[k])
+                chars[rnd.randrange(len(chars))] = rnd.choice("0123456789 -.eE%\tx")
+                lines[k] = "".join(chars)
+            if not lines:
+                lines = [""]
+        path.write_text("\n".join(lines) + "\n")
+        for mode in (0, 1, -1):
+            try:
+                A = psb.io.load_market(path, symmetric=mode)
+                assert A.shape[0] >= 0 and A.nnz <= 10
+                ok += 1
+            except RuntimeError as e:
+                assert "psb200_market_load" in str(e)
+                err += 1
+        try:
+            psb.io.load_market_vector(path)
+        except RuntimeError as e:
+            assert "psb200_market_load_vector" in str(e)
+    assert ok > 50 and err > 50
+    path.write_text("%%MatrixMarket matrix coordinate real general\n3 3 99999999999999\n1 1 1\n")
+    with pytest.raises(RuntimeError, match="too short"):
+        psb.io.load_market(path)
+    path.write_text("%%MatrixMarket matrix array real general\n99999999999 1\n1\n")
+    with pytest.raises(RuntimeError, match="too short"):
+        psb.io.load_market_vector(path)
