@@ -36,6 +36,16 @@ void DistPlanHost::build(long long n, long long nnz, const int *outer, const int
         throw std::invalid_argument("psb200 dist: the matrix size is not a multiple of the block size");
     if (world_ < 1 || world_ > kMaxRanks || rank_ < 0 || rank_ >= world_)
         throw std::invalid_argument("psb200 dist: rank/world out of range (world <= 8)");
+    // the plan indexes `inner` and its own arrays with these values: reject what is not a compressed-column pattern before
+    // anything is allocated (Solver::analyze_pattern makes the same checks; the host-only plan entry point arrives here
+    // directly)
+    if (n < 0 || nnz < 0 || !outer || (!inner && nnz > 0) || n > 0x7fffffffLL - 1024 || nnz > 0x7fffffffLL - 1024)
+        throw std::invalid_argument("psb200 dist: null, negative or int32-overflowing pattern arguments");
+    if (outer[0] != 0 || outer[n] != nnz)
+        throw std::invalid_argument("psb200 dist: matrix is not compressed (outer[0] != 0 or outer[n] != nnz)");
+    for (long long c = 0; c < n; ++c)
+        if (outer[c] > outer[c + 1] || outer[c] < 0)
+            throw std::invalid_argument("psb200 dist: outer index array is not non-decreasing");
     rank = rank_;
     world = world_;
     n_global = n;

@@ -220,6 +220,8 @@ class Solver:
     def dist_plan_host(n, outer, inner, rank, world, halo_cap=1 << 20, align=1):
         """Host-only partition / halo plan of one rank (no GPU needed)."""
         L = _lib.lib()
+        if len(outer) != n + 1 or not 0 <= int(outer[n]) <= len(inner):
+            raise RuntimeError("psb200_dist_plan_host: outer must hold n + 1 entries and outer[n] <= len(inner)")
         nnz = int(outer[n])
         offsets = np.zeros(world + 1, np.int64)
         counts = np.zeros(3, np.int64)

@@ -182,6 +182,42 @@ def test_plan_randomised_matrices_and_rank_counts(psb, orc):
     assert longest > 1.0   # the case the n-entry buffer could not hold is exercised
 
 
+def test_plan_rejects_corrupted_index_arrays(psb):
+    """The host-only plan entry point validates the pattern itself (outer monotone from 0 to nnz, inner in range): 600
+    corrupted inputs come back as errors -- a non-monotone outer array once corrupted the heap."""
+    import random
+    rnd = random.Random(9)
+    rng = np.random.default_rng(9)
+    ok = err = 0
+    for _ in range(600):
+        n = rnd.randint(1, 40)
+        world = rnd.randint(1, 8)
+        A = sp.csc_matrix(sp.random(n, n, density=rnd.choice([0.05, 0.3]), random_state=rng, format="csc") + sp.identity(n, format="csc"))
+        A.sort_indices()
+        o, i = A.indptr.astype(np.int32).copy(), A.indices.astype(np.int32).copy()
+        m = rnd.random()
+        corrupted = False
+        if m < 0.35:
+            i[rnd.randrange(len(i))] = rnd.choice([-1, n, n + 5, 2 ** 31 - 1, -2 ** 31])
+            corrupted = True
+        elif m < 0.7:
+            k = rnd.randrange(len(o))
+            new = rnd.choice([-1, len(i) + 3, 2 ** 31 - 1])
+            lo = o[k - 1] if k > 0 else 0
+            hi = o[k + 1] if k + 1 < len(o) else new - 1
+            corrupted = not (lo <= new <= hi) or k == 0 or k == n
+            o[k] = new
+        try:
+            for r in range(world):
+                psb.Solver.dist_plan_host(n, o, i, r, world, HALO_CAP)
+            ok += 1
+            assert not corrupted
+        except RuntimeError:
+            err += 1
+            assert corrupted
+    assert ok > 100 and err > 100
+
+
 def test_plan_halo_capacity_error(psb, orc):
     o, i, v = orc.poisson3d(12)
     with pytest.raises(RuntimeError):
