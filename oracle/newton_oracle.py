@@ -190,6 +190,8 @@ def minimize(problem, x, params, linsolve):
     if params.get("solver", "Newton") in ("L-BFGS", "LBFGS"):       # Solver.cpp:83-85
         lbfgs = LbfgsStrategy(params.get("L-BFGS", {}).get("history_size", 6))
         strategies.append(["L-BFGS", False, 0.0])
+    elif params.get("solver", "Newton") in ("GradientDescent", "gradient_descent"):   # Solver.cpp:86-89: GD alone
+        pass
     else:
         if not nw.get("force_psd_projection", False):
             strategies.append(["Newton", False, 0.0])
@@ -210,6 +212,7 @@ def minimize(problem, x, params, linsolve):
     status = "NotStarted"
     lin_iters = []
     problem.solution_changed(x)
+    problem.post_step(0, x, np.zeros(n))   # Solver.cpp:285-286: once before the loop, gradient still zero
     g0n = dx0n = NaN
 
     def handle_error(s):

@@ -81,6 +81,72 @@ def test_newton_oracle_converges_on_reference_problems():
             assert min(np.linalg.norm(x - s) for s in prob.solutions()) < 1e-7 or info["grad_norm"] < 1e-7
 
 
+class _Recorder:
+    """wraps a problem and records what post_step is handed"""
+    def __init__(self, p):
+        self.p, self.n, self.steps = p, p.n, []
+    def __getattr__(self, k): return getattr(self.p, k)
+    def post_step(self, it, x, g): self.steps.append((int(it), np.array(x, float), np.array(g, float)))
+
+
+# Criteria.cpp:98-133 (status_message): the text the driver reports for the restatement's status names
+_STATUS_TEXT = {"GradNormTolerance": "Gradient vector norm too small", "XDeltaTolerance": "Change in parameter vector too small",
+                "RelXDeltaTolerance": "Relative change in parameter vector too small",
+                "RelGradNormTolerance": "Relative gradient vector too small",
+                "FDeltaTolerance": "Change in cost function value too small", "IterationLimit": "Iteration limit reached"}
+_GD_VARIANTS = [
+    {}, {"x_delta_tol": 1e-3}, {"rel_x_delta_tol": 1e-2}, {"rel_grad_norm_tol": 1e-2}, {"first_grad_norm_tol": 1e3},
+    {"advanced": {"f_delta_tol": 1e-4, "f_delta_step_tol": 3}}, {"max_iterations": 5, "allow_out_of_iterations": True},
+    {"max_iterations": 5}, {"line_search": {"method": "Backtracking", "use_grad_norm_tol": 1e-4}},
+    {"line_search": {"method": "Armijo", "Armijo": {"c": 0.3}}},
+    {"line_search": {"method": "RobustArmijo", "RobustArmijo": {"delta_relative_tolerance": 0.1}}},
+    {"line_search": {"method": "Backtracking", "default_init_step_size": 0.5, "step_ratio": 0.3}},
+    {"line_search": {"method": "Armijo", "min_step_size": 1e-3, "max_step_size_iter": 4}},
+    {"line_search": {"method": "None"}},
+]
+
+
+@pytest.mark.filterwarnings("ignore::RuntimeWarning")
+@pytest.mark.parametrize("variant", range(len(_GD_VARIANTS)))
+def test_driver_outer_loop_matches_oracle_on_cpu(psb, variant):
+    """CPU (no linear solve involved): with "solver": "GradientDescent" (Solver.cpp:92-94) the C++ driver runs without a
+    GPU, so its outer loop, every stopping criterion (Criteria.cpp:59-96), the iteration-limit error and the three line
+    searches are compared with the restatement step for step: identical status, iteration count, error text and
+    BIT-IDENTICAL iterates / gradients at every post_step call (Solver.cpp:286,536)."""
+    from oracle import newton_oracle as NO
+    v = _GD_VARIANTS[variant]
+    base = {"solver": "GradientDescent", "grad_norm_tol": 1e-6, "rel_grad_norm_tol": 0, "max_iterations": 300}
+    for method in (["Backtracking", "Armijo", "RobustArmijo"] if "line_search" not in v else [None]):
+        P = dict(base, **v)
+        if method:
+            P["line_search"] = {"method": method}
+        for prob in (Quadratic(12), Rosenbrock(4)):
+            x0 = np.random.default_rng(1).uniform(-1, 1, prob.n)
+            po, pd = _Recorder(prob), _Recorder(prob)
+            xo = eo = ed = None
+            io = info = {}
+            try:
+                xo, io = NO.minimize(po, x0.copy(), P, direct)
+            except RuntimeError as e:
+                eo = str(e)
+            x = x0.copy()
+            s = psb.NonlinearSolver.create(P, {"solver": "CUDA"})
+            try:
+                s.minimize(pd, x)
+                info = s.get_info()
+            except RuntimeError as e:
+                ed = str(e)
+            assert (eo is None) == (ed is None), (P, eo, ed)
+            if eo is not None:
+                assert eo.split(";")[0] in ed                 # the driver prefixes "[strategy][line search] "
+            else:
+                assert info["iterations"] == io["iterations"] and np.array_equal(x, xo), (P, info, io)
+                assert info["status"] == _STATUS_TEXT[io["status"]], (P, info["status"], io["status"])
+            assert len(po.steps) == len(pd.steps) >= 1
+            for (ia, xa, ga), (ib, xb, gb) in zip(po.steps, pd.steps):
+                assert ia == ib and np.array_equal(xa, xb) and np.array_equal(ga, gb), (P, ia)
+
+
 class HugeOffset(Base):
     """f = C + 0.5 |x - 1|^2 with C = 1e17: the energy difference of a good step drowns in the rounding error of C, so plain
     Armijo (Armijo.cpp:20-32) rejects every step size while RobustArmijo's gradient-based estimate (RobustArmijo.cpp:30-44)
