@@ -147,6 +147,70 @@ def test_driver_outer_loop_matches_oracle_on_cpu(psb, variant):
                 assert ia == ib and np.array_equal(xa, xb) and np.array_equal(ga, gb), (P, ia)
 
 
+class _Hooked(Quadratic):
+    """Quadratic with every optional Problem callback active (Problem.hpp:79-143): a step-size cap, a validity box, a
+    custom stop, a region where the energy is NaN; records the order in which the solver calls them."""
+    def __init__(self, cap=1.0, box=None, stop_at=None, nan_region=None):
+        super().__init__(12)
+        self.cap, self.box, self.stop_at, self.nan_region, self.calls = cap, box, stop_at, nan_region, []
+    def value(self, x):
+        if self.nan_region is not None and np.abs(x).max() > self.nan_region:
+            return float("nan")
+        return super().value(x)
+    def solution_changed(self, x): self.calls.append("changed")
+    def max_step_size(self, x0, x1):
+        self.calls.append("max")
+        return self.cap
+    def is_step_valid(self, x0, x1):
+        self.calls.append("valid")
+        return True if self.box is None else bool(np.all(np.abs(x1) < self.box))
+    def line_search_begin(self, x0, x1): self.calls.append("begin")
+    def line_search_end(self): self.calls.append("end")
+    def stop(self, x):
+        self.calls.append("stop")
+        return self.stop_at is not None and super().value(x) < self.stop_at
+
+
+@pytest.mark.filterwarnings("ignore::RuntimeWarning")
+@pytest.mark.parametrize("hooks", [dict(cap=0.3), dict(box=0.9), dict(stop_at=-1.0), dict(nan_region=1.5),
+                                   dict(cap=0.5, box=1.2, stop_at=-1.2)])
+def test_driver_calls_the_problem_hooks_like_the_oracle_on_cpu(psb, hooks):
+    """CPU: max_step_size / is_step_valid / line_search_begin / line_search_end / solution_changed / stop
+    (LineSearch.cpp:73-254, Solver.cpp:255-582) -- same status or error, bit-identical iterates and the SAME SEQUENCE of
+    callback invocations as the restatement, for the three line searches."""
+    from oracle import newton_oracle as NO
+    for method in ("Backtracking", "Armijo", "RobustArmijo"):
+        P = {"solver": "GradientDescent", "grad_norm_tol": 1e-6, "rel_grad_norm_tol": 0, "max_iterations": 300,
+             "line_search": {"method": method}}
+        x0 = np.random.default_rng(1).uniform(-0.8, 0.8, 12)
+        if "nan_region" in hooks:
+            x0 = np.clip(3.0 * x0, -1.4, 1.4)
+        po, pd = _Recorder(_Hooked(**hooks)), _Recorder(_Hooked(**hooks))
+        xo = eo = ed = None
+        io = info = {}
+        try:
+            xo, io = NO.minimize(po, x0.copy(), P, direct)
+        except RuntimeError as e:
+            eo = str(e)
+        x = x0.copy()
+        s = psb.NonlinearSolver.create(P, {"solver": "CUDA"})
+        try:
+            s.minimize(pd, x)
+            info = s.get_info()
+        except RuntimeError as e:
+            ed = str(e)
+        assert (eo is None) == (ed is None), (hooks, method, eo, ed)
+        if eo is None:
+            assert info["iterations"] == io["iterations"] and np.array_equal(x, xo)
+            if io["status"] == "ObjectiveCustomStop":
+                assert info["status"] == "Objective function specified to stop"   # Criteria.cpp:120-121
+        else:
+            assert eo.split(";")[0] in ed
+        assert po.p.calls == pd.p.calls and len(po.p.calls) > 10
+        assert len(po.steps) == len(pd.steps)
+        assert all(a[0] == b[0] and np.array_equal(a[1], b[1]) for a, b in zip(po.steps, pd.steps))
+
+
 class HugeOffset(Base):
     """f = C + 0.5 |x - 1|^2 with C = 1e17: the energy difference of a good step drowns in the rounding error of C, so plain
     Armijo (Armijo.cpp:20-32) rejects every step size while RobustArmijo's gradient-based estimate (RobustArmijo.cpp:30-44)
