@@ -24,6 +24,15 @@ extern "C" {
 
 typedef struct psb200_nl_solver *psb200_nl_handle;
 
+/* The solver's current Criteria (Criteria.hpp:34-57) as handed to Problem::callback. */
+typedef struct psb200_nl_criteria
+{
+    int64_t iterations;
+    double xDelta, fDelta, gradNorm, firstGradNorm, xDeltaDotGrad, relGradNorm, relXDelta, newtonDecrement;
+    int64_t fDeltaCount;
+    double energy, alpha, step;
+} psb200_nl_criteria;
+
 /* polysolve::nonlinear::Problem as callbacks. value, gradient and hessian are required, the rest may be NULL
  * (the defaults of Problem.hpp apply: steps are valid, max step size 1, no-ops). Vectors have length n. */
 typedef struct psb200_nl_problem
@@ -58,11 +67,28 @@ typedef struct psb200_nl_problem
      * a structurally present diagonal). When set, it is used instead of `hessian`. */
     int (*hessian_device)(void *user, const double *x, int64_t n, int project_to_psd, int64_t *nnz, const int32_t **outer,
                           const int32_t **inner, const double **d_vals);
+    /* ---- the remaining optional Problem virtuals (may be NULL: zero-initialise the struct). norm_type: 0 Euclidean,
+     * 1 L2, 2 Linf -- "norm_type" of the solver parameters (Problem.hpp:14-19, Solver.cpp:117-121,224). */
+    /* Problem::is_residual -- Problem.hpp:35: non-zero skips the descent-direction test (Solver.cpp:425) */
+    int (*is_residual)(void *user);
+    /* Problem::after_line_search_custom_operation -- Problem.hpp:103: non-zero => solution_changed(x1) (Solver.cpp:495-499) */
+    int (*after_line_search_custom_operation)(void *user, const double *x0, const double *x1, int64_t n);
+    /* Problem::callback(state, x) -- Problem.hpp:109: called at the end of every trip, zero ends the loop (Solver.cpp:558) */
+    int (*callback)(void *user, const psb200_nl_criteria *state, const double *x, int64_t n);
+    /* Problem::grad_norm / step_norm -- Problem.hpp:120-121 (defaults: Euclidean norm). Used for the stopping criteria,
+     * by the line search (LineSearch.cpp:138-142, Backtracking.cpp:76-80). The Newton residual check ||H dx + g||
+     * (Newton.cpp:207) is evaluated on the device and stays Euclidean. */
+    double (*grad_norm)(void *user, const double *grad, int64_t n, int norm_type);
+    double (*step_norm)(void *user, const double *dx, int64_t n, int norm_type);
+    /* Problem::grad_norm_rescaling (which = 0) / step_norm_rescaling (1) / energy_norm_rescaling (2) -- Problem.hpp:116-118:
+     * factors applied to the absolute tolerances (Solver.hpp:118-131) */
+    double (*norm_rescaling)(void *user, int which, int norm_type);
 } psb200_nl_problem;
 
 /* nonlinear::Solver::create. solver_params: the reference's nonlinear JSON (keys and defaults of
  * nonlinear-solver-spec.json: "solver": "Newton", "line_search": {"method": "Backtracking"|"Armijo"|"None", ...},
- * "grad_norm_tol", "max_iterations", "Newton": {"residual_tolerance", "reg_weight_min", ...}, ...).
+ * "grad_norm_tol", "max_iterations", "norm_type", "newton_decrement_tol", "iterations_per_strategy" (one value or one per
+ * strategy + 1, Solver.cpp:232-245), "Newton": {"residual_tolerance", "reg_weight_min", ...}, ...).
  * linear_params: the linear-solver JSON handed to every strategy's linear::Solver ({"solver": "CUDA", "CUDA": {...}}).
  * Either may be NULL for the defaults. */
 int psb200_nl_create(psb200_nl_handle *out, const char *solver_params_json, const char *linear_params_json);

@@ -26,6 +26,8 @@ def check_convergence(stop, cur):
         return "RelXDeltaTolerance"
     if stop["relGradNorm"] > 0 and cur["relGradNorm"] < stop["relGradNorm"]:
         return "RelGradNormTolerance"
+    if stop.get("newtonDecrement", 0) > 0 and cur["newtonDecrement"] < stop["newtonDecrement"]:
+        return "NewtonDecrementTolerance"
     if stop["xDelta"] > 0 and cur["xDelta"] < stop["xDelta"]:
         return "XDeltaTolerance"
     if stop["fDelta"] > 0 and cur["fDelta"] < stop["fDelta"] and cur["fDeltaCount"] >= stop["fDeltaCount"]:
@@ -35,8 +37,25 @@ def check_convergence(stop, cur):
     return "Continue"
 
 
+def _grad_norm(f, g, nt):
+    """Problem::grad_norm (Problem.hpp:120), default Euclidean"""
+    return float(f.grad_norm(g, nt)) if hasattr(f, "grad_norm") else float(np.linalg.norm(g))
+
+
+def _step_norm(f, d, nt):
+    """Problem::step_norm (Problem.hpp:121)"""
+    return float(f.step_norm(d, nt)) if hasattr(f, "step_norm") else float(np.linalg.norm(d))
+
+
+def _rescaling(f, which, nt):
+    """Problem::grad_norm_rescaling / step_norm_rescaling / energy_norm_rescaling (Problem.hpp:116-118), default 1"""
+    fn = getattr(f, which + "_norm_rescaling", None)
+    return float(fn(nt)) if fn else 1.0
+
+
 class LineSearch:
     def __init__(self, p):
+        self.norm_type = p.get("norm_type", "L2")        # Solver.cpp:253
         ls = p.get("line_search", {})
         self.method = ls.get("method", "RobustArmijo")
         self.min_step = ls.get("min_step_size", 1e-10)
@@ -79,14 +98,14 @@ class LineSearch:
             f.line_search_end()
             return NaN
         step = step * ms  # the reference rounds this product downward (LineSearch.cpp:243-248); exact for ms == 1
-        gn = float(np.linalg.norm(g0))
+        gn = _grad_norm(f, g0, self.norm_type)
         if gn < 1e-30:
             self.total += it
             return step
         if self.method == "None":
             f.line_search_end()
             return step
-        use_gn = gn < self.use_grad_norm_tol
+        use_gn = gn < self.use_grad_norm_tol * _rescaling(f, "grad", self.norm_type)   # LineSearch.cpp:142
         arm = self.c * float(dx @ g0)
         while step > mn and it < mx:
             nx = x + step * dx
@@ -104,7 +123,8 @@ class LineSearch:
                             eps = step / 2 * abs(float(dx @ (ng - g0)))
                             ok = dE + eps <= step * arm
                     elif use_gn:
-                        ok = np.linalg.norm(f.gradient(nx)) < gn
+                        # Backtracking.cpp:76-80 evaluates both norms at every trial ("TODO cache old grad norm")
+                        ok = _grad_norm(f, np.asarray(f.gradient(nx), float), self.norm_type) < _grad_norm(f, g0, self.norm_type)
                     else:
                         ok = e < e0
             if ok:
@@ -178,9 +198,14 @@ class LbfgsStrategy:
 def minimize(problem, x, params, linsolve):
     """Returns (x, info). Raises RuntimeError where the reference throws."""
     adv = params.get("advanced", {})
-    stop = dict(xDelta=params.get("x_delta_tol", 0), fDelta=adv.get("f_delta_tol", 0), gradNorm=params.get("grad_norm_tol", 1e-10),
-                firstGradNorm=params.get("first_grad_norm_tol", 1e-12), xDeltaDotGrad=-adv.get("derivative_along_delta_x_tol", 0),
+    nt = params.get("norm_type", "L2")
+    rg, rs, re = _rescaling(problem, "grad", nt), _rescaling(problem, "step", nt), _rescaling(problem, "energy", nt)
+    # Solver.cpp:206-219 + Solver.hpp:118-131 (reset_stopping_criteria)
+    stop = dict(xDelta=params.get("x_delta_tol", 0) * rs, fDelta=adv.get("f_delta_tol", 0) * re,
+                gradNorm=params.get("grad_norm_tol", 1e-10) * rg, firstGradNorm=params.get("first_grad_norm_tol", 1e-12) * rg,
+                xDeltaDotGrad=-adv.get("derivative_along_delta_x_tol", 0) * re,
                 relGradNorm=params.get("rel_grad_norm_tol", 1e-10), relXDelta=params.get("rel_x_delta_tol", 0),
+                newtonDecrement=params.get("newton_decrement_tol", 0) * re,
                 iterations=params.get("max_iterations", 500), fDeltaCount=adv.get("f_delta_step_tol", 100))
     nw = params.get("Newton", {})
     res_tol = nw.get("residual_tolerance", 1e-5)
@@ -200,7 +225,13 @@ def minimize(problem, x, params, linsolve):
         if wmin > 0:
             strategies.append(["RegularizedNewton", nw.get("use_psd_projection_in_regularized", True), wmin])
     strategies.append(["GradientDescent", False, 0.0])
-    per = params.get("iterations_per_strategy", 5)
+    per = params.get("iterations_per_strategy", 5)                  # Solver.cpp:232-245: one value or one per strategy + 1
+    if isinstance(per, (list, tuple)):
+        if len(per) != len(strategies) + 1:
+            raise RuntimeError(f"Invalit iter_per_strategy size: {len(per)}!={len(strategies) + 1}")
+        per = list(per)
+    else:
+        per = [per] * (len(strategies) + 1)
     ls = LineSearch(params)
     x = np.array(x, float)
     n = x.size
@@ -228,20 +259,28 @@ def minimize(problem, x, params, linsolve):
         if lbfgs is not None:
             lbfgs.reset()
 
+    def keep_going():
+        # Problem::callback(state, x) (Problem.hpp:109) is the first operand of the do-while condition (Solver.cpp:558):
+        # it runs at the end of EVERY trip, also after the `continue`s of a strategy fallback
+        return bool(problem.callback(dict(cur), x)) if hasattr(problem, "callback") else True
+
+    is_residual = bool(problem.is_residual()) if hasattr(problem, "is_residual") else False
+    cur.update(energy=NaN, alpha=NaN, step=NaN, newtonDecrement=0.0, firstGradNorm=0.0)
     while True:
         ls.final = strategy == len(strategies) - 1
         energy = problem.value(x)
+        cur["energy"] = energy
         if not math.isfinite(energy):
             raise RuntimeError("f(x) is nan or inf; stopping")
         cur["fDelta"] = abs(old_energy - energy)
         grad = np.asarray(problem.gradient(x), float)
-        cur["gradNorm"] = float(np.linalg.norm(grad))
+        cur["gradNorm"] = _grad_norm(problem, grad, nt)
         if cur["iterations"] == 0:
             g0n = cur["gradNorm"]
             cur["relGradNorm"] = NaN
         else:
             cur["relGradNorm"] = cur["gradNorm"] / g0n
-        cur["xDelta"] = cur["xDeltaDotGrad"] = cur["relXDelta"] = NaN
+        cur["xDelta"] = cur["xDeltaDotGrad"] = cur["relXDelta"] = cur["newtonDecrement"] = NaN
         status = check_convergence(stop, cur)
         if status != "Continue":
             break
@@ -262,7 +301,7 @@ def minimize(problem, x, params, linsolve):
                 ok = not (math.isnan(r) or r > res_tol)
             except ArithmeticError:
                 ok = False
-        cur["xDelta"] = float(np.linalg.norm(dx))
+        cur["xDelta"] = _step_norm(problem, dx, nt)
         if cur["iterations"] == 0:
             dx0n = cur["xDelta"]
             cur["relXDelta"] = NaN
@@ -273,33 +312,49 @@ def minimize(problem, x, params, linsolve):
                 strategy += 1
             if strategy >= len(strategies):
                 raise RuntimeError("Update direction could not be computed on last strategy; stopping")
+            if not keep_going():
+                break
             continue
         cur["xDeltaDotGrad"] = float(dx @ grad)
-        if cur["gradNorm"] != 0 and cur["xDeltaDotGrad"] >= 0:
+        if stop["newtonDecrement"] > 0:                       # Solver.cpp:409-423: 1/2 x^T H x (sic), NaN on failure
+            try:
+                cur["newtonDecrement"] = 0.5 * float(x @ (sp.csc_matrix(problem.hessian(x, False)) @ x))
+            except RuntimeError:
+                cur["newtonDecrement"] = NaN
+        if (not is_residual) and cur["gradNorm"] != 0 and cur["xDeltaDotGrad"] >= 0:
             if not handle_error(s):
                 strategy += 1
             if strategy >= len(strategies):
                 raise RuntimeError("Search direction not a descent direction on last strategy; stopping")
+            if not keep_going():
+                break
             continue
         status = check_convergence(stop, cur)
         if status != "Continue":
             break
         rate = ls.line_search(x, dx, problem)
+        cur["alpha"] = rate
         if math.isnan(rate):
             if not handle_error(s):
                 strategy += 1
             if strategy >= len(strategies):
                 raise RuntimeError("Line search failed on last strategy; stopping")
+            if not keep_going():
+                break
             continue
-        x = x + rate * dx
+        x1 = x + rate * dx
+        if hasattr(problem, "after_line_search_custom_operation") and problem.after_line_search_custom_operation(x, x1):
+            problem.solution_changed(x1)                      # Solver.cpp:495-499
+        x = x1
         old_energy = energy
         if strategy != prev:
             cur_iter = 0
-        if strategy != 0 and cur_iter >= per:
+        if strategy != 0 and cur_iter >= per[strategy]:
             strategy = 0
             reset()
         prev = strategy
         cur_iter += 1
+        cur["step"] = float(np.linalg.norm(rate * dx))
         problem.post_step(cur["iterations"], x, grad)
         if problem.stop(x):
             status = "ObjectiveCustomStop"
@@ -307,7 +362,7 @@ def minimize(problem, x, params, linsolve):
         cur["iterations"] += 1
         if cur["iterations"] >= stop["iterations"]:
             status = "IterationLimit"
-        if status != "Continue":
+        if (not keep_going()) or status != "Continue":
             break
     if status == "IterationLimit" and not params.get("allow_out_of_iterations", False):
         raise RuntimeError("Reached iteration limit")

@@ -100,6 +100,12 @@ struct Criteria
     double energy = 0, alpha = 0, step = 0;
 };
 
+psb200_nl_criteria as_c(const Criteria &c)
+{
+    return {c.iterations, c.xDelta, c.fDelta, c.gradNorm, c.firstGradNorm, c.xDeltaDotGrad, c.relGradNorm, c.relXDelta, c.newtonDecrement,
+            c.fDeltaCount, c.energy, c.alpha, c.step};
+}
+
 // Criteria.cpp:59-96
 Status check_convergence(const Criteria &stop, const Criteria &cur)
 {
@@ -196,6 +202,34 @@ struct Problem
             p->post_step(p->user, it, x.data(), g.data(), n);
     }
     bool stop(const std::vector<double> &x) const { return p->stop ? p->stop(p->user, x.data(), n) != 0 : false; }
+    // Problem.hpp:35,103,109,116-121 -- optional, with the reference's defaults
+    int norm_type = 1; // "norm_type": Euclidean 0, L2 1 (spec default), Linf 2
+    bool is_residual() const { return p->is_residual ? p->is_residual(p->user) != 0 : false; }
+    bool after_line_search_custom_operation(const std::vector<double> &x0, const std::vector<double> &x1) const
+    {
+        return p->after_line_search_custom_operation ? p->after_line_search_custom_operation(p->user, x0.data(), x1.data(), n) != 0 : false;
+    }
+    bool callback(const psb200_nl_criteria &state, const std::vector<double> &x) const
+    {
+        return p->callback ? p->callback(p->user, &state, x.data(), n) != 0 : true;
+    }
+    double grad_norm(const std::vector<double> &g) const { return p->grad_norm ? p->grad_norm(p->user, g.data(), n, norm_type) : norm2(g); }
+    double step_norm(const std::vector<double> &d) const { return p->step_norm ? p->step_norm(p->user, d.data(), n, norm_type) : norm2(d); }
+    double rescaling(int which) const { return p->norm_rescaling ? p->norm_rescaling(p->user, which, norm_type) : 1.0; }
+    // 1/2 x^T H x with the host Hessian (Solver.cpp:409-423); NaN when the assembly fails
+    double half_xHx(const std::vector<double> &x) const
+    {
+        int64_t nnz = 0;
+        const int32_t *outer = nullptr, *inner = nullptr;
+        const double *vals = nullptr;
+        if (!p->hessian || p->hessian(p->user, x.data(), n, 0, &nnz, &outer, &inner, &vals) != 0 || !outer || (nnz > 0 && (!inner || !vals)))
+            return NaN;
+        double s = 0;
+        for (int64_t c = 0; c < n; ++c)
+            for (int32_t k = outer[c]; k < outer[c + 1]; ++k)
+                s += x[(size_t)inner[k]] * vals[k] * x[(size_t)c];
+        return 0.5 * s;
+    }
 };
 
 void axpy(std::vector<double> &out, const std::vector<double> &x, double a, const std::vector<double> &d)
@@ -284,7 +318,7 @@ struct LineSearch
             else if (use_grad_norm)
             {
                 f.gradient(nx, ng);
-                ok = norm2(ng) < norm2(old_grad);
+                ok = f.grad_norm(ng) < f.grad_norm(old_grad); // Backtracking.cpp:76-80
             }
             else
                 ok = e < old_energy;
@@ -325,7 +359,7 @@ struct LineSearch
             step *= mx;
             std::fesetround(rnd);
         }
-        const double gn = norm2(g0);
+        const double gn = f.grad_norm(g0);
         if (gn < 1e-30)
         {
             total_iterations += cur_iter;
@@ -336,7 +370,7 @@ struct LineSearch
             f.line_search_end();
             return step;
         }
-        const bool use_grad_norm = gn < use_grad_norm_tol;
+        const bool use_grad_norm = gn < use_grad_norm_tol * f.rescaling(0); // LineSearch.cpp:142
         step = descent_step(x, dx, f, use_grad_norm, e0, g0, step);
         total_iterations += cur_iter;
         if (std::isnan(step))
@@ -594,6 +628,7 @@ struct psb200_nl_solver
     std::vector<int> iter_per_strategy;
     LineSearch ls;
     std::string solver_name = "Newton";
+    int norm_type = 1;
     Status status = Status::NotStarted;
 };
 
@@ -616,8 +651,18 @@ void build(psb200_nl_solver &S, const std::string &solver_json, const std::strin
     S.stop.fDeltaCount = (int)jget(adv, "f_delta_step_tol", 100);
     S.allow_out_of_iterations = jgetb(j, "allow_out_of_iterations", false);
     S.allow_non_grad_convergence = jgetb(j, "allow_non_grad_convergence", false);
-    if (S.stop.newtonDecrement > 0)
-        throw std::runtime_error("newton_decrement_tol > 0 is not supported by this driver");
+    {
+        // Solver.cpp:117-121,224; spec default "L2" (nonlinear-solver-spec.json:91-99)
+        const std::string nt = jgets(j, "norm_type", "L2");
+        if (nt == "Euclidean")
+            S.norm_type = 0;
+        else if (nt == "L2")
+            S.norm_type = 1;
+        else if (nt == "Linf")
+            S.norm_type = 2;
+        else
+            throw std::runtime_error("Unknown norm_type " + nt + " (Euclidean, L2, Linf)");
+    }
 
     const JValue lsj = jsub(j, "line_search");
     S.ls.method = jgets(lsj, "method", "RobustArmijo");
@@ -682,13 +727,30 @@ void build(psb200_nl_solver &S, const std::string &solver_json, const std::strin
     else
         throw std::runtime_error("Unrecognized solver type: " + S.solver_name + " (this driver provides Newton, L-BFGS and GradientDescent)");
     // Solver.cpp:232-245
-    S.iter_per_strategy.assign(S.strategies.size() + 1, (int)jget(j, "iterations_per_strategy", 5));
+    if (j.contains("iterations_per_strategy") && j.at("iterations_per_strategy").kind == JValue::Arr)
+    {
+        const auto &a = j.at("iterations_per_strategy").arr;
+        if (a.size() != S.strategies.size() + 1)
+            throw std::runtime_error("Invalit iter_per_strategy size: " + std::to_string(a.size()) + "!=" + std::to_string(S.strategies.size() + 1));
+        S.iter_per_strategy.clear();
+        for (const JValue &v : a)
+            S.iter_per_strategy.push_back((int)v.as_num());
+    }
+    else
+        S.iter_per_strategy.assign(S.strategies.size() + 1, (int)jget(j, "iterations_per_strategy", 5));
 }
 
 // Solver.cpp:255-582. Returns false where the reference throws; err holds the message.
 bool minimize(psb200_nl_solver &S, const Problem &f, std::vector<double> &x)
 {
-    const Criteria &stop = S.stop; // Problem rescalings default to 1 (Problem.hpp:116-118)
+    // Solver.hpp:118-131 reset_stopping_criteria: absolute tolerances scaled by the Problem's rescalings (default 1)
+    Criteria stop = S.stop;
+    stop.xDelta *= f.rescaling(1);
+    stop.fDelta *= f.rescaling(2);
+    stop.gradNorm *= f.rescaling(0);
+    stop.firstGradNorm *= f.rescaling(0);
+    stop.xDeltaDotGrad *= f.rescaling(2);
+    stop.newtonDecrement *= f.rescaling(2);
     Criteria cur;
     size_t strategy = 0, previous_strategy = 0;
     int current_strategy_iter = 0;
@@ -728,7 +790,7 @@ bool minimize(psb200_nl_solver &S, const Problem &f, std::vector<double> &x)
             ScopedTimer t(grad_time);
             f.gradient(x, grad);
         }
-        cur.gradNorm = norm2(grad);
+        cur.gradNorm = f.grad_norm(grad);
         if (cur.iterations == 0)
         {
             initial_grad_norm = cur.gradNorm;
@@ -760,7 +822,7 @@ bool minimize(psb200_nl_solver &S, const Problem &f, std::vector<double> &x)
                 break;
             }
         }
-        cur.xDelta = norm2(dx);
+        cur.xDelta = f.step_norm(dx);
         if (cur.iterations == 0)
         {
             initial_dx_norm = cur.xDelta;
@@ -781,7 +843,9 @@ bool minimize(psb200_nl_solver &S, const Problem &f, std::vector<double> &x)
             continue;
         }
         cur.xDeltaDotGrad = dot(dx, grad);
-        if (S.strategies[strategy]->is_direction_descent() && cur.gradNorm != 0 && cur.xDeltaDotGrad >= 0)
+        if (stop.newtonDecrement > 0)
+            cur.newtonDecrement = f.half_xHx(x); // Solver.cpp:409-423 (x^T H x / 2, NaN when the Hessian cannot be assembled)
+        if (!f.is_residual() && S.strategies[strategy]->is_direction_descent() && cur.gradNorm != 0 && cur.xDeltaDotGrad >= 0)
         {
             if (!S.strategies[strategy]->handle_error())
                 ++strategy;
@@ -815,6 +879,8 @@ bool minimize(psb200_nl_solver &S, const Problem &f, std::vector<double> &x)
             continue;
         }
         axpy(x1, x, rate, dx);
+        if (f.after_line_search_custom_operation(x, x1)) // Solver.cpp:495-499
+            f.solution_changed(x1);
         x = x1;
         old_energy = energy;
         if (strategy != previous_strategy)
@@ -827,14 +893,14 @@ bool minimize(psb200_nl_solver &S, const Problem &f, std::vector<double> &x)
         }
         previous_strategy = strategy;
         ++current_strategy_iter;
-        cur.step = std::abs(rate) * cur.xDelta;
+        cur.step = std::abs(rate) * norm2(dx); // Solver.cpp:528: (rate * delta_x).norm()
         f.post_step((int)cur.iterations, x, grad);
         if (f.stop(x))
             S.status = Status::ObjectiveCustomStop;
         cur.fDeltaCount = (cur.fDelta < stop.fDelta) ? cur.fDeltaCount + 1 : 0;
         if (++cur.iterations >= stop.iterations)
             S.status = Status::IterationLimit;
-    } while (S.status == Status::Continue);
+    } while (f.callback(as_c(cur), x) && S.status == Status::Continue); // Solver.cpp:558
     total_time = now_s() - t_start;
 
     if (ok && !S.allow_out_of_iterations && S.status == Status::IterationLimit)
@@ -920,7 +986,8 @@ int psb200_nl_minimize(psb200_nl_handle h, const psb200_nl_problem *problem, dou
     {
         h->err.clear();
         std::vector<double> x(x_inout, x_inout + n);
-        const Problem f{problem, n};
+        Problem f{problem, n};
+        f.norm_type = h->norm_type;
         const bool ok = minimize(*h, f, x);
         std::copy(x.begin(), x.end(), x_inout);
         return ok ? PSB200_OK : PSB200_ERR_NUMERIC;

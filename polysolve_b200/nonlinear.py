@@ -46,6 +46,15 @@ class Problem:
     def stop(self, x):
         return False
 
+    # Optional, forwarded only when the problem object defines them (reference defaults otherwise, Problem.hpp:35,103-121):
+    #   is_residual() -> bool
+    #   after_line_search_custom_operation(x0, x1) -> bool      (True => solution_changed(x1))
+    #   callback(state: dict of the solver's Criteria, x) -> bool   (False ends the loop)
+    #   grad_norm(grad, norm_type) / step_norm(dx, norm_type) -> float     norm_type in "Euclidean" | "L2" | "Linf"
+    #   grad_norm_rescaling(norm_type) / step_norm_rescaling(norm_type) / energy_norm_rescaling(norm_type) -> float
+
+
+NORM_TYPES = ("Euclidean", "L2", "Linf")
 
 _f64p = C.POINTER(C.c_double)
 _i32p = C.POINTER(C.c_int32)
@@ -63,11 +72,25 @@ _STOP = C.CFUNCTYPE(C.c_int, C.c_void_p, _f64p, C.c_int64)
 _HOOK = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p)
 
 
+class _CCriteria(C.Structure):
+    _fields_ = [("iterations", C.c_int64), ("xDelta", C.c_double), ("fDelta", C.c_double), ("gradNorm", C.c_double),
+                ("firstGradNorm", C.c_double), ("xDeltaDotGrad", C.c_double), ("relGradNorm", C.c_double),
+                ("relXDelta", C.c_double), ("newtonDecrement", C.c_double), ("fDeltaCount", C.c_int64),
+                ("energy", C.c_double), ("alpha", C.c_double), ("step", C.c_double)]
+
+
+_ISRES = C.CFUNCTYPE(C.c_int, C.c_void_p)
+_CALLB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(_CCriteria), _f64p, C.c_int64)
+_NORM = C.CFUNCTYPE(C.c_double, C.c_void_p, _f64p, C.c_int64, C.c_int)
+_RESC = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_int, C.c_int)
+
+
 class _CProblem(C.Structure):
     _fields_ = [("user", C.c_void_p), ("value", _VALUE), ("gradient", _GRAD), ("hessian", _HESS),
                 ("solution_changed", _VOIDX), ("is_step_valid", _STEPV), ("max_step_size", _MAXST),
                 ("line_search_begin", _LSBEG), ("line_search_end", _LSEND), ("post_step", _POST), ("stop", _STOP),
-                ("hessian_device", _HESS)]
+                ("hessian_device", _HESS), ("is_residual", _ISRES), ("after_line_search_custom_operation", _STEPV),
+                ("callback", _CALLB), ("grad_norm", _NORM), ("step_norm", _NORM), ("norm_rescaling", _RESC)]
 
 
 def _vec(p, n):
@@ -203,9 +226,42 @@ class NonlinearSolver:
         def stop(_, xp, nn):
             return 1 if problem.stop(_vec(xp, nn)) else 0
 
+        @guard(0)
+        def is_residual(_):
+            return 1 if problem.is_residual() else 0
+
+        @guard(0)
+        def after_ls(_, x0, x1, nn):
+            return 1 if problem.after_line_search_custom_operation(_vec(x0, nn), _vec(x1, nn)) else 0
+
+        @guard(0)
+        def callback(_, st, xp, nn):
+            state = {k: getattr(st.contents, k) for k, _t in _CCriteria._fields_}
+            return 1 if problem.callback(state, _vec(xp, nn)) else 0
+
+        @guard(float("nan"))
+        def grad_norm(_, gp, nn, nt):
+            return float(problem.grad_norm(_vec(gp, nn), NORM_TYPES[nt]))
+
+        @guard(float("nan"))
+        def step_norm(_, dp, nn, nt):
+            return float(problem.step_norm(_vec(dp, nn), NORM_TYPES[nt]))
+
+        @guard(1.0)
+        def rescaling(_, which, nt):
+            fn = getattr(problem, ("grad_norm_rescaling", "step_norm_rescaling", "energy_norm_rescaling")[which], None)
+            return float(fn(NORM_TYPES[nt])) if fn else 1.0
+
+        def opt(name, ctype, fn):
+            return ctype(fn) if hasattr(problem, name) else C.cast(None, ctype)
+
+        has_resc = any(hasattr(problem, k) for k in ("grad_norm_rescaling", "step_norm_rescaling", "energy_norm_rescaling"))
         cp = _CProblem(None, _VALUE(value), _GRAD(gradient), _HESS(hessian), _VOIDX(solution_changed), _STEPV(is_step_valid),
                        _MAXST(max_step_size), _LSBEG(ls_begin), _LSEND(ls_end), _POST(post_step), _STOP(stop),
-                       _HESS(hessian_device) if hasattr(problem, "hessian_device") else C.cast(None, _HESS))
+                       opt("hessian_device", _HESS, hessian_device), opt("is_residual", _ISRES, is_residual),
+                       opt("after_line_search_custom_operation", _STEPV, after_ls), opt("callback", _CALLB, callback),
+                       opt("grad_norm", _NORM, grad_norm), opt("step_norm", _NORM, step_norm),
+                       _RESC(rescaling) if has_resc else C.cast(None, _RESC))
         rc = self._L.psb200_nl_minimize(self._h, C.byref(cp), x, n)
         if errors:
             raise errors[0]

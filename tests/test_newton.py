@@ -211,6 +211,92 @@ def test_driver_calls_the_problem_hooks_like_the_oracle_on_cpu(psb, hooks):
         assert all(a[0] == b[0] and np.array_equal(a[1], b[1]) for a, b in zip(po.steps, pd.steps))
 
 
+class _Normed(Quadratic):
+    """Quadratic with the remaining optional Problem virtuals (Problem.hpp:35,103-121): custom gradient / step norms per
+    norm type and tolerance rescalings (what PolyFEM's problems do with their mass matrix), callback(state, x),
+    after_line_search_custom_operation, is_residual. Records calls and the Criteria handed to callback."""
+    def __init__(self, resc=(1, 1, 1), cb_stop=None, after=False, residual=False):
+        super().__init__(12)
+        self.resc, self.cb_stop, self.after, self.residual, self.calls, self.states = resc, cb_stop, after, residual, [], []
+    @staticmethod
+    def _norm(v, nt):
+        return float(np.abs(v).max()) if nt == "Linf" else float(np.sqrt(np.sum(v * v) / (len(v) if nt == "L2" else 1)))
+    def grad_norm(self, g, nt):
+        self.calls.append(("gn", nt))
+        return self._norm(g, nt)
+    def step_norm(self, d, nt):
+        self.calls.append(("sn", nt))
+        return self._norm(d, nt)
+    def grad_norm_rescaling(self, nt): return self.resc[0]
+    def step_norm_rescaling(self, nt): return self.resc[1]
+    def energy_norm_rescaling(self, nt): return self.resc[2]
+    def callback(self, state, x):
+        self.states.append(dict(state))
+        return not (self.cb_stop is not None and state["iterations"] >= self.cb_stop)
+    def after_line_search_custom_operation(self, x0, x1):
+        self.calls.append("after")
+        return self.after
+    def solution_changed(self, x): self.calls.append("changed")
+    def is_residual(self): return self.residual
+
+
+_NORMED_CASES = [
+    (dict(), {"norm_type": "L2"}), (dict(), {"norm_type": "Linf"}), (dict(), {"norm_type": "Euclidean"}), (dict(), {}),
+    (dict(resc=(10, 1, 1)), {"norm_type": "Linf"}), (dict(resc=(1, 100, 1)), {"x_delta_tol": 1e-4}),
+    (dict(resc=(1, 1, 50)), {"advanced": {"f_delta_tol": 1e-6, "f_delta_step_tol": 2}}),
+    (dict(cb_stop=3), {}), (dict(after=True), {}), (dict(residual=True), {}), (dict(), {"newton_decrement_tol": 0.5}),
+    (dict(), {"line_search": {"method": "Backtracking", "use_grad_norm_tol": 1e-2}}),
+    (dict(resc=(1e4, 1, 1)), {"line_search": {"method": "Backtracking", "use_grad_norm_tol": 1e-5}}),
+]
+
+
+@pytest.mark.parametrize("case", range(len(_NORMED_CASES)))
+def test_driver_norms_rescalings_callback_match_oracle_on_cpu(psb, case):
+    """CPU: "norm_type" with Problem::grad_norm / step_norm, the tolerance rescalings (Solver.hpp:118-131), the line
+    search's use_grad_norm switch (LineSearch.cpp:142, Backtracking.cpp:76-80), "newton_decrement_tol" (Solver.cpp:409-423),
+    Problem::callback as the loop condition (Solver.cpp:558), after_line_search_custom_operation (:495-499), is_residual
+    (:425): same status, iterates bit-identical, the same sequence of norm / solution_changed calls and the same Criteria
+    at every callback as the restatement."""
+    from oracle import newton_oracle as NO
+    kw, pv = _NORMED_CASES[case]
+    P = dict({"solver": "GradientDescent", "grad_norm_tol": 1e-6, "rel_grad_norm_tol": 0, "max_iterations": 300,
+              "line_search": {"method": "Backtracking"}}, **pv)
+    x0 = np.random.default_rng(1).uniform(-0.8, 0.8, 12)
+    po, pd = _Recorder(_Normed(**kw)), _Recorder(_Normed(**kw))
+    xo, io = NO.minimize(po, x0.copy(), P, direct)
+    x = x0.copy()
+    s = psb.NonlinearSolver.create(P, {"solver": "CUDA"})
+    s.minimize(pd, x)
+    info = s.get_info()
+    assert info["iterations"] == io["iterations"] and np.array_equal(x, xo)
+    if io["status"] in _STATUS_TEXT:
+        assert info["status"] == _STATUS_TEXT[io["status"]]
+    elif io["status"] == "NewtonDecrementTolerance":
+        assert info["status"] == "Newton decrement too small"            # Criteria.cpp:118-119
+    else:
+        assert io["status"] == "Continue" and info["status"] == "Convergence criteria not reached"   # callback said stop
+    assert po.p.calls == pd.p.calls and len(po.p.calls) > 5
+    assert len(po.steps) == len(pd.steps) and all(a[0] == b[0] and np.array_equal(a[1], b[1]) for a, b in zip(po.steps, pd.steps))
+    assert len(po.p.states) == len(pd.p.states) >= 1
+    for a, b in zip(po.p.states, pd.p.states):
+        for k in ("iterations", "fDeltaCount"):
+            assert a[k] == b[k]
+        for k in ("xDelta", "fDelta", "gradNorm", "xDeltaDotGrad", "relGradNorm", "relXDelta", "newtonDecrement", "energy", "alpha", "step"):
+            u, v = float(a[k]), float(b[k])
+            # numpy's dot and the driver's loop add in different orders: 4 ulp on the dot products, exact elsewhere
+            assert (np.isnan(u) and np.isnan(v)) or abs(u - v) <= 1e-15 * max(abs(u), abs(v)) * 4, (k, u, v)
+    with pytest.raises(RuntimeError, match="norm_type"):
+        psb.NonlinearSolver.create(dict(P, norm_type="L3"), {"solver": "CUDA"})
+
+
+def test_iterations_per_strategy_list_is_validated(psb):
+    """Solver.cpp:232-245: a list needs one entry per strategy + 1 (the reference's message, typo included)."""
+    with pytest.raises(RuntimeError, match="Invalit iter_per_strategy size: 2!=5"):
+        psb.NonlinearSolver.create({"solver": "Newton", "iterations_per_strategy": [1, 2]}, {"solver": "CUDA"})
+    psb.NonlinearSolver.create({"solver": "Newton", "iterations_per_strategy": [1, 2, 3, 4, 5]}, {"solver": "CUDA"})
+    psb.NonlinearSolver.create({"solver": "GradientDescent", "iterations_per_strategy": [1, 2]}, {"solver": "CUDA"})
+
+
 class HugeOffset(Base):
     """f = C + 0.5 |x - 1|^2 with C = 1e17: the energy difference of a good step drowns in the rounding error of C, so plain
     Armijo (Armijo.cpp:20-32) rejects every step size while RobustArmijo's gradient-based estimate (RobustArmijo.cpp:30-44)
