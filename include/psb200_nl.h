@@ -5,7 +5,8 @@
  *   nonlinear::Solver::create(solver_params, linear_solver_params, ...)   src/polysolve/nonlinear/Solver.cpp:124-186
  *   nonlinear::Solver::minimize(Problem&, TVector&)                       src/polysolve/nonlinear/Solver.cpp:255-582
  *   Newton / ProjectedNewton / RegularizedNewton (+ GradientDescent)      src/polysolve/nonlinear/descent_strategies/Newton.cpp:14-58,144-214,275-330
- *   LineSearch::line_search + Backtracking / Armijo                       src/polysolve/nonlinear/line_search/LineSearch.cpp:73-254, Backtracking.cpp:15-83, Armijo.cpp:13-32
+ *   LineSearch::line_search + Backtracking / Armijo / RobustArmijo /      src/polysolve/nonlinear/line_search/LineSearch.cpp:73-254, Backtracking.cpp:15-83, Armijo.cpp:13-32,
+ *   ResidualBacktracking / NoLineSearch                                   RobustArmijo.cpp:16-46, ResidualBacktracking.cpp:15-28, NoLineSearch.cpp:11-22
  *   checkConvergence                                                      src/polysolve/nonlinear/Criteria.cpp:59-96
  * A polysolve::nonlinear::Problem subclass (src/polysolve/nonlinear/Problem.hpp:22-143) becomes a
  * table of callbacks. In a polysolve build nothing of this is needed -- nonlinear::Solver keeps calling
@@ -86,7 +87,7 @@ typedef struct psb200_nl_problem
 } psb200_nl_problem;
 
 /* nonlinear::Solver::create. solver_params: the reference's nonlinear JSON (keys and defaults of
- * nonlinear-solver-spec.json: "solver": "Newton", "line_search": {"method": "Backtracking"|"Armijo"|"None", ...},
+ * nonlinear-solver-spec.json: "solver": "Newton", "line_search": {"method": "RobustArmijo"|"Armijo"|"Backtracking"|"ResidualBacktracking"|"None", ...},
  * "grad_norm_tol", "max_iterations", "norm_type", "newton_decrement_tol", "iterations_per_strategy" (one value or one per
  * strategy + 1, Solver.cpp:232-245), "Newton": {"residual_tolerance", "reg_weight_min", ...}, ...).
  * linear_params: the linear-solver JSON handed to every strategy's linear::Solver ({"solver": "CUDA", "CUDA": {...}}).

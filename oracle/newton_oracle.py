@@ -102,12 +102,11 @@ class LineSearch:
         if gn < 1e-30:
             self.total += it
             return step
-        if self.method == "None":
-            f.line_search_end()
-            return step
         use_gn = gn < self.use_grad_norm_tol * _rescaling(f, "grad", self.norm_type)   # LineSearch.cpp:142
         arm = self.c * float(dx @ g0)
-        while step > mn and it < mx:
+        if self.method == "None":
+            f.solution_changed(x + step * dx)                  # NoLineSearch.cpp:11-22; the checks below still apply
+        while self.method != "None" and step > mn and it < mx:
             nx = x + step * dx
             f.solution_changed(nx)
             ok = False
@@ -122,7 +121,7 @@ class LineSearch:
                             dE = step / 2 * float(dx @ (ng + g0))
                             eps = step / 2 * abs(float(dx @ (ng - g0)))
                             ok = dE + eps <= step * arm
-                    elif use_gn:
+                    elif use_gn or self.method == "ResidualBacktracking":   # ResidualBacktracking.cpp:15-28
                         # Backtracking.cpp:76-80 evaluates both norms at every trial ("TODO cache old grad norm")
                         ok = _grad_norm(f, np.asarray(f.gradient(nx), float), self.norm_type) < _grad_norm(f, g0, self.norm_type)
                     else:

@@ -315,7 +315,7 @@ struct LineSearch
                     ok = deltaE_approx + abs_eps_est <= step * armijo_criteria;
                 }
             }
-            else if (use_grad_norm)
+            else if (use_grad_norm || method == "ResidualBacktracking") // ResidualBacktracking.cpp:15-28: always the gradient norm
             {
                 f.gradient(nx, ng);
                 ok = f.grad_norm(ng) < f.grad_norm(old_grad); // Backtracking.cpp:76-80
@@ -365,13 +365,15 @@ struct LineSearch
             total_iterations += cur_iter;
             return step;
         }
+        const bool use_grad_norm = gn < use_grad_norm_tol * f.rescaling(0); // LineSearch.cpp:142
         if (method == "None")
         {
-            f.line_search_end();
-            return step;
+            // NoLineSearch.cpp:11-22: the starting step, announced through solution_changed; the checks below still apply
+            axpy(nx, x, step, dx);
+            f.solution_changed(nx);
         }
-        const bool use_grad_norm = gn < use_grad_norm_tol * f.rescaling(0); // LineSearch.cpp:142
-        step = descent_step(x, dx, f, use_grad_norm, e0, g0, step);
+        else
+            step = descent_step(x, dx, f, use_grad_norm, e0, g0, step);
         total_iterations += cur_iter;
         if (std::isnan(step))
             return NaN;
@@ -666,8 +668,9 @@ void build(psb200_nl_solver &S, const std::string &solver_json, const std::strin
 
     const JValue lsj = jsub(j, "line_search");
     S.ls.method = jgets(lsj, "method", "RobustArmijo");
-    if (S.ls.method != "Backtracking" && S.ls.method != "Armijo" && S.ls.method != "RobustArmijo" && S.ls.method != "None")
-        throw std::runtime_error("Unknown line search " + S.ls.method);
+    if (S.ls.method != "Backtracking" && S.ls.method != "Armijo" && S.ls.method != "RobustArmijo" && S.ls.method != "ResidualBacktracking" &&
+        S.ls.method != "None") // LineSearch.cpp:24-52
+        throw std::runtime_error("Unknown line search " + S.ls.method + "!");
     S.ls.use_grad_norm_tol = jget(lsj, "use_grad_norm_tol", 1e-6);
     S.ls.min_step_size = jget(lsj, "min_step_size", 1e-10);
     S.ls.max_step_size_iter = (int)jget(lsj, "max_step_size_iter", 30);

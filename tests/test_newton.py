@@ -103,6 +103,9 @@ _GD_VARIANTS = [
     {"line_search": {"method": "Backtracking", "default_init_step_size": 0.5, "step_ratio": 0.3}},
     {"line_search": {"method": "Armijo", "min_step_size": 1e-3, "max_step_size_iter": 4}},
     {"line_search": {"method": "None"}},
+    {"line_search": {"method": "ResidualBacktracking"}},
+    {"line_search": {"method": "ResidualBacktracking", "step_ratio": 0.7, "max_step_size_iter": 12}},
+    {"line_search": {"method": "None", "default_init_step_size": 0.05}},
 ]
 
 
@@ -173,15 +176,15 @@ class _Hooked(Quadratic):
 
 @pytest.mark.filterwarnings("ignore::RuntimeWarning")
 @pytest.mark.parametrize("hooks", [dict(cap=0.3), dict(box=0.9), dict(stop_at=-1.0), dict(nan_region=1.5),
-                                   dict(cap=0.5, box=1.2, stop_at=-1.2)])
+                                   dict(cap=0.5, box=1.2, stop_at=-1.2), dict(cap=1e-11)])
 def test_driver_calls_the_problem_hooks_like_the_oracle_on_cpu(psb, hooks):
     """CPU: max_step_size / is_step_valid / line_search_begin / line_search_end / solution_changed / stop
     (LineSearch.cpp:73-254, Solver.cpp:255-582) -- same status or error, bit-identical iterates and the SAME SEQUENCE of
     callback invocations as the restatement, for the three line searches."""
     from oracle import newton_oracle as NO
-    for method in ("Backtracking", "Armijo", "RobustArmijo"):
+    for method in ("Backtracking", "Armijo", "RobustArmijo", "ResidualBacktracking", "None"):
         P = {"solver": "GradientDescent", "grad_norm_tol": 1e-6, "rel_grad_norm_tol": 0, "max_iterations": 300,
-             "line_search": {"method": method}}
+             "line_search": {"method": method, "default_init_step_size": 0.1 if method == "None" else 1.0}}
         x0 = np.random.default_rng(1).uniform(-0.8, 0.8, 12)
         if "nan_region" in hooks:
             x0 = np.clip(3.0 * x0, -1.4, 1.4)
