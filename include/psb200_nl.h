@@ -87,7 +87,10 @@ typedef struct psb200_nl_problem
 } psb200_nl_problem;
 
 /* nonlinear::Solver::create. solver_params: the reference's nonlinear JSON (keys and defaults of
- * nonlinear-solver-spec.json: "solver": "Newton", "line_search": {"method": "RobustArmijo"|"Armijo"|"Backtracking"|"ResidualBacktracking"|"None", ...},
+ * nonlinear-solver-spec.json: "solver": "Newton" | "L-BFGS" | "GradientDescent" (each followed by the GradientDescent fallback,
+ * Solver.cpp:156-181) or a LIST of strategies [{"type": "Newton"|"ProjectedNewton"|"RegularizedNewton"|
+ * "RegularizedProjectedNewton"|"L-BFGS"|"GradientDescent", ...per-strategy parameters}] used in that order (Solver.cpp:147-154),
+ * "line_search": {"method": "RobustArmijo"|"Armijo"|"Backtracking"|"ResidualBacktracking"|"None", ...},
  * "grad_norm_tol", "max_iterations", "norm_type", "newton_decrement_tol", "iterations_per_strategy" (one value or one per
  * strategy + 1, Solver.cpp:232-245), "Newton": {"residual_tolerance", "reg_weight_min", ...}, ...).
  * linear_params: the linear-solver JSON handed to every strategy's linear::Solver ({"solver": "CUDA", "CUDA": {...}}).

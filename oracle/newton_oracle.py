@@ -209,21 +209,47 @@ def minimize(problem, x, params, linsolve):
     nw = params.get("Newton", {})
     res_tol = nw.get("residual_tolerance", 1e-5)
     wmin, wmax, winc = nw.get("reg_weight_min", 1e-8), nw.get("reg_weight_max", 1e8), nw.get("reg_weight_inc", 10)
+    # a strategy: [name, project_to_psd, reg_weight, residual_tolerance, reg_weight_min, reg_weight_max, reg_weight_inc]
     strategies = []
     lbfgs = None
-    if params.get("solver", "Newton") in ("L-BFGS", "LBFGS"):       # Solver.cpp:83-85
-        lbfgs = LbfgsStrategy(params.get("L-BFGS", {}).get("history_size", 6))
-        strategies.append(["L-BFGS", False, 0.0])
-    elif params.get("solver", "Newton") in ("GradientDescent", "gradient_descent"):   # Solver.cpp:86-89: GD alone
-        pass
+    if isinstance(params.get("solver"), (list, tuple)):
+        # Solver.cpp:147-154: the strategies of the list in order, each from its own entry, no GradientDescent fallback;
+        # parameters by extract_param (Utils.cpp:78-84): entry[Type][name], else entry[name], else the /solver/*/ default
+        for e in params["solver"]:
+            t = e["type"]
+
+            def ex(key, name, default, e=e):
+                return e[key][name] if isinstance(e.get(key), dict) and name in e[key] else e.get(name, default)
+            if t in ("Newton", "SparseNewton", "sparse_newton"):
+                strategies.append(["Newton", False, 0.0, ex("Newton", "residual_tolerance", 1e-5), 0, 0, 0])
+            elif t == "ProjectedNewton":
+                strategies.append(["ProjectedNewton", True, 0.0, ex(t, "residual_tolerance", 1e-5), 0, 0, 0])
+            elif t in ("RegularizedNewton", "RegularizedProjectedNewton"):
+                k = "RegularizedNewton"
+                w0 = ex(k, "reg_weight_min", 1e-8)
+                strategies.append(["RegularizedNewton", t == "RegularizedProjectedNewton", w0, ex(k, "residual_tolerance", 1e-5), w0,
+                                   ex(k, "reg_weight_max", 1e8), ex(k, "reg_weight_inc", 10)])
+            elif t in ("L-BFGS", "LBFGS"):
+                lbfgs = LbfgsStrategy(ex("L-BFGS", "history_size", 6))
+                strategies.append(["L-BFGS", False, 0.0, 0, 0, 0, 0])
+            elif t in ("GradientDescent", "gradient_descent"):
+                strategies.append(["GradientDescent", False, 0.0, 0, 0, 0, 0])
+            else:
+                raise RuntimeError("Unrecognized solver type: " + t)
     else:
-        if not nw.get("force_psd_projection", False):
-            strategies.append(["Newton", False, 0.0])
-        if nw.get("use_psd_projection", True):
-            strategies.append(["ProjectedNewton", True, 0.0])
-        if wmin > 0:
-            strategies.append(["RegularizedNewton", nw.get("use_psd_projection_in_regularized", True), wmin])
-    strategies.append(["GradientDescent", False, 0.0])
+        if params.get("solver", "Newton") in ("L-BFGS", "LBFGS"):       # Solver.cpp:83-85
+            lbfgs = LbfgsStrategy(params.get("L-BFGS", {}).get("history_size", 6))
+            strategies.append(["L-BFGS", False, 0.0, 0, 0, 0, 0])
+        elif params.get("solver", "Newton") in ("GradientDescent", "gradient_descent"):   # Solver.cpp:92-94: GD alone
+            pass
+        else:
+            if not nw.get("force_psd_projection", False):
+                strategies.append(["Newton", False, 0.0, res_tol, 0, 0, 0])
+            if nw.get("use_psd_projection", True):
+                strategies.append(["ProjectedNewton", True, 0.0, res_tol, 0, 0, 0])
+            if wmin > 0:
+                strategies.append(["RegularizedNewton", nw.get("use_psd_projection_in_regularized", True), wmin, res_tol, wmin, wmax, winc])
+        strategies.append(["GradientDescent", False, 0.0, 0, 0, 0, 0])   # Solver.cpp:176-181
     per = params.get("iterations_per_strategy", 5)                  # Solver.cpp:232-245: one value or one per strategy + 1
     if isinstance(per, (list, tuple)):
         if len(per) != len(strategies) + 1:
@@ -248,13 +274,13 @@ def minimize(problem, x, params, linsolve):
     def handle_error(s):
         if s[0] != "RegularizedNewton":
             return False
-        s[2] *= winc
-        return s[2] < wmax
+        s[2] *= s[6]
+        return s[2] < s[5]
 
     def reset():
         for s in strategies:
             if s[0] == "RegularizedNewton":
-                s[2] = wmin
+                s[2] = s[4]
         if lbfgs is not None:
             lbfgs.reset()
 
@@ -297,7 +323,7 @@ def minimize(problem, x, params, linsolve):
                 dx, it = linsolve(H, -grad, dx.copy())
                 lin_iters.append(it)
                 r = float(np.linalg.norm(H @ dx + grad))
-                ok = not (math.isnan(r) or r > res_tol)
+                ok = not (math.isnan(r) or r > s[3])
             except ArithmeticError:
                 ok = False
         cur["xDelta"] = _step_norm(problem, dx, nt)

@@ -681,8 +681,68 @@ void build(psb200_nl_solver &S, const std::string &solver_json, const std::strin
     S.ls.armijo_c = jget(jsub(lsj, "Armijo"), "c", 1e-4);
     S.ls.delta_relative_tolerance = jget(jsub(lsj, "RobustArmijo"), "delta_relative_tolerance", 0.1);
 
-    S.solver_name = jgets(j, "solver", "Newton");
-    if (S.solver_name == "Newton" || S.solver_name == "SparseNewton" || S.solver_name == "sparse_newton")
+    if (j.contains("solver") && j.at("solver").kind == JValue::Arr)
+    {
+        // Solver.cpp:147-154: "solver": [{"type": "Newton", ...}, {"type": "L-BFGS"}, ...] -- the strategies in the order
+        // given, each built from its own entry (create_solver, Solver.cpp:34-106), and NO automatic GradientDescent fallback.
+        // Parameters follow extract_param (Utils.cpp:78-84): entry[Type][name] when the entry has a Type object, else
+        // entry[name], else the default of /solver/*/name (nonlinear-solver-spec.json).
+        S.solver_name = "list";
+        int device = -1;
+        if (!linear_json.empty())
+        {
+            const JValue lj = psb::JParser::parse(linear_json);
+            if (lj.is_obj() && lj.contains("CUDA") && lj.at("CUDA").is_obj() && lj.at("CUDA").contains("device"))
+                device = (int)lj.at("CUDA").at("device").as_num();
+        }
+        for (const JValue &e : j.at("solver").arr)
+        {
+            if (!e.is_obj() || !e.contains("type"))
+                throw std::runtime_error("every entry of the \"solver\" list needs a \"type\"");
+            const std::string t = e.at("type").as_str();
+            auto ex = [&](const char *key, const char *name, double def) {
+                if (e.contains(key) && e.at(key).is_obj() && e.at(key).contains(name))
+                    return e.at(key).at(name).as_num();
+                return jget(e, name, def);
+            };
+            if (t == "Newton" || t == "SparseNewton" || t == "sparse_newton")
+                S.strategies.push_back(std::make_unique<NewtonStrategy>(0, false, ex("Newton", "residual_tolerance", 1e-5), linear_json));
+            else if (t == "ProjectedNewton")
+                S.strategies.push_back(std::make_unique<NewtonStrategy>(1, true, ex("ProjectedNewton", "residual_tolerance", 1e-5), linear_json));
+            else if (t == "RegularizedNewton" || t == "RegularizedProjectedNewton")
+            {
+                const char *k = "RegularizedNewton";
+                const double wmin = ex(k, "reg_weight_min", 1e-8), wmax = ex(k, "reg_weight_max", 1e8), winc = ex(k, "reg_weight_inc", 10);
+                if (wmin <= 0) // Newton.cpp:117-118
+                    throw std::runtime_error("Newton reg_weight_min must be  > 0");
+                if (winc <= 1)
+                    throw std::runtime_error("Newton reg_weight_inc must be > 1");
+                if (wmax <= wmin)
+                    throw std::runtime_error("Newton reg_weight_max must be > reg_weight_min");
+                auto r = std::make_unique<NewtonStrategy>(2, t == "RegularizedProjectedNewton", ex(k, "residual_tolerance", 1e-5), linear_json);
+                r->reg_weight_min = wmin;
+                r->reg_weight_max = wmax;
+                r->reg_weight_inc = winc;
+                r->reg_weight = wmin;
+                S.strategies.push_back(std::move(r));
+            }
+            else if (t == "LBFGS" || t == "L-BFGS")
+            {
+                const int history = (int)ex("L-BFGS", "history_size", 6);
+                if (history <= 0)
+                    throw std::runtime_error("L-BFGS history_size must be >=1, instead got " + std::to_string(history));
+                S.strategies.push_back(std::make_unique<LbfgsStrategy>(history, device));
+            }
+            else if (t == "GradientDescent" || t == "gradient_descent")
+                S.strategies.push_back(std::make_unique<GradientDescent>());
+            else
+                throw std::runtime_error("Unrecognized solver type: " + t +
+                                         " (this driver provides Newton, ProjectedNewton, Regularized[Projected]Newton, L-BFGS and GradientDescent)");
+        }
+        if (S.strategies.empty())
+            throw std::runtime_error("the \"solver\" list is empty");
+    }
+    else if ((S.solver_name = jgets(j, "solver", "Newton")) == "Newton" || S.solver_name == "SparseNewton" || S.solver_name == "sparse_newton")
     {
         // Newton.cpp:14-58
         const JValue nj = jsub(j, "Newton");

@@ -300,6 +300,74 @@ def test_iterations_per_strategy_list_is_validated(psb):
     psb.NonlinearSolver.create({"solver": "GradientDescent", "iterations_per_strategy": [1, 2]}, {"solver": "CUDA"})
 
 
+_GD = {"type": "GradientDescent"}
+_LIST_CASES = [
+    # non-final strategies may halve the step only twice: the line search fails on Rosenbrock, the next strategy takes over
+    # (the last one with the *_final limits, LineSearch.hpp current_min_step_size / current_max_step_size_iter) and after
+    # iterations_per_strategy[k] successful steps the solver returns to strategy 0 (Solver.cpp:512-522)
+    ({"solver": [_GD, _GD], "line_search": {"method": "Backtracking", "max_step_size_iter": 2}, "iterations_per_strategy": [3, 2, 1]}, 4),
+    ({"solver": [_GD, _GD, _GD], "line_search": {"method": "Armijo", "max_step_size_iter": 3, "max_step_size_iter_final": 40},
+      "iterations_per_strategy": 2}, 4),
+    ({"solver": [_GD, _GD], "line_search": {"method": "RobustArmijo", "min_step_size": 0.2, "min_step_size_final": 1e-12},
+      "iterations_per_strategy": [1, 4, 1]}, 6),
+    ({"solver": [_GD], "line_search": {"method": "Backtracking"}}, 5),
+    ({"solver": [_GD, _GD], "line_search": {"method": "Backtracking", "max_step_size_iter": 1, "max_step_size_iter_final": 1}}, 4),
+]
+
+
+@pytest.mark.filterwarnings("ignore::RuntimeWarning")
+@pytest.mark.parametrize("case", range(len(_LIST_CASES)))
+def test_driver_strategy_fallback_matches_oracle_on_cpu(psb, case):
+    """CPU: "solver" as a LIST of strategies (Solver.cpp:147-154; no automatic GradientDescent fallback) made of
+    GradientDescent entries drives the strategy machinery without a linear solve: line-search failure -> next strategy,
+    final-strategy limits, return to strategy 0 after iterations_per_strategy[k] steps, failure on the last strategy.
+    Same status / error, iteration count, total line-search iterations and bit-identical iterates as the restatement."""
+    from oracle import newton_oracle as NO
+    pv, n = _LIST_CASES[case]
+    prob = Rosenbrock(n)
+    P = dict({"grad_norm_tol": 1e-5, "rel_grad_norm_tol": 0, "max_iterations": 60, "allow_out_of_iterations": True}, **pv)
+    x0 = np.random.default_rng(2).uniform(-1, 1, n)
+    po, pd = _Recorder(prob), _Recorder(prob)
+    xo = eo = ed = None
+    io = info = {}
+    try:
+        xo, io = NO.minimize(po, x0.copy(), P, direct)
+    except RuntimeError as e:
+        eo = str(e)
+    x = x0.copy()
+    s = psb.NonlinearSolver.create(P, {"solver": "CUDA"})
+    try:
+        s.minimize(pd, x)
+        info = s.get_info()
+    except RuntimeError as e:
+        ed = str(e)
+    assert (eo is None) == (ed is None)
+    if eo is None:
+        assert info["iterations"] == io["iterations"] and np.array_equal(x, xo)
+        assert info["line_search_iterations"] == io["line_search_iterations"] and info["final_strategy"] == io["final_strategy"]
+        assert info["status"] == _STATUS_TEXT[io["status"]]
+    else:
+        assert eo.split(";")[0] in ed
+    assert len(po.steps) == len(pd.steps) and all(a[0] == b[0] and np.array_equal(a[1], b[1]) for a, b in zip(po.steps, pd.steps))
+
+
+def test_solver_list_is_validated(psb):
+    lin = {"solver": "CUDA"}
+    for bad, msg in [([], "empty"), ([{"x": 1}], "type"), ([{"type": "ADAM"}], "Unrecognized solver type: ADAM"),
+                     ([{"type": "RegularizedNewton", "reg_weight_min": 0}], "reg_weight_min"),
+                     ([{"type": "L-BFGS", "history_size": 0}], "history_size"),
+                     ([{"type": "Newton", "residual_tolerance": -1}], "residual_tolerance")]:
+        with pytest.raises(RuntimeError, match=msg):
+            psb.NonlinearSolver.create({"solver": bad}, lin)
+    # every provided type, per-entry parameters in both spellings of extract_param (Utils.cpp:78-84)
+    psb.NonlinearSolver.create({"solver": [{"type": "Newton", "residual_tolerance": 1e-6}, {"type": "ProjectedNewton"},
+                                           {"type": "RegularizedNewton", "RegularizedNewton": {"reg_weight_min": 1e-6}},
+                                           {"type": "RegularizedProjectedNewton"}, {"type": "L-BFGS", "history_size": 4},
+                                           {"type": "GradientDescent"}], "iterations_per_strategy": [1, 2, 3, 4, 5, 6, 7]}, lin)
+    with pytest.raises(RuntimeError, match="Invalit iter_per_strategy size: 2!=3"):
+        psb.NonlinearSolver.create({"solver": [_GD, _GD], "iterations_per_strategy": [1, 2]}, lin)
+
+
 class HugeOffset(Base):
     """f = C + 0.5 |x - 1|^2 with C = 1e17: the energy difference of a good step drowns in the rounding error of C, so plain
     Armijo (Armijo.cpp:20-32) rejects every step size while RobustArmijo's gradient-based estimate (RobustArmijo.cpp:30-44)
