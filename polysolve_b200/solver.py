@@ -83,6 +83,10 @@ class Solver:
         import scipy.sparse as sp
         if not sp.isspmatrix_csc(A):
             A = sp.csc_matrix(A)
+        if not A.has_canonical_format:
+            # StiffnessMatrix is a compressed Eigen matrix: row indices ascending inside a column, no duplicates
+            A = A.copy()
+            A.sum_duplicates()
         outer = np.ascontiguousarray(A.indptr, np.int32)
         inner = np.ascontiguousarray(A.indices, np.int32)
         vals = np.ascontiguousarray(A.data, np.float64)
@@ -92,15 +96,27 @@ class Solver:
         n, outer, inner, _ = self._csc(A)
         self.analyze_pattern_raw(n, outer, inner, precond_num)
 
+    @staticmethod
+    def _raw_sizes(n, outer, inner, vals=None):
+        """The C ABI takes plain pointers and sizes: check here that the arrays are as long as those sizes say."""
+        if n < 0 or len(outer) != n + 1:
+            raise RuntimeError("outer must hold n + 1 column pointers")
+        nnz = int(outer[n])
+        if nnz < 0 or len(inner) < nnz or (vals is not None and len(vals) < nnz):
+            raise RuntimeError("inner / values are shorter than outer[n] entries")
+        return nnz
+
     def analyze_pattern_raw(self, n, outer, inner, precond_num):
-        self._check(self._L.psb200_analyze_pattern_csc(self._h, n, int(outer[n]), outer, inner, int(precond_num)))
+        nnz = self._raw_sizes(n, outer, inner)
+        self._check(self._L.psb200_analyze_pattern_csc(self._h, n, nnz, outer, inner, int(precond_num)))
 
     def factorize(self, A):
         n, outer, inner, vals = self._csc(A)
         self.factorize_raw(n, outer, inner, vals)
 
     def factorize_raw(self, n, outer, inner, vals):
-        self._check(self._L.psb200_factorize_csc(self._h, n, int(outer[n]), outer, inner, vals))
+        nnz = self._raw_sizes(n, outer, inner, vals)
+        self._check(self._L.psb200_factorize_csc(self._h, n, nnz, outer, inner, vals))
 
     def factorize_device(self, n, nnz, vals_ptr, diag_shift=0.0):
         """factorize() with the values already in GPU memory (CSC order of the analyzed pattern); diag_shift is

@@ -77,8 +77,15 @@ def test_protocol_errors(psb):
         s.solve(b, x)  # no factorize yet (and, on a CPU box, no device)
     with pytest.raises(RuntimeError, match="not compressed|null|no CUDA device"):
         outer = np.array([1, 2, 3, 4, 5], np.int32)
-        inner = np.zeros(4, np.int32)
+        inner = np.zeros(5, np.int32)
         s.analyze_pattern_raw(4, outer, inner, 4)
+    # the Python mirror checks the array lengths against the sizes it passes (the C ABI takes plain pointers)
+    with pytest.raises(RuntimeError, match="shorter than outer"):
+        s.analyze_pattern_raw(4, np.array([0, 1, 2, 3, 5], np.int32), np.zeros(4, np.int32), 4)
+    with pytest.raises(RuntimeError, match="shorter than outer"):
+        s.factorize_raw(4, np.array([0, 1, 2, 3, 4], np.int32), np.zeros(4, np.int32), np.zeros(3))
+    with pytest.raises(RuntimeError, match="n \\+ 1 column pointers"):
+        s.analyze_pattern_raw(4, np.array([0, 1, 2, 3], np.int32), np.zeros(4, np.int32), 4)
 
 
 def test_malformed_outer_array_is_rejected_before_any_kernel(psb):
