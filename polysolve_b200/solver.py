@@ -99,7 +99,7 @@ class Solver:
     @staticmethod
     def _raw_sizes(n, outer, inner, vals=None):
         """The C ABI takes plain pointers and sizes: check here that the arrays are as long as those sizes say."""
-        if n < 0 or len(outer) != n + 1:
+        if n < 0 or len(outer) < n + 1:
             raise RuntimeError("outer must hold n + 1 column pointers")
         nnz = int(outer[n])
         if nnz < 0 or len(inner) < nnz or (vals is not None and len(vals) < nnz):
