@@ -103,6 +103,15 @@ int psb200_nl_destroy(psb200_nl_handle h);
  * driver all-gathers every Newton step (psb200_dist_allgather), so each rank keeps the whole iterate and evaluates the
  * Problem redundantly; the Problem must then be deterministic across ranks. `lin` is the linear solver handle of psb200.h (a psb200_handle). */
 int psb200_nl_set_linear_solver_hook(psb200_nl_handle h, void (*hook)(void *user, void *lin), void *user);
+/* Solver::set_iteration_callback (Solver.hpp: "Iteration callback"; Solver.cpp:548-552): called once per completed
+ * iteration with the current Criteria (alpha = the accepted line-search step); non-zero ends the solve with status
+ * "ObjectiveCustomStop" (not an error). NULL removes it. The reference's test "iteration-callback"
+ * (tests/test_nonlinear_solver.cpp:714-754) is replayed in tests/test_newton.py. */
+int psb200_nl_set_iteration_callback(psb200_nl_handle h, int (*callback)(void *user, const psb200_nl_criteria *state), void *user);
+/* Solver::set_direction_filter (Solver.hpp:80-86; Solver.cpp:353-358,392-403): filter(user, x, dx_inout, n) is applied to
+ * every successfully computed update direction before it is vetted and searched, and to -grad when descent is measured
+ * (dx . grad becomes -dx . filter(-grad)). NULL removes it. */
+int psb200_nl_set_direction_filter(psb200_nl_handle h, void (*filter)(void *user, const double *x, double *dx_inout, int64_t n), void *user);
 /* nonlinear::Solver::minimize(problem, x): x is in/out. Returns 0 when the loop ended with a converged status;
  * non-zero (message in psb200_nl_last_error) where the reference throws (NaN, iteration limit without
  * allow_out_of_iterations, failure on the last strategy). x always holds the last iterate. */

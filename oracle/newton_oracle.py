@@ -194,8 +194,9 @@ class LbfgsStrategy:
         return d
 
 
-def minimize(problem, x, params, linsolve):
-    """Returns (x, info). Raises RuntimeError where the reference throws."""
+def minimize(problem, x, params, linsolve, iteration_callback=None, direction_filter=None):
+    """Returns (x, info). Raises RuntimeError where the reference throws. iteration_callback(state) -> bool and
+    direction_filter(x, dx) (in place) are Solver::set_iteration_callback / set_direction_filter (Solver.hpp:76-86)."""
     adv = params.get("advanced", {})
     nt = params.get("norm_type", "L2")
     rg, rs, re = _rescaling(problem, "grad", nt), _rescaling(problem, "step", nt), _rescaling(problem, "energy", nt)
@@ -326,6 +327,9 @@ def minimize(problem, x, params, linsolve):
                 ok = not (math.isnan(r) or r > s[3])
             except ArithmeticError:
                 ok = False
+        if direction_filter is not None and ok:               # Solver.cpp:353-358
+            dx = np.array(dx, float)
+            direction_filter(x, dx)
         cur["xDelta"] = _step_norm(problem, dx, nt)
         if cur["iterations"] == 0:
             dx0n = cur["xDelta"]
@@ -340,7 +344,12 @@ def minimize(problem, x, params, linsolve):
             if not keep_going():
                 break
             continue
-        cur["xDeltaDotGrad"] = float(dx @ grad)
+        if direction_filter is not None:                      # Solver.cpp:392-403
+            ng = -grad
+            direction_filter(x, ng)
+            cur["xDeltaDotGrad"] = -float(dx @ ng)
+        else:
+            cur["xDeltaDotGrad"] = float(dx @ grad)
         if stop["newtonDecrement"] > 0:                       # Solver.cpp:409-423: 1/2 x^T H x (sic), NaN on failure
             try:
                 cur["newtonDecrement"] = 0.5 * float(x @ (sp.csc_matrix(problem.hessian(x, False)) @ x))
@@ -384,6 +393,8 @@ def minimize(problem, x, params, linsolve):
         if problem.stop(x):
             status = "ObjectiveCustomStop"
         cur["fDeltaCount"] = cur["fDeltaCount"] + 1 if cur["fDelta"] < stop["fDelta"] else 0
+        if iteration_callback is not None and iteration_callback(dict(cur)):   # Solver.cpp:548-552
+            status = "ObjectiveCustomStop"
         cur["iterations"] += 1
         if cur["iterations"] >= stop["iterations"]:
             status = "IterationLimit"

@@ -31,7 +31,7 @@ SYMBOLS = [
     # include/psb200_nl.h
     "psb200_nl_create", "psb200_nl_destroy", "psb200_nl_minimize", "psb200_nl_get_info", "psb200_nl_last_error",
     "psb200_lbfgs_create", "psb200_lbfgs_destroy", "psb200_lbfgs_reset", "psb200_lbfgs_direction", "psb200_lbfgs_direction_device",
-    "psb200_lbfgs_last_error", "psb200_nl_set_linear_solver_hook",
+    "psb200_lbfgs_last_error", "psb200_nl_set_linear_solver_hook", "psb200_nl_set_iteration_callback", "psb200_nl_set_direction_filter",
     # include/psb200_problems.h
     "psb200_nh_create", "psb200_nh_destroy", "psb200_nh_pattern", "psb200_nh_value", "psb200_nh_gradient", "psb200_nh_hessian_device",
     "psb200_nh_hessian_host", "psb200_nh_last_error",

@@ -632,6 +632,11 @@ struct psb200_nl_solver
     std::string solver_name = "Newton";
     int norm_type = 1;
     Status status = Status::NotStarted;
+    // Solver::set_iteration_callback / set_direction_filter (Solver.hpp:76-86)
+    int (*iteration_callback)(void *, const psb200_nl_criteria *) = nullptr;
+    void *iteration_user = nullptr;
+    void (*direction_filter)(void *, const double *, double *, int64_t) = nullptr;
+    void *filter_user = nullptr;
 };
 
 namespace {
@@ -885,6 +890,8 @@ bool minimize(psb200_nl_solver &S, const Problem &f, std::vector<double> &x)
                 break;
             }
         }
+        if (S.direction_filter && dir_ok) // Solver.cpp:353-358
+            S.direction_filter(S.filter_user, x.data(), dx.data(), f.n);
         cur.xDelta = f.step_norm(dx);
         if (cur.iterations == 0)
         {
@@ -905,7 +912,17 @@ bool minimize(psb200_nl_solver &S, const Problem &f, std::vector<double> &x)
             S.status = Status::Continue;
             continue;
         }
-        cur.xDeltaDotGrad = dot(dx, grad);
+        if (S.direction_filter)
+        {
+            // Solver.cpp:392-403: with a filter, descent is measured against the filtered steepest-descent direction
+            std::vector<double> neg_grad(grad.size());
+            for (size_t i = 0; i < grad.size(); ++i)
+                neg_grad[i] = -grad[i];
+            S.direction_filter(S.filter_user, x.data(), neg_grad.data(), f.n);
+            cur.xDeltaDotGrad = -dot(dx, neg_grad);
+        }
+        else
+            cur.xDeltaDotGrad = dot(dx, grad);
         if (stop.newtonDecrement > 0)
             cur.newtonDecrement = f.half_xHx(x); // Solver.cpp:409-423 (x^T H x / 2, NaN when the Hessian cannot be assembled)
         if (!f.is_residual() && S.strategies[strategy]->is_direction_descent() && cur.gradNorm != 0 && cur.xDeltaDotGrad >= 0)
@@ -961,6 +978,12 @@ bool minimize(psb200_nl_solver &S, const Problem &f, std::vector<double> &x)
         if (f.stop(x))
             S.status = Status::ObjectiveCustomStop;
         cur.fDeltaCount = (cur.fDelta < stop.fDelta) ? cur.fDeltaCount + 1 : 0;
+        if (S.iteration_callback)
+        {
+            const psb200_nl_criteria c = as_c(cur);
+            if (S.iteration_callback(S.iteration_user, &c)) // Solver.cpp:548-552
+                S.status = Status::ObjectiveCustomStop;
+        }
         if (++cur.iterations >= stop.iterations)
             S.status = Status::IterationLimit;
     } while (f.callback(as_c(cur), x) && S.status == Status::Continue); // Solver.cpp:558
@@ -1038,6 +1061,24 @@ int psb200_nl_set_linear_solver_hook(psb200_nl_handle h, void (*hook)(void *user
     for (auto &st : h->strategies)
         if (auto *ns = dynamic_cast<NewtonStrategy *>(st.get()))
             hook(user, ns->lin);
+    return PSB200_OK;
+}
+
+int psb200_nl_set_iteration_callback(psb200_nl_handle h, int (*callback)(void *user, const psb200_nl_criteria *state), void *user)
+{
+    if (!h)
+        return PSB200_ERR_INVALID;
+    h->iteration_callback = callback;
+    h->iteration_user = user;
+    return PSB200_OK;
+}
+
+int psb200_nl_set_direction_filter(psb200_nl_handle h, void (*filter)(void *user, const double *x, double *dx_inout, int64_t n), void *user)
+{
+    if (!h)
+        return PSB200_ERR_INVALID;
+    h->direction_filter = filter;
+    h->filter_user = user;
     return PSB200_OK;
 }
 

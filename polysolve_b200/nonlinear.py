@@ -83,6 +83,8 @@ _ISRES = C.CFUNCTYPE(C.c_int, C.c_void_p)
 _CALLB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(_CCriteria), _f64p, C.c_int64)
 _NORM = C.CFUNCTYPE(C.c_double, C.c_void_p, _f64p, C.c_int64, C.c_int)
 _RESC = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_int, C.c_int)
+_ITCB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(_CCriteria))
+_FILT = C.CFUNCTYPE(None, C.c_void_p, _f64p, _f64p, C.c_int64)
 
 
 class _CProblem(C.Structure):
@@ -142,6 +144,36 @@ class NonlinearSolver:
             raise errors[0]
         if rc:
             raise RuntimeError("psb200_nl_set_linear_solver_hook failed")
+
+    def set_iteration_callback(self, fn):
+        """Solver::set_iteration_callback: fn(state: dict of the solver's Criteria) -> bool, True stops the solve with status
+        "Objective function specified to stop" (no error). None removes it."""
+        self._L.psb200_nl_set_iteration_callback.argtypes = [C.c_void_p, _ITCB, C.c_void_p]
+        self._it_errors = []
+
+        def cb(_, st):
+            try:
+                return 1 if fn({k: getattr(st.contents, k) for k, _t in _CCriteria._fields_}) else 0
+            except Exception as e:  # noqa: BLE001 -- exceptions must not cross the C frame
+                self._it_errors.append(e)
+                return 1
+        self._it_cb = _ITCB(cb) if fn is not None else C.cast(None, _ITCB)   # kept alive with the solver
+        if self._L.psb200_nl_set_iteration_callback(self._h, self._it_cb, None):
+            raise RuntimeError("psb200_nl_set_iteration_callback failed")
+
+    def set_direction_filter(self, fn):
+        """Solver::set_direction_filter: fn(x, dx) edits dx in place (numpy views). None removes it."""
+        self._L.psb200_nl_set_direction_filter.argtypes = [C.c_void_p, _FILT, C.c_void_p]
+        self._it_errors = getattr(self, "_it_errors", [])
+
+        def cb(_, xp, dp, nn):
+            try:
+                fn(_vec(xp, nn), _vec(dp, nn))
+            except Exception as e:  # noqa: BLE001
+                self._it_errors.append(e)
+        self._filt_cb = _FILT(cb) if fn is not None else C.cast(None, _FILT)
+        if self._L.psb200_nl_set_direction_filter(self._h, self._filt_cb, None):
+            raise RuntimeError("psb200_nl_set_direction_filter failed")
 
     def minimize(self, problem, x):
         """x is in/out (float64, contiguous). Raises RuntimeError where the reference throws."""
@@ -263,6 +295,9 @@ class NonlinearSolver:
                        opt("grad_norm", _NORM, grad_norm), opt("step_norm", _NORM, step_norm),
                        _RESC(rescaling) if has_resc else C.cast(None, _RESC))
         rc = self._L.psb200_nl_minimize(self._h, C.byref(cp), x, n)
+        errors.extend(getattr(self, "_it_errors", []))
+        if getattr(self, "_it_errors", None):
+            self._it_errors.clear()
         if errors:
             raise errors[0]
         if rc:

@@ -368,6 +368,131 @@ def test_solver_list_is_validated(psb):
         psb.NonlinearSolver.create({"solver": [_GD, _GD], "iterations_per_strategy": [1, 2]}, lin)
 
 
+class RefQuadratic(Base):
+    """tests/test_nonlinear_solver.cpp:78-129 QuadraticProblem: (x0+2)^2 + (x1-3)^2 + (x2-1)^2, minimum (-2, 3, 1)."""
+    n = 3
+    def value(self, x): return float((x[0] + 2) ** 2 + (x[1] - 3) ** 2 + (x[2] - 1) ** 2)
+    def gradient(self, x): return np.array([2 * (x[0] + 2), 2 * (x[1] - 3), 2 * (x[2] - 1)])
+    def hessian(self, x, psd=False): return 2 * sp.identity(3, format="csc")
+    def solutions(self): return [np.array([-2.0, 3.0, 1.0])]
+
+
+class Beale(Base):
+    """tests/test_nonlinear_solver.cpp:207-241 Beale, minimum (3, 0.5)."""
+    n = 2
+    def _t(self, x): return [c - x[0] + x[0] * x[1] ** k for k, c in ((1, 1.5), (2, 2.25), (3, 2.625))]
+    def value(self, x): return float(sum(t * t for t in self._t(x)))
+    def gradient(self, x):
+        t = self._t(x)
+        d0 = [-1 + x[1] ** k for k in (1, 2, 3)]
+        d1 = [k * x[0] * x[1] ** (k - 1) for k in (1, 2, 3)]
+        return np.array([2 * sum(a * b for a, b in zip(t, d0)), 2 * sum(a * b for a, b in zip(t, d1))])
+    def hessian(self, x, psd=False):
+        t = self._t(x)
+        d0 = [-1 + x[1] ** k for k in (1, 2, 3)]
+        d1 = [k * x[0] * x[1] ** (k - 1) for k in (1, 2, 3)]
+        d01 = [k * x[1] ** (k - 1) for k in (1, 2, 3)]
+        d11 = [k * (k - 1) * x[0] * x[1] ** (k - 2) if k > 1 else 0.0 for k in (1, 2, 3)]
+        h00 = 2 * sum(a * a for a in d0)
+        h01 = 2 * sum(a * b + c * d for a, b, c, d in zip(d0, d1, t, d01))
+        h11 = 2 * sum(b * b + c * d for b, c, d in zip(d1, t, d11))
+        return sp.csc_matrix(np.array([[h00, h01], [h01, h11]]))
+    def solutions(self): return [np.array([3.0, 0.5])]
+
+
+def test_reference_problem_derivatives():
+    """the hand-written derivatives of the replayed problems against central differences"""
+    rng = np.random.default_rng(4)
+    for prob in (RefQuadratic(), Beale(), Rosenbrock(10), Sphere(10)):
+        x = rng.uniform(-1, 1, prob.n)
+        g = prob.gradient(x)
+        H = prob.hessian(x).toarray()
+        for i in range(prob.n):
+            e = np.zeros(prob.n)
+            e[i] = 1e-6
+            assert abs((prob.value(x + e) - prob.value(x - e)) / 2e-6 - g[i]) < 1e-5 * max(1, abs(g[i]))
+            assert np.abs((prob.gradient(x + e) - prob.gradient(x - e)) / 2e-6 - H[:, i]).max() < 1e-4 * max(1, np.abs(H).max())
+
+
+@pytest.mark.filterwarnings("ignore::RuntimeWarning")
+@pytest.mark.parametrize("method", ["Armijo", "RobustArmijo", "Backtracking", "ResidualBacktracking", "None"])
+def test_reference_nonlinear_test_replayed_with_gradient_descent_on_cpu(psb, method):
+    """The reference's TEST_CASE("nonlinear") (tests/test_nonlinear_solver.cpp:262-349,422-426) for the solver that needs no
+    GPU: every problem x every available line search from x = 0 with max_iterations 1000, rel_grad_norm_tol 0; an
+    exception (no convergence) is tolerated exactly as there, but a run that RETURNS must satisfy the reference's check
+    min_sol |x - sol| < 1e-7 or |grad| < 1e-7 -- and the driver must agree with the restatement on which runs return."""
+    from oracle import newton_oracle as NO
+    P = {"solver": "GradientDescent", "line_search": {"method": method}, "max_iterations": 1000, "rel_grad_norm_tol": 0}
+    returned = 0
+    for prob in (RefQuadratic(), Rosenbrock(10), Sphere(10), Beale()):
+        x = np.zeros(prob.n)
+        s = psb.NonlinearSolver.create(P, {"solver": "CUDA"})
+        try:
+            s.minimize(prob, x)
+            ok = True
+        except RuntimeError:
+            ok = False
+        try:
+            xo, _ = NO.minimize(prob, np.zeros(prob.n), P, direct)
+            oko = True
+        except RuntimeError:
+            oko = False
+        assert ok == oko
+        if ok:
+            returned += 1
+            assert np.array_equal(x, xo)
+            err = min(np.linalg.norm(x - sol) for sol in prob.solutions())
+            if err >= 1e-7:
+                err = np.linalg.norm(prob.gradient(x))
+            assert err < 1e-7, (type(prob).__name__, method, err)
+    assert returned >= (0 if method == "None" else 2)     # the quadratic bowls converge with every real line search
+
+
+def test_reference_iteration_callback_test_replayed_on_cpu(psb):
+    """The reference's TEST_CASE("iteration-callback") (tests/test_nonlinear_solver.cpp:714-754) with GradientDescent in
+    place of Newton (the strategy that runs without a GPU; the callback sits in the shared outer loop): it fires every
+    iteration with a finite positive line-search alpha, asks to stop at iterations >= 2, the solver returns WITHOUT
+    throwing (ObjectiveCustomStop) before it has converged; driver == restatement."""
+    from oracle import newton_oracle as NO
+    P = {"solver": "GradientDescent", "line_search": {"method": "Backtracking"}, "max_iterations": 100, "rel_grad_norm_tol": 0}
+    prob = Rosenbrock(10)
+    calls, calls_o = [], []
+    s = psb.NonlinearSolver.create(P, {"solver": "CUDA"})
+    s.set_iteration_callback(lambda st: (calls.append(dict(st)), st["iterations"] >= 2)[1])
+    x = np.zeros(prob.n)
+    s.minimize(prob, x)                                            # REQUIRE_NOTHROW
+    assert 1 <= len(calls) <= 4 and all(np.isfinite(c["alpha"]) and c["alpha"] > 0 for c in calls)
+    assert np.linalg.norm(prob.gradient(x)) > 1e-7                 # stopped before converging
+    assert s.get_info()["status"] == "Objective function specified to stop"
+    xo, io = NO.minimize(prob, np.zeros(prob.n), P, direct, iteration_callback=lambda st: (calls_o.append(dict(st)), st["iterations"] >= 2)[1])
+    assert io["status"] == "ObjectiveCustomStop" and np.array_equal(x, xo) and len(calls) == len(calls_o)
+    assert [c["alpha"] for c in calls] == [c["alpha"] for c in calls_o] and [c["iterations"] for c in calls] == [c["iterations"] for c in calls_o]
+    s.set_iteration_callback(None)                                 # removed: runs to the iteration limit, which throws
+    with pytest.raises(RuntimeError, match="Reached iteration limit"):
+        s.minimize(prob, np.zeros(prob.n))
+
+
+def test_direction_filter_matches_oracle_on_cpu(psb):
+    """Solver::set_direction_filter (Solver.hpp:80-86; Solver.cpp:353-358,392-403): a filter that pins the first three
+    dofs. They never move, descent is measured on the filtered gradient, driver == restatement bit for bit."""
+    from oracle import newton_oracle as NO
+    P = {"solver": "GradientDescent", "line_search": {"method": "Backtracking"}, "max_iterations": 400, "grad_norm_tol": 1e-9,
+         "rel_grad_norm_tol": 0, "x_delta_tol": 1e-6, "allow_non_grad_convergence": True}
+    prob = Quadratic(12)
+    x0 = np.random.default_rng(3).uniform(-1, 1, 12)
+
+    def pin(x, dx):
+        dx[:3] = 0.0
+    s = psb.NonlinearSolver.create(P, {"solver": "CUDA"})
+    s.set_direction_filter(pin)
+    x = x0.copy()
+    s.minimize(prob, x)
+    xo, io = NO.minimize(prob, x0.copy(), P, direct, direction_filter=pin)
+    assert np.array_equal(x[:3], x0[:3]) and np.array_equal(x, xo) and s.get_info()["iterations"] == io["iterations"]
+    assert np.abs(prob.gradient(x)[3:]).max() < 1e-5               # minimised over the free dofs
+    assert s.get_info()["status"] == _STATUS_TEXT[io["status"]]
+
+
 class HugeOffset(Base):
     """f = C + 0.5 |x - 1|^2 with C = 1e17: the energy difference of a good step drowns in the rounding error of C, so plain
     Armijo (Armijo.cpp:20-32) rejects every step size while RobustArmijo's gradient-based estimate (RobustArmijo.cpp:30-44)
