@@ -1,0 +1,34 @@
+#!/bin/bash
+# Host code of libpsb200.so under AddressSanitizer + UBSan, no GPU needed: newton.cpp, market.cpp and the host parts of
+# dist.cu (plan builder) and capi.cu are rebuilt instrumented into a scratch directory, linked with the regular device
+# objects, and the CPU tests that exercise them (Newton driver vs the restatement, Matrix Market reader incl. hostile
+# files, host plan incl. corrupted index arrays, parameter parser) run against that library.
+set -e
+cd "$(dirname "$0")/.."
+OUT=gpurun_out/asan
+mkdir -p $OUT
+C=polysolve_b200/csrc
+make -C $C libpsb200.so > /dev/null
+SAN="-fsanitize=address,undefined -fno-omit-frame-pointer"
+for f in newton market; do /usr/bin/g++ -O1 -g -std=c++17 -fPIC $SAN -c $C/$f.cpp -o $OUT/$f.o; done
+for f in dist capi; do
+  /usr/local/cuda/bin/nvcc -O1 -std=c++17 -gencode arch=compute_100a,code=sm_100a --expt-relaxed-constexpr -ccbin /usr/bin/g++ \
+    -Xcompiler -fPIC,-fsanitize=address,-fno-omit-frame-pointer -c $C/$f.cu -o $OUT/$f.o
+done
+/usr/local/cuda/bin/nvcc -shared -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -Xcompiler -fsanitize=address -o $OUT/libpsb200.so \
+  $OUT/capi.o $C/solver.o $C/amg.o $C/amg_dist.o $C/spgemm.o $C/dense.o $OUT/dist.o $C/fem.o $C/lbfgs.o $C/neohookean.o $OUT/newton.o $OUT/market.o \
+  -lcudart_static -ldl -lrt -lpthread -lubsan
+cat > $OUT/run.py <<'PY'
+import sys
+sys.path.insert(0, '.')
+import polysolve_b200._lib as L
+L.LIB_PATH = 'gpurun_out/asan/libpsb200.so'
+import pytest
+sys.exit(pytest.main(['tests/test_newton.py', 'tests/test_market_io.py', 'tests/test_dist_cpu.py', 'tests/test_capi_cpu.py', '-q', '-x', '-s',
+                      '-m', 'not gpu', '-p', 'no:cacheprovider', '-k', 'not gloo and not headers_are_plain_c and not fails_loudly']))
+PY
+GCCLIB=$(dirname "$(gcc -print-file-name=libasan.so)")
+LD_PRELOAD="$GCCLIB/libasan.so $(gcc -print-file-name=libstdc++.so.6)" ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 \
+  UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 python $OUT/run.py 2>&1 | tee $OUT/out.log | tail -3
+if grep -q "ERROR: AddressSanitizer\|runtime error" $OUT/out.log; then echo "SANITIZER FINDINGS"; exit 1; fi
+echo "sanitizers: clean"
