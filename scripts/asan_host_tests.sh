@@ -1,6 +1,6 @@
 #!/bin/bash
 # Host code of libpsb200.so under AddressSanitizer + UBSan, no GPU needed: newton.cpp, market.cpp and the host parts of
-# dist.cu (plan builder) and capi.cu are rebuilt instrumented into a scratch directory, linked with the regular device
+# dist.cu (plan builder), solver.cu (parameters, validation) and capi.cu are rebuilt instrumented into a scratch directory, linked with the regular device
 # objects, and the CPU tests that exercise them (Newton driver vs the restatement, Matrix Market reader incl. hostile
 # files, host plan incl. corrupted index arrays, parameter parser) run against that library.
 set -e
@@ -11,12 +11,12 @@ C=polysolve_b200/csrc
 make -C $C libpsb200.so > /dev/null
 SAN="-fsanitize=address,undefined -fno-omit-frame-pointer"
 for f in newton market; do /usr/bin/g++ -O1 -g -std=c++17 -fPIC $SAN -c $C/$f.cpp -o $OUT/$f.o; done
-for f in dist capi; do
+for f in dist capi solver; do
   /usr/local/cuda/bin/nvcc -O1 -std=c++17 -gencode arch=compute_100a,code=sm_100a --expt-relaxed-constexpr -ccbin /usr/bin/g++ \
     -Xcompiler -fPIC,-fsanitize=address,-fno-omit-frame-pointer -c $C/$f.cu -o $OUT/$f.o
 done
 /usr/local/cuda/bin/nvcc -shared -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -Xcompiler -fsanitize=address -o $OUT/libpsb200.so \
-  $OUT/capi.o $C/solver.o $C/amg.o $C/amg_dist.o $C/spgemm.o $C/dense.o $OUT/dist.o $C/fem.o $C/lbfgs.o $C/neohookean.o $OUT/newton.o $OUT/market.o \
+  $OUT/capi.o $OUT/solver.o $C/amg.o $C/amg_dist.o $C/spgemm.o $C/dense.o $OUT/dist.o $C/fem.o $C/lbfgs.o $C/neohookean.o $OUT/newton.o $OUT/market.o \
   -lcudart_static -ldl -lrt -lpthread -lubsan
 cat > $OUT/run.py <<'PY'
 import sys
