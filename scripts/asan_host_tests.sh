@@ -30,5 +30,20 @@ PY
 GCCLIB=$(dirname "$(gcc -print-file-name=libasan.so)")
 LD_PRELOAD="$GCCLIB/libasan.so $(gcc -print-file-name=libstdc++.so.6)" ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 \
   UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 python $OUT/run.py 2>&1 | tee $OUT/out.log | tail -3
-if grep -q "ERROR: AddressSanitizer\|runtime error" $OUT/out.log; then echo "SANITIZER FINDINGS"; exit 1; fi
+# the CPU oracle (test infrastructure) under the same sanitizers: a memory error there would undermine every parity claim
+/usr/bin/g++ -O1 -g -march=x86-64-v3 -std=c++17 -fopenmp -fPIC $SAN -shared -o $OUT/liboracle.so oracle/oracle.cpp oracle/amg_oracle.cpp
+cat > $OUT/run_oracle.py <<'PY'
+import os
+import sys
+sys.path.insert(0, '.')
+import oracle.oracle as O
+O._HERE = os.path.abspath('gpurun_out/asan')      # load the instrumented liboracle.so
+O.build = lambda: None
+import pytest
+sys.exit(pytest.main(['tests/test_oracle.py', 'tests/test_dist_amg_cpu.py', 'tests/test_fem.py', 'tests/test_saddle_point.py', '-q', '-x', '-s',
+                      '-m', 'not gpu', '-p', 'no:cacheprovider', '-k', 'not gloo']))
+PY
+LD_PRELOAD="$GCCLIB/libasan.so $(gcc -print-file-name=libstdc++.so.6)" ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 \
+  UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 OMP_NUM_THREADS=4 python $OUT/run_oracle.py 2>&1 | tee $OUT/out_oracle.log | tail -2
+if grep -q "ERROR: AddressSanitizer\|runtime error" $OUT/out.log $OUT/out_oracle.log; then echo "SANITIZER FINDINGS"; exit 1; fi
 echo "sanitizers: clean"
