@@ -218,6 +218,25 @@ def test_plan_rejects_corrupted_index_arrays(psb):
     assert ok > 100 and err > 100
 
 
+def test_plan_threaded_path_matches_oracle(psb, orc):
+    """Above 2^20 entries the plan builder splits its passes over host threads (column ranges dealt in order): a
+    2.6 M-entry matrix on 3 and 8 ranks still equals the oracle bit for bit, and repeated builds are identical."""
+    o, i, v = orc.poisson3d(72)
+    n = 72 ** 3
+    assert int(o[-1]) > 2 * (1 << 20)
+    rp, ci, perm = orc.csc_to_csr(n, o, i)
+    for world in (3, 8):
+        off0 = orc.partition_rows(rp, world)
+        for r in (0, world // 2, world - 1):
+            P = psb.Solver.dist_plan_host(n, o, i, r, world, 1 << 16)
+            a, b = int(off0[r]), int(off0[r + 1])
+            lc0, halo0 = orc.halo_for_rank(rp, ci, a, b)
+            assert np.array_equal(P["offsets"], off0) and np.array_equal(P["rp"], rp[a:b + 1] - rp[a])
+            assert np.array_equal(P["halo_cols"], halo0) and np.array_equal(P["perm"], perm[rp[a]:rp[b]])
+            Q = psb.Solver.dist_plan_host(n, o, i, r, world, 1 << 16)
+            assert all(np.array_equal(P[k], Q[k]) for k in ("ci", "perm", "send_rows", "send_begin", "recv_count", "halo_cols"))
+
+
 def test_plan_halo_capacity_error(psb, orc):
     o, i, v = orc.poisson3d(12)
     with pytest.raises(RuntimeError):
