@@ -45,5 +45,24 @@ sys.exit(pytest.main(['tests/test_oracle.py', 'tests/test_dist_amg_cpu.py', 'tes
 PY
 LD_PRELOAD="$GCCLIB/libasan.so $(gcc -print-file-name=libstdc++.so.6)" ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 \
   UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 OMP_NUM_THREADS=4 python $OUT/run_oracle.py 2>&1 | tee $OUT/out_oracle.log | tail -2
-if grep -q "ERROR: AddressSanitizer\|runtime error" $OUT/out.log $OUT/out_oracle.log; then echo "SANITIZER FINDINGS"; exit 1; fi
+# ThreadSanitizer on the multi-threaded host plan builder (dist.cu: DistPlanHost::build splits its passes over host threads
+# above 2^20 entries)
+T=gpurun_out/tsan
+mkdir -p $T
+/usr/local/cuda/bin/nvcc -O1 -std=c++17 -gencode arch=compute_100a,code=sm_100a --expt-relaxed-constexpr -ccbin /usr/bin/g++ \
+  -Xcompiler -fPIC,-fsanitize=thread,-g -c $C/dist.cu -o $T/dist.o
+/usr/local/cuda/bin/nvcc -shared -gencode arch=compute_100a,code=sm_100a -ccbin /usr/bin/g++ -Xcompiler -fsanitize=thread -o $T/libpsb200.so \
+  $C/capi.o $C/solver.o $C/amg.o $C/amg_dist.o $C/spgemm.o $C/dense.o $T/dist.o $C/fem.o $C/lbfgs.o $C/neohookean.o $C/newton.o $C/market.o \
+  -lcudart_static -ldl -lrt -lpthread
+cat > $T/run.py <<'PY'
+import sys
+sys.path.insert(0, '.')
+import polysolve_b200._lib as L
+L.LIB_PATH = 'gpurun_out/tsan/libpsb200.so'
+import pytest
+sys.exit(pytest.main(['tests/test_dist_cpu.py', '-q', '-x', '-s', '-m', 'not gpu', '-p', 'no:cacheprovider', '-k', 'threaded or randomised or bit_exact']))
+PY
+LD_PRELOAD="$(gcc -print-file-name=libtsan.so) $(gcc -print-file-name=libstdc++.so.6)" TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0" \
+  python $T/run.py 2>&1 | tee $T/out.log | tail -2
+if grep -q "ERROR: AddressSanitizer\|runtime error" $OUT/out.log $OUT/out_oracle.log || grep -q "WARNING: ThreadSanitizer" $T/out.log; then echo "SANITIZER FINDINGS"; exit 1; fi
 echo "sanitizers: clean"
